@@ -1,0 +1,9 @@
+"""B200-native (sm_100a) TruncGPTQ solve-and-quantize hot path.
+
+Drop-in for the reference's `gptq_utils` names; see gptq_svd_b200/gptq_utils.py."""
+from .gptq_utils import (HessianAccumulator, Quantizer, QuantizedLinear, SpectralFactors,  # noqa: F401
+                         gptq_fwrd, gptq_quantize, log_quantization_error, pack_codes,
+                         process_hessian_alt, spectral_solve)
+
+__all__ = ["HessianAccumulator", "Quantizer", "QuantizedLinear", "SpectralFactors", "gptq_fwrd",
+           "gptq_quantize", "log_quantization_error", "pack_codes", "process_hessian_alt", "spectral_solve"]

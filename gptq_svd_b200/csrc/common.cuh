@@ -1,0 +1,70 @@
+// Shared host/device helpers for libtruncgptq (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/truncgptq.h"
+
+namespace tq {
+
+void set_error(const char* fmt, ...);
+int check_device();  // TQ_OK when the current device is sm_100 (B200)
+
+#define TQ_CUDA_CHECK(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      tq::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return TQ_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define TQ_REQUIRE(cond, ...)      \
+  do {                             \
+    if (!(cond)) {                 \
+      tq::set_error(__VA_ARGS__);  \
+      return TQ_ERR_INVALID;       \
+    }                              \
+  } while (0)
+
+#define TQ_TRY(expr)            \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != TQ_OK) return _s; \
+  } while (0)
+
+#define TQ_LAUNCH_CHECK() TQ_CUDA_CHECK(cudaGetLastError())
+
+static inline int64_t imin(int64_t a, int64_t b) { return a < b ? a : b; }
+static inline int64_t imax(int64_t a, int64_t b) { return a > b ? a : b; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// Bump allocator over the caller-provided workspace.
+struct Workspace {
+  char* base;
+  size_t size;
+  size_t off;
+  bool overflow;
+  Workspace(void* p, size_t n) : base(static_cast<char*>(p)), size(n), off(0), overflow(false) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t a = align_up(off, 256);
+    size_t need = count * sizeof(T);
+    if (base == nullptr || a + need > size) {
+      overflow = true;
+      off = a + need;
+      return nullptr;
+    }
+    off = a + need;
+    return reinterpret_cast<T*>(base + a);
+  }
+};
+
+static inline size_t ws_bytes_for(size_t count, size_t elem) { return align_up(count * elem, 256) + 256; }
+
+int num_sms();
+
+}  // namespace tq

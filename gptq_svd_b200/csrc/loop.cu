@@ -1,0 +1,472 @@
+// Quantisation grid + blocked GPTQ column loop (strict fp32) for sm_100a.
+//
+// Replaces Quantizer.find_params (reference gptq_utils.py:249-266), gptq_fwrd
+// (:459-565) and the Triton in-block kernel (:298-386).  Rows of W are independent
+// in the GPTQ recurrence, so rows are the parallel dimension and columns are the
+// serial one.  Layout in HBM (all fp32, row-major):
+//   Wp  m x n   working copy of W in PERMUTED column order; column c is overwritten
+//               by its dequantised value once quantised, so Wp ends as Q_final[:, perm]
+//   U   k x n   propagation factors U[c,j] = R[c,j]/R[c,c] (rounded as the reference
+//               rounds them, see prep_u_kernel)
+//   E   m x 128 per-block quantisation errors (the GEMM operand of the lazy update)
+//   Cp  m x n   uint8 codes (permuted order), optional
+// Per block of 128 permuted columns: gptq_block_kernel (register-resident column loop,
+// one warp per 8 rows, lanes across columns, error broadcast by warp shuffle) then
+// trailing_update_kernel  W[:, c0+128:] -= E . U[c0:c0+128, c0+128:]  (strict-fp32 SIMT
+// GEMM; the tcgen05 3xTF32 variant lives in trailing_tc.cu).
+#include "common.cuh"
+
+namespace tq {
+
+constexpr int kBlk = 128;        // columns per block step
+constexpr int kRowsPerWarp = 8;  // rows interleaved per warp for ILP
+constexpr int kWarpsPerCta = 4;
+
+// ------------------------------------------------------------------ find_params
+// One warp per (row, group).  Bit-exact with torch: amin/amax, (mx-mn).clamp(1e-5)/max_q,
+// round-half-even of -mn/scale, clamp to [0, max_q]  (gptq_utils.py:257-266).
+__global__ void find_params_kernel(const float* __restrict__ W, int64_t ldw, int64_t m, int64_t n,
+                                   int g, int ng, float max_q, int sym, float* __restrict__ scale,
+                                   float* __restrict__ zero) {
+  int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= m * ng) return;
+  int64_t r = warp / ng;
+  int gi = int(warp % ng);
+  const float* p = W + r * ldw + int64_t(gi) * g;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int j = lane; j < g; j += 32) {
+    float v = p[j];
+    if (sym) v = fabsf(v);
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) {
+    float s, z;
+    if (sym) {
+      s = __fdiv_rn(fmaxf(mx, 1e-5f), max_q);
+      z = 0.f;
+    } else {
+      s = __fdiv_rn(fmaxf(__fsub_rn(mx, mn), 1e-5f), max_q);
+      z = fminf(fmaxf(rintf(__fdiv_rn(-mn, s)), 0.f), max_q);
+    }
+    scale[warp] = s;
+    zero[warp] = z;
+  }
+}
+
+// ------------------------------------------------------------------ U preparation
+// Triton semantics: pairs inside one reference block use R[c,j] * (1/R[c,c])
+// (gptq_utils.py:374-377), pairs across reference blocks use R[c,j] / R[c,c] (:541).
+// Torch semantics: U = R (the error itself is divided by the diagonal, :528-531).
+template <typename TR>
+__global__ void prep_u_kernel(const TR* __restrict__ R, int64_t ldr, int64_t k, int64_t n,
+                              int ref_block, int semantics, float* __restrict__ U,
+                              float* __restrict__ dvec) {
+  int64_t c = blockIdx.y;
+  float d = float(R[c * ldr + c]);
+  float inv = __fdiv_rn(1.0f, d);
+  int64_t blk_end = (c / ref_block + 1) * int64_t(ref_block);
+  if (blk_end > k) blk_end = k;
+  for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
+       j += int64_t(gridDim.x) * blockDim.x) {
+    float r = float(R[c * ldr + j]);
+    float u;
+    if (semantics == TQ_LOOP_TORCH) u = r;
+    else if (j < c) u = 0.f;
+    else if (j < blk_end) u = __fmul_rn(r, inv);
+    else u = __fdiv_rn(r, d);
+    U[c * n + j] = u;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) dvec[c] = d;
+}
+
+__global__ void perm_meta_kernel(const int64_t* __restrict__ perm, int64_t n, int g,
+                                 int* __restrict__ invperm, int* __restrict__ gidx,
+                                 int* __restrict__ bad) {
+  int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int64_t p = perm[j];
+  if (p < 0 || p >= n) {
+    atomicExch(bad, 1);
+    return;
+  }
+  invperm[p] = int(j);
+  gidx[j] = int(p / g);
+}
+
+__global__ void gather_cols_kernel(const float* __restrict__ W, int64_t ldw, int64_t m, int64_t n,
+                                   const int64_t* __restrict__ perm, float* __restrict__ Wp) {
+  int64_t r = blockIdx.y;
+  for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
+       j += int64_t(gridDim.x) * blockDim.x)
+    Wp[r * n + j] = W[r * ldw + perm[j]];
+}
+
+// ------------------------------------------------------------------ quantise one value
+template <bool kHalfUp>
+__device__ __forceinline__ void quantize(float w, float s, float z, float min_q, float max_q,
+                                         float& q, float& qv) {
+  float x = __fadd_rn(__fdiv_rn(w, s), z);
+  q = kHalfUp ? floorf(__fadd_rn(x, 0.5f)) : rintf(x);
+  q = fminf(fmaxf(q, min_q), max_q);
+  qv = __fmul_rn(__fsub_rn(q, z), s);
+}
+
+// ------------------------------------------------------------------ in-block column loop
+// CTA = 4 warps x 8 rows.  Lane L owns block columns 4L..4L+3 of its 8 rows in
+// registers; the 128 x 128 diagonal block of U sits in shared memory.  For column c
+// the owner lane quantises 8 rows (independent chains -> ILP), the errors are
+// broadcast with __shfl_sync and every lane applies the rank-1 update to its columns > c.
+template <int SEM>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+gptq_block_kernel(float* __restrict__ Wp, int64_t n, const float* __restrict__ U,
+                  const float* __restrict__ dvec, const float* __restrict__ scale,
+                  const float* __restrict__ zero, int ng, const int* __restrict__ gidx, int64_t m,
+                  int64_t c0, int cnt, float min_q, float max_q, float* __restrict__ E,
+                  uint8_t* __restrict__ Cp) {
+  extern __shared__ float Us[];  // [kBlk][kBlk]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int idx = tid; idx < kBlk * kBlk; idx += blockDim.x) {
+    int rr = idx / kBlk, cc = idx % kBlk;
+    Us[idx] = (rr < cnt && cc < cnt) ? U[(c0 + rr) * n + c0 + cc] : 0.f;
+  }
+  const int64_t r0 = (int64_t(blockIdx.x) * kWarpsPerCta + warp) * kRowsPerWarp;
+  float w[kRowsPerWarp][4], s[kRowsPerWarp][4], z[kRowsPerWarp][4], eo[kRowsPerWarp][4];
+  uint32_t code[kRowsPerWarp];
+#pragma unroll
+  for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+    int64_t r = r0 + rr;
+    code[rr] = 0;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      int col = 4 * lane + cc;
+      bool ok = (r < m) && (col < cnt);
+      w[rr][cc] = ok ? Wp[r * n + c0 + col] : 0.f;
+      int g = ok ? gidx[c0 + col] : 0;
+      s[rr][cc] = ok ? scale[r * ng + g] : 1.f;
+      z[rr][cc] = ok ? zero[r * ng + g] : 0.f;
+      eo[rr][cc] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  for (int L = 0; L < 32; ++L) {
+    if (4 * L >= cnt) break;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = 4 * L + cc;
+      if (c < cnt) {
+        const float4 u = *reinterpret_cast<const float4*>(&Us[c * kBlk + 4 * lane]);
+        float dd = 1.f;
+        if (SEM == TQ_LOOP_TORCH) dd = dvec[c0 + c];
+        float e[kRowsPerWarp];
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+          float q, qv;
+          quantize<SEM == TQ_LOOP_TRITON>(w[rr][cc], s[rr][cc], z[rr][cc], min_q, max_q, q, qv);
+          float ev = __fsub_rn(w[rr][cc], qv);
+          if (SEM == TQ_LOOP_TORCH) ev = __fdiv_rn(ev, dd);
+          if (lane == L) {
+            w[rr][cc] = qv;
+            eo[rr][cc] = ev;
+            code[rr] |= uint32_t(int(q - min_q) & 0xff) << (8 * cc);
+          }
+          e[rr] = __shfl_sync(0xffffffffu, ev, L);
+        }
+        const bool p0 = 4 * lane + 0 > c, p1 = 4 * lane + 1 > c, p2 = 4 * lane + 2 > c,
+                   p3 = 4 * lane + 3 > c;
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+          if (SEM == TQ_LOOP_TRITON) {
+            if (p0) w[rr][0] = fmaf(-e[rr], u.x, w[rr][0]);
+            if (p1) w[rr][1] = fmaf(-e[rr], u.y, w[rr][1]);
+            if (p2) w[rr][2] = fmaf(-e[rr], u.z, w[rr][2]);
+            if (p3) w[rr][3] = fmaf(-e[rr], u.w, w[rr][3]);
+          } else {
+            if (p0) w[rr][0] = __fsub_rn(w[rr][0], __fmul_rn(e[rr], u.x));
+            if (p1) w[rr][1] = __fsub_rn(w[rr][1], __fmul_rn(e[rr], u.y));
+            if (p2) w[rr][2] = __fsub_rn(w[rr][2], __fmul_rn(e[rr], u.z));
+            if (p3) w[rr][3] = __fsub_rn(w[rr][3], __fmul_rn(e[rr], u.w));
+          }
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+    int64_t r = r0 + rr;
+    if (r >= m) continue;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      int col = 4 * lane + cc;
+      E[r * kBlk + col] = (col < cnt) ? eo[rr][cc] : 0.f;
+      if (col < cnt) {
+        Wp[r * n + c0 + col] = w[rr][cc];
+        if (Cp) Cp[r * n + c0 + col] = uint8_t((code[rr] >> (8 * cc)) & 0xff);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ lazy trailing update (SIMT)
+// C[m x N] -= A[m x K] . B[K x N], K <= 128, strict fp32 (the reference disables TF32,
+// gptq_utils.py:474-475).  64 x 64 tile per CTA, 4 x 4 per thread.
+constexpr int kTM = 64, kTN = 64, kTK = 32;
+__global__ void __launch_bounds__(256)
+trailing_update_kernel(float* __restrict__ C, int64_t ldc, const float* __restrict__ A, int64_t lda,
+                       const float* __restrict__ B, int64_t ldb, int64_t m, int64_t N, int K) {
+  __shared__ float As[kTK][kTM + 4];  // As[k][row]
+  __shared__ float Bs[kTK][kTN];      // Bs[k][col]
+  const int tid = threadIdx.x;
+  const int64_t row0 = int64_t(blockIdx.y) * kTM, col0 = int64_t(blockIdx.x) * kTN;
+  const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += kTK) {
+    for (int idx = tid; idx < kTM * kTK; idx += 256) {
+      int r = idx / kTK, kk = idx % kTK;
+      int64_t gr = row0 + r;
+      As[kk][r] = (gr < m && k0 + kk < K) ? A[gr * lda + k0 + kk] : 0.f;
+    }
+    for (int idx = tid; idx < kTK * kTN; idx += 256) {
+      int kk = idx / kTN, c = idx % kTN;
+      int64_t gc = col0 + c;
+      Bs[kk][c] = (gc < N && k0 + kk < K) ? B[int64_t(k0 + kk) * ldb + gc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kTK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][tr]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tc]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t gr = row0 + tr + i;
+    if (gr >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t gc = col0 + tc + j;
+      if (gc < N) C[gr * ldc + gc] = __fsub_rn(C[gr * ldc + gc], acc[i][j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ tail RTN (columns >= k)
+// Half-even rounding of the error-compensated tail, no propagation (gptq_utils.py:547-553).
+__global__ void tail_rtn_kernel(float* __restrict__ Wp, int64_t n, int64_t m, int64_t k,
+                                const float* __restrict__ scale, const float* __restrict__ zero,
+                                int ng, const int* __restrict__ gidx, float min_q, float max_q,
+                                uint8_t* __restrict__ Cp) {
+  int64_t r = blockIdx.y;
+  for (int64_t j = k + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
+       j += int64_t(gridDim.x) * blockDim.x) {
+    int g = gidx[j];
+    float q, qv;
+    quantize<false>(Wp[r * n + j], scale[r * ng + g], zero[r * ng + g], min_q, max_q, q, qv);
+    Wp[r * n + j] = qv;
+    if (Cp) Cp[r * n + j] = uint8_t(int(q - min_q));
+  }
+}
+
+// Restore the original column order (gptq_utils.py:556-557) with coalesced writes.
+__global__ void unpermute_kernel(const float* __restrict__ Wp, const uint8_t* __restrict__ Cp,
+                                 int64_t m, int64_t n, const int* __restrict__ invperm,
+                                 float* __restrict__ Wq, int64_t ldq, uint8_t* __restrict__ codes,
+                                 int64_t ldc) {
+  int64_t r = blockIdx.y;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    int j = invperm[i];
+    Wq[r * ldq + i] = Wp[r * n + j];
+    if (codes) codes[r * ldc + i] = Cp[r * n + j];
+  }
+}
+
+// ------------------------------------------------------------------ packing
+// Row bit-stream, value j at bits [j*bits, (j+1)*bits), little-endian uint32 words.
+__global__ void pack_codes_kernel(const uint8_t* __restrict__ codes, int64_t ldc, int64_t m,
+                                  int64_t n, int bits, uint32_t* __restrict__ packed, int64_t ldp,
+                                  int64_t nwords) {
+  int64_t r = blockIdx.y;
+  for (int64_t w = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; w < nwords;
+       w += int64_t(gridDim.x) * blockDim.x) {
+    int64_t bit0 = w * 32;
+    int64_t j = bit0 / bits;
+    int off = int(bit0 - j * bits);  // bits of value j already consumed by the previous word
+    uint64_t acc = 0;
+    int have = 0;
+    if (off) {
+      acc = uint64_t(codes[r * ldc + j]) >> off;
+      have = bits - off;
+      ++j;
+    }
+    while (have < 32 && j < n) {
+      acc |= uint64_t(codes[r * ldc + j]) << have;
+      have += bits;
+      ++j;
+    }
+    packed[r * ldp + w] = uint32_t(acc & 0xffffffffu);
+  }
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" int tq_find_params(const float* W, int64_t ldw, int64_t m, int64_t n, int bits, int group,
+                              int sym, float* scale, float* zero, void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(W && scale && zero, "tq_find_params: null pointer");
+  TQ_REQUIRE(m > 0 && n > 0 && ldw >= n, "tq_find_params: bad shape m=%lld n=%lld ldw=%lld",
+             (long long)m, (long long)n, (long long)ldw);
+  TQ_REQUIRE(bits >= 2 && bits <= 8, "tq_find_params: bits=%d outside [2,8]", bits);
+  int64_t g = group > 0 ? group : n;
+  TQ_REQUIRE(n % g == 0, "tq_find_params: in_features %lld not divisible by group size %lld",
+             (long long)n, (long long)g);
+  int ng = int(n / g);
+  float max_q = sym ? float((1 << (bits - 1)) - 1) : float((1 << bits) - 1);
+  int64_t warps = m * ng;
+  int threads = 256;
+  int64_t blocks = ceil_div(warps * 32, threads);
+  find_params_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      W, ldw, m, n, int(g), ng, max_q, sym, scale, zero);
+  TQ_LAUNCH_CHECK();
+  return TQ_OK;
+}
+
+extern "C" int tq_gptq_loop_workspace(int64_t m, int64_t n, int64_t k, size_t* bytes) {
+  TQ_REQUIRE(bytes && m > 0 && n > 0 && k >= 0 && k <= n, "tq_gptq_loop_workspace: bad arguments");
+  size_t b = 0;
+  b += ws_bytes_for(size_t(m) * n, 4);     // Wp
+  b += ws_bytes_for(size_t(k) * n, 4);     // U
+  b += ws_bytes_for(size_t(m) * kBlk, 4);  // E
+  b += ws_bytes_for(size_t(m) * n, 1);     // Cp
+  b += ws_bytes_for(size_t(n), 4) * 2;     // invperm, gidx
+  b += ws_bytes_for(size_t(k) + 1, 4);     // dvec
+  b += ws_bytes_for(1, 4);                 // bad flag
+  *bytes = b;
+  return TQ_OK;
+}
+
+extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dtype, int64_t ldr,
+                            int64_t k, const int64_t* perm, const float* scale, const float* zero,
+                            int64_t m, int64_t n, int bits, int group, int sym, int ref_block,
+                            int semantics, float* Wq_out, int64_t ldq, uint8_t* codes_out,
+                            int64_t ldc, void* ws, size_t ws_bytes, void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(W && perm && scale && zero && Wq_out, "tq_gptq_loop: null pointer");
+  TQ_REQUIRE(m > 0 && n > 0 && k >= 0 && k <= n, "tq_gptq_loop: bad shape m=%lld n=%lld k=%lld",
+             (long long)m, (long long)n, (long long)k);
+  TQ_REQUIRE(k == 0 || R, "tq_gptq_loop: null R");
+  TQ_REQUIRE(ldw >= n && ldq >= n && (k == 0 || ldr >= n) && (!codes_out || ldc >= n),
+             "tq_gptq_loop: leading dimension too small");
+  TQ_REQUIRE(bits >= 2 && bits <= 8, "tq_gptq_loop: bits=%d outside [2,8]", bits);
+  TQ_REQUIRE(r_dtype == TQ_F64 || r_dtype == TQ_F32, "tq_gptq_loop: R must be fp64 or fp32");
+  TQ_REQUIRE(semantics == TQ_LOOP_TRITON || semantics == TQ_LOOP_TORCH, "tq_gptq_loop: bad semantics");
+  TQ_REQUIRE(ref_block > 0, "tq_gptq_loop: ref_block must be positive");
+  int64_t g = group > 0 ? group : n;
+  TQ_REQUIRE(n % g == 0, "tq_gptq_loop: in_features %lld not divisible by group size %lld",
+             (long long)n, (long long)g);
+  const int ng = int(n / g);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  Workspace wsp(ws, ws_bytes);
+  float* Wp = wsp.take<float>(size_t(m) * n);
+  float* U = wsp.take<float>(size_t(k) * n);
+  float* E = wsp.take<float>(size_t(m) * kBlk);
+  uint8_t* Cp = wsp.take<uint8_t>(size_t(m) * n);
+  int* invperm = wsp.take<int>(n);
+  int* gidx = wsp.take<int>(n);
+  float* dvec = wsp.take<float>(k + 1);
+  int* bad = wsp.take<int>(1);
+  if (wsp.overflow) {
+    set_error("tq_gptq_loop: workspace too small (%zu < %zu)", ws_bytes, wsp.off);
+    return TQ_ERR_WORKSPACE;
+  }
+  if (!codes_out) Cp = nullptr;
+
+  const float max_q = sym ? float((1 << (bits - 1)) - 1) : float((1 << bits) - 1);
+  const float min_q = sym ? -max_q : 0.f;
+
+  TQ_CUDA_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+  perm_meta_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(perm, n, int(g), invperm, gidx, bad);
+  TQ_LAUNCH_CHECK();
+  {
+    dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)m);
+    gather_cols_kernel<<<grid, 256, 0, st>>>(W, ldw, m, n, perm, Wp);
+    TQ_LAUNCH_CHECK();
+  }
+  if (k > 0) {
+    dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)k);
+    if (r_dtype == TQ_F64)
+      prep_u_kernel<double><<<grid, 256, 0, st>>>((const double*)R, ldr, k, n, ref_block, semantics, U, dvec);
+    else
+      prep_u_kernel<float><<<grid, 256, 0, st>>>((const float*)R, ldr, k, n, ref_block, semantics, U, dvec);
+    TQ_LAUNCH_CHECK();
+  }
+
+  const size_t smem = size_t(kBlk) * kBlk * sizeof(float);
+  static thread_local bool attr_done = false;
+  if (!attr_done) {
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(gptq_block_kernel<TQ_LOOP_TRITON>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(gptq_block_kernel<TQ_LOOP_TORCH>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const unsigned row_ctas = (unsigned)ceil_div(m, kRowsPerWarp * kWarpsPerCta);
+  for (int64_t c0 = 0; c0 < k; c0 += kBlk) {
+    int cnt = int(imin(kBlk, k - c0));
+    if (semantics == TQ_LOOP_TRITON)
+      gptq_block_kernel<TQ_LOOP_TRITON><<<row_ctas, kWarpsPerCta * 32, smem, st>>>(
+          Wp, n, U, dvec, scale, zero, ng, gidx, m, c0, cnt, min_q, max_q, E, Cp);
+    else
+      gptq_block_kernel<TQ_LOOP_TORCH><<<row_ctas, kWarpsPerCta * 32, smem, st>>>(
+          Wp, n, U, dvec, scale, zero, ng, gidx, m, c0, cnt, min_q, max_q, E, Cp);
+    TQ_LAUNCH_CHECK();
+    int64_t j0 = c0 + cnt;
+    if (j0 < n) {
+      int64_t N = n - j0;
+      dim3 grid((unsigned)ceil_div(N, kTN), (unsigned)ceil_div(m, kTM));
+      trailing_update_kernel<<<grid, 256, 0, st>>>(Wp + j0, n, E, kBlk, U + c0 * n + j0, n, m, N, cnt);
+      TQ_LAUNCH_CHECK();
+    }
+  }
+  if (k < n) {
+    dim3 grid((unsigned)imin(ceil_div(n - k, 256), 64), (unsigned)m);
+    tail_rtn_kernel<<<grid, 256, 0, st>>>(Wp, n, m, k, scale, zero, ng, gidx, min_q, max_q, Cp);
+    TQ_LAUNCH_CHECK();
+  }
+  {
+    dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)m);
+    unpermute_kernel<<<grid, 256, 0, st>>>(Wp, Cp, m, n, invperm, Wq_out, ldq, codes_out, ldc);
+    TQ_LAUNCH_CHECK();
+  }
+  return TQ_OK;
+}
+
+extern "C" int tq_pack_codes(const uint8_t* codes, int64_t ldc, int64_t m, int64_t n, int bits,
+                             uint32_t* packed, int64_t ldp, void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(codes && packed && m > 0 && n > 0 && ldc >= n, "tq_pack_codes: bad arguments");
+  TQ_REQUIRE(bits >= 1 && bits <= 8, "tq_pack_codes: bits=%d outside [1,8]", bits);
+  int64_t nwords = (n * bits + 31) / 32;
+  TQ_REQUIRE(ldp >= nwords, "tq_pack_codes: ldp %lld < %lld words", (long long)ldp, (long long)nwords);
+  dim3 grid((unsigned)imin(ceil_div(nwords, 128), 64), (unsigned)m);
+  pack_codes_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(codes, ldc, m, n, bits, packed, ldp, nwords);
+  TQ_LAUNCH_CHECK();
+  return TQ_OK;
+}

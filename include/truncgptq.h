@@ -1,0 +1,173 @@
+/*
+ * truncgptq.h - C ABI of libtruncgptq.so: the B200-native (sm_100a) TruncGPTQ
+ * solve-and-quantize hot path.
+ *
+ * The reference (davidtweedle/gptq-svd) has no FFI boundary: its hot path is the
+ * Python module src/TruncGPTQ/gptq_utils.py imported at src/TruncGPTQ/quantize.py:14.
+ * Each entry point below replaces the body of one of those Python functions; the
+ * host-side mirror (gptq_svd_b200/gptq_utils.py) keeps the Python signatures and
+ * calls these through ctypes.  INTEGRATION.md shows the binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless
+ *     the parameter name ends in _host;
+ *   - matrices are row-major with an explicit leading dimension (elements);
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered.  The
+ *     only host synchronisations are the documented ones (rank k read-back in
+ *     tq_spectral_solve / tq_rank_select and the D&C merge control in tq_eigh);
+ *   - workspace is caller-provided (query with the *_workspace function);
+ *   - return value: TQ_OK (0) or a negative status; tq_last_error() returns a
+ *     thread-local description of the last failure;
+ *   - no global mutable state, one host thread per GPU; there is NO CPU fallback:
+ *     every compute entry point fails with TQ_ERR_CUDA when no sm_100 device is
+ *     current.
+ */
+#ifndef TRUNCGPTQ_H_
+#define TRUNCGPTQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQ_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define TQ_OK 0
+#define TQ_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer)    */
+#define TQ_ERR_CUDA (-2)        /* CUDA runtime / driver failure                    */
+#define TQ_ERR_WORKSPACE (-3)   /* workspace too small                              */
+#define TQ_ERR_NOCONV (-4)      /* an iterative stage did not converge              */
+#define TQ_ERR_UNSUPPORTED (-5) /* valid request outside the implemented envelope   */
+
+/* element types */
+#define TQ_F16 0
+#define TQ_BF16 1
+#define TQ_F32 2
+#define TQ_F64 3
+
+/* rank rules of process_hessian_alt (gptq_utils.py:97-108) */
+#define TQ_RANK_ENERGY 0
+#define TQ_RANK_MEAN_TRIMMED 1
+#define TQ_RANK_FULL 2
+
+/* loop arithmetic (gptq_utils.py:507-534) */
+#define TQ_LOOP_TRITON 0 /* Triton kernel semantics: half-up, un-scaled error (:345-386) */
+#define TQ_LOOP_TORCH 1  /* torch fallback semantics: half-even, error / diag (:516-534)  */
+
+int tq_version(void);
+const char* tq_last_error(void);
+
+/* --------------------------------------------------------------------------
+ * (1) Hessian accumulation - replaces HessianAccumulator.add_batch / get_hessian
+ *     (gptq_utils.py:218-228).
+ * -------------------------------------------------------------------------- */
+
+/* H (n x n fp64, fully symmetric on return) += X^T X, X = rows x n (x_dtype TQ_F16 or
+ * TQ_BF16), computed as a tcgen05/TMEM SYRK: fp16 products are exact in fp32, TMEM
+ * accumulates `kc_tokens` tokens at a time (0 = default 1024), chunk sums are added in
+ * fp32 registers and the batch total is added to H in fp64.  Requires ldx % 8 == 0 and a
+ * 16-byte aligned X (TMA).  gptq_utils.py:221-222. */
+int tq_syrk_accum(double* H, int64_t ldh, const void* X, int x_dtype, int64_t rows, int64_t n,
+                  int64_t ldx, int kc_tokens, void* stream);
+
+/* out = H / n_samples (out = H when n_samples == 0).  gptq_utils.py:225-228. */
+int tq_hessian_scale(const double* H, int64_t ldh, int64_t n, int64_t n_samples, double* out,
+                     int64_t ldo, void* stream);
+
+/* dst(fp16) = src (TQ_F32 / TQ_F64 / TQ_BF16 rows x n) for activations that arrive in
+ * another float type (the reference casts to fp64, gptq_utils.py:221). */
+int tq_cast_to_f16(const void* src, int src_dtype, int64_t rows, int64_t n, int64_t lds, void* dst,
+                   int64_t ldd, void* stream);
+
+/* --------------------------------------------------------------------------
+ * (2) Spectral solver - replaces process_hessian_alt (gptq_utils.py:87-126).
+ * -------------------------------------------------------------------------- */
+
+int tq_solver_workspace(int64_t n, size_t* bytes);
+
+/* Whole solver.  H: n x n symmetric (fp64).  Outputs (all device, caller-allocated):
+ *   R, Rx   n x n row-major buffers, leading dimension n; rows [0,k) are written
+ *           (upper-trapezoidal, diag > 0): R^T R = P^T H_k^+ P, Rx^T Rx = P^T H_k P;
+ *   perm    n int64 (column pivots of the QRCP, gptq_utils.py:114-115);
+ *   eigvals n fp64, clamped at 1e-12, DESCENDING (gptq_utils.py:94);
+ *   k_host  retained rank, written on the host after an internal 8-byte D2H copy.
+ * threshold / method as gptq_utils.py:97-108. */
+int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double threshold, int method,
+                      double* R, double* Rx, int64_t* perm, double* eigvals, int64_t* k_host,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* Stages of the solver, exposed for stage-wise parity tests and profiling. */
+
+/* Symmetric eigendecomposition (blocked tridiagonal reduction + divide & conquer +
+ * Householder back-transform).  w: n eigenvalues ascending; V: n x n, eigenvector i is
+ * ROW i of V (row-major), i.e. V = torch.linalg.eigh(H)[1].T.  gptq_utils.py:93. */
+int tq_eigh(const double* H, int64_t ldh, int64_t n, double* w, double* V, int64_t ldv, void* ws,
+            size_t ws_bytes, void* stream);
+
+/* eig_desc = clamp(w, 1e-12) reversed; k by the rank rule.  gptq_utils.py:94-108. */
+int tq_rank_select(const double* w_asc, int64_t n, double threshold, int method, double* eig_desc,
+                   int64_t* k_host, void* ws, size_t ws_bytes, void* stream);
+
+/* Column-pivoted Householder QR (LAPACK dgeqp3/dlaqps semantics) of the k x n matrix
+ * A (row-major, lda); returns Rx (k x n upper-trapezoidal, sign-normalised to diag > 0)
+ * and perm.  A is not modified.  gptq_utils.py:114-116,122-123. */
+int tq_qrcp(const double* A, int64_t lda, int64_t k, int64_t n, double* Rx, int64_t ldr,
+            int64_t* perm, void* ws, size_t ws_bytes, void* stream);
+
+/* R factor (sign-normalised) of the unpivoted Householder QR of the k x n matrix A
+ * (row-major).  Q is never formed.  gptq_utils.py:120-121,124. */
+int tq_qr_r(const double* A, int64_t lda, int64_t k, int64_t n, double* R, int64_t ldr, void* ws,
+            size_t ws_bytes, void* stream);
+
+/* --------------------------------------------------------------------------
+ * (3) Quantisation grid and blocked GPTQ loop - replaces Quantizer.find_params
+ *     (gptq_utils.py:249-266) and gptq_fwrd (:459-565) incl. the Triton kernel (:298-386).
+ * -------------------------------------------------------------------------- */
+
+/* scale, zero: m x (n / g) fp32, g = group > 0 ? group : n.  n % g != 0 -> TQ_ERR_INVALID
+ * (the reference asserts, gptq_utils.py:253). */
+int tq_find_params(const float* W, int64_t ldw, int64_t m, int64_t n, int bits, int group, int sym,
+                   float* scale, float* zero, void* stream);
+
+int tq_gptq_loop_workspace(int64_t m, int64_t n, int64_t k, size_t* bytes);
+
+/* Blocked GPTQ column loop.
+ *   W      m x n fp32, original column order (not modified);
+ *   R      k x n upper-trapezoidal factor (r_dtype TQ_F64 or TQ_F32; cast to fp32 first,
+ *          gptq_utils.py:483), row-major, ldr;
+ *   perm   n int64; scale/zero from tq_find_params (static grid of the ORIGINAL W);
+ *   ref_block  the reference's block_size: pairs (c, j) inside one ref_block use
+ *          R[c,j] * (1/R[c,c]), pairs across blocks use R[c,j] / R[c,c]
+ *          (gptq_utils.py:374-377 vs :541); the kernel's own tiling is independent of it;
+ *   semantics  TQ_LOOP_TRITON or TQ_LOOP_TORCH;
+ *   Wq_out m x n fp32 dequantised weights, original column order (gptq_utils.py:556-557);
+ *   codes_out  optional m x n uint8, code - min_q, original column order (new: the
+ *          reference has no integer output, README.md:133). */
+int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dtype, int64_t ldr, int64_t k,
+                 const int64_t* perm, const float* scale, const float* zero, int64_t m, int64_t n,
+                 int bits, int group, int sym, int ref_block, int semantics, float* Wq_out,
+                 int64_t ldq, uint8_t* codes_out, int64_t ldc, void* ws, size_t ws_bytes,
+                 void* stream);
+
+/* Pack biased codes (m x n uint8, value < 2^bits) LSB-first along the input dimension into
+ * little-endian uint32 words, ceil(n*bits/32) words per row. */
+int tq_pack_codes(const uint8_t* codes, int64_t ldc, int64_t m, int64_t n, int bits,
+                  uint32_t* packed, int64_t ldp, void* stream);
+
+int tq_quant_error_workspace(int64_t m, int64_t n, int64_t k, size_t* bytes);
+
+/* out2[0] = ||(W - Wq)[:,perm] Rx^T||_F^2, out2[1] = ||W[:,perm] Rx^T||_F^2 in fp32
+ * arithmetic with fp64 norm accumulation.  Replaces log_quantization_error
+ * (gptq_utils.py:275-291). */
+int tq_quant_error(const float* W, int64_t ldw, const float* Wq, int64_t ldq, const void* Rx,
+                   int rx_dtype, int64_t ldr, int64_t k, const int64_t* perm, int64_t m, int64_t n,
+                   double* out2, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRUNCGPTQ_H_ */

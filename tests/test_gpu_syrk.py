@@ -1,0 +1,97 @@
+"""GPU parity: Hessian accumulation (tq_syrk_accum, tcgen05 SYRK) against the golden H
+of the unmodified reference, the CPU oracle and an fp64 torch reference.
+Tolerance (north_star): relative Frobenius error <= 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import truncgptq_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gptq_svd_b200 as G
+    return G
+
+
+def _rel(a, b):
+    return float(torch.linalg.norm(a - b) / torch.linalg.norm(b))
+
+
+@pytest.mark.parametrize("name", ["llm_n128_w4a", "flat_n128_w4a"])
+def test_hessian_vs_reference_golden(G, name, golden):
+    g = golden(name)
+    X = torch.from_numpy(g["X"]).cuda()
+    n = X.shape[1]
+    acc = G.HessianAccumulator(n, "cuda")
+    for c in range(0, X.shape[0], 1024):
+        xb = X[c:c + 1024]
+        acc.add_batch(xb.reshape(2, -1, n) if c == 0 else xb)
+    H = acc.get_hessian()
+    assert acc.n_samples == int(g["n_tokens"])
+    Href = torch.from_numpy(g["H"]).cuda()
+    assert _rel(H, Href) <= TOL
+    assert torch.equal(H, H.T)
+
+
+@pytest.mark.parametrize("rows,n,dtype", [
+    (1000, 192, torch.float16),      # ragged token count, n not a multiple of the tile
+    (64, 64, torch.float16),
+    (1, 128, torch.float16),         # single token
+    (4096, 320, torch.bfloat16),
+    (3000, 1024, torch.float16),     # Qwen3-0.6B hidden size
+    (2049, 520, torch.float32),      # fp32 activations take the cast path
+])
+def test_hessian_vs_fp64(G, rows, n, dtype):
+    torch.manual_seed(rows + n)
+    X = (torch.randn(rows, n, device="cuda") * torch.logspace(0, -2, n, device="cuda")).to(dtype)
+    acc = G.HessianAccumulator(n, "cuda")
+    acc.add_batch(X)
+    Xr = X.half() if dtype == torch.float32 else X
+    ref = Xr.double().T @ Xr.double()
+    assert _rel(acc.H, ref) <= TOL
+    assert torch.equal(acc.H, acc.H.T)
+    if rows * n <= 1 << 18:            # also against the CPU oracle on small cases
+        o = O.HessianAccumulator(n)
+        o.add_batch(Xr.cpu().numpy() if dtype != torch.bfloat16 else Xr.float().cpu().numpy())
+        assert _rel(acc.H.cpu(), torch.from_numpy(o.H)) <= TOL
+
+
+def test_empty_and_linearity(G):
+    n = 256
+    acc = G.HessianAccumulator(n, "cuda")
+    assert acc.get_hessian() is acc.H and acc.n_samples == 0
+    acc.add_batch(torch.empty(0, n, device="cuda", dtype=torch.float16))
+    assert acc.n_samples == 0 and float(acc.H.abs().max()) == 0.0
+    torch.manual_seed(1)
+    X1 = torch.randn(700, n, device="cuda").half()
+    X2 = torch.randn(1300, n, device="cuda").half()
+    a = G.HessianAccumulator(n, "cuda"); a.add_batch(X1); a.add_batch(X2)
+    b = G.HessianAccumulator(n, "cuda"); b.add_batch(torch.cat([X1, X2]))
+    assert a.n_samples == b.n_samples == 2000
+    assert _rel(a.H, b.H) <= 1e-6
+    with pytest.raises(RuntimeError):
+        a.add_batch(torch.randn(4, n).half())          # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("n", [4096])
+def test_full_size_batch(G, n):
+    """One reference-sized add_batch call: 32 x 2048 tokens x 4096 features (Qwen3-8B)."""
+    torch.manual_seed(0)
+    X = torch.randn(32, 2048, n, device="cuda", dtype=torch.float16)
+    acc = G.HessianAccumulator(n, "cuda")
+    acc.add_batch(X)
+    X2 = X.reshape(-1, n)
+    ref = torch.zeros(n, n, device="cuda", dtype=torch.float64)
+    for c in range(0, X2.shape[0], 8192):
+        xb = X2[c:c + 8192].double()
+        ref += xb.T @ xb
+    err = _rel(acc.H, ref)
+    print(f"n={n} rows={X2.shape[0]} rel_fro={err:.3e}")
+    assert err <= TOL
+    # trace identity: tr(X^T X) = ||X||_F^2
+    tr = float(torch.diagonal(acc.H).sum())
+    assert abs(tr - float((X2.double() ** 2).sum())) <= 1e-5 * tr
