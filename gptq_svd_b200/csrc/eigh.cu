@@ -1,0 +1,804 @@
+// Symmetric eigendecomposition in fp64 (reference: torch.linalg.eigh -> cuSOLVER syevd,
+// gptq_utils.py:93), written from scratch for sm_100a:
+//   1. sytrd  blocked Householder tridiagonal reduction (lower).  Per column the work is
+//             BLAS-2 and HBM-bound (one pass over the trailing matrix: dots3_kernel);
+//             per panel the rank-2k trailing update is DGEMM.
+//   2. stedc  divide & conquer on the tridiagonal matrix: QL leaves (one warp per leaf),
+//             then rank-one merges.  Deflation is decided on the host from d and z (O(n)
+//             per merge); the secular equation (one warp per root, "middle way" rational
+//             interpolation with a bisection safeguard), the Gu/Eisenstat z-hat recomputation
+//             and the eigenvector formation run on the device; the eigenvector update is DGEMM.
+//   3. ormtr  back-transformation Z <- Q Z with compact-WY block reflectors (DGEMM).
+// All matrices are column-major with leading dimension n.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "solver_kernels.cuh"
+
+namespace tq {
+
+constexpr int kTrdNb = 64;   // sytrd panel width
+constexpr int kLeaf = 32;    // D&C leaf size (one warp)
+constexpr int kOrmNb = 64;   // back-transform block
+
+// ======================================================================= sytrd kernels
+// A[r, c] -= sum_t V[r,t] W[c,t] + W[r,t] V[c,t]   (t < i),  r in [c, n);  d[c] = A[c,c]
+__global__ void sytrd_col_update_kernel(double* __restrict__ A, int64_t lda, int64_t n, int64_t j0, int i,
+                                        const double* __restrict__ W, int64_t ldw, double* __restrict__ d) {
+  const int64_t c = j0 + i;
+  for (int64_t r = c + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n;
+       r += int64_t(gridDim.x) * blockDim.x) {
+    double s = 0.0;
+    for (int t = 0; t < i; ++t) {
+      s = fma(A[r + (j0 + t) * lda], W[c + t * ldw], s);
+      s = fma(W[r + t * ldw], A[c + (j0 + t) * lda], s);
+    }
+    const double a = A[r + c * lda] - s;
+    A[r + c * lda] = a;
+    if (r == c) d[c] = a;
+  }
+}
+
+// w[r] = tau * (y[r] - sum_t V[r,t] tmp1[t] - sum_t W[r,t] tmp2[t]),  r in [c+1, n)
+__global__ void sytrd_w_kernel(const double* __restrict__ A, int64_t lda, int64_t n, int64_t j0, int i,
+                               double* __restrict__ W, int64_t ldw, const double* __restrict__ y,
+                               const double* __restrict__ tmp1, const double* __restrict__ tmp2,
+                               const double* __restrict__ tau_p) {
+  const int64_t c = j0 + i;
+  const double tau = *tau_p;
+  for (int64_t r = c + 1 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n;
+       r += int64_t(gridDim.x) * blockDim.x) {
+    double s = y[r];
+    for (int t = 0; t < i; ++t) {
+      s = fma(-A[r + (j0 + t) * lda], tmp1[t], s);
+      s = fma(-W[r + t * ldw], tmp2[t], s);
+    }
+    W[r + int64_t(i) * ldw] = tau * s;
+  }
+}
+
+// w += (-tau/2 * w.v) v      (single CTA)
+__global__ void __launch_bounds__(1024)
+sytrd_w_finish_kernel(double* __restrict__ w, const double* __restrict__ v, int64_t len,
+                      const double* __restrict__ tau_p) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int64_t r = threadIdx.x; r < len; r += blockDim.x) s = fma(w[r], v[r], s);
+  s = block_sum(s, sh);
+  const double alpha = -0.5 * (*tau_p) * s;
+  for (int64_t r = threadIdx.x; r < len; r += blockDim.x) w[r] = fma(alpha, v[r], w[r]);
+}
+
+// Reduces A (n x n, symmetric, both triangles valid) to tridiagonal form.  On exit
+// d[0:n], e[0:n-1], tau[0:n-1]; reflector c lives in A[c+1:, c] with an explicit unit at
+// A[c+1, c].
+static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double* d, double* e, double* tau,
+                       double* W, double* y, double* tmp /*2*kTrdNb*/) {
+  const int64_t lda = n, ldw = n;
+  const double one = 1.0, mone = -1.0;
+  DotSeg none{nullptr, 0, 0, nullptr};
+  TQ_CUDA_CHECK(cudaMemsetAsync(tau, 0, sizeof(double) * n, st));
+  TQ_CUDA_CHECK(cudaMemsetAsync(e, 0, sizeof(double) * n, st));
+  for (int64_t j0 = 0; j0 < n; j0 += kTrdNb) {
+    const int jb = int(imin(kTrdNb, n - j0));
+    for (int i = 0; i < jb; ++i) {
+      const int64_t c = j0 + i;
+      const int64_t rows = n - c;
+      sytrd_col_update_kernel<<<(unsigned)imin(ceil_div(rows, 256), 592), 256, 0, st>>>(A, lda, n, j0, i, W, ldw,
+                                                                                       d);
+      TQ_LAUNCH_CHECK();
+      const int64_t len = n - c - 1;
+      if (len <= 0) continue;
+      double* v = A + (c + 1) + c * lda;
+      larfg_kernel<<<1, 1024, 0, st>>>(v, len, tau + c, e + c, nullptr);
+      TQ_LAUNCH_CHECK();
+      DotSeg s0{A + (c + 1) + (c + 1) * lda, lda, len, y + c + 1};
+      DotSeg s1{W + (c + 1), ldw, i, tmp};
+      DotSeg s2{A + (c + 1) + j0 * lda, lda, i, tmp + kTrdNb};
+      dots3_kernel<<<dots_grid(len + 2 * i), 256, 0, st>>>(s0, s1, s2, v, len, nullptr);
+      TQ_LAUNCH_CHECK();
+      sytrd_w_kernel<<<(unsigned)imin(ceil_div(len, 256), 592), 256, 0, st>>>(A, lda, n, j0, i, W, ldw, y, tmp,
+                                                                             tmp + kTrdNb, tau + c);
+      TQ_LAUNCH_CHECK();
+      sytrd_w_finish_kernel<<<1, 1024, 0, st>>>(W + (c + 1) + int64_t(i) * ldw, v, len, tau + c);
+      TQ_LAUNCH_CHECK();
+    }
+    const int64_t r0 = j0 + jb;
+    const int64_t s2 = n - r0;
+    if (s2 > 0) {
+      // A22 -= V2 W2^T + W2 V2^T   (full square, keeps both triangles valid)
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(s2), int(s2), jb, &mone, A + r0 + j0 * lda,
+                                  int(lda), W + r0, int(ldw), &one, A + r0 + r0 * lda, int(lda)));
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(s2), int(s2), jb, &mone, W + r0, int(ldw),
+                                  A + r0 + j0 * lda, int(lda), &one, A + r0 + r0 * lda, int(lda)));
+    }
+  }
+  return TQ_OK;
+}
+
+// ======================================================================= D&C kernels
+// rank-one tears at every cut point of the D&C tree (LAPACK DLAED0): serial, ncuts < n/16
+__global__ void dc_tear_serial_kernel(double* d, const double* e, const int* cuts, int ncuts) {
+  for (int t = 0; t < ncuts; ++t) {
+    int cp = cuts[t];
+    double b = fabs(e[cp]);
+    d[cp] -= b;
+    d[cp + 1] -= b;
+  }
+}
+
+// QL implicit (EISPACK tql2 / "tqli") on leaves of size <= 32: one warp per leaf.
+// Lane 0 runs the scalar recurrence and records the plane rotations of one sweep; every
+// lane then applies them to its own row of the leaf's eigenvector block.
+__global__ void __launch_bounds__(32)
+dc_leaf_kernel(double* __restrict__ d, const double* __restrict__ e, double* __restrict__ Z, int64_t ldz,
+               const int* __restrict__ leaf_off, const int* __restrict__ leaf_len, int* __restrict__ fail) {
+  __shared__ double sd[kLeaf], se[kLeaf], rc[kLeaf], rs[kLeaf], zz[kLeaf][kLeaf + 1];
+  __shared__ int ctl[4];   // 0: first rotation index (high), 1: last rotation index (low), 2: done flag
+  __shared__ int order[kLeaf];
+  const int lane = threadIdx.x;
+  const int off = leaf_off[blockIdx.x], len = leaf_len[blockIdx.x];
+  if (lane < len) {
+    sd[lane] = d[off + lane];
+    se[lane] = (lane < len - 1) ? e[off + lane] : 0.0;
+  }
+  for (int c = 0; c < len; ++c)
+    if (lane < len) zz[lane][c] = (lane == c) ? 1.0 : 0.0;
+  __syncwarp();
+  const double eps = 1.1102230246251565e-16;
+  for (int l = 0; l < len; ++l) {
+    int iter = 0;
+    while (true) {
+      if (lane == 0) {
+        int m = l;
+        for (; m < len - 1; ++m) {
+          double dd = fabs(sd[m]) + fabs(sd[m + 1]);
+          if (fabs(se[m]) <= eps * dd) break;
+        }
+        if (m == l) {
+          ctl[2] = 1;
+        } else if (iter++ >= 60) {
+          ctl[2] = 1;
+          atomicExch(fail, 1);
+        } else {
+          ctl[2] = 0;
+          double g = (sd[l + 1] - sd[l]) / (2.0 * se[l]);
+          double r = hypot(g, 1.0);
+          g = sd[m] - sd[l] + se[l] / (g + copysign(r, g));
+          double s = 1.0, c = 1.0, p = 0.0;
+          int i = m - 1;
+          bool early = false;
+          for (; i >= l; --i) {
+            double f = s * se[i], b = c * se[i];
+            r = hypot(f, g);
+            se[i + 1] = r;
+            if (r == 0.0) {
+              sd[i + 1] -= p;
+              se[m] = 0.0;
+              early = true;
+              break;
+            }
+            s = f / r;
+            c = g / r;
+            g = sd[i + 1] - p;
+            r = (sd[i] - g) * s + 2.0 * c * b;
+            p = s * r;
+            sd[i + 1] = g + p;
+            g = c * r - b;
+            rc[i] = c;
+            rs[i] = s;
+          }
+          ctl[0] = m - 1;
+          ctl[1] = early ? i + 1 : l;
+          if (!early) {
+            sd[l] -= p;
+            se[l] = g;
+            se[m] = 0.0;
+          }
+        }
+      }
+      __syncwarp();
+      if (ctl[2]) break;
+      if (lane < len) {
+        for (int i = ctl[0]; i >= ctl[1]; --i) {
+          double f = zz[lane][i + 1];
+          zz[lane][i + 1] = rs[i] * zz[lane][i] + rc[i] * f;
+          zz[lane][i] = rc[i] * zz[lane][i] - rs[i] * f;
+        }
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+  // ascending order (selection sort on lane 0)
+  if (lane == 0) {
+    for (int i = 0; i < len; ++i) order[i] = i;
+    for (int i = 0; i < len - 1; ++i) {
+      int kmin = i;
+      for (int j = i + 1; j < len; ++j)
+        if (sd[order[j]] < sd[order[kmin]]) kmin = j;
+      int t = order[i];
+      order[i] = order[kmin];
+      order[kmin] = t;
+    }
+  }
+  __syncwarp();
+  if (lane < len) {
+    d[off + lane] = sd[order[lane]];
+    for (int c = 0; c < len; ++c) Z[(off + lane) + int64_t(off + c) * ldz] = zz[lane][order[c]];
+  }
+}
+
+// z = [last row of Q1, sign * first row of Q2] / sqrt(2)
+__global__ void dc_build_z_kernel(const double* __restrict__ Zb, int64_t ldz, int n1, int len, double sign,
+                                  double* __restrict__ z) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= len) return;
+  const double r = 0.70710678118654752440;
+  z[j] = (j < n1) ? Zb[(n1 - 1) + int64_t(j) * ldz] * r : sign * Zb[n1 + int64_t(j) * ldz] * r;
+}
+
+struct DcRot {
+  int pj, nj;
+  double c, s;
+};
+
+// columns (pj, nj) of the block: x' = c x + s y, y' = c y - s x, in list order; thread per row
+__global__ void dc_apply_rot_kernel(double* __restrict__ Zb, int64_t ldz, int len, const DcRot* __restrict__ rot,
+                                    int nrot) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= len) return;
+  for (int q = 0; q < nrot; ++q) {
+    DcRot R = rot[q];
+    double x = Zb[r + int64_t(R.pj) * ldz], y = Zb[r + int64_t(R.nj) * ldz];
+    Zb[r + int64_t(R.pj) * ldz] = R.c * x + R.s * y;
+    Zb[r + int64_t(R.nj) * ldz] = R.c * y - R.s * x;
+  }
+}
+
+// dst[:, p] = src[:, idx[p]]  (len rows)
+__global__ void dc_gather_kernel(const double* __restrict__ src, int64_t lds, int len, const int* __restrict__ idx,
+                                 int ncols, double* __restrict__ dst, int64_t ldd) {
+  int p = blockIdx.y;
+  if (p >= ncols) return;
+  const double* s = src + int64_t(idx[p]) * lds;
+  double* t = dst + int64_t(p) * ldd;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < len; r += gridDim.x * blockDim.x) t[r] = s[r];
+}
+
+// Secular equation 1 + sum_i z2_i / (dl_i - lam) = 0 (z2 = rho z^2, dl ascending, distinct):
+// one warp per root j in (dl_j, dl_{j+1}).  Output: origin pole org[j] and offset tau[j]
+// (lam_j = dl[org_j] + tau_j, with dl_i - lam_j = (dl_i - dl[org_j]) - tau_j computed
+// without cancellation).
+__global__ void __launch_bounds__(256)
+dc_secular_kernel(const double* __restrict__ dl, const double* __restrict__ z2, int K, int* __restrict__ org,
+                  double* __restrict__ tau, double* __restrict__ lam) {
+  const int lane = threadIdx.x & 31;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= K) return;
+  const double eps = 1.1102230246251565e-16;
+  int o;
+  double lo, hi;
+  if (j < K - 1) {
+    const double gap = dl[j + 1] - dl[j];
+    double f = 0.0;
+    for (int i = lane; i < K; i += 32) f += z2[i] / ((dl[i] - dl[j]) - 0.5 * gap);
+    f = 1.0 + warp_sum(f);
+    if (f > 0.0) {
+      o = j;
+      lo = 0.0;
+      hi = 0.5 * gap;
+    } else {
+      o = j + 1;
+      lo = -0.5 * gap;
+      hi = 0.0;
+    }
+  } else {
+    double s = 0.0;
+    for (int i = lane; i < K; i += 32) s += z2[i];
+    s = warp_sum(s);
+    o = j;
+    lo = 0.0;
+    hi = s;
+  }
+  const double dorg = dl[o];
+  double t = 0.5 * (lo + hi);
+  for (int it = 0; it < 200; ++it) {
+    double psi = 0, phi = 0, dpsi = 0, dphi = 0, sabs = 0;
+    for (int i = lane; i < K; i += 32) {
+      const double D = (dl[i] - dorg) - t;
+      const double term = z2[i] / D;
+      const double dterm = term / D;
+      if (i <= j) {
+        psi += term;
+        dpsi += dterm;
+      } else {
+        phi += term;
+        dphi += dterm;
+      }
+      sabs += fabs(term);
+    }
+    psi = warp_sum(psi);
+    phi = warp_sum(phi);
+    dpsi = warp_sum(dpsi);
+    dphi = warp_sum(dphi);
+    sabs = warp_sum(sabs);
+    const double g = 1.0 + psi + phi;
+    if (fabs(g) <= 8.0 * eps * (1.0 + sabs)) break;
+    if (g < 0.0) lo = t;
+    else hi = t;
+    if (hi - lo <= 4.0 * eps * fmax(fabs(lo), fabs(hi))) {
+      t = 0.5 * (lo + hi);
+      break;
+    }
+    const double Dj = (dl[j] - dorg) - t;
+    const double S = Dj * Dj * dpsi, s0 = psi - Dj * dpsi;
+    double cand0 = NAN, cand1 = NAN;
+    if (j < K - 1) {
+      const double Dj1 = (dl[j + 1] - dorg) - t;
+      const double Rr = Dj1 * Dj1 * dphi, r0 = phi - Dj1 * dphi;
+      const double c = 1.0 + s0 + r0;
+      const double a2 = c, a1 = -(c * (Dj + Dj1) + S + Rr), a0 = c * Dj * Dj1 + S * Dj1 + Rr * Dj;
+      if (a2 == 0.0) {
+        if (a1 != 0.0) cand0 = -a0 / a1;
+      } else {
+        const double disc = a1 * a1 - 4.0 * a2 * a0;
+        if (disc >= 0.0) {
+          const double q = -0.5 * (a1 + copysign(sqrt(disc), a1));
+          if (q != 0.0) cand0 = a0 / q;
+          cand1 = q / a2;
+        }
+      }
+    } else {
+      const double c = 1.0 + s0;
+      if (c != 0.0) cand0 = Dj + S / c;
+    }
+    double tn = 0.5 * (lo + hi);
+    const double x0 = t + cand0, x1 = t + cand1;
+    if (x0 > lo && x0 < hi) tn = x0;
+    else if (x1 > lo && x1 < hi) tn = x1;
+    t = tn;
+  }
+  if (lane == 0) {
+    org[j] = o;
+    tau[j] = t;
+    lam[j] = dorg + t;
+  }
+}
+
+// Gu/Eisenstat: zhat_i = sign(z_i) sqrt( -prod_j (dl_i - lam_j) / prod_{j != i} (dl_i - dl_j) ); warp per i
+__global__ void __launch_bounds__(256)
+dc_zhat_kernel(const double* __restrict__ dl, const double* __restrict__ zl, const int* __restrict__ org,
+               const double* __restrict__ tau, int K, double* __restrict__ zhat) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= K) return;
+  const double di = dl[i];
+  double p = 1.0;
+  for (int j = lane; j < K; j += 32) {
+    const double num = (di - dl[org[j]]) - tau[j];
+    p *= (j == i) ? num : num / (di - dl[j]);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) p *= __shfl_xor_sync(0xffffffffu, p, o);
+  if (lane == 0) zhat[i] = copysign(sqrt(fabs(p)), zl[i]);
+}
+
+// U[rowpos[i], j] = zhat_i / (dl_i - lam_j), column-normalised; CTA per column j
+__global__ void __launch_bounds__(256)
+dc_u_kernel(const double* __restrict__ dl, const double* __restrict__ zhat, const int* __restrict__ org,
+            const double* __restrict__ tau, const int* __restrict__ rowpos, int K, double* __restrict__ U,
+            int64_t ldu) {
+  __shared__ double sh[32];
+  const int j = blockIdx.x;
+  const double dorg = dl[org[j]], t = tau[j];
+  double ss = 0.0;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const double u = zhat[i] / ((dl[i] - dorg) - t);
+    ss = fma(u, u, ss);
+  }
+  ss = block_sum(ss, sh);
+  const double inv = 1.0 / sqrt(ss);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const double u = zhat[i] / ((dl[i] - dorg) - t);
+    U[rowpos[i] + int64_t(j) * ldu] = u * inv;
+  }
+}
+
+// Merge the ascending lists lam[0:K) and dd[0:nd) into ascending order: src[rank] = source
+// column (j for a secular root, K + t for a deflated value), dout[rank] = value.
+__global__ void dc_merge_order_kernel(const double* __restrict__ lam, int K, const double* __restrict__ dd, int nd,
+                                      int* __restrict__ src, double* __restrict__ dout) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= K + nd) return;
+  int rank;
+  double v;
+  if (t < K) {
+    v = lam[t];
+    int lo = 0, hi = nd;          // # deflated values strictly below v
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (dd[mid] < v) lo = mid + 1;
+      else hi = mid;
+    }
+    rank = t + lo;
+  } else {
+    v = dd[t - K];
+    int lo = 0, hi = K;           // # roots <= v
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (lam[mid] <= v) lo = mid + 1;
+      else hi = mid;
+    }
+    rank = (t - K) + lo;
+  }
+  src[rank] = t;
+  dout[rank] = v;
+}
+
+// Zb[:, rank] = (src < K ? Zo[:, src] : Zg[:, src])
+__global__ void dc_scatter_kernel(const double* __restrict__ Zo, const double* __restrict__ Zg, int64_t lds,
+                                  int len, int K, const int* __restrict__ src, double* __restrict__ Zb,
+                                  int64_t ldz) {
+  int p = blockIdx.y;
+  int s = src[p];
+  const double* from = (s < K ? Zo : Zg) + int64_t(s) * lds;
+  double* to = Zb + int64_t(p) * ldz;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < len; r += gridDim.x * blockDim.x) to[r] = from[r];
+}
+
+// ======================================================================= D&C driver
+struct DcBuffers {
+  double *Zg, *Zo, *U;            // n x n each
+  double *z, *dl, *z2, *zl, *tau, *lam, *zhat, *dd, *dout;   // n each
+  int *org, *rowpos, *gidx, *src;                             // n each
+  DcRot* rot;                                                 // n
+  // pinned host staging
+  double *h_d, *h_z, *h_dl, *h_z2, *h_zl, *h_dd;
+  int *h_rowpos, *h_gidx;
+  DcRot* h_rot;
+};
+
+struct DcNode {
+  int off, len;
+};
+
+static void dc_collect(int off, int len, std::vector<DcNode>& leaves, std::vector<int>& cuts,
+                       std::vector<DcNode>& merges /*post-order*/, std::vector<int>& merge_n1) {
+  if (len <= kLeaf) {
+    leaves.push_back({off, len});
+    return;
+  }
+  int n1 = len / 2;
+  cuts.push_back(off + n1 - 1);
+  dc_collect(off, n1, leaves, cuts, merges, merge_n1);
+  dc_collect(off + n1, len - n1, leaves, cuts, merges, merge_n1);
+  merges.push_back({off, len});
+  merge_n1.push_back(n1);
+}
+
+static int dc_merge(cublasHandle_t h, cudaStream_t st, double* d, double* Z, int64_t n, int off, int n1, int len,
+                    double beta, DcBuffers& B) {
+  const int64_t ldz = n;
+  double* Zb = Z + off + int64_t(off) * ldz;
+  const double eps = 1.1102230246251565e-16;
+  dc_build_z_kernel<<<(unsigned)ceil_div(len, 256), 256, 0, st>>>(Zb, ldz, n1, len, beta < 0 ? -1.0 : 1.0, B.z);
+  TQ_LAUNCH_CHECK();
+  TQ_CUDA_CHECK(cudaMemcpyAsync(B.h_d, d + off, sizeof(double) * len, cudaMemcpyDeviceToHost, st));
+  TQ_CUDA_CHECK(cudaMemcpyAsync(B.h_z, B.z, sizeof(double) * len, cudaMemcpyDeviceToHost, st));
+  TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+
+  // ---------------- host: deflation (LAPACK DLAED2 logic) ----------------
+  double* hd = B.h_d;
+  double* hz = B.h_z;
+  const double rho = 2.0 * std::fabs(beta);
+  double dmax = 0, zmax = 0;
+  for (int j = 0; j < len; ++j) {
+    dmax = std::max(dmax, std::fabs(hd[j]));
+    zmax = std::max(zmax, std::fabs(hz[j]));
+  }
+  const double tol = 8.0 * eps * std::max(dmax, zmax);
+  std::vector<int> order(len);
+  for (int j = 0; j < len; ++j) order[j] = j;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hd[a] < hd[b]; });
+  std::vector<int> nondef, defl, ctype(len);
+  for (int j = 0; j < len; ++j) ctype[j] = j < n1 ? 1 : 3;
+  int nrot = 0;
+  if (rho * zmax <= tol) {
+    defl = order;
+  } else {
+    int pj = -1;
+    for (int q = 0; q < len; ++q) {
+      const int jj = order[q];
+      if (rho * std::fabs(hz[jj]) <= tol) {
+        defl.push_back(jj);
+        continue;
+      }
+      if (pj < 0) {
+        pj = jj;
+        continue;
+      }
+      const int nj = jj;
+      double s = hz[pj], c = hz[nj];
+      const double tau_ = std::hypot(c, s);
+      const double t = hd[nj] - hd[pj];
+      c /= tau_;
+      s = -s / tau_;
+      if (std::fabs(t * c * s) <= tol) {
+        hz[nj] = tau_;
+        hz[pj] = 0.0;
+        if (ctype[nj] != ctype[pj]) ctype[nj] = 2;
+        B.h_rot[nrot++] = DcRot{pj, nj, c, s};
+        const double tt = hd[pj] * c * c + hd[nj] * s * s;
+        hd[nj] = hd[pj] * s * s + hd[nj] * c * c;
+        hd[pj] = tt;
+        defl.push_back(pj);
+        pj = nj;
+      } else {
+        nondef.push_back(pj);
+        pj = nj;
+      }
+    }
+    if (pj >= 0) nondef.push_back(pj);
+  }
+  const int K = int(nondef.size());
+  const int nd = len - K;
+  // deflated values ascending (rotations may perturb the order slightly)
+  std::stable_sort(defl.begin(), defl.end(), [&](int a, int b) { return hd[a] < hd[b]; });
+  // secular poles must be strictly increasing; DLAED2's rotation keeps them ordered, but guard anyway
+  for (int q = 1; q < K; ++q) {
+    if (!(hd[nondef[q]] > hd[nondef[q - 1]])) {
+      set_error("stedc: non-increasing poles after deflation (merge off=%d len=%d)", off, len);
+      return TQ_ERR_NOCONV;
+    }
+  }
+  // group the non-deflated columns by type [1 | 2 | 3] for the two half GEMMs
+  int K1 = 0, K2 = 0, K3 = 0;
+  for (int q = 0; q < K; ++q) {
+    int ty = ctype[nondef[q]];
+    K1 += ty == 1;
+    K2 += ty == 2;
+    K3 += ty == 3;
+  }
+  int p1 = 0, p2 = K1, p3 = K1 + K2;
+  for (int q = 0; q < K; ++q) {
+    const int jj = nondef[q];
+    const int ty = ctype[jj];
+    const int pos = ty == 1 ? p1++ : (ty == 2 ? p2++ : p3++);
+    B.h_rowpos[q] = pos;
+    B.h_gidx[pos] = jj;
+    B.h_dl[q] = hd[jj];
+    B.h_zl[q] = hz[jj];
+    B.h_z2[q] = rho * hz[jj] * hz[jj];
+  }
+  for (int t = 0; t < nd; ++t) {
+    B.h_gidx[K + t] = defl[t];
+    B.h_dd[t] = hd[defl[t]];
+  }
+
+  // ---------------- device: rotations, gather, secular solve, GEMM, reorder ----------------
+  if (nrot > 0) {
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.rot, B.h_rot, sizeof(DcRot) * nrot, cudaMemcpyHostToDevice, st));
+    dc_apply_rot_kernel<<<(unsigned)ceil_div(len, 128), 128, 0, st>>>(Zb, ldz, len, B.rot, nrot);
+    TQ_LAUNCH_CHECK();
+  }
+  TQ_CUDA_CHECK(cudaMemcpyAsync(B.gidx, B.h_gidx, sizeof(int) * len, cudaMemcpyHostToDevice, st));
+  if (nd > 0) TQ_CUDA_CHECK(cudaMemcpyAsync(B.dd, B.h_dd, sizeof(double) * nd, cudaMemcpyHostToDevice, st));
+  const int64_t lds = len;   // scratch matrices are packed len x len
+  {
+    dim3 grid((unsigned)imin(ceil_div(len, 256), 32), (unsigned)len);
+    dc_gather_kernel<<<grid, 256, 0, st>>>(Zb, ldz, len, B.gidx, len, B.Zg, lds);
+    TQ_LAUNCH_CHECK();
+  }
+  if (K > 0) {
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.dl, B.h_dl, sizeof(double) * K, cudaMemcpyHostToDevice, st));
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.zl, B.h_zl, sizeof(double) * K, cudaMemcpyHostToDevice, st));
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.z2, B.h_z2, sizeof(double) * K, cudaMemcpyHostToDevice, st));
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.rowpos, B.h_rowpos, sizeof(int) * K, cudaMemcpyHostToDevice, st));
+    const unsigned wgrid = (unsigned)ceil_div(int64_t(K) * 32, 256);
+    dc_secular_kernel<<<wgrid, 256, 0, st>>>(B.dl, B.z2, K, B.org, B.tau, B.lam);
+    TQ_LAUNCH_CHECK();
+    dc_zhat_kernel<<<wgrid, 256, 0, st>>>(B.dl, B.zl, B.org, B.tau, K, B.zhat);
+    TQ_LAUNCH_CHECK();
+    dc_u_kernel<<<K, 256, 0, st>>>(B.dl, B.zhat, B.org, B.tau, B.rowpos, K, B.U, K);
+    TQ_LAUNCH_CHECK();
+    const double one = 1.0, zero = 0.0;
+    const int n2 = len - n1;
+    const int K12 = K1 + K2, K23 = K2 + K3;
+    if (K12 > 0)
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n1, K, K12, &one, B.Zg, int(lds), B.U, K, &zero,
+                                  B.Zo, int(lds)));
+    else
+      TQ_CUDA_CHECK(cudaMemset2DAsync(B.Zo, sizeof(double) * lds, 0, sizeof(double) * n1, K, st));
+    if (K23 > 0)
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n2, K, K23, &one, B.Zg + n1 + int64_t(K1) * lds,
+                                  int(lds), B.U + K1, K, &zero, B.Zo + n1, int(lds)));
+    else
+      TQ_CUDA_CHECK(cudaMemset2DAsync(B.Zo + n1, sizeof(double) * lds, 0, sizeof(double) * n2, K, st));
+  }
+  dc_merge_order_kernel<<<(unsigned)ceil_div(len, 256), 256, 0, st>>>(B.lam, K, B.dd, nd, B.src, B.dout);
+  TQ_LAUNCH_CHECK();
+  {
+    dim3 grid((unsigned)imin(ceil_div(len, 256), 32), (unsigned)len);
+    dc_scatter_kernel<<<grid, 256, 0, st>>>(B.Zo, B.Zg, lds, len, K, B.src, Zb, ldz);
+    TQ_LAUNCH_CHECK();
+  }
+  TQ_CUDA_CHECK(cudaMemcpyAsync(d + off, B.dout, sizeof(double) * len, cudaMemcpyDeviceToDevice, st));
+  return TQ_OK;
+}
+
+// Eigen-decomposition of the symmetric tridiagonal (d, e): d <- eigenvalues ascending,
+// Z (n x n) <- eigenvectors (columns).  e is read only.
+static int stedc(cublasHandle_t h, cudaStream_t st, double* d, const double* e, double* Z, int64_t n,
+                 Workspace& ws) {
+  DcBuffers B;
+  B.Zg = ws.take<double>(size_t(n) * n);
+  B.Zo = ws.take<double>(size_t(n) * n);
+  B.U = ws.take<double>(size_t(n) * n);
+  double** dv[] = {&B.z, &B.dl, &B.z2, &B.zl, &B.tau, &B.lam, &B.zhat, &B.dd, &B.dout};
+  for (auto p : dv) *p = ws.take<double>(n);
+  int** iv[] = {&B.org, &B.rowpos, &B.gidx, &B.src};
+  for (auto p : iv) *p = ws.take<int>(n);
+  B.rot = ws.take<DcRot>(n);
+  int* d_leaf_off = ws.take<int>(n);
+  int* d_leaf_len = ws.take<int>(n);
+  int* d_cuts = ws.take<int>(n);
+  int* d_fail = ws.take<int>(1);
+  if (ws.overflow) {
+    set_error("stedc: workspace too small");
+    return TQ_ERR_WORKSPACE;
+  }
+  // pinned host staging (one allocation)
+  const size_t hbytes = sizeof(double) * n * 6 + sizeof(int) * n * 2 + sizeof(DcRot) * n + sizeof(double) * n;
+  char* hbuf = nullptr;
+  TQ_CUDA_CHECK(cudaMallocHost(&hbuf, hbytes));
+  struct Free {
+    char* p;
+    ~Free() { cudaFreeHost(p); }
+  } freer{hbuf};
+  char* hp = hbuf;
+  auto htake = [&](size_t bytes) {
+    char* r = hp;
+    hp += (bytes + 15) / 16 * 16;
+    return r;
+  };
+  B.h_d = (double*)htake(sizeof(double) * n);
+  B.h_z = (double*)htake(sizeof(double) * n);
+  B.h_dl = (double*)htake(sizeof(double) * n);
+  B.h_z2 = (double*)htake(sizeof(double) * n);
+  B.h_zl = (double*)htake(sizeof(double) * n);
+  B.h_dd = (double*)htake(sizeof(double) * n);
+  B.h_rowpos = (int*)htake(sizeof(int) * n);
+  B.h_gidx = (int*)htake(sizeof(int) * n);
+  B.h_rot = (DcRot*)htake(sizeof(DcRot) * n);
+  std::vector<double> he(n);
+  TQ_CUDA_CHECK(cudaMemcpyAsync(he.data(), e, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+
+  std::vector<DcNode> leaves, merges;
+  std::vector<int> cuts, merge_n1;
+  dc_collect(0, int(n), leaves, cuts, merges, merge_n1);
+  std::vector<int> lo(leaves.size()), ll(leaves.size());
+  for (size_t i = 0; i < leaves.size(); ++i) {
+    lo[i] = leaves[i].off;
+    ll[i] = leaves[i].len;
+  }
+  TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  TQ_CUDA_CHECK(cudaMemcpyAsync(d_leaf_off, lo.data(), sizeof(int) * lo.size(), cudaMemcpyHostToDevice, st));
+  TQ_CUDA_CHECK(cudaMemcpyAsync(d_leaf_len, ll.data(), sizeof(int) * ll.size(), cudaMemcpyHostToDevice, st));
+  if (!cuts.empty())
+    TQ_CUDA_CHECK(cudaMemcpyAsync(d_cuts, cuts.data(), sizeof(int) * cuts.size(), cudaMemcpyHostToDevice, st));
+  TQ_CUDA_CHECK(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+  TQ_CUDA_CHECK(cudaMemsetAsync(Z, 0, sizeof(double) * n * n, st));
+  if (!cuts.empty()) {
+    dc_tear_serial_kernel<<<1, 1, 0, st>>>(d, e, d_cuts, int(cuts.size()));
+    TQ_LAUNCH_CHECK();
+  }
+  dc_leaf_kernel<<<(unsigned)leaves.size(), 32, 0, st>>>(d, e, Z, n, d_leaf_off, d_leaf_len, d_fail);
+  TQ_LAUNCH_CHECK();
+  TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (size_t q = 0; q < merges.size(); ++q) {
+    const int off = merges[q].off, len = merges[q].len, n1 = merge_n1[q];
+    TQ_TRY(dc_merge(h, st, d, Z, n, off, n1, len, he[off + n1 - 1], B));
+  }
+  int fail = 0;
+  TQ_CUDA_CHECK(cudaMemcpyAsync(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (fail) {
+    set_error("stedc: QL iteration did not converge on a leaf");
+    return TQ_ERR_NOCONV;
+  }
+  return TQ_OK;
+}
+
+// ======================================================================= ormtr
+// Z <- Q Z, Q = H_0 H_1 ... H_{n-2} from sytrd_lower.
+static int ormtr_lower(cublasHandle_t h, cudaStream_t st, const double* A, const double* tau, int64_t n, double* Z,
+                       int64_t ncolsZ, double* Vc, double* G, double* T, double* w1, double* w2) {
+  const int64_t lda = n, ldz = n;
+  const int64_t nref = n - 1;
+  if (nref <= 0) return TQ_OK;
+  const int64_t nblk = ceil_div(nref, kOrmNb);
+  for (int64_t b = nblk - 1; b >= 0; --b) {
+    const int64_t j0 = b * kOrmNb;
+    const int jb = int(imin(kOrmNb, nref - j0));
+    const int64_t s = n - j0 - 1;
+    dim3 grid((unsigned)imin(ceil_div(s, 256), 256), (unsigned)jb);
+    copy_reflectors_kernel<<<grid, 256, 0, st>>>(A + (j0 + 1) + j0 * lda, lda, s, jb, Vc, s);
+    TQ_LAUNCH_CHECK();
+    TQ_TRY(build_t_factor(h, st, Vc, s, s, jb, tau + j0, G, T));
+    TQ_TRY(apply_block_reflector(h, Vc, s, s, jb, T, jb, /*trans_t=*/false, Z + (j0 + 1), ldz, ncolsZ, w1, w2));
+  }
+  return TQ_OK;
+}
+
+__global__ void copy_sym_kernel(const double* __restrict__ H, int64_t ldh, int64_t n, double* __restrict__ A) {
+  int64_t c = blockIdx.y;
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += int64_t(gridDim.x) * blockDim.x)
+    A[r + c * n] = H[c * ldh + r];   // row-major (c, r) == column-major (r, c) of H^T = H
+}
+
+size_t eigh_ws_bytes(int64_t n) {
+  size_t b = 0;
+  b += ws_bytes_for(size_t(n) * n, 8) * 4;                 // A, Zg, Zo, U
+  b += ws_bytes_for(n, 8) * 12 + ws_bytes_for(n, 4) * 8 + ws_bytes_for(n, sizeof(DcRot));
+  b += ws_bytes_for(size_t(n) * kTrdNb, 8) * 2;            // W, Vc
+  b += ws_bytes_for(size_t(kOrmNb) * n, 8) * 2;            // w1, w2
+  b += ws_bytes_for(kTrdNb * kTrdNb, 8) * 2 + ws_bytes_for(4 * kTrdNb, 8);
+  return b;
+}
+
+// w (n, ascending) and Zout (n x n column-major, ld n: column i = eigenvector i)
+int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ldh, int64_t n, double* w,
+                  double* Zout, Workspace& ws) {
+  double* A = ws.take<double>(size_t(n) * n);
+  double* e = ws.take<double>(n);
+  double* tau = ws.take<double>(n);
+  double* y = ws.take<double>(n);
+  double* W = ws.take<double>(size_t(n) * kTrdNb);
+  double* tmp = ws.take<double>(4 * kTrdNb);
+  double* G = ws.take<double>(kTrdNb * kTrdNb);
+  double* T = ws.take<double>(kTrdNb * kTrdNb);
+  if (ws.overflow) {
+    set_error("eigh: workspace too small");
+    return TQ_ERR_WORKSPACE;
+  }
+  dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)n);
+  copy_sym_kernel<<<grid, 256, 0, st>>>(H, ldh, n, A);
+  TQ_LAUNCH_CHECK();
+  TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp));
+  {
+    Workspace sub = ws;   // D&C scratch is released afterwards
+    TQ_TRY(stedc(h, st, w, e, Zout, n, sub));
+    if (sub.overflow) return TQ_ERR_WORKSPACE;
+    // back-transform scratch overlays the D&C scratch
+    Workspace sub2 = ws;
+    double* Vc = sub2.take<double>(size_t(n) * kOrmNb);
+    double* w1 = sub2.take<double>(size_t(kOrmNb) * n);
+    double* w2 = sub2.take<double>(size_t(kOrmNb) * n);
+    if (sub2.overflow) {
+      set_error("eigh: workspace too small (ormtr)");
+      return TQ_ERR_WORKSPACE;
+    }
+    TQ_TRY(ormtr_lower(h, st, A, tau, n, Zout, n, Vc, G, T, w1, w2));
+  }
+  return TQ_OK;
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" int tq_eigh(const double* H, int64_t ldh, int64_t n, double* w, double* V, int64_t ldv, void* ws,
+                       size_t ws_bytes, void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(H && w && V && n > 0 && ldh >= n, "tq_eigh: bad arguments");
+  TQ_REQUIRE(ldv == n, "tq_eigh: V must be contiguous (ldv == n)");
+  TQ_REQUIRE(n < (1 << 30), "tq_eigh: n too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace wsp(ws, ws_bytes);
+  cublasHandle_t h;
+  TQ_TRY(get_cublas(&h, st));
+  // column-major Z (column i = eigenvector i) is the same memory as row-major V (row i = eigenvector i)
+  return eigh_colmajor(h, st, H, ldh, n, w, V, wsp);
+}

@@ -1,0 +1,430 @@
+// Householder QR factorizations of the spectral solver (fp64, column-major inside).
+//
+//  * qrcp_colmajor: column-pivoted QR with LAPACK DGEQP3 / DLAQPS semantics (the
+//    reference calls jax.scipy.linalg.qr(pivoting=True) -> MAGMA dgeqp3, gptq_utils.py:114):
+//    pivot = first index of the largest downdated partial norm, norms downdated with the
+//    DLAQPS cancellation safeguard (a failing column ends the panel and is recomputed
+//    exactly), lazy panel update through F, trailing update by DGEMM.
+//    The per-column work is BLAS-2 and HBM-bound: dots3_kernel streams the whole trailing
+//    matrix once per column (F(:,k) = tau A^T v).
+//  * qr_r_colmajor: unpivoted blocked Householder QR that never forms Q (the reference
+//    calls torch.linalg.qr and discards Q, gptq_utils.py:120): panel by BLAS-2 kernels,
+//    trailing update by compact-WY DGEMMs.
+#include "solver_kernels.cuh"
+
+namespace tq {
+
+constexpr int kQrNb = 64;    // unpivoted QR panel width
+constexpr int kQrcpNb = 32;  // pivoted QR panel width (DLAQPS)
+
+// ------------------------------------------------------------------ layout helpers
+// dst (col-major k x n, ld ldd) = src (row-major k x n, ld lds), 32x32 tiles through smem
+__global__ void rowmajor_to_colmajor_kernel(const double* __restrict__ src, int64_t lds, int64_t k, int64_t n,
+                                            double* __restrict__ dst, int64_t ldd) {
+  __shared__ double t[32][33];
+  int64_t i0 = int64_t(blockIdx.y) * 32, j0 = int64_t(blockIdx.x) * 32;
+  for (int a = threadIdx.y; a < 32; a += blockDim.y) {
+    int64_t i = i0 + a, j = j0 + threadIdx.x;
+    t[a][threadIdx.x] = (i < k && j < n) ? src[i * lds + j] : 0.0;
+  }
+  __syncthreads();
+  for (int a = threadIdx.y; a < 32; a += blockDim.y) {
+    int64_t j = j0 + a, i = i0 + threadIdx.x;
+    if (i < k && j < n) dst[i + j * ldd] = t[threadIdx.x][a];
+  }
+}
+
+// R_out (row-major k x n, ld ldr) = sign(diag) * triu(A) with A col-major (gptq_utils.py:121-124)
+__global__ void emit_r_kernel(const double* __restrict__ A, int64_t lda, int64_t k, int64_t n,
+                              double* __restrict__ R, int64_t ldr) {
+  __shared__ double t[32][33];
+  int64_t i0 = int64_t(blockIdx.y) * 32, j0 = int64_t(blockIdx.x) * 32;
+  for (int a = threadIdx.y; a < 32; a += blockDim.y) {
+    int64_t j = j0 + a, i = i0 + threadIdx.x;
+    t[a][threadIdx.x] = (i < k && j < n && i <= j) ? A[i + j * lda] : 0.0;
+  }
+  __syncthreads();
+  for (int a = threadIdx.y; a < 32; a += blockDim.y) {
+    int64_t i = i0 + a, j = j0 + threadIdx.x;
+    if (i < k && j < n) {
+      double d = A[i + i * lda];
+      double sg = d > 0.0 ? 1.0 : (d < 0.0 ? -1.0 : 0.0);   // torch.sign
+      R[i * ldr + j] = sg * t[threadIdx.x][a];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ unpivoted QR panel
+// A[r, c+1+j] -= tau * v[r] * w[j]   for r in [c, k), j in [0, ncols)
+__global__ void qr_panel_rank1_kernel(double* __restrict__ A, int64_t lda, int64_t c, int64_t k, int ncols,
+                                      const double* __restrict__ tau, const double* __restrict__ w) {
+  const int j = blockIdx.y;
+  const double tw = tau[0] * w[j];
+  const double* v = A + c + c * lda;
+  double* col = A + c + (c + 1 + j) * lda;
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < k - c;
+       r += int64_t(gridDim.x) * blockDim.x)
+    col[r] = fma(-tw, v[r], col[r]);
+}
+
+__global__ void set_diag_kernel(double* __restrict__ A, int64_t lda, int64_t j0, int jb,
+                                const double* __restrict__ beta) {
+  int t = threadIdx.x;
+  if (t < jb) A[(j0 + t) + (j0 + t) * lda] = beta[j0 + t];
+}
+
+// in place: on exit triu(A[0:k, 0:n]) = R (diagonal sign arbitrary)
+int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n,
+                  Workspace& ws) {
+  double* tau = ws.take<double>(k);
+  double* beta = ws.take<double>(k);
+  double* wdot = ws.take<double>(kQrNb);
+  double* Vc = ws.take<double>(size_t(k) * kQrNb);
+  double* G = ws.take<double>(kQrNb * kQrNb);
+  double* T = ws.take<double>(kQrNb * kQrNb);
+  double* w1 = ws.take<double>(size_t(kQrNb) * n);
+  double* w2 = ws.take<double>(size_t(kQrNb) * n);
+  if (ws.overflow) {
+    set_error("qr_r: workspace too small");
+    return TQ_ERR_WORKSPACE;
+  }
+  DotSeg none{nullptr, 0, 0, nullptr};
+  for (int64_t j0 = 0; j0 < k; j0 += kQrNb) {
+    const int jb = int(imin(kQrNb, k - j0));
+    for (int64_t c = j0; c < j0 + jb; ++c) {
+      const int64_t len = k - c;
+      larfg_kernel<<<1, 1024, 0, st>>>(A + c + c * lda, len, tau + c, beta + c, nullptr);
+      TQ_LAUNCH_CHECK();
+      const int rem = int(j0 + jb - 1 - c);
+      if (rem > 0) {
+        DotSeg s0{A + c + (c + 1) * lda, lda, rem, wdot};
+        dots3_kernel<<<dots_grid(rem), 256, 0, st>>>(s0, none, none, A + c + c * lda, len, nullptr);
+        TQ_LAUNCH_CHECK();
+        dim3 grid((unsigned)imin(ceil_div(len, 256), 64), (unsigned)rem);
+        qr_panel_rank1_kernel<<<grid, 256, 0, st>>>(A, lda, c, k, rem, tau + c, wdot);
+        TQ_LAUNCH_CHECK();
+      }
+    }
+    const int64_t s = k - j0;
+    const int64_t nc = n - j0 - jb;
+    if (nc > 0) {
+      dim3 grid((unsigned)imin(ceil_div(s, 256), 256), (unsigned)jb);
+      copy_reflectors_kernel<<<grid, 256, 0, st>>>(A + j0 + j0 * lda, lda, s, jb, Vc, s);
+      TQ_LAUNCH_CHECK();
+    }
+    set_diag_kernel<<<1, kQrNb, 0, st>>>(A, lda, j0, jb, beta);
+    TQ_LAUNCH_CHECK();
+    if (nc > 0) {
+      TQ_TRY(build_t_factor(h, st, Vc, s, s, jb, tau + j0, G, T));
+      TQ_TRY(apply_block_reflector(h, Vc, s, s, jb, T, jb, /*trans_t=*/true, A + j0 + (j0 + jb) * lda, lda, nc,
+                                   w1, w2));
+    }
+  }
+  return TQ_OK;
+}
+
+// ------------------------------------------------------------------ pivoted QR (DLAQPS)
+struct QrcpCtl {
+  int stop;       // panel is over (a norm failed the safeguard in an earlier step)
+  int stop_next;  // set during the step that flags a column
+  int kb;         // columns factored in this panel
+  int pad;
+};
+
+__global__ void col_norms_kernel(const double* __restrict__ A, int64_t lda, int64_t row0, int64_t k, int64_t n,
+                                 double* __restrict__ vn1, double* __restrict__ vn2, int only_flagged) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t j = warp; j < n; j += nwarps) {
+    if (only_flagged && vn2[j] >= 0.0) continue;
+    const double* col = A + j * lda;
+    double s = 0.0;
+    for (int64_t r = row0 + lane; r < k; r += 32) s = fma(col[r], col[r], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      double nrm = sqrt(s);
+      vn1[j] = nrm;
+      vn2[j] = nrm;
+    }
+  }
+}
+
+__global__ void init_perm_kernel(int64_t* perm, int64_t n) {
+  int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j < n) perm[j] = j;
+}
+
+// Step 1: commit the stop flag, pick the pivot (first index of max vn1[c:]) and swap.
+__global__ void __launch_bounds__(1024)
+qrcp_pivot_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t n, int64_t j0, int i,
+                  double* __restrict__ F, int64_t ldf, int64_t* __restrict__ perm, double* __restrict__ vn1,
+                  double* __restrict__ vn2, QrcpCtl* ctl) {
+  __shared__ double sval[32];
+  __shared__ int64_t sidx[32];
+  __shared__ int64_t spvt;
+  if (ctl->stop_next) {
+    if (threadIdx.x == 0) ctl->stop = 1;
+    return;
+  }
+  if (ctl->stop) return;
+  const int64_t c = j0 + i;
+  double best = -1.0;
+  int64_t bidx = n;
+  for (int64_t j = c + threadIdx.x; j < n; j += blockDim.x) {
+    double v = vn1[j];
+    if (v > best) {   // strided scan keeps the smallest index among equal values per thread
+      best = v;
+      bidx = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ov > best || (ov == best && oi < bidx)) {
+      best = ov;
+      bidx = oi;
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    sval[w] = best;
+    sidx[w] = bidx;
+  }
+  __syncthreads();
+  if (w == 0) {
+    best = sval[lane];
+    bidx = sidx[lane];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx)) {
+        best = ov;
+        bidx = oi;
+      }
+    }
+    if (lane == 0) spvt = bidx;
+  }
+  __syncthreads();
+  const int64_t pvt = spvt;
+  if (pvt == c || pvt >= n) return;
+  for (int64_t r = threadIdx.x; r < k; r += blockDim.x) {
+    double a = A[r + pvt * lda], b = A[r + c * lda];
+    A[r + pvt * lda] = b;
+    A[r + c * lda] = a;
+  }
+  for (int t = threadIdx.x; t < i; t += blockDim.x) {
+    double a = F[(pvt - j0) + t * ldf], b = F[(c - j0) + t * ldf];
+    F[(pvt - j0) + t * ldf] = b;
+    F[(c - j0) + t * ldf] = a;
+  }
+  if (threadIdx.x == 0) {
+    int64_t p = perm[pvt];
+    perm[pvt] = perm[c];
+    perm[c] = p;
+    vn1[pvt] = vn1[c];
+    vn2[pvt] = vn2[c];
+  }
+}
+
+// Step 2: A[rk:, c] -= A[rk:, j0:c] F[c-j0, 0:i]^T
+__global__ void qrcp_col_update_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t j0, int i,
+                                       const double* __restrict__ F, int64_t ldf, const QrcpCtl* ctl) {
+  if (ctl->stop) return;
+  const int64_t c = j0 + i;
+  for (int64_t r = c + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < k;
+       r += int64_t(gridDim.x) * blockDim.x) {
+    double s = 0.0;
+    for (int t = 0; t < i; ++t) s = fma(A[r + (j0 + t) * lda], F[(c - j0) + t * ldf], s);
+    A[r + c * lda] -= s;
+  }
+}
+
+// Step 5 (after larfg and the dots): finish F(:, i), update the pivot row and downdate
+// the partial norms of every trailing column.  One thread per trailing column.
+__global__ void qrcp_row_update_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t n, int64_t j0, int i,
+                                       double* __restrict__ F, int64_t ldf, const double* __restrict__ auxraw,
+                                       const double* __restrict__ tau_p, const double* __restrict__ beta_p,
+                                       double* __restrict__ vn1, double* __restrict__ vn2, QrcpCtl* ctl,
+                                       double tol3z) {
+  if (ctl->stop) return;
+  const int64_t c = j0 + i;   // pivot column == pivot row
+  const double tau = *tau_p;
+  const int64_t col = c + 1 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (col == c + 1) {          // exactly one thread (or none when c is the last column): bookkeeping
+    ctl->kb = i + 1;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    A[c + c * lda] = *beta_p;  // restore akk (nobody reads A[c, c] in this kernel)
+    if (c + 1 >= n) ctl->kb = i + 1;
+  }
+  if (col >= n) return;
+  const int64_t fr = col - j0;
+  double f = tau * F[fr + int64_t(i) * ldf];
+  for (int t = 0; t < i; ++t) f = fma(F[fr + t * ldf], -tau * auxraw[t], f);
+  F[fr + int64_t(i) * ldf] = f;
+  // pivot row: A[c, col] -= sum_{t<=i} F[fr, t] * A[c, j0+t], with A[c, c] == 1 during the step
+  double s = f;
+  for (int t = 0; t < i; ++t) s = fma(F[fr + t * ldf], A[c + (j0 + t) * lda], s);
+  const double a = A[c + col * lda] - s;
+  A[c + col * lda] = a;
+  if (c < k - 1) {
+    const double v1 = vn1[col];
+    if (v1 != 0.0) {
+      double temp = fabs(a) / v1;
+      temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
+      const double q = v1 / vn2[col];
+      const double temp2 = temp * (q * q);
+      if (temp2 <= tol3z) {
+        vn2[col] = -1.0;        // flagged: recomputed exactly after the panel's trailing update
+        ctl->stop_next = 1;
+      } else {
+        vn1[col] = v1 * sqrt(temp);
+      }
+    }
+  }
+}
+
+__global__ void qrcp_panel_begin_kernel(QrcpCtl* ctl) {
+  ctl->stop = 0;
+  ctl->stop_next = 0;
+  ctl->kb = 0;
+}
+
+// in place: triu(A[0:k, :]) = R_x (sign arbitrary), perm = column pivots
+int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n, int64_t* perm,
+                  Workspace& ws) {
+  double* vn1 = ws.take<double>(n);
+  double* vn2 = ws.take<double>(n);
+  double* F = ws.take<double>(size_t(n) * kQrcpNb);
+  double* auxraw = ws.take<double>(kQrcpNb);
+  double* tau = ws.take<double>(k + 1);
+  double* beta = ws.take<double>(k + 1);
+  QrcpCtl* ctl = ws.take<QrcpCtl>(1);
+  if (ws.overflow) {
+    set_error("qrcp: workspace too small");
+    return TQ_ERR_WORKSPACE;
+  }
+  const double eps = 1.1102230246251565e-16;   // dlamch('Epsilon')
+  const double tol3z = sqrt(eps);
+  const int64_t ldf = n;
+  init_perm_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(perm, n);
+  TQ_LAUNCH_CHECK();
+  col_norms_kernel<<<dots_grid(n), 256, 0, st>>>(A, lda, 0, k, n, vn1, vn2, 0);
+  TQ_LAUNCH_CHECK();
+  DotSeg none{nullptr, 0, 0, nullptr};
+  int64_t j0 = 0;
+  while (j0 < k) {
+    const int jb = int(imin(kQrcpNb, k - j0));
+    qrcp_panel_begin_kernel<<<1, 1, 0, st>>>(ctl);
+    TQ_LAUNCH_CHECK();
+    for (int i = 0; i < jb; ++i) {
+      const int64_t c = j0 + i;
+      const int64_t len = k - c;
+      qrcp_pivot_kernel<<<1, 1024, 0, st>>>(A, lda, k, n, j0, i, F, ldf, perm, vn1, vn2, ctl);
+      TQ_LAUNCH_CHECK();
+      if (i > 0) {
+        qrcp_col_update_kernel<<<(unsigned)imin(ceil_div(len, 256), 592), 256, 0, st>>>(A, lda, k, j0, i, F, ldf,
+                                                                                       ctl);
+        TQ_LAUNCH_CHECK();
+      }
+      larfg_kernel<<<1, 1024, 0, st>>>(A + c + c * lda, len, tau + c, beta + c, &ctl->stop);
+      TQ_LAUNCH_CHECK();
+      const int64_t ntrail = n - c - 1;
+      if (ntrail > 0 || i > 0) {
+        DotSeg s0{A + c + (c + 1) * lda, lda, ntrail, F + (c + 1 - j0) + int64_t(i) * ldf};
+        DotSeg s1{A + c + j0 * lda, lda, i, auxraw};
+        dots3_kernel<<<dots_grid(ntrail + i), 256, 0, st>>>(s0, s1, none, A + c + c * lda, len, &ctl->stop);
+        TQ_LAUNCH_CHECK();
+      }
+      qrcp_row_update_kernel<<<(unsigned)imax(1, ceil_div(ntrail, 256)), 256, 0, st>>>(
+          A, lda, k, n, j0, i, F, ldf, auxraw, tau + c, beta + c, vn1, vn2, ctl, tol3z);
+      TQ_LAUNCH_CHECK();
+    }
+    QrcpCtl hc;
+    TQ_CUDA_CHECK(cudaMemcpyAsync(&hc, ctl, sizeof(QrcpCtl), cudaMemcpyDeviceToHost, st));
+    TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+    const int kb = hc.kb;
+    if (kb <= 0) {
+      set_error("qrcp: panel at column %lld made no progress", (long long)j0);
+      return TQ_ERR_NOCONV;
+    }
+    const int64_t r0 = j0 + kb;          // first row / column after the factored block
+    if (r0 < k && r0 < n) {
+      const double one = 1.0, mone = -1.0;
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(k - r0), int(n - r0), kb, &mone,
+                                  A + r0 + j0 * lda, int(lda), F + kb, int(ldf), &one, A + r0 + r0 * lda,
+                                  int(lda)));
+    }
+    if (hc.stop_next || hc.stop) {
+      col_norms_kernel<<<dots_grid(n), 256, 0, st>>>(A, lda, r0, k, n, vn1, vn2, 1);
+      TQ_LAUNCH_CHECK();
+    }
+    j0 = r0;
+  }
+  return TQ_OK;
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+static size_t qr_ws_bytes(int64_t k, int64_t n) {
+  size_t b = ws_bytes_for(size_t(k) * n, 8);                       // column-major working copy
+  b += ws_bytes_for(k + 1, 8) * 4 + ws_bytes_for(kQrNb, 8) + ws_bytes_for(size_t(k) * kQrNb, 8);
+  b += ws_bytes_for(kQrNb * kQrNb, 8) * 2 + ws_bytes_for(size_t(kQrNb) * n, 8) * 2;
+  b += ws_bytes_for(n, 8) * 2 + ws_bytes_for(size_t(n) * kQrcpNb, 8) + ws_bytes_for(64, 8) * 2;
+  return b;
+}
+
+namespace tq {
+size_t qr_stage_ws_bytes(int64_t k, int64_t n) { return qr_ws_bytes(k, n); }
+}
+
+extern "C" int tq_qr_r(const double* A, int64_t lda, int64_t k, int64_t n, double* R, int64_t ldr, void* ws,
+                       size_t ws_bytes, void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(A && R && k > 0 && n >= k && lda >= n && ldr >= n, "tq_qr_r: bad arguments (k=%lld n=%lld)",
+             (long long)k, (long long)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace wsp(ws, ws_bytes);
+  double* Ac = wsp.take<double>(size_t(k) * n);
+  if (wsp.overflow) {
+    set_error("tq_qr_r: workspace too small (need %zu bytes, see tq_solver_workspace)", qr_ws_bytes(k, n));
+    return TQ_ERR_WORKSPACE;
+  }
+  dim3 tg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(k, 32));
+  rowmajor_to_colmajor_kernel<<<tg, dim3(32, 8), 0, st>>>(A, lda, k, n, Ac, k);
+  TQ_LAUNCH_CHECK();
+  cublasHandle_t h;
+  TQ_TRY(get_cublas(&h, st));
+  TQ_TRY(qr_r_colmajor(h, st, Ac, k, k, n, wsp));
+  emit_r_kernel<<<tg, dim3(32, 8), 0, st>>>(Ac, k, k, n, R, ldr);
+  TQ_LAUNCH_CHECK();
+  return TQ_OK;
+}
+
+extern "C" int tq_qrcp(const double* A, int64_t lda, int64_t k, int64_t n, double* Rx, int64_t ldr, int64_t* perm,
+                       void* ws, size_t ws_bytes, void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(A && Rx && perm && k > 0 && n >= k && lda >= n && ldr >= n, "tq_qrcp: bad arguments (k=%lld n=%lld)",
+             (long long)k, (long long)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace wsp(ws, ws_bytes);
+  double* Ac = wsp.take<double>(size_t(k) * n);
+  if (wsp.overflow) {
+    set_error("tq_qrcp: workspace too small (need %zu bytes, see tq_solver_workspace)", qr_ws_bytes(k, n));
+    return TQ_ERR_WORKSPACE;
+  }
+  dim3 tg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(k, 32));
+  rowmajor_to_colmajor_kernel<<<tg, dim3(32, 8), 0, st>>>(A, lda, k, n, Ac, k);
+  TQ_LAUNCH_CHECK();
+  cublasHandle_t h;
+  TQ_TRY(get_cublas(&h, st));
+  TQ_TRY(qrcp_colmajor(h, st, Ac, k, k, n, perm, wsp));
+  emit_r_kernel<<<tg, dim3(32, 8), 0, st>>>(Ac, k, k, n, Rx, ldr);
+  TQ_LAUNCH_CHECK();
+  return TQ_OK;
+}

@@ -1,9 +1,237 @@
-// placeholder - replaced by the spectral solver
-#include "common.cuh"
+// Spectral solver glue - replaces process_hessian_alt (reference gptq_utils.py:87-126):
+//   eigh (eigh.cu) -> clamp / sqrt / flip and the retained-rank rule (block prefix scan
+//   built from warp-level scans) -> S = Lambda^1/2 V_k^T -> column-pivoted QR (qr.cu) ->
+//   B = Lambda^-1/2 V_k^T[:, perm] -> unpivoted QR -> sign-normalised R_x, R (row-major).
+#include "solver_kernels.cuh"
+
+namespace tq {
+
+int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ldh, int64_t n, double* w,
+                  double* Zout, Workspace& ws);
+size_t eigh_ws_bytes(int64_t n);
+int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n, Workspace& ws);
+int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n, int64_t* perm,
+                  Workspace& ws);
+size_t qr_stage_ws_bytes(int64_t k, int64_t n);
+__global__ void emit_r_kernel(const double* __restrict__ A, int64_t lda, int64_t k, int64_t n,
+                              double* __restrict__ R, int64_t ldr);
+
+// ------------------------------------------------------------------ rank rule
+__device__ __forceinline__ double warp_incl_scan(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// Single CTA (1024 threads).  eig_desc[i] = max(w[n-1-i], 1e-12); S = sqrt(eig_desc);
+// energy = S*S (the reference squares the square root, gptq_utils.py:94,98).
+//   energy:        k = #{ i : cumsum(energy)_i <= (1 - thr) * sum(energy) };  k += (k < n)
+//   mean_trimmed:  k = #{ i : S_i > thr * mean(S[1:33]) }
+//   otherwise:     k = n
+__global__ void __launch_bounds__(1024)
+rank_select_kernel(const double* __restrict__ w, int64_t n, double thr, int method, double* __restrict__ eig_desc,
+                   long long* __restrict__ k_out) {
+  __shared__ double wsum[32];
+  __shared__ double carry_s, total_s, ref_s;
+  __shared__ unsigned long long count_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int64_t i = tid; i < n; i += blockDim.x) eig_desc[i] = fmax(w[n - 1 - i], 1e-12);
+  if (tid == 0) {
+    carry_s = 0.0;
+    count_s = 0ull;
+  }
+  __syncthreads();
+  if (method == TQ_RANK_FULL) {
+    if (tid == 0) *k_out = (long long)n;
+    return;
+  }
+  if (method == TQ_RANK_MEAN_TRIMMED) {
+    if (tid == 0) {
+      const int64_t ref_k = n < 33 ? n : 33;
+      double s = 0.0;
+      for (int64_t i = 1; i < ref_k; ++i) s += sqrt(eig_desc[i]);
+      ref_s = n > 1 ? s / double(ref_k - 1) : sqrt(eig_desc[0]);
+    }
+    __syncthreads();
+    unsigned long long c = 0;
+    for (int64_t i = tid; i < n; i += blockDim.x) c += (sqrt(eig_desc[i]) > thr * ref_s) ? 1ull : 0ull;
+    atomicAdd(&count_s, c);
+    __syncthreads();
+    if (tid == 0) *k_out = (long long)count_s;
+    return;
+  }
+  // energy: pass 1 total (fixed order: chunked block scan), pass 2 count
+  for (int pass = 0; pass < 2; ++pass) {
+    if (tid == 0) carry_s = 0.0;
+    __syncthreads();
+    const double target = pass ? (1.0 - thr) * total_s : 0.0;
+    unsigned long long c = 0;
+    for (int64_t base = 0; base < n; base += blockDim.x) {
+      const int64_t i = base + tid;
+      double en = 0.0;
+      if (i < n) {
+        const double s = sqrt(eig_desc[i]);
+        en = s * s;
+      }
+      double v = warp_incl_scan(en, lane);
+      if (lane == 31) wsum[wid] = v;
+      __syncthreads();
+      if (wid == 0) {
+        double t = wsum[lane];
+        t = warp_incl_scan(t, lane);
+        wsum[lane] = t;
+      }
+      __syncthreads();
+      const double prefix = carry_s + (wid ? wsum[wid - 1] : 0.0) + v;
+      if (pass && i < n && prefix <= target) ++c;
+      __syncthreads();
+      if (tid == blockDim.x - 1) carry_s = prefix;
+      __syncthreads();
+    }
+    if (pass == 0) {
+      if (tid == 0) total_s = carry_s;
+    } else {
+      atomicAdd(&count_s, c);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    long long k = (long long)count_s;
+    if (k < n) k += 1;
+    *k_out = k;
+  }
+}
+
+// ------------------------------------------------------------------ S and B builders
+// V is row-major: row r = eigenvector of w[r] (ascending).  Descending index i <-> row n-1-i.
+// S (col-major k x n): S[i + j k] = sqrt(e_i) * V[n-1-i][j]              (gptq_utils.py:112)
+__global__ void build_s_kernel(const double* __restrict__ V, int64_t n, int64_t k, const double* __restrict__ eig,
+                               double* __restrict__ S) {
+  __shared__ double t[32][33];
+  const int64_t i0 = int64_t(blockIdx.y) * 32, j0 = int64_t(blockIdx.x) * 32;
+  for (int a = threadIdx.y; a < 32; a += blockDim.y) {
+    int64_t i = i0 + a, j = j0 + threadIdx.x;
+    t[a][threadIdx.x] = (i < k && j < n) ? sqrt(eig[i]) * V[(n - 1 - i) * n + j] : 0.0;
+  }
+  __syncthreads();
+  for (int a = threadIdx.y; a < 32; a += blockDim.y) {
+    int64_t j = j0 + a, i = i0 + threadIdx.x;
+    if (i < k && j < n) S[i + j * k] = t[threadIdx.x][a];
+  }
+}
+
+// B (col-major k x n): B[i + j k] = (1 / sqrt(e_i)) * V[n-1-i][perm[j]]   (gptq_utils.py:111,118-119)
+__global__ void build_b_kernel(const double* __restrict__ V, int64_t n, int64_t k, const double* __restrict__ eig,
+                               const int64_t* __restrict__ perm, double* __restrict__ B) {
+  __shared__ double t[32][33];
+  const int64_t i0 = int64_t(blockIdx.y) * 32, j0 = int64_t(blockIdx.x) * 32;
+  const int64_t jj = j0 + threadIdx.x;
+  const int64_t pj = jj < n ? perm[jj] : 0;
+  for (int a = threadIdx.y; a < 32; a += blockDim.y) {
+    int64_t i = i0 + a;
+    t[a][threadIdx.x] = (i < k && jj < n) ? (1.0 / sqrt(eig[i])) * V[(n - 1 - i) * n + pj] : 0.0;
+  }
+  __syncthreads();
+  for (int a = threadIdx.y; a < 32; a += blockDim.y) {
+    int64_t j = j0 + a, i = i0 + threadIdx.x;
+    if (i < k && j < n) B[i + j * k] = t[threadIdx.x][a];
+  }
+}
+
+static size_t solver_ws_bytes(int64_t n) {
+  // V (n^2) + eigh scratch, later overlaid by S/B (n^2) + QR scratch
+  size_t a = ws_bytes_for(size_t(n) * n, 8) + ws_bytes_for(n, 8) * 2 + 1024;
+  size_t e = eigh_ws_bytes(n);
+  size_t q = ws_bytes_for(size_t(n) * n, 8) + qr_stage_ws_bytes(n, n);
+  return a + (e > q ? e : q) + (size_t(1) << 20);
+}
+
+}  // namespace tq
+
 using namespace tq;
-extern "C" int tq_solver_workspace(int64_t n, size_t* bytes) { *bytes = 256; return TQ_OK; }
-extern "C" int tq_spectral_solve(const double*, int64_t, int64_t, double, int, double*, double*, int64_t*, double*, int64_t*, void*, size_t, void*) { set_error("not implemented"); return TQ_ERR_UNSUPPORTED; }
-extern "C" int tq_eigh(const double*, int64_t, int64_t, double*, double*, int64_t, void*, size_t, void*) { set_error("not implemented"); return TQ_ERR_UNSUPPORTED; }
-extern "C" int tq_rank_select(const double*, int64_t, double, int, double*, int64_t*, void*, size_t, void*) { set_error("not implemented"); return TQ_ERR_UNSUPPORTED; }
-extern "C" int tq_qrcp(const double*, int64_t, int64_t, int64_t, double*, int64_t, int64_t*, void*, size_t, void*) { set_error("not implemented"); return TQ_ERR_UNSUPPORTED; }
-extern "C" int tq_qr_r(const double*, int64_t, int64_t, int64_t, double*, int64_t, void*, size_t, void*) { set_error("not implemented"); return TQ_ERR_UNSUPPORTED; }
+
+extern "C" int tq_solver_workspace(int64_t n, size_t* bytes) {
+  TQ_REQUIRE(bytes && n > 0, "tq_solver_workspace: bad arguments");
+  *bytes = solver_ws_bytes(n);
+  return TQ_OK;
+}
+
+extern "C" int tq_rank_select(const double* w_asc, int64_t n, double threshold, int method, double* eig_desc,
+                              int64_t* k_host, void* ws, size_t ws_bytes, void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(w_asc && eig_desc && k_host && n > 0, "tq_rank_select: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace wsp(ws, ws_bytes);
+  long long* kd = wsp.take<long long>(1);
+  if (wsp.overflow) {
+    set_error("tq_rank_select: workspace too small");
+    return TQ_ERR_WORKSPACE;
+  }
+  rank_select_kernel<<<1, 1024, 0, st>>>(w_asc, n, threshold, method, eig_desc, kd);
+  TQ_LAUNCH_CHECK();
+  long long kh = 0;
+  TQ_CUDA_CHECK(cudaMemcpyAsync(&kh, kd, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  *k_host = kh;
+  return TQ_OK;
+}
+
+extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double threshold, int method, double* R,
+                                 double* Rx, int64_t* perm, double* eigvals, int64_t* k_host, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(H && R && Rx && perm && eigvals && k_host, "tq_spectral_solve: null pointer");
+  TQ_REQUIRE(n > 0 && ldh >= n && n < (1 << 30), "tq_spectral_solve: bad shape n=%lld", (long long)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace wsp(ws, ws_bytes);
+  double* V = wsp.take<double>(size_t(n) * n);
+  double* w = wsp.take<double>(n);
+  long long* kd = wsp.take<long long>(1);
+  if (wsp.overflow) {
+    set_error("tq_spectral_solve: workspace too small (%zu bytes given, %zu needed)", ws_bytes, solver_ws_bytes(n));
+    return TQ_ERR_WORKSPACE;
+  }
+  cublasHandle_t h;
+  TQ_TRY(get_cublas(&h, st));
+  {
+    Workspace sub = wsp;
+    TQ_TRY(eigh_colmajor(h, st, H, ldh, n, w, V, sub));
+  }
+  rank_select_kernel<<<1, 1024, 0, st>>>(w, n, threshold, method, eigvals, kd);
+  TQ_LAUNCH_CHECK();
+  long long kh = 0;
+  TQ_CUDA_CHECK(cudaMemcpyAsync(&kh, kd, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  *k_host = kh;
+  const int64_t k = kh;
+  if (k <= 0) return TQ_OK;   // nothing retained (mean_trimmed can return 0): R, Rx are empty
+  TQ_REQUIRE(k <= n, "tq_spectral_solve: rank rule returned k=%lld > n", (long long)k);
+
+  Workspace sub = wsp;
+  double* SB = sub.take<double>(size_t(k) * n);
+  if (sub.overflow) {
+    set_error("tq_spectral_solve: workspace too small for S");
+    return TQ_ERR_WORKSPACE;
+  }
+  dim3 tg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(k, 32));
+  build_s_kernel<<<tg, dim3(32, 8), 0, st>>>(V, n, k, eigvals, SB);
+  TQ_LAUNCH_CHECK();
+  {
+    Workspace s2 = sub;
+    TQ_TRY(qrcp_colmajor(h, st, SB, k, k, n, perm, s2));
+  }
+  emit_r_kernel<<<tg, dim3(32, 8), 0, st>>>(SB, k, k, n, Rx, n);
+  TQ_LAUNCH_CHECK();
+  build_b_kernel<<<tg, dim3(32, 8), 0, st>>>(V, n, k, eigvals, perm, SB);
+  TQ_LAUNCH_CHECK();
+  {
+    Workspace s2 = sub;
+    TQ_TRY(qr_r_colmajor(h, st, SB, k, k, n, s2));
+  }
+  emit_r_kernel<<<tg, dim3(32, 8), 0, st>>>(SB, k, k, n, R, n);
+  TQ_LAUNCH_CHECK();
+  return TQ_OK;
+}

@@ -134,7 +134,7 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict
     ptx::setmaxnreg_inc<224>();
     epilogue_role(bars, tmem_base, num_chunks, warp, lane, i0, j0, n, H, ldh);
   } else {
-  ptx::setmaxnreg_dec<64>();
+  ptx::setmaxnreg_dec<56>();
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
     if (lane == 0) {

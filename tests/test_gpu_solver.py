@@ -1,0 +1,159 @@
+"""GPU parity: spectral solver (tq_eigh, tq_rank_select, tq_qrcp, tq_qr_r,
+tq_spectral_solve) stage by stage against the golden vectors of the unmodified
+reference and the CPU oracle.  Tolerances (north_star): k identical, eigenvalues within
+1e-4 relative (we hold 1e-10), pivot order identical, R within eps*cond."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cases
+from oracle import truncgptq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gptq_svd_b200 as G
+    return G
+
+
+@pytest.fixture(scope="module")
+def S():
+    from gptq_svd_b200 import stages
+    return stages
+
+
+def _gpu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _sym_cases():
+    rng = np.random.RandomState(5)
+    out = {}
+    for n in (1, 2, 3, 31, 32, 33, 64, 100, 257, 700):
+        A = rng.standard_normal((n, n))
+        out[f"rand{n}"] = (A + A.T) / 2
+    X = rng.standard_normal((3000, 300)) * np.logspace(0, -5, 300)[None, :]
+    out["graded300"] = X.T @ X / 3000
+    out["identity50"] = np.eye(50)
+    out["diag200"] = np.diag(np.linspace(1, 2, 200))
+    Q, _ = np.linalg.qr(rng.standard_normal((240, 240)))
+    out["clusters240"] = (Q * np.repeat(rng.standard_normal(8), 30)) @ Q.T       # 8 clusters of 30
+    out["lowrank150"] = (Q[:150, :5] @ Q[:150, :5].T)                             # rank 5 PSD
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(_sym_cases()))
+def test_eigh_vs_lapack(S, name):
+    H = _sym_cases()[name]
+    H = (H + H.T) / 2
+    n = H.shape[0]
+    w, V = S.eigh(_gpu(H))
+    w, V = w.cpu().numpy(), V.cpu().numpy()
+    wr = np.linalg.eigvalsh(H)
+    scale = max(np.abs(wr).max(), 1e-300)
+    assert np.all(np.diff(w) >= 0)
+    assert np.abs(w - wr).max() <= 1e-12 * scale * max(1, n ** 0.5)
+    assert np.linalg.norm(H @ V - V * w[None, :]) <= 1e-12 * max(np.linalg.norm(H), 1e-300) * n ** 0.5
+    assert np.linalg.norm(V.T @ V - np.eye(n)) <= 1e-12 * n
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_eigh_golden(S, name, golden):
+    g = golden(name)
+    w, V = S.eigh(_gpu(g["H"]))
+    e = np.maximum(w.cpu().numpy(), 1e-12)[::-1]
+    sig = e > 1e-10 * e[0]
+    assert np.abs(e[sig] / g["eig"][sig] - 1).max() <= 1e-4          # north_star tolerance
+    assert np.abs(e - g["eig"]).max() <= 1e-12 * e[0]               # what we actually hold
+
+
+@pytest.mark.parametrize("thr,method", [(1e-2, "energy"), (1e-4, "energy"), (1e-7, "energy"), (0.0, "energy"),
+                                        (1.0, "energy"), (5e-4, "mean_trimmed"), (0.5, "mean_trimmed"), (0.1, "none")])
+def test_rank_select(S, thr, method, golden):
+    g = golden("llm_n256_w3a")
+    w = np.linalg.eigvalsh(g["H"])
+    eig, k = S.rank_select(_gpu(w), thr, method)
+    e = np.maximum(w, 1e-12)[::-1]
+    assert np.array_equal(eig.cpu().numpy(), e)
+    assert k == O.rank_rule(np.sqrt(e) ** 2, thr, method)
+
+
+def _qr_inputs():
+    rng = np.random.RandomState(3)
+    out = {}
+    for (k, n) in ((1, 1), (5, 9), (32, 32), (33, 70), (64, 64), (100, 260), (129, 129), (200, 520), (300, 300)):
+        out[f"{k}x{n}"] = rng.standard_normal((k, n)) * np.logspace(0, -6, n)[rng.permutation(n)][None, :]
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(_qr_inputs()))
+def test_qrcp_vs_oracle(S, name):
+    A = _qr_inputs()[name]
+    k, n = A.shape
+    R, perm = S.qrcp(_gpu(A))
+    R, perm = R.cpu().numpy(), perm.cpu().numpy()
+    Ro, po = O.dgeqp3(A)
+    Ro = Ro * np.sign(np.diagonal(Ro))[:, None]
+    assert sorted(perm.tolist()) == list(range(n))
+    assert np.array_equal(perm[:k], po[:k])
+    assert np.abs(R - Ro).max() <= 1e-11 * np.abs(Ro).max()
+    assert np.all(np.diagonal(R) >= 0)
+    assert np.abs(np.tril(R, -1)).max() == 0.0
+    # R^T R = (A^T A)[perm][:, perm]
+    G_ = (A.T @ A)[np.ix_(perm, perm)]
+    assert np.linalg.norm(R.T @ R - G_) <= 1e-12 * np.linalg.norm(G_) * n ** 0.5
+
+
+@pytest.mark.parametrize("name", sorted(_qr_inputs()))
+def test_qr_r_vs_lapack(S, name):
+    A = _qr_inputs()[name]
+    R = S.qr_r(_gpu(A)).cpu().numpy()
+    Rr = np.linalg.qr(A, mode="r")
+    Rr = Rr * np.sign(np.diagonal(Rr))[:, None]
+    assert np.abs(R - Rr).max() <= 1e-10 * np.abs(Rr).max()
+    assert np.abs(np.tril(R, -1)).max() == 0.0
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_process_hessian_alt_golden(G, name, golden):
+    g = golden(name)
+    f = G.spectral_solve(_gpu(g["H"]), float(g["eps"]), str(g["method"]))
+    k = int(g["k"])
+    assert f.k == k                                                          # retained rank identical
+    perm = f.perm.cpu().numpy()
+    assert sorted(perm.tolist()) == list(range(len(perm)))
+    assert np.array_equal(perm[:k], g["perm"][:k])                          # pivot order identical
+    e = f.eigvals.cpu().numpy()
+    cond = e[0] / e[k - 1]
+    R, Rx = f.R.cpu().numpy(), f.R_x.cpu().numpy()
+    assert R.shape == g["R"].shape and Rx.shape == g["R_x"].shape
+    assert np.abs(Rx - g["R_x"]).max() <= 1e-10 * np.abs(g["R_x"]).max()
+    assert np.abs(R - g["R"]).max() <= (2e-14 * cond + 1e-12) * np.abs(g["R"]).max()
+    assert np.all(np.diagonal(R) > 0) and np.all(np.diagonal(Rx) > 0)
+    # drop-in signature
+    R2, Rx2, p2 = G.process_hessian_alt(_gpu(g["H"]), float(g["eps"]), str(g["method"]))
+    assert R2.shape == R.shape and p2.dtype == torch.int64 and R2.dtype == torch.float64
+
+
+@pytest.mark.parametrize("n,eps", [(1024, 1e-4), (2048, 1e-6)])
+def test_solver_invariants_medium(G, n, eps):
+    """Oracle-free invariants at Qwen3-0.6B widths, plus the oracle at n=1024."""
+    X = O.make_activations(4 * n, n, seed=n, dist="llm").astype(np.float64)
+    H = X.T @ X / X.shape[0]
+    f = G.spectral_solve(_gpu(H), eps, "energy")
+    k = f.k
+    P = f.perm.cpu().numpy()
+    L, V = np.linalg.eigh(H)
+    L = np.maximum(L, 1e-12)[::-1]
+    V = V[:, ::-1]
+    assert k == O.rank_rule(np.sqrt(L) ** 2, eps, "energy")
+    Hk = (V[:, :k] * L[:k]) @ V[:, :k].T
+    Hkp = (V[:, :k] / L[:k]) @ V[:, :k].T
+    R, Rx = f.R.cpu().numpy(), f.R_x.cpu().numpy()
+    assert np.linalg.norm(Rx.T @ Rx - Hk[np.ix_(P, P)]) <= 1e-11 * np.linalg.norm(H)
+    assert np.linalg.norm(R.T @ R - Hkp[np.ix_(P, P)]) <= 1e-7 * np.linalg.norm(Hkp)
+    if n == 1024:
+        fo = O.process_hessian_alt(H, eps, "energy")
+        assert np.array_equal(P[:k], fo.perm[:k])
