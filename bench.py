@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""
+bench.py - TruncGPTQ solve-and-quantize hot path on B200 (driver contract in the task
+statement; metric / config from BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path)
+  python bench.py --impl reference --steps K --warmup W    # CPU reference arm (oracle port)
+
+Workload (configs[1] of BASELINE.json): Qwen3-8B-shaped decoder block, random-init weights,
+4-bit symmetric g128, eps 1e-4 'energy', 128 x 2048 synthetic calibration tokens fed in 4
+batches of 32 x 2048 like the reference run (run_benchmark.py:37), block_size 1024.
+One STEP = one decoder layer through the whole hot path:
+  4 groups x [H += X^T X over 262144 tokens  ->  process_hessian_alt]  +  7 Linears x gptq_fwrd
+(q/k/v share one H, gate/up share one H: quantize.py:110-219, model_utils.py:77-108).
+All 36 layers of the model have the same shapes, so the headline
+  value = "Qwen3-8B end-to-end quantize time (s)" = 36 x mean step time / n_gpus
+(with N GPUs the independent layers are sharded across ranks, no data-path collective:
+weak scaling).  `--steps 36` times a whole model per rank.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAYERS = 36
+TOKENS = 128 * 2048
+CHUNK = 32 * 2048
+# (in_features, [out_features of every Linear sharing this H])
+GROUPS = [(4096, [4096, 1024, 1024]), (4096, [4096]), (4096, [12288, 12288]), (12288, [4096])]
+SMALL_GROUPS = [(512, [512, 128, 128]), (512, [512]), (512, [1536, 1536]), (1536, [512])]   # --tiny (CI)
+METRIC = "qwen3_8b_truncgptq_quantize_time"
+UNIT = "s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU baseline
+def cpu_sample(seed: int = 0):
+    """Bounded sample of the same workload through the CPU oracle (numpy / LAPACK port of the
+    reference; /root/reference itself is Python and does not travel to the GPU box).
+    One n=4096 group: H from 8192 tokens, full solver, loop on 256 rows of a 4096-wide Linear.
+    Returns per-stage seconds and the extrapolation to one model."""
+    import numpy as np
+    import scipy.linalg as sla
+    from oracle import truncgptq_oracle as O
+
+    n, Ts, ms = 4096, 8192, 256
+    rng = np.random.RandomState(seed)
+    A = rng.standard_normal((n, n)).astype(np.float32) * np.logspace(0, -1, n, dtype=np.float32)[None, :]
+    X = (rng.standard_normal((Ts, n)).astype(np.float32) @ A.T / np.sqrt(n) * 3).astype(np.float16)
+    W = O.make_weight(ms, n, seed + 1)
+    t0 = time.perf_counter()
+    acc = O.HessianAccumulator(n)
+    acc.add_batch(X)
+    H = acc.get_hessian()
+    t1 = time.perf_counter()
+
+    def lapack_qrcp(S):
+        _, r, p = sla.qr(S, mode="economic", pivoting=True)       # LAPACK dgeqp3, as the reference's stub
+        return r, p.astype(np.int64)
+
+    f = O.process_hessian_alt(H, 1e-4, "energy", qrcp=lapack_qrcp)
+    t2 = time.perf_counter()
+    q = O.Quantizer(4, 128, True)
+    fw, k = O.gptq_fwrd(W, f.R, q, f.perm, block_size=1024, use_triton=False)
+    O.quantization_error(W, fw, f.R_x, f.perm)
+    t3 = time.perf_counter()
+    tH, tS, tL = t1 - t0, t2 - t1, t3 - t2
+    per_layer = tH * (TOKENS / Ts) * (3 + 9) + tS * (3 + 27) + tL * (71680 / ms)
+    return {"t_hessian": tH, "t_solver": tS, "t_loop": tL, "k": int(k), "model_s": per_layer * LAYERS,
+            "sample": (f"oracle port on one n=4096 group: H from {Ts} tokens, full eigh+dgeqp3+qr, loop on {ms} rows; "
+                       "extrapolated by T*n^2 (H), n^3 (solver), m*n^2 (loop) to 36 Qwen3-8B layers")}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_sample(0)
+    vals = []
+    t0 = time.perf_counter()
+    steps = max(1, min(args.steps, 3))
+    for s in range(steps):
+        vals.append(cpu_sample(s))
+    wall = time.perf_counter() - t0
+    v = sum(x["model_s"] for x in vals) / len(vals)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": min(args.warmup, 1), "ms_per_step": wall / steps * 1e3, "higher_is_better": False,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": _config(args, None),
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": vals[0]["sample"]},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def _config(args, k_list):
+    return {"workload": "Qwen3-8B-shaped random-init, 4-bit sym g128, 128x2048 synthetic tokens (BASELINE configs[1])"
+            if not args.tiny else "tiny CI shapes",
+            "step": "one decoder layer: 4 x (SYRK over 262144 tokens + spectral solve) + 7 x gptq_fwrd",
+            "layers_per_model": LAYERS, "value_is": "36 x mean step seconds / n_gpus",
+            "bits": args.bits, "sym": bool(args.sym), "group_size": 128, "eps": args.eps, "threshold_method": "energy",
+            "block_size": 1024, "activations": f"randn @ A^T, column scales logspace(0,{args.decay}), 8 outlier channels x30",
+            "retained_rank": k_list, "l2": "inputs per step (12.9 GB) exceed the 126 MB L2; no explicit flush",
+            "parallelism": f"layers sharded over {args.gpus} rank(s), no collective"}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def make_x(torch, rows, n, seed, decay):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn(n, n, device="cuda", generator=g) * torch.logspace(0, decay, n, device="cuda")[None, :]
+    out = torch.empty(rows, n, device="cuda", dtype=torch.float16)
+    for c in range(0, rows, 8192):
+        z = torch.randn(min(8192, rows - c), n, device="cuda", generator=g)
+        out[c:c + 8192] = (z @ A.T / (n ** 0.5) * 3).half()
+    out[:, :8] *= 30
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bits", type=int, default=4)
+    ap.add_argument("--sym", type=int, default=1)
+    ap.add_argument("--eps", type=float, default=1e-4)
+    ap.add_argument("--decay", type=float, default=-1.0)
+    ap.add_argument("--tiny", action="store_true", help="small shapes (functional check only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import gptq_svd_b200 as G
+    from gptq_svd_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:      # not under torchrun: re-launch ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    groups = SMALL_GROUPS if args.tiny else GROUPS
+    tokens, chunk = (8192, 2048) if args.tiny else (TOKENS, CHUNK)
+    dev = torch.device("cuda", local)
+
+    # ---- synthetic inputs: resident in HBM for `value`, mirrored in pinned host memory for `e2e`
+    Xs, Ws = [], []
+    for gi, (n, outs) in enumerate(groups):
+        Xs.append(make_x(torch, tokens, n, 1000 * rank + gi, args.decay))
+        Ws.append([(torch.randn(m, n, device=dev, generator=torch.Generator(device="cuda").manual_seed(2000 * rank + 10 * gi + li))
+                    * 0.02).half() for li, m in enumerate(outs)])
+    ranks_seen = []
+
+    def layer_step(x_src, w_src, host: bool, sink=None):
+        """One decoder layer through the public API.  host=True: inputs come from pinned host
+        buffers (H2D inside), dequantised fp16 weights go back to pinned host buffers (D2H)."""
+        ks = []
+        for gi, (n, outs) in enumerate(groups):
+            acc = G.HessianAccumulator(n, dev)
+            for c in range(0, tokens, chunk):
+                xb = x_src[gi][c:c + chunk]
+                if host:
+                    xb = xb.to(dev, non_blocking=True)
+                acc.add_batch(xb.view(-1, 2048, n) if (xb.shape[0] % 2048 == 0) else xb)
+            H = acc.get_hessian()
+            R, R_x, perm = G.process_hessian_alt(H, args.eps, "energy")
+            ks.append(int(R.shape[0]))
+            for li, m in enumerate(outs):
+                W = w_src[gi][li]
+                if host:
+                    W = W.to(dev, non_blocking=True)
+                q = G.Quantizer(args.bits, 128, bool(args.sym))
+                fw, k = G.gptq_fwrd(W, R, q, perm, block_size=1024, use_triton=True, R_x=R_x)
+                if host:
+                    sink[gi][li].copy_(fw, non_blocking=True)
+            del acc, H, R, R_x, perm
+        return ks
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        ranks_seen = layer_step(Xs, Ws, False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.tq_profile_begin(16)
+    l0 = lib.tq_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        layer_step(Xs, Ws, False)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    launches = torch.tensor([lib.tq_launch_count() - l0], device=dev, dtype=torch.float64)
+    import ctypes as C
+    pb, pms, psamp, ptot = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_int64(0)
+    lib.tq_profile_end(C.byref(pb), C.byref(pms), C.byref(psamp), C.byref(ptot))
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    ms_per_step = float(ms.item()) / args.steps
+    value = LAYERS * ms_per_step / 1e3 / world
+
+    # ---- e2e: same step through the public API with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    try:
+        Xh = [x.cpu().pin_memory() for x in Xs]
+        Wh = [[w.cpu().pin_memory() for w in ws] for ws in Ws]
+        Oh = [[torch.empty_like(w).pin_memory() for w in ws] for ws in Wh]
+        layer_step(Xh, Wh, True, Oh)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.e2e_steps):
+            layer_step(Xh, Wh, True, Oh)
+        t1.record()
+        barrier()
+        ems = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        h2d = sum(x.numel() * 2 for x in Xh) + sum(w.numel() * 2 for ws in Wh for w in ws)
+        d2h = sum(w.numel() * 2 for ws in Oh for w in ws)
+        e2e = {"value": LAYERS * float(ems.item()) / args.e2e_steps / 1e3 / world, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+               "note": "pinned host X / W -> device inside the timed region, dequantised fp16 weights read back"}
+        del Xh, Wh, Oh
+    except Exception as ex:       # pinned allocation can fail on a small host
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
+
+    if rank == 0:
+        peak, which = _peaks()
+        achieved = (pb.value / 1e9) / (pms.value / 1e3) if pms.value > 0 else None
+        roof = {"bound": "hbm", "kernel": "dots3_kernel (sytrd / QRCP panel: trailing matrix x reflector)",
+                "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "sampled_launches": int(psamp.value), "total_launches": int(ptot.value),
+                "avg_launch_ms": (pms.value / psamp.value) if psamp.value else None,
+                "avg_alg_bytes": (pb.value / psamp.value) if psamp.value else None}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline and not args.tiny:
+            try:
+                s = cpu_sample(0)
+                cpu = {"value": s["model_s"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": s["sample"],
+                       "stage_seconds": {"hessian": s["t_hessian"], "solver": s["t_solver"], "loop": s["t_loop"]}}
+            except Exception as ex:
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"[:200]}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64 solver / f32 loop / f16 SYRK inputs", "data": "synthetic", "config": _config(args, ranks_seen),
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()), "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,9 @@ _i64, _i32, _vp, _sz, _dbl = C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_dou
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
     "tq_version": [],
+    "tq_launch_count": [],
+    "tq_profile_begin": [_i32],
+    "tq_profile_end": [C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_i64), C.POINTER(_i64)],
     "tq_last_error": [],
     "tq_syrk_accum": [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _i32, _vp],
     "tq_hessian_scale": [_vp, _i64, _i64, _i64, _vp, _i64, _vp],
@@ -41,7 +44,7 @@ SIGNATURES = {
     "tq_quant_error_workspace": [_i64, _i64, _i64, C.POINTER(_sz)],
     "tq_quant_error": [_vp, _i64, _vp, _i64, _vp, _i32, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _sz, _vp],
 }
-_RESTYPES = {"tq_last_error": C.c_char_p}
+_RESTYPES = {"tq_last_error": C.c_char_p, "tq_launch_count": C.c_int64}
 
 _lib = None
 

@@ -1,11 +1,41 @@
 // Version, error string and device check of libtruncgptq.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <time.h>
+
+#include <vector>
 
 #include "common.cuh"
 
 namespace tq {
 
 static thread_local char g_err[512] = "";
+thread_local int64_t g_launch_count = 0;
+
+struct ProfSlot {
+  cudaEvent_t e0, e1;
+  double bytes;
+};
+static thread_local bool g_prof_on = false;
+static thread_local int g_prof_every = 1;
+static thread_local int64_t g_prof_seen = 0;
+static thread_local std::vector<ProfSlot> g_prof_slots;
+
+int prof_begin_launch(cudaStream_t st, double alg_bytes) {
+  if (!g_prof_on) return -1;
+  const int64_t idx = g_prof_seen++;
+  if (idx % g_prof_every != 0 || g_prof_slots.size() >= 8192) return -1;
+  ProfSlot s;
+  if (cudaEventCreate(&s.e0) != cudaSuccess || cudaEventCreate(&s.e1) != cudaSuccess) return -1;
+  s.bytes = alg_bytes;
+  cudaEventRecord(s.e0, st);
+  g_prof_slots.push_back(s);
+  return int(g_prof_slots.size()) - 1;
+}
+
+void prof_end_launch(cudaStream_t st, int slot) {
+  if (slot >= 0) cudaEventRecord(g_prof_slots[slot].e1, st);
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -35,6 +65,34 @@ int check_device() {
   return TQ_OK;
 }
 
+bool trace_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TQ_TRACE");
+    v = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+static double now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+StageTimer::StageTimer(cudaStream_t s, const char* n) : st(s), name(n), t0(0) {
+  if (trace_enabled()) {
+    cudaStreamSynchronize(st);
+    t0 = now_ms();
+  }
+}
+StageTimer::~StageTimer() {
+  if (trace_enabled()) {
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[tq-trace] %-18s %10.3f ms\n", name, now_ms() - t0);
+  }
+}
+
 int num_sms() {
   static thread_local int cached = 0;
   if (cached) return cached;
@@ -45,6 +103,42 @@ int num_sms() {
 }
 
 }  // namespace tq
+
+extern "C" int64_t tq_launch_count(void) { return tq::g_launch_count; }
+
+extern "C" int tq_profile_begin(int sample_every) {
+  using namespace tq;
+  for (auto& s : g_prof_slots) {
+    cudaEventDestroy(s.e0);
+    cudaEventDestroy(s.e1);
+  }
+  g_prof_slots.clear();
+  g_prof_on = true;
+  g_prof_every = sample_every > 0 ? sample_every : 1;
+  g_prof_seen = 0;
+  return TQ_OK;
+}
+
+extern "C" int tq_profile_end(double* alg_bytes, double* ms, int64_t* sampled, int64_t* total) {
+  using namespace tq;
+  double b = 0, t = 0;
+  for (auto& s : g_prof_slots) {
+    float f = 0;
+    if (cudaEventSynchronize(s.e1) == cudaSuccess && cudaEventElapsedTime(&f, s.e0, s.e1) == cudaSuccess) {
+      b += s.bytes;
+      t += f;
+    }
+    cudaEventDestroy(s.e0);
+    cudaEventDestroy(s.e1);
+  }
+  if (alg_bytes) *alg_bytes = b;
+  if (ms) *ms = t;
+  if (sampled) *sampled = int64_t(g_prof_slots.size());
+  if (total) *total = g_prof_seen;
+  g_prof_slots.clear();
+  g_prof_on = false;
+  return TQ_OK;
+}
 
 extern "C" int tq_version(void) { return TQ_VERSION; }
 extern "C" const char* tq_last_error(void) { return tq::g_err; }

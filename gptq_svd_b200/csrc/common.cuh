@@ -35,7 +35,16 @@ int check_device();  // TQ_OK when the current device is sm_100 (B200)
     if (_s != TQ_OK) return _s; \
   } while (0)
 
-#define TQ_LAUNCH_CHECK() TQ_CUDA_CHECK(cudaGetLastError())
+extern thread_local int64_t g_launch_count;
+#define TQ_LAUNCH_CHECK()                \
+  do {                                   \
+    ++tq::g_launch_count;                \
+    TQ_CUDA_CHECK(cudaGetLastError());   \
+  } while (0)
+
+// sampled event timing of the dominant BLAS-2 kernel (see tq_profile_begin)
+int prof_begin_launch(cudaStream_t st, double alg_bytes);   // returns a slot or -1
+void prof_end_launch(cudaStream_t st, int slot);
 
 static inline int64_t imin(int64_t a, int64_t b) { return a < b ? a : b; }
 static inline int64_t imax(int64_t a, int64_t b) { return a > b ? a : b; }
@@ -66,5 +75,15 @@ struct Workspace {
 static inline size_t ws_bytes_for(size_t count, size_t elem) { return align_up(count * elem, 256) + 256; }
 
 int num_sms();
+
+// TQ_TRACE=1: print per-stage milliseconds (synchronises the stream at stage boundaries)
+bool trace_enabled();
+struct StageTimer {
+  cudaStream_t st;
+  const char* name;
+  double t0;
+  StageTimer(cudaStream_t s, const char* n);
+  ~StageTimer();
+};
 
 }  // namespace tq

@@ -96,7 +96,9 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
       DotSeg s0{A + (c + 1) + (c + 1) * lda, lda, len, y + c + 1};
       DotSeg s1{W + (c + 1), ldw, i, tmp};
       DotSeg s2{A + (c + 1) + j0 * lda, lda, i, tmp + kTrdNb};
+      const int pslot = prof_begin_launch(st, double(len) * double(len + 2 * i) * 8.0);
       dots3_kernel<<<dots_grid(len + 2 * i), 256, 0, st>>>(s0, s1, s2, v, len, nullptr);
+      prof_end_launch(st, pslot);
       TQ_LAUNCH_CHECK();
       sytrd_w_kernel<<<(unsigned)imin(ceil_div(len, 256), 592), 256, 0, st>>>(A, lda, n, j0, i, W, ldw, y, tmp,
                                                                              tmp + kTrdNb, tau + c);
@@ -766,10 +768,16 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)n);
   copy_sym_kernel<<<grid, 256, 0, st>>>(H, ldh, n, A);
   TQ_LAUNCH_CHECK();
-  TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp));
+  {
+    StageTimer tm(st, "sytrd");
+    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp));
+  }
   {
     Workspace sub = ws;   // D&C scratch is released afterwards
-    TQ_TRY(stedc(h, st, w, e, Zout, n, sub));
+    {
+      StageTimer tm(st, "stedc");
+      TQ_TRY(stedc(h, st, w, e, Zout, n, sub));
+    }
     if (sub.overflow) return TQ_ERR_WORKSPACE;
     // back-transform scratch overlays the D&C scratch
     Workspace sub2 = ws;
@@ -780,6 +788,7 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
       set_error("eigh: workspace too small (ormtr)");
       return TQ_ERR_WORKSPACE;
     }
+    StageTimer tm(st, "ormtr");
     TQ_TRY(ormtr_lower(h, st, A, tau, n, Zout, n, Vc, G, T, w1, w2));
   }
   return TQ_OK;

@@ -336,7 +336,9 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
       if (ntrail > 0 || i > 0) {
         DotSeg s0{A + c + (c + 1) * lda, lda, ntrail, F + (c + 1 - j0) + int64_t(i) * ldf};
         DotSeg s1{A + c + j0 * lda, lda, i, auxraw};
+        const int pslot = prof_begin_launch(st, double(len) * double(ntrail + i) * 8.0);
         dots3_kernel<<<dots_grid(ntrail + i), 256, 0, st>>>(s0, s1, none, A + c + c * lda, len, &ctl->stop);
+        prof_end_launch(st, pslot);
         TQ_LAUNCH_CHECK();
       }
       qrcp_row_update_kernel<<<(unsigned)imax(1, ceil_div(ntrail, 256)), 256, 0, st>>>(

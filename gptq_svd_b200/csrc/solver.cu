@@ -221,6 +221,7 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
   TQ_LAUNCH_CHECK();
   {
     Workspace s2 = sub;
+    StageTimer tm(st, "qrcp");
     TQ_TRY(qrcp_colmajor(h, st, SB, k, k, n, perm, s2));
   }
   emit_r_kernel<<<tg, dim3(32, 8), 0, st>>>(SB, k, k, n, Rx, n);
@@ -229,6 +230,7 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
   TQ_LAUNCH_CHECK();
   {
     Workspace s2 = sub;
+    StageTimer tm(st, "qr_r");
     TQ_TRY(qr_r_colmajor(h, st, SB, k, k, n, s2));
   }
   emit_r_kernel<<<tg, dim3(32, 8), 0, st>>>(SB, k, k, n, R, n);

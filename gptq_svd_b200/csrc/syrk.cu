@@ -295,7 +295,7 @@ extern "C" int tq_syrk_accum(double* H, int64_t ldh, const void* X, int x_dtype,
              "tq_syrk_accum: TMA needs a 16-byte aligned X and ldx %% 8 == 0 (ldx=%lld)", (long long)ldx);
   TQ_REQUIRE(n < (1 << 30) && rows < (int64_t(1) << 31), "tq_syrk_accum: shape too large");
   if (rows == 0) return TQ_OK;
-  if (kc_tokens <= 0) kc_tokens = 1024;
+  if (kc_tokens <= 0) kc_tokens = 512;
   int kc_blocks = max(1, kc_tokens / kTokBlk);
   cudaStream_t st = (cudaStream_t)stream;
 

@@ -68,7 +68,7 @@ const char* tq_last_error(void);
 
 /* H (n x n fp64, fully symmetric on return) += X^T X, X = rows x n (x_dtype TQ_F16 or
  * TQ_BF16), computed as a tcgen05/TMEM SYRK: fp16 products are exact in fp32, TMEM
- * accumulates `kc_tokens` tokens at a time (0 = default 1024), chunk sums are added in
+ * accumulates `kc_tokens` tokens at a time (0 = default 512), chunk sums are added in
  * fp32 registers and the batch total is added to H in fp64.  Requires ldx % 8 == 0 and a
  * 16-byte aligned X (TMA).  gptq_utils.py:221-222. */
 int tq_syrk_accum(double* H, int64_t ldh, const void* X, int x_dtype, int64_t rows, int64_t n,
@@ -166,6 +166,22 @@ int tq_quant_error_workspace(int64_t m, int64_t n, int64_t k, size_t* bytes);
 int tq_quant_error(const float* W, int64_t ldw, const float* Wq, int64_t ldq, const void* Rx,
                    int rx_dtype, int64_t ldr, int64_t k, const int64_t* perm, int64_t m, int64_t n,
                    double* out2, void* ws, size_t ws_bytes, void* stream);
+
+/* --------------------------------------------------------------------------
+ * Diagnostics (measurement only; no effect on results).
+ * -------------------------------------------------------------------------- */
+
+/* Number of libtruncgptq kernels launched by the calling thread since load (cuBLAS calls
+ * are not counted). */
+int64_t tq_launch_count(void);
+
+/* Sampled timing of the solver's dominant HBM-bound kernel (dots3_kernel: one pass over the
+ * trailing matrix per reflector in the tridiagonal reduction and the pivoted QR).  After
+ * tq_profile_begin(every), every `every`-th launch is bracketed by CUDA events on its own
+ * stream; tq_profile_end synchronises them and returns the algorithmic bytes
+ * (rows * columns * 8) and the milliseconds of the sampled launches. */
+int tq_profile_begin(int sample_every);
+int tq_profile_end(double* alg_bytes, double* ms, int64_t* sampled, int64_t* total);
 
 #ifdef __cplusplus
 }
