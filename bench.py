@@ -256,7 +256,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    lib.tq_profile_begin(16)
+    lib.tq_profile_begin(4)
     l0 = lib.tq_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -305,7 +305,7 @@ def main():
     if rank == 0:
         peak, which = _peaks()
         achieved = (pb.value / 1e9) / (pms.value / 1e3) if pms.value > 0 else None
-        roof = {"bound": "hbm", "kernel": "dots3_kernel (sytrd / QRCP panel: trailing matrix x reflector)",
+        roof = {"bound": "hbm", "kernel": "sytrd_panel_kernel + qrcp_panel_kernel (persistent panels: trailing matrix x reflector per column)",
                 "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None,
                 "sampled_launches": int(psamp.value), "total_launches": int(ptot.value),

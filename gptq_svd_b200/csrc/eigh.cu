@@ -14,7 +14,11 @@
 #include <cmath>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "solver_kernels.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace tq {
 
@@ -70,41 +74,203 @@ sytrd_w_finish_kernel(double* __restrict__ w, const double* __restrict__ v, int6
   for (int64_t r = threadIdx.x; r < len; r += blockDim.x) w[r] = fma(alpha, v[r], w[r]);
 }
 
+// ----------------------------------------------------------------------- persistent panel
+// One cooperative launch factors a whole panel of up to kTrdNb columns: the per-column
+// phases are separated by grid-wide barriers instead of kernel launches (4 per column).
+//   P1  column update (own rows) + partial sum of squares          | grid.sync
+//   P2  Householder scalars (every CTA, same order), scale v        | grid.sync
+//   P3  y = A22 v, W^T v, V^T v: one warp per column (HBM-bound)    | grid.sync
+//   P4  w' = tau (y - V W^T v - W V^T v) (own rows), partial w'.v   | grid.sync
+//   P5  w = w' - tau/2 (w'.v) v (own rows); every CTA keeps W[c+1, i] for the next P1
+// Row r is always handled by the same thread (r = global thread id + q * total threads),
+// so values a thread wrote for its own rows need no barrier before it reads them again.
+constexpr int kPanelThreads = 512;
+
+struct TrdPanelArgs {
+  double* A;
+  int64_t n;
+  int64_t j0;
+  int jb;
+  double* W;       // n x kTrdNb
+  double* d;
+  double* e;
+  double* tau;
+  double* y;       // n
+  double* tmp;     // 2 * kTrdNb
+  double* part;    // 2 * gridDim.x
+  double* scal;    // small scalar scratch
+};
+
+__device__ __forceinline__ double grid_total(const double* part, int nb, double* sh) {
+  double v = (threadIdx.x < nb) ? part[threadIdx.x] : 0.0;
+  for (int q = threadIdx.x + blockDim.x; q < nb; q += blockDim.x) v += part[q];
+  return block_sum(v, sh);
+}
+
+__global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[32];
+  __shared__ double shd[2][32];
+  __shared__ double wrow_s;          // W[c, i-1] computed locally at the end of the previous column
+  double* const A = a.A;
+  double* const W = a.W;
+  const int64_t n = a.n, lda = a.n, ldw = a.n, j0 = a.j0;
+  const int64_t gt = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  const int nb = gridDim.x;
+  double* part1 = a.part;
+  double* part2 = a.part + nb;
+  if (threadIdx.x == 0) wrow_s = 0.0;
+  __syncthreads();
+
+  for (int i = 0; i < a.jb; ++i) {
+    const int64_t c = j0 + i;
+    // ---------------- P1
+    double ss = 0.0;
+    for (int64_t r = gt; r < n; r += nthreads) {
+      if (r < c) continue;
+      double s = 0.0;
+      for (int t = 0; t < i; ++t) {
+        const double wc = (t == i - 1) ? wrow_s : W[c + t * ldw];
+        const double vc = (t == i - 1) ? 1.0 : A[c + (j0 + t) * lda];   // V[c, i-1] is the unit entry
+        s = fma(A[r + (j0 + t) * lda], wc, s);
+        s = fma(W[r + t * ldw], vc, s);
+      }
+      const double v = A[r + c * lda] - s;
+      A[r + c * lda] = v;
+      if (r == c) a.d[c] = v;
+      if (r == c + 1) a.scal[0] = v;
+      if (r >= c + 2) ss = fma(v, v, ss);
+    }
+    const int64_t len = n - c - 1;
+    if (len <= 0) break;               // last column: only the diagonal entry (uniform across the grid)
+    ss = block_sum(ss, sh);
+    if (threadIdx.x == 0) part1[blockIdx.x] = ss;
+    grid.sync();
+    // ---------------- P2
+    const double sumsq = grid_total(part1, nb, sh);
+    const double alpha = a.scal[0];
+    double tau, beta, scl;
+    if (len <= 1 || sumsq == 0.0) {
+      tau = 0.0;
+      beta = alpha;
+      scl = 0.0;
+    } else {
+      const double xnorm = sqrt(sumsq);
+      beta = -copysign(hypot(alpha, xnorm), alpha);
+      tau = (beta - alpha) / beta;
+      scl = 1.0 / (alpha - beta);
+    }
+    for (int64_t r = gt; r < n; r += nthreads) {
+      if (r == c + 1) A[r + c * lda] = 1.0;
+      else if (r >= c + 2 && tau != 0.0) A[r + c * lda] *= scl;
+    }
+    if (gt == 0) {
+      a.tau[c] = tau;
+      a.e[c] = beta;
+    }
+    grid.sync();
+    // ---------------- P3: dots with v = A[c+1:, c]
+    const double* v = A + (c + 1) + c * lda;
+    {
+      const int64_t total = len + 2 * i;
+      int par = 0;
+      for (int64_t j = blockIdx.x; j < total; j += gridDim.x, par ^= 1) {
+        const double* col;
+        double* out;
+        if (j < len) {
+          col = A + (c + 1) + (c + 1 + j) * lda;
+          out = a.y + c + 1 + j;
+        } else if (j < len + i) {
+          col = W + (c + 1) + (j - len) * ldw;
+          out = a.tmp + (j - len);
+        } else {
+          col = A + (c + 1) + (j0 + (j - len - i)) * lda;
+          out = a.tmp + kTrdNb + (j - len - i);
+        }
+        cta_dot_store(col, v, len, shd[par], out);
+      }
+    }
+    grid.sync();
+    // ---------------- P4
+    double wp[2] = {0.0, 0.0};         // w' of this thread's (at most two) rows
+    double sdot = 0.0;
+    {
+      int slot = 0;
+      for (int64_t r = gt; r < n; r += nthreads, ++slot) {
+        if (r < c + 1) continue;
+        double s = a.y[r];
+        for (int t = 0; t < i; ++t) {
+          s = fma(-A[r + (j0 + t) * lda], a.tmp[t], s);
+          s = fma(-W[r + t * ldw], a.tmp[kTrdNb + t], s);
+        }
+        s *= tau;
+        if (slot < 2) wp[slot] = s;
+        else W[r + int64_t(i) * ldw] = s;          // n > 2 * total threads: spill w' to W
+        sdot = fma(s, A[r + c * lda], sdot);
+      }
+    }
+    sdot = block_sum(sdot, sh);
+    if (threadIdx.x == 0) part2[blockIdx.x] = sdot;
+    grid.sync();
+    // ---------------- P5
+    const double wv = grid_total(part2, nb, sh);
+    const double alpha2 = -0.5 * tau * wv;
+    {
+      int slot = 0;
+      for (int64_t r = gt; r < n; r += nthreads, ++slot) {
+        if (r < c + 1) continue;
+        const double w0 = (slot < 2) ? wp[slot] : W[r + int64_t(i) * ldw];
+        W[r + int64_t(i) * ldw] = fma(alpha2, A[r + c * lda], w0);
+      }
+    }
+    if (threadIdx.x == 0) {            // W[c+1, i] for the next column's P1 (v[c+1] = 1)
+      const int64_t r = c + 1;
+      double s = a.y[r];
+      for (int t = 0; t < i; ++t) {
+        s = fma(-A[r + (j0 + t) * lda], a.tmp[t], s);
+        s = fma(-W[r + t * ldw], a.tmp[kTrdNb + t], s);
+      }
+      wrow_s = fma(alpha2, 1.0, s * tau);
+    }
+    __syncthreads();
+  }
+}
+
 // Reduces A (n x n, symmetric, both triangles valid) to tridiagonal form.  On exit
 // d[0:n], e[0:n-1], tau[0:n-1]; reflector c lives in A[c+1:, c] with an explicit unit at
 // A[c+1, c].
 static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double* d, double* e, double* tau,
-                       double* W, double* y, double* tmp /*2*kTrdNb*/) {
+                       double* W, double* y, double* tmp /*2*kTrdNb*/, double* part /*2*1024*/, double* scal /*8*/) {
   const int64_t lda = n, ldw = n;
   const double one = 1.0, mone = -1.0;
-  DotSeg none{nullptr, 0, 0, nullptr};
   TQ_CUDA_CHECK(cudaMemsetAsync(tau, 0, sizeof(double) * n, st));
   TQ_CUDA_CHECK(cudaMemsetAsync(e, 0, sizeof(double) * n, st));
+  static thread_local int coop_blocks = 0;
+  if (!coop_blocks) {
+    int per_sm = 0;
+    TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sytrd_panel_kernel, kPanelThreads, 0));
+    if (per_sm < 1) {
+      set_error("sytrd: panel kernel cannot be made resident");
+      return TQ_ERR_CUDA;
+    }
+    coop_blocks = num_sms() * (per_sm > 2 ? 2 : per_sm);
+  }
   for (int64_t j0 = 0; j0 < n; j0 += kTrdNb) {
     const int jb = int(imin(kTrdNb, n - j0));
-    for (int i = 0; i < jb; ++i) {
-      const int64_t c = j0 + i;
-      const int64_t rows = n - c;
-      sytrd_col_update_kernel<<<(unsigned)imin(ceil_div(rows, 256), 592), 256, 0, st>>>(A, lda, n, j0, i, W, ldw,
-                                                                                       d);
-      TQ_LAUNCH_CHECK();
-      const int64_t len = n - c - 1;
-      if (len <= 0) continue;
-      double* v = A + (c + 1) + c * lda;
-      larfg_kernel<<<1, 1024, 0, st>>>(v, len, tau + c, e + c, nullptr);
-      TQ_LAUNCH_CHECK();
-      DotSeg s0{A + (c + 1) + (c + 1) * lda, lda, len, y + c + 1};
-      DotSeg s1{W + (c + 1), ldw, i, tmp};
-      DotSeg s2{A + (c + 1) + j0 * lda, lda, i, tmp + kTrdNb};
-      const int pslot = prof_begin_launch(st, double(len) * double(len + 2 * i) * 8.0);
-      dots3_kernel<<<dots_grid(len + 2 * i), 256, 0, st>>>(s0, s1, s2, v, len, nullptr);
+    {
+      TrdPanelArgs pa{A, n, j0, jb, W, d, e, tau, y, tmp, part, scal};
+      void* kargs[] = {&pa};
+      double bytes = 0.0;      // algorithmic bytes of the panel: every column streams the trailing matrix once
+      for (int i = 0; i < jb; ++i) {
+        const double len = double(n - (j0 + i) - 1);
+        bytes += len * (len + 2.0 * i) * 8.0;
+      }
+      const int pslot = prof_begin_launch(st, bytes);
+      TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sytrd_panel_kernel, dim3(coop_blocks), dim3(kPanelThreads),
+                                                kargs, 0, st));
       prof_end_launch(st, pslot);
-      TQ_LAUNCH_CHECK();
-      sytrd_w_kernel<<<(unsigned)imin(ceil_div(len, 256), 592), 256, 0, st>>>(A, lda, n, j0, i, W, ldw, y, tmp,
-                                                                             tmp + kTrdNb, tau + c);
-      TQ_LAUNCH_CHECK();
-      sytrd_w_finish_kernel<<<1, 1024, 0, st>>>(W + (c + 1) + int64_t(i) * ldw, v, len, tau + c);
-      TQ_LAUNCH_CHECK();
+      ++g_launch_count;
     }
     const int64_t r0 = j0 + jb;
     const int64_t s2 = n - r0;
@@ -759,6 +925,8 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   double* y = ws.take<double>(n);
   double* W = ws.take<double>(size_t(n) * kTrdNb);
   double* tmp = ws.take<double>(4 * kTrdNb);
+  double* part = ws.take<double>(2048);
+  double* scal = ws.take<double>(8);
   double* G = ws.take<double>(kTrdNb * kTrdNb);
   double* T = ws.take<double>(kTrdNb * kTrdNb);
   if (ws.overflow) {
@@ -770,7 +938,7 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   TQ_LAUNCH_CHECK();
   {
     StageTimer tm(st, "sytrd");
-    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp));
+    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, part, scal));
   }
   {
     Workspace sub = ws;   // D&C scratch is released afterwards

@@ -10,7 +10,11 @@
 //  * qr_r_colmajor: unpivoted blocked Householder QR that never forms Q (the reference
 //    calls torch.linalg.qr and discards Q, gptq_utils.py:120): panel by BLAS-2 kernels,
 //    trailing update by compact-WY DGEMMs.
+#include <cooperative_groups.h>
+
 #include "solver_kernels.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace tq {
 
@@ -73,12 +77,330 @@ __global__ void set_diag_kernel(double* __restrict__ A, int64_t lda, int64_t j0,
   if (t < jb) A[(j0 + t) + (j0 + t) * lda] = beta[j0 + t];
 }
 
+struct QrcpCtl {
+  int stop;       // panel is over (a norm failed the safeguard in an earlier step)
+  int stop_next;  // set during the step that flags a column
+  int kb;         // columns factored in this panel
+  int pad;
+};
+
+// ----------------------------------------------------------------------- persistent panels
+// One cooperative launch factors a whole panel; phases are separated by grid barriers.
+constexpr int kQrPanelThreads = 512;
+
+__device__ __forceinline__ double grid_total(const double* part, int nb, double* sh) {
+  double v = (threadIdx.x < nb) ? part[threadIdx.x] : 0.0;
+  for (int q = threadIdx.x + blockDim.x; q < nb; q += blockDim.x) v += part[q];
+  return block_sum(v, sh);
+}
+
+struct QrPanelArgs {
+  double* A;
+  int64_t lda, k;
+  int64_t j0;
+  int jb;
+  double* tau;
+  double* beta;
+  double* wdot;    // kQrNb
+  double* part;
+  double* scal;
+};
+
+// Unpivoted Householder panel (DGEQR2 on columns [j0, j0+jb), rows [j0, k)):
+//   P1  apply the previous reflector to the remaining panel columns (own rows) and take the
+//       partial sum of squares of the current column                     | grid.sync
+//   P2  reflector scalars, scale v (own rows)                            | grid.sync
+//   P3  w = A[c:, c+1:panel_end]^T v (one warp per column)               | grid.sync
+__global__ void __launch_bounds__(kQrPanelThreads, 2) qr_panel_kernel(QrPanelArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[32];
+  __shared__ double shd[2][32];
+  __shared__ double wd[kQrNb];
+  double* const A = a.A;
+  const int64_t lda = a.lda, k = a.k, j0 = a.j0;
+  const int64_t gt = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  const int nb = gridDim.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t gwarp = gt >> 5, nwarps = nthreads >> 5;
+  const int64_t pend = j0 + a.jb;
+  double tau_prev = 0.0;
+  for (int i = 0; i < a.jb; ++i) {
+    const int64_t c = j0 + i;
+    // ---------------- P1
+    if (i > 0) {
+      for (int t = threadIdx.x; t < int(pend - c); t += blockDim.x) wd[t] = a.wdot[t];
+      __syncthreads();
+    }
+    double ss = 0.0;
+    for (int64_t r = gt; r < k; r += nthreads) {
+      if (r < c - 1) continue;
+      if (i > 0) {
+        const double tv = tau_prev * ((r == c - 1) ? 1.0 : A[r + (c - 1) * lda]);
+        for (int64_t cc = c; cc < pend; ++cc) A[r + cc * lda] = fma(-tv, wd[cc - c], A[r + cc * lda]);
+      }
+      const double v = A[r + c * lda];
+      if (r == c) a.scal[0] = v;
+      if (r > c) ss = fma(v, v, ss);
+    }
+    ss = block_sum(ss, sh);
+    if (threadIdx.x == 0) a.part[blockIdx.x] = ss;
+    grid.sync();
+    // ---------------- P2
+    const int64_t len = k - c;
+    const double sumsq = grid_total(a.part, nb, sh);
+    const double alpha = a.scal[0];
+    double tau, beta, scl;
+    if (len <= 1 || sumsq == 0.0) {
+      tau = 0.0;
+      beta = alpha;
+      scl = 0.0;
+    } else {
+      const double xnorm = sqrt(sumsq);
+      beta = -copysign(hypot(alpha, xnorm), alpha);
+      tau = (beta - alpha) / beta;
+      scl = 1.0 / (alpha - beta);
+    }
+    for (int64_t r = gt; r < k; r += nthreads) {
+      if (r == c) A[r + c * lda] = 1.0;
+      else if (r > c && tau != 0.0) A[r + c * lda] *= scl;
+    }
+    if (gt == 0) {
+      a.tau[c] = tau;
+      a.beta[c] = beta;
+    }
+    tau_prev = tau;
+    const int rem = int(pend - 1 - c);
+    if (rem <= 0) break;                      // last panel column: nothing left to update (uniform)
+    grid.sync();
+    // ---------------- P3
+    const double* v = A + c + c * lda;
+    {
+      int par = 0;
+      for (int64_t j = blockIdx.x; j < rem; j += gridDim.x, par ^= 1)
+        cta_dot_store(A + c + (c + 1 + j) * lda, v, len, shd[par], a.wdot + j);
+    }
+    grid.sync();
+  }
+}
+
+struct QrcpPanelArgs {
+  double* A;
+  int64_t lda, k, n;
+  int64_t j0;
+  int jb;
+  double* F;
+  int64_t ldf;
+  int64_t* perm;
+  double* vn1;
+  double* vn2;
+  double* tau;
+  double* beta;
+  double* auxraw;   // kQrcpNb
+  double* part;
+  double* scal;
+  QrcpCtl* ctl;
+  double tol3z;
+};
+
+// DLAQPS panel (see the phase list in the file header):
+//   P0/P1 pivot = first argmax of vn1[c:] (every CTA, same result); swap columns pvt <-> c and
+//         apply the panel's earlier reflectors to column c (own rows), partial norm  | grid.sync
+//   P2    reflector scalars, scale v; CTA 0 swaps perm / norms / F rows               | grid.sync
+//   P3    F(:, i) = A[c:, c+1:]^T v and aux = A[c:, j0:c]^T v (one warp per column)    | grid.sync
+//   P4    finish F(:, i), update the pivot row, downdate the partial norms (thread per
+//         trailing column), flag cancellation                                         | grid.sync
+__global__ void __launch_bounds__(kQrPanelThreads, 2) qrcp_panel_kernel(QrcpPanelArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[32];
+  __shared__ double shd[2][32];
+  __shared__ double sval[32];
+  __shared__ int64_t sidx[32];
+  __shared__ int64_t spvt;
+  __shared__ double frow[kQrcpNb];
+  __shared__ double arow[kQrcpNb];
+  double* const A = a.A;
+  double* const F = a.F;
+  const int64_t lda = a.lda, ldf = a.ldf, k = a.k, n = a.n, j0 = a.j0;
+  const int64_t gt = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  const int nb = gridDim.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t gwarp = gt >> 5, nwarps = nthreads >> 5;
+  for (int i = 0; i < a.jb; ++i) {
+    const int64_t c = j0 + i;
+    // ---------------- P0: pivot
+    {
+      double best = -1.0;
+      int64_t bidx = n;
+      for (int64_t j = c + threadIdx.x; j < n; j += blockDim.x) {
+        const double v = a.vn1[j];
+        if (v > best) {
+          best = v;
+          bidx = j;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ov > best || (ov == best && oi < bidx)) {
+          best = ov;
+          bidx = oi;
+        }
+      }
+      if (lane == 0) {
+        sval[wid] = best;
+        sidx[wid] = bidx;
+      }
+      __syncthreads();
+      if (wid == 0) {
+        best = (lane < (blockDim.x >> 5)) ? sval[lane] : -2.0;
+        bidx = (lane < (blockDim.x >> 5)) ? sidx[lane] : n;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+          if (ov > best || (ov == best && oi < bidx)) {
+            best = ov;
+            bidx = oi;
+          }
+        }
+        if (lane == 0) spvt = (bidx >= n) ? c : bidx;
+      }
+      __syncthreads();
+    }
+    const int64_t pvt = spvt;
+    // F row of the pivot column (still at its old position) for the column update
+    if (threadIdx.x < i) frow[threadIdx.x] = F[(pvt - j0) + int64_t(threadIdx.x) * ldf];
+    __syncthreads();
+    // ---------------- P1: swap + column update + partial norm
+    double ss = 0.0;
+    for (int64_t r = gt; r < k; r += nthreads) {
+      double ac = A[r + c * lda];
+      if (pvt != c) {
+        const double ap = A[r + pvt * lda];
+        A[r + pvt * lda] = ac;
+        ac = ap;
+      }
+      if (r >= c) {
+        double s = 0.0;
+        for (int t = 0; t < i; ++t) s = fma(A[r + (j0 + t) * lda], frow[t], s);
+        ac -= s;
+        if (r == c) a.scal[0] = ac;
+        else ss = fma(ac, ac, ss);
+      }
+      A[r + c * lda] = ac;
+    }
+    ss = block_sum(ss, sh);
+    if (threadIdx.x == 0) a.part[blockIdx.x] = ss;
+    grid.sync();
+    // ---------------- P2
+    const int64_t len = k - c;
+    const double sumsq = grid_total(a.part, nb, sh);
+    const double alpha = a.scal[0];
+    double tau, beta, scl;
+    if (len <= 1 || sumsq == 0.0) {
+      tau = 0.0;
+      beta = alpha;
+      scl = 0.0;
+    } else {
+      const double xnorm = sqrt(sumsq);
+      beta = -copysign(hypot(alpha, xnorm), alpha);
+      tau = (beta - alpha) / beta;
+      scl = 1.0 / (alpha - beta);
+    }
+    for (int64_t r = gt; r < k; r += nthreads) {
+      if (r == c) A[r + c * lda] = 1.0;
+      else if (r > c && tau != 0.0) A[r + c * lda] *= scl;
+    }
+    if (blockIdx.x == 0) {
+      if (threadIdx.x == 0) {
+        a.tau[c] = tau;
+        a.beta[c] = beta;
+        if (pvt != c) {
+          const int64_t p = a.perm[pvt];
+          a.perm[pvt] = a.perm[c];
+          a.perm[c] = p;
+          a.vn1[pvt] = a.vn1[c];
+          a.vn2[pvt] = a.vn2[c];
+        }
+      }
+      if (pvt != c && threadIdx.x < i) {
+        const int t = threadIdx.x;
+        const double fa = F[(pvt - j0) + int64_t(t) * ldf], fb = F[(c - j0) + int64_t(t) * ldf];
+        F[(pvt - j0) + int64_t(t) * ldf] = fb;
+        F[(c - j0) + int64_t(t) * ldf] = fa;
+      }
+    }
+    grid.sync();
+    // ---------------- P3: dots with v = A[c:, c]
+    const int64_t ntrail = n - c - 1;
+    {
+      const double* v = A + c + c * lda;
+      const int64_t total = ntrail + i;
+      int par = 0;
+      for (int64_t j = blockIdx.x; j < total; j += gridDim.x, par ^= 1) {
+        const double* col;
+        double* out;
+        if (j < ntrail) {
+          col = A + c + (c + 1 + j) * lda;
+          out = F + (c + 1 + j - j0) + int64_t(i) * ldf;
+        } else {
+          col = A + c + (j0 + (j - ntrail)) * lda;
+          out = a.auxraw + (j - ntrail);
+        }
+        cta_dot_store(col, v, len, shd[par], out);
+      }
+    }
+    grid.sync();
+    // ---------------- P4: row update + norm downdate (thread per trailing column)
+    if (threadIdx.x < i) {
+      frow[threadIdx.x] = -tau * a.auxraw[threadIdx.x];            // auxv
+      arow[threadIdx.x] = A[c + (j0 + threadIdx.x) * lda];          // A[c, j0:c]
+    }
+    __syncthreads();
+    for (int64_t q = gt; q < ntrail; q += nthreads) {
+      const int64_t col = c + 1 + q;
+      const int64_t fr = col - j0;
+      double f = tau * F[fr + int64_t(i) * ldf];
+      for (int t = 0; t < i; ++t) f = fma(F[fr + t * ldf], frow[t], f);
+      F[fr + int64_t(i) * ldf] = f;
+      double s = f;                                                 // A[c, c] == 1 during the step
+      for (int t = 0; t < i; ++t) s = fma(F[fr + t * ldf], arow[t], s);
+      const double av = A[c + col * lda] - s;
+      A[c + col * lda] = av;
+      if (c < k - 1) {
+        const double v1 = a.vn1[col];
+        if (v1 != 0.0) {
+          double temp = fabs(av) / v1;
+          temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
+          const double qq = v1 / a.vn2[col];
+          const double temp2 = temp * (qq * qq);
+          if (temp2 <= a.tol3z) {
+            a.vn2[col] = -1.0;
+            a.ctl->stop_next = 1;
+          } else {
+            a.vn1[col] = v1 * sqrt(temp);
+          }
+        }
+      }
+    }
+    if (gt == 0) a.ctl->kb = i + 1;
+    grid.sync();
+    if (gt == 0) A[c + c * lda] = beta;          // restore akk (read by nobody until the trailing GEMM)
+    if (a.ctl->stop_next) break;                 // uniform: read after the barrier
+  }
+}
+
 // in place: on exit triu(A[0:k, 0:n]) = R (diagonal sign arbitrary)
 int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n,
                   Workspace& ws) {
   double* tau = ws.take<double>(k);
   double* beta = ws.take<double>(k);
   double* wdot = ws.take<double>(kQrNb);
+  double* part = ws.take<double>(1024);
+  double* scal = ws.take<double>(8);
   double* Vc = ws.take<double>(size_t(k) * kQrNb);
   double* G = ws.take<double>(kQrNb * kQrNb);
   double* T = ws.take<double>(kQrNb * kQrNb);
@@ -88,22 +410,27 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
     set_error("qr_r: workspace too small");
     return TQ_ERR_WORKSPACE;
   }
-  DotSeg none{nullptr, 0, 0, nullptr};
+  static thread_local int coop_blocks = 0;
+  if (!coop_blocks) {
+    int per_sm = 0;
+    TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_panel_kernel, kQrPanelThreads, 0));
+    if (per_sm < 1) {
+      set_error("qr_r: panel kernel cannot be made resident");
+      return TQ_ERR_CUDA;
+    }
+    coop_blocks = num_sms() * (per_sm > 2 ? 2 : per_sm);
+  }
   for (int64_t j0 = 0; j0 < k; j0 += kQrNb) {
     const int jb = int(imin(kQrNb, k - j0));
-    for (int64_t c = j0; c < j0 + jb; ++c) {
-      const int64_t len = k - c;
-      larfg_kernel<<<1, 1024, 0, st>>>(A + c + c * lda, len, tau + c, beta + c, nullptr);
-      TQ_LAUNCH_CHECK();
-      const int rem = int(j0 + jb - 1 - c);
-      if (rem > 0) {
-        DotSeg s0{A + c + (c + 1) * lda, lda, rem, wdot};
-        dots3_kernel<<<dots_grid(rem), 256, 0, st>>>(s0, none, none, A + c + c * lda, len, nullptr);
-        TQ_LAUNCH_CHECK();
-        dim3 grid((unsigned)imin(ceil_div(len, 256), 64), (unsigned)rem);
-        qr_panel_rank1_kernel<<<grid, 256, 0, st>>>(A, lda, c, k, rem, tau + c, wdot);
-        TQ_LAUNCH_CHECK();
-      }
+    {
+      // a tall-skinny panel does not need the whole machine: fewer CTAs make the barriers cheaper
+      const int64_t rows = k - j0;
+      int blocks = int(imin(coop_blocks, imax(8, ceil_div(rows, kQrPanelThreads) * 4)));
+      QrPanelArgs pa{A, lda, k, j0, jb, tau, beta, wdot, part, scal};
+      void* kargs[] = {&pa};
+      TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(blocks), dim3(kQrPanelThreads), kargs,
+                                                0, st));
+      ++g_launch_count;
     }
     const int64_t s = k - j0;
     const int64_t nc = n - j0 - jb;
@@ -124,13 +451,6 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
 }
 
 // ------------------------------------------------------------------ pivoted QR (DLAQPS)
-struct QrcpCtl {
-  int stop;       // panel is over (a norm failed the safeguard in an earlier step)
-  int stop_next;  // set during the step that flags a column
-  int kb;         // columns factored in this panel
-  int pad;
-};
-
 __global__ void col_norms_kernel(const double* __restrict__ A, int64_t lda, int64_t row0, int64_t k, int64_t n,
                                  double* __restrict__ vn1, double* __restrict__ vn2, int only_flagged) {
   const int lane = threadIdx.x & 31;
@@ -303,6 +623,8 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
   double* tau = ws.take<double>(k + 1);
   double* beta = ws.take<double>(k + 1);
   QrcpCtl* ctl = ws.take<QrcpCtl>(1);
+  double* part = ws.take<double>(1024);
+  double* scal = ws.take<double>(8);
   if (ws.overflow) {
     set_error("qrcp: workspace too small");
     return TQ_ERR_WORKSPACE;
@@ -310,40 +632,35 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
   const double eps = 1.1102230246251565e-16;   // dlamch('Epsilon')
   const double tol3z = sqrt(eps);
   const int64_t ldf = n;
+  static thread_local int coop_blocks = 0;
+  if (!coop_blocks) {
+    int per_sm = 0;
+    TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qrcp_panel_kernel, kQrPanelThreads, 0));
+    if (per_sm < 1) {
+      set_error("qrcp: panel kernel cannot be made resident");
+      return TQ_ERR_CUDA;
+    }
+    coop_blocks = num_sms() * (per_sm > 2 ? 2 : per_sm);
+  }
   init_perm_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(perm, n);
   TQ_LAUNCH_CHECK();
   col_norms_kernel<<<dots_grid(n), 256, 0, st>>>(A, lda, 0, k, n, vn1, vn2, 0);
   TQ_LAUNCH_CHECK();
-  DotSeg none{nullptr, 0, 0, nullptr};
   int64_t j0 = 0;
   while (j0 < k) {
     const int jb = int(imin(kQrcpNb, k - j0));
     qrcp_panel_begin_kernel<<<1, 1, 0, st>>>(ctl);
     TQ_LAUNCH_CHECK();
-    for (int i = 0; i < jb; ++i) {
-      const int64_t c = j0 + i;
-      const int64_t len = k - c;
-      qrcp_pivot_kernel<<<1, 1024, 0, st>>>(A, lda, k, n, j0, i, F, ldf, perm, vn1, vn2, ctl);
-      TQ_LAUNCH_CHECK();
-      if (i > 0) {
-        qrcp_col_update_kernel<<<(unsigned)imin(ceil_div(len, 256), 592), 256, 0, st>>>(A, lda, k, j0, i, F, ldf,
-                                                                                       ctl);
-        TQ_LAUNCH_CHECK();
-      }
-      larfg_kernel<<<1, 1024, 0, st>>>(A + c + c * lda, len, tau + c, beta + c, &ctl->stop);
-      TQ_LAUNCH_CHECK();
-      const int64_t ntrail = n - c - 1;
-      if (ntrail > 0 || i > 0) {
-        DotSeg s0{A + c + (c + 1) * lda, lda, ntrail, F + (c + 1 - j0) + int64_t(i) * ldf};
-        DotSeg s1{A + c + j0 * lda, lda, i, auxraw};
-        const int pslot = prof_begin_launch(st, double(len) * double(ntrail + i) * 8.0);
-        dots3_kernel<<<dots_grid(ntrail + i), 256, 0, st>>>(s0, s1, none, A + c + c * lda, len, &ctl->stop);
-        prof_end_launch(st, pslot);
-        TQ_LAUNCH_CHECK();
-      }
-      qrcp_row_update_kernel<<<(unsigned)imax(1, ceil_div(ntrail, 256)), 256, 0, st>>>(
-          A, lda, k, n, j0, i, F, ldf, auxraw, tau + c, beta + c, vn1, vn2, ctl, tol3z);
-      TQ_LAUNCH_CHECK();
+    {
+      QrcpPanelArgs pa{A, lda, k, n, j0, jb, F, ldf, perm, vn1, vn2, tau, beta, auxraw, part, scal, ctl, tol3z};
+      void* kargs[] = {&pa};
+      double bytes = 0.0;      // algorithmic bytes of the panel: every step streams the trailing matrix once
+      for (int i = 0; i < jb; ++i) bytes += double(k - (j0 + i)) * double(n - (j0 + i) - 1 + i) * 8.0;
+      const int pslot = prof_begin_launch(st, bytes);
+      TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)qrcp_panel_kernel, dim3(coop_blocks), dim3(kQrPanelThreads),
+                                                kargs, 0, st));
+      prof_end_launch(st, pslot);
+      ++g_launch_count;
     }
     QrcpCtl hc;
     TQ_CUDA_CHECK(cudaMemcpyAsync(&hc, ctl, sizeof(QrcpCtl), cudaMemcpyDeviceToHost, st));

@@ -39,6 +39,47 @@ __device__ __forceinline__ double block_sum(double v, double* sh /*32 doubles*/)
   return v;
 }
 
+// Whole-CTA dot product of two length-len vectors (one trailing-matrix column against the
+// reflector): every thread keeps 8 independent 8-byte loads in flight (64 KB per SM at
+// 1024 resident threads, enough to cover HBM latency), then a fixed-order reduction
+// (warp shuffles, then warp 0 over the per-warp partials) makes the result deterministic.
+// Thread 0 of the CTA stores the sum to *out.  `shbuf` is 32 doubles; callers alternate
+// between two buffers on consecutive calls so that one __syncthreads per call suffices.
+__device__ __forceinline__ void cta_dot_store(const double* __restrict__ col, const double* __restrict__ v,
+                                              int64_t len, double* shbuf, double* out) {
+  const int64_t step = blockDim.x;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+  int64_t r = threadIdx.x;
+  for (; r + 7 * step < len; r += 8 * step) {
+    const double m0 = col[r], m1 = col[r + step], m2 = col[r + 2 * step], m3 = col[r + 3 * step];
+    const double m4 = col[r + 4 * step], m5 = col[r + 5 * step], m6 = col[r + 6 * step], m7 = col[r + 7 * step];
+    a0 = fma(m0, v[r], a0);
+    a1 = fma(m1, v[r + step], a1);
+    a2 = fma(m2, v[r + 2 * step], a2);
+    a3 = fma(m3, v[r + 3 * step], a3);
+    a4 = fma(m4, v[r + 4 * step], a4);
+    a5 = fma(m5, v[r + 5 * step], a5);
+    a6 = fma(m6, v[r + 6 * step], a6);
+    a7 = fma(m7, v[r + 7 * step], a7);
+  }
+  for (; r + step < len; r += 2 * step) {
+    const double m0 = col[r], m1 = col[r + step];
+    a0 = fma(m0, v[r], a0);
+    a1 = fma(m1, v[r + step], a1);
+  }
+  if (r < len) a2 = fma(col[r], v[r], a2);
+  double sres = warp_sum(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) shbuf[w] = sres;
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    double t = lane < nw ? shbuf[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) *out = t;
+  }
+}
+
 // out[j] = dot(M[:, j], x) over `rows` rows for up to three column sets sharing x.
 // `skip` (optional device flag): when *skip != 0 the kernel does nothing.
 static __global__ void __launch_bounds__(256)

@@ -175,11 +175,12 @@ int tq_quant_error(const float* W, int64_t ldw, const float* Wq, int64_t ldq, co
  * are not counted). */
 int64_t tq_launch_count(void);
 
-/* Sampled timing of the solver's dominant HBM-bound kernel (dots3_kernel: one pass over the
- * trailing matrix per reflector in the tridiagonal reduction and the pivoted QR).  After
- * tq_profile_begin(every), every `every`-th launch is bracketed by CUDA events on its own
- * stream; tq_profile_end synchronises them and returns the algorithmic bytes
- * (rows * columns * 8) and the milliseconds of the sampled launches. */
+/* Sampled timing of the solver's dominant HBM-bound kernels (sytrd_panel_kernel and
+ * qrcp_panel_kernel: one pass over the trailing matrix per reflector in the tridiagonal
+ * reduction and in the pivoted QR).  After tq_profile_begin(every), every `every`-th panel
+ * launch is bracketed by CUDA events on its own stream; tq_profile_end synchronises them and
+ * returns the algorithmic bytes (sum over the panel's columns of rows * columns * 8) and the
+ * milliseconds of the sampled launches. */
 int tq_profile_begin(int sample_every);
 int tq_profile_end(double* alg_bytes, double* ms, int64_t* sampled, int64_t* total);
 
