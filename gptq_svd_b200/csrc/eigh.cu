@@ -14,11 +14,7 @@
 #include <cmath>
 #include <vector>
 
-#include <cooperative_groups.h>
-
 #include "solver_kernels.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace tq {
 
@@ -75,16 +71,22 @@ sytrd_w_finish_kernel(double* __restrict__ w, const double* __restrict__ v, int6
 }
 
 // ----------------------------------------------------------------------- persistent panel
-// One cooperative launch factors a whole panel of up to kTrdNb columns: the per-column
-// phases are separated by grid-wide barriers instead of kernel launches (4 per column).
-//   P1  column update (own rows) + partial sum of squares          | grid.sync
-//   P2  Householder scalars (every CTA, same order), scale v        | grid.sync
-//   P3  y = A22 v, W^T v, V^T v: one warp per column (HBM-bound)    | grid.sync
-//   P4  w' = tau (y - V W^T v - W V^T v) (own rows), partial w'.v   | grid.sync
-//   P5  w = w' - tau/2 (w'.v) v (own rows); every CTA keeps W[c+1, i] for the next P1
-// Row r is always handled by the same thread (r = global thread id + q * total threads),
-// so values a thread wrote for its own rows need no barrier before it reads them again.
+// One cooperative launch factors a whole panel of up to kTrdNb columns.  The per-column
+// phases are separated by two grid-wide barriers (grid_barrier) instead of kernel launches:
+//   A  column update A[c:, c] -= V W[c,:]^T + W V[c,:]^T (own rows), partial sum of squares,
+//      d[c]                                                                      | barrier
+//   B  Householder scalars (every CTA, same order).  One CTA per trailing column streams it
+//      against the RAW column u = [alpha; x]; since v = [1; scl x], the per-warp partial is
+//      fixed up as  scl * p + col[0] (1 - scl alpha)  by the warp that owns row 0.  Per-warp
+//      partials of y = A22 v, W^T v, V^T v go to ypart/tmppart (no block barrier while
+//      streaming); v^T y is accumulated on the fly                               | barrier
+//   C  v scaled in place (own rows), w = tau (y - V W^T v - W V^T v) - tau/2 (w.v) v with
+//      w.v = tau (v^T y - 2 (W^T v).(V^T v)) known without another reduction.
+// Row r is always handled by the same thread (r = global thread id + q * total threads), so
+// values a thread wrote for its own rows need no barrier before it reads them again; the one
+// foreign value the next column update needs, W[c+1, i], is recomputed by every CTA.
 constexpr int kPanelThreads = 512;
+constexpr int kPanelWarps = kPanelThreads / 32;
 
 struct TrdPanelArgs {
   double* A;
@@ -95,10 +97,12 @@ struct TrdPanelArgs {
   double* d;
   double* e;
   double* tau;
-  double* y;       // n
-  double* tmp;     // 2 * kTrdNb
-  double* part;    // 2 * gridDim.x
-  double* scal;    // small scalar scratch
+  double* ypart;   // kPanelWarps x n          per-warp partials of y = A22 v
+  double* tmppart; // kPanelWarps x 2 kTrdNb   per-warp partials of W^T v | V^T v
+  double* part;    // 2 x gridDim.x
+  double* scal;    // scalar scratch; [8..15] phase cycle counters when tracing
+  unsigned int* bar;
+  int trace;
 };
 
 __device__ __forceinline__ double grid_total(const double* part, int nb, double* sh) {
@@ -108,35 +112,52 @@ __device__ __forceinline__ double grid_total(const double* part, int nb, double*
 }
 
 __global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelArgs a) {
-  cg::grid_group grid = cg::this_grid();
   __shared__ double sh[32];
-  __shared__ double shd[2][32];
-  __shared__ double wrow_s;          // W[c, i-1] computed locally at the end of the previous column
+  __shared__ double tmps[2 * kTrdNb];
+  __shared__ double wrow_s;          // W[c, i-1], computed locally at the end of the previous column
   double* const A = a.A;
   double* const W = a.W;
   const int64_t n = a.n, lda = a.n, ldw = a.n, j0 = a.j0;
   const int64_t gt = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
-  const int nb = gridDim.x;
+  const unsigned int nb = gridDim.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* part1 = a.part;
   double* part2 = a.part + nb;
+  unsigned int bar_target = 0;
   if (threadIdx.x == 0) wrow_s = 0.0;
   __syncthreads();
 
+  long long tk = a.trace ? clock64() : 0;
+#define TQ_PHASE(idx)                                   \
+  if (a.trace && gt == 0) {                             \
+    const long long now = clock64();                    \
+    a.scal[8 + (idx)] += double(now - tk);              \
+    tk = now;                                           \
+  }
   for (int i = 0; i < a.jb; ++i) {
     const int64_t c = j0 + i;
-    // ---------------- P1
+    // ---------------- A
     double ss = 0.0;
     for (int64_t r = gt; r < n; r += nthreads) {
       if (r < c) continue;
-      double s = 0.0;
-      for (int t = 0; t < i; ++t) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int t = 0;
+      for (; t + 1 < i - 1; t += 2) {          // t, t+1 <= i-2: plain panel entries, 4 loads in flight
+        const double v0 = A[r + (j0 + t) * lda], w0 = W[r + t * ldw];
+        const double v1 = A[r + (j0 + t + 1) * lda], w1 = W[r + (t + 1) * ldw];
+        s0 = fma(v0, W[c + t * ldw], s0);
+        s1 = fma(w0, A[c + (j0 + t) * lda], s1);
+        s2 = fma(v1, W[c + (t + 1) * ldw], s2);
+        s3 = fma(w1, A[c + (j0 + t + 1) * lda], s3);
+      }
+      for (; t < i; ++t) {
         const double wc = (t == i - 1) ? wrow_s : W[c + t * ldw];
         const double vc = (t == i - 1) ? 1.0 : A[c + (j0 + t) * lda];   // V[c, i-1] is the unit entry
-        s = fma(A[r + (j0 + t) * lda], wc, s);
-        s = fma(W[r + t * ldw], vc, s);
+        s0 = fma(A[r + (j0 + t) * lda], wc, s0);
+        s1 = fma(W[r + t * ldw], vc, s1);
       }
-      const double v = A[r + c * lda] - s;
+      const double v = A[r + c * lda] - ((s0 + s1) + (s2 + s3));
       A[r + c * lda] = v;
       if (r == c) a.d[c] = v;
       if (r == c + 1) a.scal[0] = v;
@@ -146,8 +167,10 @@ __global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelA
     if (len <= 0) break;               // last column: only the diagonal entry (uniform across the grid)
     ss = block_sum(ss, sh);
     if (threadIdx.x == 0) part1[blockIdx.x] = ss;
-    grid.sync();
-    // ---------------- P2
+    TQ_PHASE(0)
+    grid_barrier(a.bar, bar_target, nb);
+    TQ_PHASE(1)
+    // ---------------- B
     const double sumsq = grid_total(part1, nb, sh);
     const double alpha = a.scal[0];
     double tau, beta, scl;
@@ -161,90 +184,93 @@ __global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelA
       tau = (beta - alpha) / beta;
       scl = 1.0 / (alpha - beta);
     }
+    const double fix = 1.0 - scl * alpha;
+    const double* u = A + (c + 1) + c * lda;       // raw column [alpha; x]
+    double vy = 0.0;                               // lane 0 of each warp: sum_j v_j * (this warp's partial of y_j)
+    {
+      const int64_t total = len + 2 * i;
+      for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
+        const double* col;
+        double* out;
+        if (j < len) {
+          col = A + (c + 1) + (c + 1 + j) * lda;
+          out = a.ypart + int64_t(wid) * n + (c + 1 + j);
+        } else if (j < len + i) {
+          col = W + (c + 1) + (j - len) * ldw;
+          out = a.tmppart + wid * (2 * kTrdNb) + (j - len);
+        } else {
+          col = A + (c + 1) + (j0 + (j - len - i)) * lda;
+          out = a.tmppart + wid * (2 * kTrdNb) + kTrdNb + (j - len - i);
+        }
+        double p = scl * cta_strided_warp_dot(col, u, len);
+        if (lane == 0) {
+          if (wid == 0) p = fma(col[0], fix, p);
+          *out = p;
+          if (j < len) vy = fma(p, (j == 0) ? 1.0 : scl * u[j], vy);
+        }
+      }
+    }
+    vy = block_sum(lane == 0 ? vy : 0.0, sh);
+    if (threadIdx.x == 0) part2[blockIdx.x] = vy;
+    TQ_PHASE(2)
+    grid_barrier(a.bar, bar_target, nb);
+    TQ_PHASE(3)
+    // ---------------- C
+    const double vtyv = grid_total(part2, nb, sh);
+    if (threadIdx.x < 2 * kTrdNb) {     // tmp1 = W^T v | tmp2 = V^T v: fixed-order sum of the per-warp partials
+      double tsum = 0.0;
+      for (int w = 0; w < kPanelWarps; ++w) tsum += a.tmppart[w * (2 * kTrdNb) + threadIdx.x];
+      tmps[threadIdx.x] = tsum;
+    }
+    __syncthreads();
+    double cross = 0.0;
+    for (int t = 0; t < i; ++t) cross = fma(tmps[t], tmps[kTrdNb + t], cross);
+    const double wv = tau * (vtyv - 2.0 * cross);          // w'.v
+    const double alpha2 = -0.5 * tau * wv;
     for (int64_t r = gt; r < n; r += nthreads) {
-      if (r == c + 1) A[r + c * lda] = 1.0;
-      else if (r >= c + 2 && tau != 0.0) A[r + c * lda] *= scl;
+      if (r < c + 1) continue;
+      const double vr = (r == c + 1) ? 1.0 : scl * A[r + c * lda];
+      A[r + c * lda] = vr;
+      double y = 0.0;
+      for (int w = 0; w < kPanelWarps; ++w) y += a.ypart[int64_t(w) * n + r];
+      double s0 = 0.0, s1 = 0.0;
+      for (int t = 0; t < i; ++t) {
+        s0 = fma(A[r + (j0 + t) * lda], tmps[t], s0);
+        s1 = fma(W[r + t * ldw], tmps[kTrdNb + t], s1);
+      }
+      W[r + int64_t(i) * ldw] = fma(alpha2, vr, tau * (y - (s0 + s1)));
     }
     if (gt == 0) {
       a.tau[c] = tau;
       a.e[c] = beta;
     }
-    grid.sync();
-    // ---------------- P3: dots with v = A[c+1:, c]
-    const double* v = A + (c + 1) + c * lda;
-    {
-      const int64_t total = len + 2 * i;
-      int par = 0;
-      for (int64_t j = blockIdx.x; j < total; j += gridDim.x, par ^= 1) {
-        const double* col;
-        double* out;
-        if (j < len) {
-          col = A + (c + 1) + (c + 1 + j) * lda;
-          out = a.y + c + 1 + j;
-        } else if (j < len + i) {
-          col = W + (c + 1) + (j - len) * ldw;
-          out = a.tmp + (j - len);
-        } else {
-          col = A + (c + 1) + (j0 + (j - len - i)) * lda;
-          out = a.tmp + kTrdNb + (j - len - i);
-        }
-        cta_dot_store(col, v, len, shd[par], out);
-      }
-    }
-    grid.sync();
-    // ---------------- P4
-    double wp[2] = {0.0, 0.0};         // w' of this thread's (at most two) rows
-    double sdot = 0.0;
-    {
-      int slot = 0;
-      for (int64_t r = gt; r < n; r += nthreads, ++slot) {
-        if (r < c + 1) continue;
-        double s = a.y[r];
-        for (int t = 0; t < i; ++t) {
-          s = fma(-A[r + (j0 + t) * lda], a.tmp[t], s);
-          s = fma(-W[r + t * ldw], a.tmp[kTrdNb + t], s);
-        }
-        s *= tau;
-        if (slot < 2) wp[slot] = s;
-        else W[r + int64_t(i) * ldw] = s;          // n > 2 * total threads: spill w' to W
-        sdot = fma(s, A[r + c * lda], sdot);
-      }
-    }
-    sdot = block_sum(sdot, sh);
-    if (threadIdx.x == 0) part2[blockIdx.x] = sdot;
-    grid.sync();
-    // ---------------- P5
-    const double wv = grid_total(part2, nb, sh);
-    const double alpha2 = -0.5 * tau * wv;
-    {
-      int slot = 0;
-      for (int64_t r = gt; r < n; r += nthreads, ++slot) {
-        if (r < c + 1) continue;
-        const double w0 = (slot < 2) ? wp[slot] : W[r + int64_t(i) * ldw];
-        W[r + int64_t(i) * ldw] = fma(alpha2, A[r + c * lda], w0);
-      }
-    }
-    if (threadIdx.x == 0) {            // W[c+1, i] for the next column's P1 (v[c+1] = 1)
+    if (threadIdx.x == 0) {            // W[c+1, i] for the next column update (v[c+1] = 1)
       const int64_t r = c + 1;
-      double s = a.y[r];
+      double y = 0.0;
+      for (int w = 0; w < kPanelWarps; ++w) y += a.ypart[int64_t(w) * n + r];
+      double s0 = 0.0, s1 = 0.0;
       for (int t = 0; t < i; ++t) {
-        s = fma(-A[r + (j0 + t) * lda], a.tmp[t], s);
-        s = fma(-W[r + t * ldw], a.tmp[kTrdNb + t], s);
+        s0 = fma(A[r + (j0 + t) * lda], tmps[t], s0);
+        s1 = fma(W[r + t * ldw], tmps[kTrdNb + t], s1);
       }
-      wrow_s = fma(alpha2, 1.0, s * tau);
+      wrow_s = fma(alpha2, 1.0, tau * (y - (s0 + s1)));
     }
     __syncthreads();
+    TQ_PHASE(4)
   }
+#undef TQ_PHASE
 }
 
 // Reduces A (n x n, symmetric, both triangles valid) to tridiagonal form.  On exit
 // d[0:n], e[0:n-1], tau[0:n-1]; reflector c lives in A[c+1:, c] with an explicit unit at
 // A[c+1, c].
 static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double* d, double* e, double* tau,
-                       double* W, double* y, double* tmp /*2*kTrdNb*/, double* part /*2*1024*/, double* scal /*8*/) {
+                       double* W, double* y /*16 n*/, double* tmp /*16*2*kTrdNb*/, double* part /*2*1024*/, double* scal /*8*/,
+                       unsigned int* bar) {
   const int64_t lda = n, ldw = n;
   const double one = 1.0, mone = -1.0;
   TQ_CUDA_CHECK(cudaMemsetAsync(tau, 0, sizeof(double) * n, st));
+  TQ_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 16, st));
   TQ_CUDA_CHECK(cudaMemsetAsync(e, 0, sizeof(double) * n, st));
   static thread_local int coop_blocks = 0;
   if (!coop_blocks) {
@@ -259,7 +285,8 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
   for (int64_t j0 = 0; j0 < n; j0 += kTrdNb) {
     const int jb = int(imin(kTrdNb, n - j0));
     {
-      TrdPanelArgs pa{A, n, j0, jb, W, d, e, tau, y, tmp, part, scal};
+      TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
+      TrdPanelArgs pa{A, n, j0, jb, W, d, e, tau, y, tmp, part, scal, bar, trace_enabled() ? 1 : 0};
       void* kargs[] = {&pa};
       double bytes = 0.0;      // algorithmic bytes of the panel: every column streams the trailing matrix once
       for (int i = 0; i < jb; ++i) {
@@ -909,7 +936,7 @@ __global__ void copy_sym_kernel(const double* __restrict__ H, int64_t ldh, int64
 size_t eigh_ws_bytes(int64_t n) {
   size_t b = 0;
   b += ws_bytes_for(size_t(n) * n, 8) * 4;                 // A, Zg, Zo, U
-  b += ws_bytes_for(n, 8) * 12 + ws_bytes_for(n, 4) * 8 + ws_bytes_for(n, sizeof(DcRot));
+  b += ws_bytes_for(n, 8) * (12 + kMaxChunks) + ws_bytes_for(2 * kTrdNb * kMaxChunks, 8) + ws_bytes_for(n, 4) * 8 + ws_bytes_for(n, sizeof(DcRot));
   b += ws_bytes_for(size_t(n) * kTrdNb, 8) * 2;            // W, Vc
   b += ws_bytes_for(size_t(kOrmNb) * n, 8) * 2;            // w1, w2
   b += ws_bytes_for(kTrdNb * kTrdNb, 8) * 2 + ws_bytes_for(4 * kTrdNb, 8);
@@ -922,11 +949,12 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   double* A = ws.take<double>(size_t(n) * n);
   double* e = ws.take<double>(n);
   double* tau = ws.take<double>(n);
-  double* y = ws.take<double>(n);
+  double* y = ws.take<double>(size_t(n) * kMaxChunks);
   double* W = ws.take<double>(size_t(n) * kTrdNb);
-  double* tmp = ws.take<double>(4 * kTrdNb);
+  double* tmp = ws.take<double>(2 * kTrdNb * kMaxChunks);
   double* part = ws.take<double>(2048);
-  double* scal = ws.take<double>(8);
+  double* scal = ws.take<double>(16);
+  unsigned int* bar = ws.take<unsigned int>(4);
   double* G = ws.take<double>(kTrdNb * kTrdNb);
   double* T = ws.take<double>(kTrdNb * kTrdNb);
   if (ws.overflow) {
@@ -938,7 +966,14 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   TQ_LAUNCH_CHECK();
   {
     StageTimer tm(st, "sytrd");
-    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, part, scal));
+    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, part, scal, bar));
+    if (trace_enabled()) {
+      double hc[16];
+      cudaMemcpyAsync(hc, scal, sizeof(hc), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      fprintf(stderr, "[tq-trace] sytrd phase Mcycles (CTA 0): A %.1f  barrier1 %.1f  B(stream) %.1f  barrier2 %.1f  C %.1f\n",
+              hc[8] * 1e-6, hc[9] * 1e-6, hc[10] * 1e-6, hc[11] * 1e-6, hc[12] * 1e-6);
+    }
   }
   {
     Workspace sub = ws;   // D&C scratch is released afterwards

@@ -10,11 +10,7 @@
 //  * qr_r_colmajor: unpivoted blocked Householder QR that never forms Q (the reference
 //    calls torch.linalg.qr and discards Q, gptq_utils.py:120): panel by BLAS-2 kernels,
 //    trailing update by compact-WY DGEMMs.
-#include <cooperative_groups.h>
-
 #include "solver_kernels.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace tq {
 
@@ -85,13 +81,32 @@ struct QrcpCtl {
 };
 
 // ----------------------------------------------------------------------- persistent panels
-// One cooperative launch factors a whole panel; phases are separated by grid barriers.
+// One cooperative launch factors a whole panel; phases are separated by grid_barrier.
+// The streaming phases dot the trailing columns against the RAW reflector column
+// u = [alpha; x] and fix the per-warp partial up to v = [1; scl x]:
+//   p_v = scl * p_u + col[0] * (1 - scl * alpha)     (the warp owning row 0 adds the last term)
+// so no barrier is needed between computing the Householder scalars and using v.
 constexpr int kQrPanelThreads = 512;
+constexpr int kQrPanelWarps = kQrPanelThreads / 32;
 
 __device__ __forceinline__ double grid_total(const double* part, int nb, double* sh) {
   double v = (threadIdx.x < nb) ? part[threadIdx.x] : 0.0;
   for (int q = threadIdx.x + blockDim.x; q < nb; q += blockDim.x) v += part[q];
   return block_sum(v, sh);
+}
+
+__device__ __forceinline__ void householder_scalars(double alpha, double sumsq, int64_t len, double& tau,
+                                                    double& beta, double& scl) {
+  if (len <= 1 || sumsq == 0.0) {
+    tau = 0.0;
+    beta = alpha;
+    scl = 0.0;
+  } else {
+    const double xnorm = sqrt(sumsq);
+    beta = -copysign(hypot(alpha, xnorm), alpha);
+    tau = (beta - alpha) / beta;
+    scl = 1.0 / (alpha - beta);
+  }
 }
 
 struct QrPanelArgs {
@@ -101,86 +116,91 @@ struct QrPanelArgs {
   int jb;
   double* tau;
   double* beta;
-  double* wdot;    // kQrNb
+  double* wpart;   // kQrPanelWarps x kQrNb per-warp partials of A[c:, c+1:pend]^T v
   double* part;
   double* scal;
+  unsigned int* bar;
 };
 
-// Unpivoted Householder panel (DGEQR2 on columns [j0, j0+jb), rows [j0, k)):
-//   P1  apply the previous reflector to the remaining panel columns (own rows) and take the
-//       partial sum of squares of the current column                     | grid.sync
-//   P2  reflector scalars, scale v (own rows)                            | grid.sync
-//   P3  w = A[c:, c+1:panel_end]^T v (one warp per column)               | grid.sync
+// Unpivoted Householder panel (DGEQR2 on columns [j0, j0+jb), rows [j0, k)), 2 barriers per column:
+//   A  finish the previous reflector (scale v, set the diagonal to beta) and apply it to the
+//      remaining panel columns (own rows); partial sum of squares of column c    | barrier
+//   B  scalars; w = A[c:, c+1:pend]^T v via raw dots (one CTA per column)         | barrier
 __global__ void __launch_bounds__(kQrPanelThreads, 2) qr_panel_kernel(QrPanelArgs a) {
-  cg::grid_group grid = cg::this_grid();
   __shared__ double sh[32];
-  __shared__ double shd[2][32];
   __shared__ double wd[kQrNb];
   double* const A = a.A;
   const int64_t lda = a.lda, k = a.k, j0 = a.j0;
   const int64_t gt = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
-  const int nb = gridDim.x;
-  const int lane = threadIdx.x & 31;
-  const int64_t gwarp = gt >> 5, nwarps = nthreads >> 5;
+  const unsigned int nb = gridDim.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t pend = j0 + a.jb;
-  double tau_prev = 0.0;
-  for (int i = 0; i < a.jb; ++i) {
+  unsigned int bar_target = 0;
+  double tau_p = 0.0, beta_p = 0.0, scl_p = 0.0;      // scalars of the previous column
+  for (int i = 0; i <= a.jb; ++i) {
     const int64_t c = j0 + i;
-    // ---------------- P1
+    const bool last = (i == a.jb);                    // epilogue pass: only finish reflector jb-1
+    // ---------------- A
     if (i > 0) {
-      for (int t = threadIdx.x; t < int(pend - c); t += blockDim.x) wd[t] = a.wdot[t];
+      const int nrem = int(pend - c);
+      for (int t = threadIdx.x; t < nrem; t += blockDim.x) {
+        double wsum = 0.0;
+        for (int w = 0; w < kQrPanelWarps; ++w) wsum += a.wpart[w * kQrNb + t];
+        wd[t] = wsum;
+      }
       __syncthreads();
     }
     double ss = 0.0;
     for (int64_t r = gt; r < k; r += nthreads) {
       if (r < c - 1) continue;
       if (i > 0) {
-        const double tv = tau_prev * ((r == c - 1) ? 1.0 : A[r + (c - 1) * lda]);
+        double vp;
+        if (r == c - 1) {
+          vp = 1.0;
+          A[r + (c - 1) * lda] = beta_p;              // R's diagonal
+        } else {
+          vp = scl_p * A[r + (c - 1) * lda];
+          A[r + (c - 1) * lda] = vp;                  // stored reflector tail
+        }
+        const double tv = tau_p * vp;
         for (int64_t cc = c; cc < pend; ++cc) A[r + cc * lda] = fma(-tv, wd[cc - c], A[r + cc * lda]);
       }
-      const double v = A[r + c * lda];
-      if (r == c) a.scal[0] = v;
-      if (r > c) ss = fma(v, v, ss);
+      if (!last) {
+        const double v = A[r + c * lda];
+        if (r == c) a.scal[0] = v;
+        if (r > c) ss = fma(v, v, ss);
+      }
     }
+    if (last) break;
     ss = block_sum(ss, sh);
     if (threadIdx.x == 0) a.part[blockIdx.x] = ss;
-    grid.sync();
-    // ---------------- P2
+    grid_barrier(a.bar, bar_target, nb);
+    // ---------------- B
     const int64_t len = k - c;
     const double sumsq = grid_total(a.part, nb, sh);
     const double alpha = a.scal[0];
     double tau, beta, scl;
-    if (len <= 1 || sumsq == 0.0) {
-      tau = 0.0;
-      beta = alpha;
-      scl = 0.0;
-    } else {
-      const double xnorm = sqrt(sumsq);
-      beta = -copysign(hypot(alpha, xnorm), alpha);
-      tau = (beta - alpha) / beta;
-      scl = 1.0 / (alpha - beta);
-    }
-    for (int64_t r = gt; r < k; r += nthreads) {
-      if (r == c) A[r + c * lda] = 1.0;
-      else if (r > c && tau != 0.0) A[r + c * lda] *= scl;
-    }
+    householder_scalars(alpha, sumsq, len, tau, beta, scl);
     if (gt == 0) {
       a.tau[c] = tau;
       a.beta[c] = beta;
     }
-    tau_prev = tau;
+    const double fix = 1.0 - scl * alpha;
+    const double* u = A + c + c * lda;
     const int rem = int(pend - 1 - c);
-    if (rem <= 0) break;                      // last panel column: nothing left to update (uniform)
-    grid.sync();
-    // ---------------- P3
-    const double* v = A + c + c * lda;
-    {
-      int par = 0;
-      for (int64_t j = blockIdx.x; j < rem; j += gridDim.x, par ^= 1)
-        cta_dot_store(A + c + (c + 1 + j) * lda, v, len, shd[par], a.wdot + j);
+    for (int64_t j = blockIdx.x; j < rem; j += gridDim.x) {
+      const double* col = A + c + (c + 1 + j) * lda;
+      double p = scl * cta_strided_warp_dot(col, u, len);
+      if (lane == 0) {
+        if (wid == 0) p = fma(col[0], fix, p);
+        a.wpart[wid * kQrNb + j] = p;
+      }
     }
-    grid.sync();
+    tau_p = tau;
+    beta_p = beta;
+    scl_p = scl;
+    grid_barrier(a.bar, bar_target, nb);
   }
 }
 
@@ -196,24 +216,25 @@ struct QrcpPanelArgs {
   double* vn2;
   double* tau;
   double* beta;
-  double* auxraw;   // kQrcpNb
+  double* auxpart;  // kQrPanelWarps x kQrcpNb per-warp partials of A[c:, j0:c]^T v
+  double* fpart;    // kQrPanelWarps x n       per-warp partials of A[c:, c+1:]^T v
   double* part;
   double* scal;
   QrcpCtl* ctl;
   double tol3z;
+  unsigned int* bar;
+  int trace;       // scal[8..15]: phase cycle counters
 };
 
-// DLAQPS panel (see the phase list in the file header):
-//   P0/P1 pivot = first argmax of vn1[c:] (every CTA, same result); swap columns pvt <-> c and
-//         apply the panel's earlier reflectors to column c (own rows), partial norm  | grid.sync
-//   P2    reflector scalars, scale v; CTA 0 swaps perm / norms / F rows               | grid.sync
-//   P3    F(:, i) = A[c:, c+1:]^T v and aux = A[c:, j0:c]^T v (one warp per column)    | grid.sync
-//   P4    finish F(:, i), update the pivot row, downdate the partial norms (thread per
-//         trailing column), flag cancellation                                         | grid.sync
+// DLAQPS panel, 3 barriers per column:
+//   A  pivot = first argmax of vn1[c:] (every CTA, same result); swap columns pvt <-> c and
+//      apply the panel's earlier reflectors to column c (own rows); partial norm  | barrier
+//   B  scalars; F(:, i) = A[c:, c+1:]^T v and aux = A[c:, j0:c]^T v via raw dots (one CTA
+//      per column); CTA 0 swaps perm / norms / F rows                             | barrier
+//   C  scale v (own rows); finish F(:, i), update the pivot row, downdate the partial norms
+//      (thread per trailing column), flag cancellation                            | barrier
 __global__ void __launch_bounds__(kQrPanelThreads, 2) qrcp_panel_kernel(QrcpPanelArgs a) {
-  cg::grid_group grid = cg::this_grid();
   __shared__ double sh[32];
-  __shared__ double shd[2][32];
   __shared__ double sval[32];
   __shared__ int64_t sidx[32];
   __shared__ int64_t spvt;
@@ -224,12 +245,19 @@ __global__ void __launch_bounds__(kQrPanelThreads, 2) qrcp_panel_kernel(QrcpPane
   const int64_t lda = a.lda, ldf = a.ldf, k = a.k, n = a.n, j0 = a.j0;
   const int64_t gt = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
-  const int nb = gridDim.x;
+  const unsigned int nb = gridDim.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t gwarp = gt >> 5, nwarps = nthreads >> 5;
+  unsigned int bar_target = 0;
+  long long tk = a.trace ? clock64() : 0;
+#define TQ_PHASE(idx)                                   \
+  if (a.trace && gt == 0) {                             \
+    const long long now = clock64();                    \
+    a.scal[8 + (idx)] += double(now - tk);              \
+    tk = now;                                           \
+  }
   for (int i = 0; i < a.jb; ++i) {
     const int64_t c = j0 + i;
-    // ---------------- P0: pivot
+    // ---------------- A: pivot
     {
       double best = -1.0;
       int64_t bidx = n;
@@ -271,10 +299,9 @@ __global__ void __launch_bounds__(kQrPanelThreads, 2) qrcp_panel_kernel(QrcpPane
       __syncthreads();
     }
     const int64_t pvt = spvt;
-    // F row of the pivot column (still at its old position) for the column update
-    if (threadIdx.x < i) frow[threadIdx.x] = F[(pvt - j0) + int64_t(threadIdx.x) * ldf];
+    if (threadIdx.x < i) frow[threadIdx.x] = F[(pvt - j0) + int64_t(threadIdx.x) * ldf];   // F row of the pivot column
     __syncthreads();
-    // ---------------- P1: swap + column update + partial norm
+    // swap + column update + partial norm
     double ss = 0.0;
     for (int64_t r = gt; r < k; r += nthreads) {
       double ac = A[r + c * lda];
@@ -284,9 +311,14 @@ __global__ void __launch_bounds__(kQrPanelThreads, 2) qrcp_panel_kernel(QrcpPane
         ac = ap;
       }
       if (r >= c) {
-        double s = 0.0;
-        for (int t = 0; t < i; ++t) s = fma(A[r + (j0 + t) * lda], frow[t], s);
-        ac -= s;
+        double s0 = 0.0, s1 = 0.0;
+        int t = 0;
+        for (; t + 1 < i; t += 2) {
+          s0 = fma(A[r + (j0 + t) * lda], frow[t], s0);
+          s1 = fma(A[r + (j0 + t + 1) * lda], frow[t + 1], s1);
+        }
+        if (t < i) s0 = fma(A[r + (j0 + t) * lda], frow[t], s0);
+        ac -= (s0 + s1);
         if (r == c) a.scal[0] = ac;
         else ss = fma(ac, ac, ss);
       }
@@ -294,27 +326,38 @@ __global__ void __launch_bounds__(kQrPanelThreads, 2) qrcp_panel_kernel(QrcpPane
     }
     ss = block_sum(ss, sh);
     if (threadIdx.x == 0) a.part[blockIdx.x] = ss;
-    grid.sync();
-    // ---------------- P2
+    TQ_PHASE(0)
+    grid_barrier(a.bar, bar_target, nb);
+    TQ_PHASE(1)
+    // ---------------- B
     const int64_t len = k - c;
     const double sumsq = grid_total(a.part, nb, sh);
     const double alpha = a.scal[0];
     double tau, beta, scl;
-    if (len <= 1 || sumsq == 0.0) {
-      tau = 0.0;
-      beta = alpha;
-      scl = 0.0;
-    } else {
-      const double xnorm = sqrt(sumsq);
-      beta = -copysign(hypot(alpha, xnorm), alpha);
-      tau = (beta - alpha) / beta;
-      scl = 1.0 / (alpha - beta);
+    householder_scalars(alpha, sumsq, len, tau, beta, scl);
+    const double fix = 1.0 - scl * alpha;
+    const int64_t ntrail = n - c - 1;
+    {
+      const double* u = A + c + c * lda;
+      const int64_t total = ntrail + i;
+      for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
+        const double* col;
+        double* out;
+        if (j < ntrail) {
+          col = A + c + (c + 1 + j) * lda;
+          out = a.fpart + int64_t(wid) * n + (c + 1 + j);
+        } else {
+          col = A + c + (j0 + (j - ntrail)) * lda;
+          out = a.auxpart + wid * kQrcpNb + (j - ntrail);
+        }
+        double p = scl * cta_strided_warp_dot(col, u, len);
+        if (lane == 0) {
+          if (wid == 0) p = fma(col[0], fix, p);
+          *out = p;
+        }
+      }
     }
-    for (int64_t r = gt; r < k; r += nthreads) {
-      if (r == c) A[r + c * lda] = 1.0;
-      else if (r > c && tau != 0.0) A[r + c * lda] *= scl;
-    }
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == gridDim.x - 1) {       // bookkeeping of the swap (nobody reads these in phase B)
       if (threadIdx.x == 0) {
         a.tau[c] = tau;
         a.beta[c] = beta;
@@ -333,40 +376,30 @@ __global__ void __launch_bounds__(kQrPanelThreads, 2) qrcp_panel_kernel(QrcpPane
         F[(c - j0) + int64_t(t) * ldf] = fa;
       }
     }
-    grid.sync();
-    // ---------------- P3: dots with v = A[c:, c]
-    const int64_t ntrail = n - c - 1;
-    {
-      const double* v = A + c + c * lda;
-      const int64_t total = ntrail + i;
-      int par = 0;
-      for (int64_t j = blockIdx.x; j < total; j += gridDim.x, par ^= 1) {
-        const double* col;
-        double* out;
-        if (j < ntrail) {
-          col = A + c + (c + 1 + j) * lda;
-          out = F + (c + 1 + j - j0) + int64_t(i) * ldf;
-        } else {
-          col = A + c + (j0 + (j - ntrail)) * lda;
-          out = a.auxraw + (j - ntrail);
-        }
-        cta_dot_store(col, v, len, shd[par], out);
-      }
-    }
-    grid.sync();
-    // ---------------- P4: row update + norm downdate (thread per trailing column)
+    TQ_PHASE(2)
+    grid_barrier(a.bar, bar_target, nb);
+    TQ_PHASE(3)
+    // ---------------- C
     if (threadIdx.x < i) {
-      frow[threadIdx.x] = -tau * a.auxraw[threadIdx.x];            // auxv
+      double asum = 0.0;
+      for (int w = 0; w < kQrPanelWarps; ++w) asum += a.auxpart[w * kQrcpNb + threadIdx.x];
+      frow[threadIdx.x] = -tau * asum;                              // auxv
       arow[threadIdx.x] = A[c + (j0 + threadIdx.x) * lda];          // A[c, j0:c]
     }
     __syncthreads();
+    for (int64_t r = gt; r < k; r += nthreads) {                    // v in place, beta on the diagonal
+      if (r == c) A[r + c * lda] = beta;
+      else if (r > c) A[r + c * lda] *= scl;
+    }
     for (int64_t q = gt; q < ntrail; q += nthreads) {
       const int64_t col = c + 1 + q;
       const int64_t fr = col - j0;
-      double f = tau * F[fr + int64_t(i) * ldf];
+      double fraw = 0.0;
+      for (int w = 0; w < kQrPanelWarps; ++w) fraw += a.fpart[int64_t(w) * n + col];
+      double f = tau * fraw;
       for (int t = 0; t < i; ++t) f = fma(F[fr + t * ldf], frow[t], f);
       F[fr + int64_t(i) * ldf] = f;
-      double s = f;                                                 // A[c, c] == 1 during the step
+      double s = f;                                                 // v[c] = 1
       for (int t = 0; t < i; ++t) s = fma(F[fr + t * ldf], arow[t], s);
       const double av = A[c + col * lda] - s;
       A[c + col * lda] = av;
@@ -387,10 +420,12 @@ __global__ void __launch_bounds__(kQrPanelThreads, 2) qrcp_panel_kernel(QrcpPane
       }
     }
     if (gt == 0) a.ctl->kb = i + 1;
-    grid.sync();
-    if (gt == 0) A[c + c * lda] = beta;          // restore akk (read by nobody until the trailing GEMM)
+    TQ_PHASE(4)
+    grid_barrier(a.bar, bar_target, nb);
+    TQ_PHASE(5)
     if (a.ctl->stop_next) break;                 // uniform: read after the barrier
   }
+#undef TQ_PHASE
 }
 
 // in place: on exit triu(A[0:k, 0:n]) = R (diagonal sign arbitrary)
@@ -398,9 +433,10 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
                   Workspace& ws) {
   double* tau = ws.take<double>(k);
   double* beta = ws.take<double>(k);
-  double* wdot = ws.take<double>(kQrNb);
+  double* wdot = ws.take<double>(kQrNb * kMaxChunks);
   double* part = ws.take<double>(1024);
   double* scal = ws.take<double>(8);
+  unsigned int* bar = ws.take<unsigned int>(4);
   double* Vc = ws.take<double>(size_t(k) * kQrNb);
   double* G = ws.take<double>(kQrNb * kQrNb);
   double* T = ws.take<double>(kQrNb * kQrNb);
@@ -426,7 +462,8 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
       // a tall-skinny panel does not need the whole machine: fewer CTAs make the barriers cheaper
       const int64_t rows = k - j0;
       int blocks = int(imin(coop_blocks, imax(8, ceil_div(rows, kQrPanelThreads) * 4)));
-      QrPanelArgs pa{A, lda, k, j0, jb, tau, beta, wdot, part, scal};
+      TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
+      QrPanelArgs pa{A, lda, k, j0, jb, tau, beta, wdot, part, scal, bar};
       void* kargs[] = {&pa};
       TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(blocks), dim3(kQrPanelThreads), kargs,
                                                 0, st));
@@ -619,12 +656,14 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
   double* vn1 = ws.take<double>(n);
   double* vn2 = ws.take<double>(n);
   double* F = ws.take<double>(size_t(n) * kQrcpNb);
-  double* auxraw = ws.take<double>(kQrcpNb);
+  double* auxraw = ws.take<double>(kQrcpNb * kMaxChunks);
+  double* fpart = ws.take<double>(size_t(n) * kMaxChunks);
   double* tau = ws.take<double>(k + 1);
   double* beta = ws.take<double>(k + 1);
   QrcpCtl* ctl = ws.take<QrcpCtl>(1);
   double* part = ws.take<double>(1024);
-  double* scal = ws.take<double>(8);
+  double* scal = ws.take<double>(16);
+  unsigned int* bar = ws.take<unsigned int>(4);
   if (ws.overflow) {
     set_error("qrcp: workspace too small");
     return TQ_ERR_WORKSPACE;
@@ -642,6 +681,7 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
     }
     coop_blocks = num_sms() * (per_sm > 2 ? 2 : per_sm);
   }
+  TQ_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 16, st));
   init_perm_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(perm, n);
   TQ_LAUNCH_CHECK();
   col_norms_kernel<<<dots_grid(n), 256, 0, st>>>(A, lda, 0, k, n, vn1, vn2, 0);
@@ -652,7 +692,9 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
     qrcp_panel_begin_kernel<<<1, 1, 0, st>>>(ctl);
     TQ_LAUNCH_CHECK();
     {
-      QrcpPanelArgs pa{A, lda, k, n, j0, jb, F, ldf, perm, vn1, vn2, tau, beta, auxraw, part, scal, ctl, tol3z};
+      TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
+      QrcpPanelArgs pa{A, lda, k, n, j0, jb, F, ldf, perm, vn1, vn2, tau, beta, auxraw, fpart, part, scal, ctl, tol3z, bar,
+                       trace_enabled() ? 1 : 0};
       void* kargs[] = {&pa};
       double bytes = 0.0;      // algorithmic bytes of the panel: every step streams the trailing matrix once
       for (int i = 0; i < jb; ++i) bytes += double(k - (j0 + i)) * double(n - (j0 + i) - 1 + i) * 8.0;
@@ -683,6 +725,13 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
     }
     j0 = r0;
   }
+  if (trace_enabled()) {
+    double hcnt[16];
+    cudaMemcpyAsync(hcnt, scal, sizeof(hcnt), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[tq-trace] qrcp phase Mcycles (CTA 0): A %.1f  bar1 %.1f  B(stream) %.1f  bar2 %.1f  C %.1f  bar3 %.1f\n",
+            hcnt[8] * 1e-6, hcnt[9] * 1e-6, hcnt[10] * 1e-6, hcnt[11] * 1e-6, hcnt[12] * 1e-6, hcnt[13] * 1e-6);
+  }
   return TQ_OK;
 }
 
@@ -694,7 +743,7 @@ static size_t qr_ws_bytes(int64_t k, int64_t n) {
   size_t b = ws_bytes_for(size_t(k) * n, 8);                       // column-major working copy
   b += ws_bytes_for(k + 1, 8) * 4 + ws_bytes_for(kQrNb, 8) + ws_bytes_for(size_t(k) * kQrNb, 8);
   b += ws_bytes_for(kQrNb * kQrNb, 8) * 2 + ws_bytes_for(size_t(kQrNb) * n, 8) * 2;
-  b += ws_bytes_for(n, 8) * 2 + ws_bytes_for(size_t(n) * kQrcpNb, 8) + ws_bytes_for(64, 8) * 2;
+  b += ws_bytes_for(n, 8) * (2 + kMaxChunks) + ws_bytes_for(size_t(n) * kQrcpNb, 8) + ws_bytes_for(2048, 8) * 4;
   return b;
 }
 

@@ -80,6 +80,110 @@ __device__ __forceinline__ void cta_dot_store(const double* __restrict__ col, co
   }
 }
 
+// Warp-level partial dot over rows [r0, r1): 8 independent 8-byte loads per lane in flight,
+// deterministic shuffle-tree reduction; every lane returns the sum.
+__device__ __forceinline__ double warp_dot_range(const double* __restrict__ col, const double* __restrict__ v,
+                                                 int64_t r0, int64_t r1, int lane) {
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+  int64_t r = r0 + lane;
+  for (; r + 224 < r1; r += 256) {
+    const double m0 = col[r], m1 = col[r + 32], m2 = col[r + 64], m3 = col[r + 96];
+    const double m4 = col[r + 128], m5 = col[r + 160], m6 = col[r + 192], m7 = col[r + 224];
+    a0 = fma(m0, v[r], a0);
+    a1 = fma(m1, v[r + 32], a1);
+    a2 = fma(m2, v[r + 64], a2);
+    a3 = fma(m3, v[r + 96], a3);
+    a4 = fma(m4, v[r + 128], a4);
+    a5 = fma(m5, v[r + 160], a5);
+    a6 = fma(m6, v[r + 192], a6);
+    a7 = fma(m7, v[r + 224], a7);
+  }
+  for (; r + 32 < r1; r += 64) {
+    const double m0 = col[r], m1 = col[r + 32];
+    a0 = fma(m0, v[r], a0);
+    a1 = fma(m1, v[r + 32], a1);
+  }
+  if (r < r1) a2 = fma(col[r], v[r], a2);
+  return warp_sum(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
+}
+
+// Grid-wide barrier for the persistent (cooperatively launched, hence co-resident) panel
+// kernels: one monotonically increasing counter in global memory, zeroed before the launch.
+// Thread 0 of every CTA releases its writes, arrives and spins with acquire loads; the
+// gpu-scope fence after the spin invalidates the SM's L1 so the CTA reads fresh data.
+// Measured several times cheaper than cooperative_groups::grid_group::sync() on B200.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += nblocks;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Partial dot of one column against v by ONE WARP of a CTA that streams the column
+// cooperatively: the CTA covers rows contiguously (thread t takes rows t, t + blockDim, ...),
+// 8 loads per thread in flight; the caller stores the per-warp partial and the consumer adds
+// the blockDim/32 partials in fixed order - no block-level barrier in the streaming loop.
+__device__ __forceinline__ double cta_strided_warp_dot(const double* __restrict__ col, const double* __restrict__ v,
+                                                       int64_t len) {
+  const int64_t step = blockDim.x;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+  int64_t r = threadIdx.x;
+  for (; r + 7 * step < len; r += 8 * step) {
+    const double m0 = col[r], m1 = col[r + step], m2 = col[r + 2 * step], m3 = col[r + 3 * step];
+    const double m4 = col[r + 4 * step], m5 = col[r + 5 * step], m6 = col[r + 6 * step], m7 = col[r + 7 * step];
+    a0 = fma(m0, v[r], a0);
+    a1 = fma(m1, v[r + step], a1);
+    a2 = fma(m2, v[r + 2 * step], a2);
+    a3 = fma(m3, v[r + 3 * step], a3);
+    a4 = fma(m4, v[r + 4 * step], a4);
+    a5 = fma(m5, v[r + 5 * step], a5);
+    a6 = fma(m6, v[r + 6 * step], a6);
+    a7 = fma(m7, v[r + 7 * step], a7);
+  }
+  if (r + 3 * step < len) {
+    const double m0 = col[r], m1 = col[r + step], m2 = col[r + 2 * step], m3 = col[r + 3 * step];
+    a0 = fma(m0, v[r], a0);
+    a1 = fma(m1, v[r + step], a1);
+    a2 = fma(m2, v[r + 2 * step], a2);
+    a3 = fma(m3, v[r + 3 * step], a3);
+    r += 4 * step;
+  }
+  if (r + step < len) {
+    const double m0 = col[r], m1 = col[r + step];
+    a4 = fma(m0, v[r], a4);
+    a5 = fma(m1, v[r + step], a5);
+    r += 2 * step;
+  }
+  if (r < len) a6 = fma(col[r], v[r], a6);
+  if (r + step < len) a7 = fma(col[r + step], v[r + step], a7);
+  return warp_sum(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
+}
+
+// Work split of the streaming phase: `cols` columns of `len` rows are cut into row chunks so
+// that there are about 8 equal units per warp (balanced tail) but no unit is shorter than 512
+// rows.  Partial sums of the (at most kMaxChunks) chunks are added in fixed order by the
+// consumer, so the result does not depend on the scheduling.
+constexpr int kMaxChunks = 16;
+__device__ __forceinline__ void chunk_plan(int64_t len, int64_t cols, int64_t nwarps, int& H, int64_t& L) {
+  int64_t h = cols > 0 ? (8 * nwarps) / cols : 1;
+  const int64_t hmax = (len + 511) / 512;
+  if (h > hmax) h = hmax;
+  if (h > kMaxChunks) h = kMaxChunks;
+  if (h < 1) h = 1;
+  L = ((len + h - 1) / h + 31) / 32 * 32;
+  if (L < 32) L = 32;
+  H = int((len + L - 1) / L);
+  if (H < 1) H = 1;
+}
+
 // out[j] = dot(M[:, j], x) over `rows` rows for up to three column sets sharing x.
 // `skip` (optional device flag): when *skip != 0 the kernel does nothing.
 static __global__ void __launch_bounds__(256)
