@@ -1,7 +1,7 @@
 // Symmetric eigendecomposition in fp64 (reference: torch.linalg.eigh -> cuSOLVER syevd,
 // gptq_utils.py:93), written from scratch for sm_100a:
 //   1. sytrd  blocked Householder tridiagonal reduction (lower).  Per column the work is
-//             BLAS-2 and HBM-bound (one pass over the trailing matrix: dots3_kernel);
+//             BLAS-2 and HBM-bound (one pass over the trailing matrix per reflector);
 //             per panel the rank-2k trailing update is DGEMM.
 //   2. stedc  divide & conquer on the tridiagonal matrix: QL leaves (one warp per leaf),
 //             then rank-one merges.  Deflation is decided on the host from d and z (O(n)
@@ -22,53 +22,8 @@ constexpr int kTrdNb = 64;   // sytrd panel width
 constexpr int kLeaf = 32;    // D&C leaf size (one warp)
 constexpr int kOrmNb = 64;   // back-transform block
 
-// ======================================================================= sytrd kernels
-// A[r, c] -= sum_t V[r,t] W[c,t] + W[r,t] V[c,t]   (t < i),  r in [c, n);  d[c] = A[c,c]
-__global__ void sytrd_col_update_kernel(double* __restrict__ A, int64_t lda, int64_t n, int64_t j0, int i,
-                                        const double* __restrict__ W, int64_t ldw, double* __restrict__ d) {
-  const int64_t c = j0 + i;
-  for (int64_t r = c + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n;
-       r += int64_t(gridDim.x) * blockDim.x) {
-    double s = 0.0;
-    for (int t = 0; t < i; ++t) {
-      s = fma(A[r + (j0 + t) * lda], W[c + t * ldw], s);
-      s = fma(W[r + t * ldw], A[c + (j0 + t) * lda], s);
-    }
-    const double a = A[r + c * lda] - s;
-    A[r + c * lda] = a;
-    if (r == c) d[c] = a;
-  }
-}
 
-// w[r] = tau * (y[r] - sum_t V[r,t] tmp1[t] - sum_t W[r,t] tmp2[t]),  r in [c+1, n)
-__global__ void sytrd_w_kernel(const double* __restrict__ A, int64_t lda, int64_t n, int64_t j0, int i,
-                               double* __restrict__ W, int64_t ldw, const double* __restrict__ y,
-                               const double* __restrict__ tmp1, const double* __restrict__ tmp2,
-                               const double* __restrict__ tau_p) {
-  const int64_t c = j0 + i;
-  const double tau = *tau_p;
-  for (int64_t r = c + 1 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n;
-       r += int64_t(gridDim.x) * blockDim.x) {
-    double s = y[r];
-    for (int t = 0; t < i; ++t) {
-      s = fma(-A[r + (j0 + t) * lda], tmp1[t], s);
-      s = fma(-W[r + t * ldw], tmp2[t], s);
-    }
-    W[r + int64_t(i) * ldw] = tau * s;
-  }
-}
 
-// w += (-tau/2 * w.v) v      (single CTA)
-__global__ void __launch_bounds__(1024)
-sytrd_w_finish_kernel(double* __restrict__ w, const double* __restrict__ v, int64_t len,
-                      const double* __restrict__ tau_p) {
-  __shared__ double sh[32];
-  double s = 0.0;
-  for (int64_t r = threadIdx.x; r < len; r += blockDim.x) s = fma(w[r], v[r], s);
-  s = block_sum(s, sh);
-  const double alpha = -0.5 * (*tau_p) * s;
-  for (int64_t r = threadIdx.x; r < len; r += blockDim.x) w[r] = fma(alpha, v[r], w[r]);
-}
 
 // ----------------------------------------------------------------------- persistent panel
 // One cooperative launch factors a whole panel of up to kTrdNb columns.  The per-column
@@ -87,6 +42,7 @@ sytrd_w_finish_kernel(double* __restrict__ w, const double* __restrict__ v, int6
 // foreign value the next column update needs, W[c+1, i], is recomputed by every CTA.
 constexpr int kPanelThreads = 512;
 constexpr int kPanelWarps = kPanelThreads / 32;
+constexpr size_t kPanelSmem = size_t(kAsyncDepth) * kPanelThreads * sizeof(double2);
 
 struct TrdPanelArgs {
   double* A;
@@ -112,6 +68,7 @@ __device__ __forceinline__ double grid_total(const double* part, int nb, double*
 }
 
 __global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelArgs a) {
+  extern __shared__ double2 dot_slots[];   // [kAsyncDepth][blockDim] cp.async staging of the streamed column
   __shared__ double sh[32];
   __shared__ double tmps[2 * kTrdNb];
   __shared__ double wrow_s;          // W[c, i-1], computed locally at the end of the previous column
@@ -202,7 +159,7 @@ __global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelA
           col = A + (c + 1) + (j0 + (j - len - i)) * lda;
           out = a.tmppart + wid * (2 * kTrdNb) + kTrdNb + (j - len - i);
         }
-        double p = scl * cta_strided_warp_dot(col, u, len);
+        double p = scl * cta_strided_warp_dot(col, u, len, dot_slots);
         if (lane == 0) {
           if (wid == 0) p = fma(col[0], fix, p);
           *out = p;
@@ -275,7 +232,10 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
   static thread_local int coop_blocks = 0;
   if (!coop_blocks) {
     int per_sm = 0;
-    TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sytrd_panel_kernel, kPanelThreads, 0));
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(sytrd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(kPanelSmem)));
+    TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sytrd_panel_kernel, kPanelThreads,
+                                                                kPanelSmem));
     if (per_sm < 1) {
       set_error("sytrd: panel kernel cannot be made resident");
       return TQ_ERR_CUDA;
@@ -295,7 +255,7 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
       }
       const int pslot = prof_begin_launch(st, bytes);
       TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sytrd_panel_kernel, dim3(coop_blocks), dim3(kPanelThreads),
-                                                kargs, 0, st));
+                                                kargs, kPanelSmem, st));
       prof_end_launch(st, pslot);
       ++g_launch_count;
     }

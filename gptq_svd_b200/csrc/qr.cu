@@ -5,8 +5,8 @@
 //    pivot = first index of the largest downdated partial norm, norms downdated with the
 //    DLAQPS cancellation safeguard (a failing column ends the panel and is recomputed
 //    exactly), lazy panel update through F, trailing update by DGEMM.
-//    The per-column work is BLAS-2 and HBM-bound: dots3_kernel streams the whole trailing
-//    matrix once per column (F(:,k) = tau A^T v).
+//    The per-column work is BLAS-2 and HBM-bound: the panel kernel streams the whole
+//    trailing matrix once per column (F(:,k) = tau A^T v).
 //  * qr_r_colmajor: unpivoted blocked Householder QR that never forms Q (the reference
 //    calls torch.linalg.qr and discards Q, gptq_utils.py:120): panel by BLAS-2 kernels,
 //    trailing update by compact-WY DGEMMs.
@@ -54,18 +54,6 @@ __global__ void emit_r_kernel(const double* __restrict__ A, int64_t lda, int64_t
   }
 }
 
-// ------------------------------------------------------------------ unpivoted QR panel
-// A[r, c+1+j] -= tau * v[r] * w[j]   for r in [c, k), j in [0, ncols)
-__global__ void qr_panel_rank1_kernel(double* __restrict__ A, int64_t lda, int64_t c, int64_t k, int ncols,
-                                      const double* __restrict__ tau, const double* __restrict__ w) {
-  const int j = blockIdx.y;
-  const double tw = tau[0] * w[j];
-  const double* v = A + c + c * lda;
-  double* col = A + c + (c + 1 + j) * lda;
-  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < k - c;
-       r += int64_t(gridDim.x) * blockDim.x)
-    col[r] = fma(-tw, v[r], col[r]);
-}
 
 __global__ void set_diag_kernel(double* __restrict__ A, int64_t lda, int64_t j0, int jb,
                                 const double* __restrict__ beta) {
@@ -88,6 +76,7 @@ struct QrcpCtl {
 // so no barrier is needed between computing the Householder scalars and using v.
 constexpr int kQrPanelThreads = 512;
 constexpr int kQrPanelWarps = kQrPanelThreads / 32;
+constexpr size_t kQrPanelSmem = size_t(kAsyncDepth) * kQrPanelThreads * sizeof(double2);
 
 __device__ __forceinline__ double grid_total(const double* part, int nb, double* sh) {
   double v = (threadIdx.x < nb) ? part[threadIdx.x] : 0.0;
@@ -127,6 +116,7 @@ struct QrPanelArgs {
 //      remaining panel columns (own rows); partial sum of squares of column c    | barrier
 //   B  scalars; w = A[c:, c+1:pend]^T v via raw dots (one CTA per column)         | barrier
 __global__ void __launch_bounds__(kQrPanelThreads, 2) qr_panel_kernel(QrPanelArgs a) {
+  extern __shared__ double2 dot_slots[];   // [kAsyncDepth][blockDim] cp.async staging of the streamed column
   __shared__ double sh[32];
   __shared__ double wd[kQrNb];
   double* const A = a.A;
@@ -191,7 +181,7 @@ __global__ void __launch_bounds__(kQrPanelThreads, 2) qr_panel_kernel(QrPanelArg
     const int rem = int(pend - 1 - c);
     for (int64_t j = blockIdx.x; j < rem; j += gridDim.x) {
       const double* col = A + c + (c + 1 + j) * lda;
-      double p = scl * cta_strided_warp_dot(col, u, len);
+      double p = scl * cta_strided_warp_dot(col, u, len, dot_slots);
       if (lane == 0) {
         if (wid == 0) p = fma(col[0], fix, p);
         a.wpart[wid * kQrNb + j] = p;
@@ -234,6 +224,7 @@ struct QrcpPanelArgs {
 //   C  scale v (own rows); finish F(:, i), update the pivot row, downdate the partial norms
 //      (thread per trailing column), flag cancellation                            | barrier
 __global__ void __launch_bounds__(kQrPanelThreads, 2) qrcp_panel_kernel(QrcpPanelArgs a) {
+  extern __shared__ double2 dot_slots[];   // [kAsyncDepth][blockDim] cp.async staging of the streamed column
   __shared__ double sh[32];
   __shared__ double sval[32];
   __shared__ int64_t sidx[32];
@@ -350,7 +341,7 @@ __global__ void __launch_bounds__(kQrPanelThreads, 2) qrcp_panel_kernel(QrcpPane
           col = A + c + (j0 + (j - ntrail)) * lda;
           out = a.auxpart + wid * kQrcpNb + (j - ntrail);
         }
-        double p = scl * cta_strided_warp_dot(col, u, len);
+        double p = scl * cta_strided_warp_dot(col, u, len, dot_slots);
         if (lane == 0) {
           if (wid == 0) p = fma(col[0], fix, p);
           *out = p;
@@ -449,7 +440,10 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
   static thread_local int coop_blocks = 0;
   if (!coop_blocks) {
     int per_sm = 0;
-    TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_panel_kernel, kQrPanelThreads, 0));
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(kQrPanelSmem)));
+    TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_panel_kernel, kQrPanelThreads,
+                                                                kQrPanelSmem));
     if (per_sm < 1) {
       set_error("qr_r: panel kernel cannot be made resident");
       return TQ_ERR_CUDA;
@@ -466,7 +460,7 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
       QrPanelArgs pa{A, lda, k, j0, jb, tau, beta, wdot, part, scal, bar};
       void* kargs[] = {&pa};
       TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(blocks), dim3(kQrPanelThreads), kargs,
-                                                0, st));
+                                                kQrPanelSmem, st));
       ++g_launch_count;
     }
     const int64_t s = k - j0;
@@ -512,137 +506,8 @@ __global__ void init_perm_kernel(int64_t* perm, int64_t n) {
   if (j < n) perm[j] = j;
 }
 
-// Step 1: commit the stop flag, pick the pivot (first index of max vn1[c:]) and swap.
-__global__ void __launch_bounds__(1024)
-qrcp_pivot_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t n, int64_t j0, int i,
-                  double* __restrict__ F, int64_t ldf, int64_t* __restrict__ perm, double* __restrict__ vn1,
-                  double* __restrict__ vn2, QrcpCtl* ctl) {
-  __shared__ double sval[32];
-  __shared__ int64_t sidx[32];
-  __shared__ int64_t spvt;
-  if (ctl->stop_next) {
-    if (threadIdx.x == 0) ctl->stop = 1;
-    return;
-  }
-  if (ctl->stop) return;
-  const int64_t c = j0 + i;
-  double best = -1.0;
-  int64_t bidx = n;
-  for (int64_t j = c + threadIdx.x; j < n; j += blockDim.x) {
-    double v = vn1[j];
-    if (v > best) {   // strided scan keeps the smallest index among equal values per thread
-      best = v;
-      bidx = j;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    double ov = __shfl_xor_sync(0xffffffffu, best, o);
-    int64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-    if (ov > best || (ov == best && oi < bidx)) {
-      best = ov;
-      bidx = oi;
-    }
-  }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) {
-    sval[w] = best;
-    sidx[w] = bidx;
-  }
-  __syncthreads();
-  if (w == 0) {
-    best = sval[lane];
-    bidx = sidx[lane];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      double ov = __shfl_xor_sync(0xffffffffu, best, o);
-      int64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (ov > best || (ov == best && oi < bidx)) {
-        best = ov;
-        bidx = oi;
-      }
-    }
-    if (lane == 0) spvt = bidx;
-  }
-  __syncthreads();
-  const int64_t pvt = spvt;
-  if (pvt == c || pvt >= n) return;
-  for (int64_t r = threadIdx.x; r < k; r += blockDim.x) {
-    double a = A[r + pvt * lda], b = A[r + c * lda];
-    A[r + pvt * lda] = b;
-    A[r + c * lda] = a;
-  }
-  for (int t = threadIdx.x; t < i; t += blockDim.x) {
-    double a = F[(pvt - j0) + t * ldf], b = F[(c - j0) + t * ldf];
-    F[(pvt - j0) + t * ldf] = b;
-    F[(c - j0) + t * ldf] = a;
-  }
-  if (threadIdx.x == 0) {
-    int64_t p = perm[pvt];
-    perm[pvt] = perm[c];
-    perm[c] = p;
-    vn1[pvt] = vn1[c];
-    vn2[pvt] = vn2[c];
-  }
-}
 
-// Step 2: A[rk:, c] -= A[rk:, j0:c] F[c-j0, 0:i]^T
-__global__ void qrcp_col_update_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t j0, int i,
-                                       const double* __restrict__ F, int64_t ldf, const QrcpCtl* ctl) {
-  if (ctl->stop) return;
-  const int64_t c = j0 + i;
-  for (int64_t r = c + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < k;
-       r += int64_t(gridDim.x) * blockDim.x) {
-    double s = 0.0;
-    for (int t = 0; t < i; ++t) s = fma(A[r + (j0 + t) * lda], F[(c - j0) + t * ldf], s);
-    A[r + c * lda] -= s;
-  }
-}
 
-// Step 5 (after larfg and the dots): finish F(:, i), update the pivot row and downdate
-// the partial norms of every trailing column.  One thread per trailing column.
-__global__ void qrcp_row_update_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t n, int64_t j0, int i,
-                                       double* __restrict__ F, int64_t ldf, const double* __restrict__ auxraw,
-                                       const double* __restrict__ tau_p, const double* __restrict__ beta_p,
-                                       double* __restrict__ vn1, double* __restrict__ vn2, QrcpCtl* ctl,
-                                       double tol3z) {
-  if (ctl->stop) return;
-  const int64_t c = j0 + i;   // pivot column == pivot row
-  const double tau = *tau_p;
-  const int64_t col = c + 1 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (col == c + 1) {          // exactly one thread (or none when c is the last column): bookkeeping
-    ctl->kb = i + 1;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    A[c + c * lda] = *beta_p;  // restore akk (nobody reads A[c, c] in this kernel)
-    if (c + 1 >= n) ctl->kb = i + 1;
-  }
-  if (col >= n) return;
-  const int64_t fr = col - j0;
-  double f = tau * F[fr + int64_t(i) * ldf];
-  for (int t = 0; t < i; ++t) f = fma(F[fr + t * ldf], -tau * auxraw[t], f);
-  F[fr + int64_t(i) * ldf] = f;
-  // pivot row: A[c, col] -= sum_{t<=i} F[fr, t] * A[c, j0+t], with A[c, c] == 1 during the step
-  double s = f;
-  for (int t = 0; t < i; ++t) s = fma(F[fr + t * ldf], A[c + (j0 + t) * lda], s);
-  const double a = A[c + col * lda] - s;
-  A[c + col * lda] = a;
-  if (c < k - 1) {
-    const double v1 = vn1[col];
-    if (v1 != 0.0) {
-      double temp = fabs(a) / v1;
-      temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
-      const double q = v1 / vn2[col];
-      const double temp2 = temp * (q * q);
-      if (temp2 <= tol3z) {
-        vn2[col] = -1.0;        // flagged: recomputed exactly after the panel's trailing update
-        ctl->stop_next = 1;
-      } else {
-        vn1[col] = v1 * sqrt(temp);
-      }
-    }
-  }
-}
 
 __global__ void qrcp_panel_begin_kernel(QrcpCtl* ctl) {
   ctl->stop = 0;
@@ -674,7 +539,10 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
   static thread_local int coop_blocks = 0;
   if (!coop_blocks) {
     int per_sm = 0;
-    TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qrcp_panel_kernel, kQrPanelThreads, 0));
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(qrcp_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(kQrPanelSmem)));
+    TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qrcp_panel_kernel, kQrPanelThreads,
+                                                                kQrPanelSmem));
     if (per_sm < 1) {
       set_error("qrcp: panel kernel cannot be made resident");
       return TQ_ERR_CUDA;
@@ -700,7 +568,7 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
       for (int i = 0; i < jb; ++i) bytes += double(k - (j0 + i)) * double(n - (j0 + i) - 1 + i) * 8.0;
       const int pslot = prof_begin_launch(st, bytes);
       TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)qrcp_panel_kernel, dim3(coop_blocks), dim3(kQrPanelThreads),
-                                                kargs, 0, st));
+                                                kargs, kQrPanelSmem, st));
       prof_end_launch(st, pslot);
       ++g_launch_count;
     }

@@ -3,20 +3,14 @@
 //
 // The BLAS-2 parts of the factorizations (tridiagonal reduction, pivoted-QR panels) are
 // HBM-bound: their dominant operation is "dot every trailing column with one vector",
-// implemented by dots3_kernel (one warp per column, coalesced down the column,
-// deterministic shuffle-tree reduction).  BLAS-3 parts go to cuBLAS DGEMM.
+// done inside the persistent panel kernels by cta_strided_warp_dot (one CTA per column,
+// per-warp partials added in fixed order by the consumer).  BLAS-3 parts go to cuBLAS DGEMM.
 #pragma once
 #include "blas.cuh"
 #include "common.cuh"
 
 namespace tq {
 
-struct DotSeg {
-  const double* M;  // first element of the first column
-  int64_t ld;
-  int64_t ncols;
-  double* out;      // out[j] = dot(M[:, j], x)
-};
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -39,73 +33,7 @@ __device__ __forceinline__ double block_sum(double v, double* sh /*32 doubles*/)
   return v;
 }
 
-// Whole-CTA dot product of two length-len vectors (one trailing-matrix column against the
-// reflector): every thread keeps 8 independent 8-byte loads in flight (64 KB per SM at
-// 1024 resident threads, enough to cover HBM latency), then a fixed-order reduction
-// (warp shuffles, then warp 0 over the per-warp partials) makes the result deterministic.
-// Thread 0 of the CTA stores the sum to *out.  `shbuf` is 32 doubles; callers alternate
-// between two buffers on consecutive calls so that one __syncthreads per call suffices.
-__device__ __forceinline__ void cta_dot_store(const double* __restrict__ col, const double* __restrict__ v,
-                                              int64_t len, double* shbuf, double* out) {
-  const int64_t step = blockDim.x;
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
-  int64_t r = threadIdx.x;
-  for (; r + 7 * step < len; r += 8 * step) {
-    const double m0 = col[r], m1 = col[r + step], m2 = col[r + 2 * step], m3 = col[r + 3 * step];
-    const double m4 = col[r + 4 * step], m5 = col[r + 5 * step], m6 = col[r + 6 * step], m7 = col[r + 7 * step];
-    a0 = fma(m0, v[r], a0);
-    a1 = fma(m1, v[r + step], a1);
-    a2 = fma(m2, v[r + 2 * step], a2);
-    a3 = fma(m3, v[r + 3 * step], a3);
-    a4 = fma(m4, v[r + 4 * step], a4);
-    a5 = fma(m5, v[r + 5 * step], a5);
-    a6 = fma(m6, v[r + 6 * step], a6);
-    a7 = fma(m7, v[r + 7 * step], a7);
-  }
-  for (; r + step < len; r += 2 * step) {
-    const double m0 = col[r], m1 = col[r + step];
-    a0 = fma(m0, v[r], a0);
-    a1 = fma(m1, v[r + step], a1);
-  }
-  if (r < len) a2 = fma(col[r], v[r], a2);
-  double sres = warp_sum(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) shbuf[w] = sres;
-  __syncthreads();
-  if (w == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-    double t = lane < nw ? shbuf[lane] : 0.0;
-    t = warp_sum(t);
-    if (lane == 0) *out = t;
-  }
-}
 
-// Warp-level partial dot over rows [r0, r1): 8 independent 8-byte loads per lane in flight,
-// deterministic shuffle-tree reduction; every lane returns the sum.
-__device__ __forceinline__ double warp_dot_range(const double* __restrict__ col, const double* __restrict__ v,
-                                                 int64_t r0, int64_t r1, int lane) {
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
-  int64_t r = r0 + lane;
-  for (; r + 224 < r1; r += 256) {
-    const double m0 = col[r], m1 = col[r + 32], m2 = col[r + 64], m3 = col[r + 96];
-    const double m4 = col[r + 128], m5 = col[r + 160], m6 = col[r + 192], m7 = col[r + 224];
-    a0 = fma(m0, v[r], a0);
-    a1 = fma(m1, v[r + 32], a1);
-    a2 = fma(m2, v[r + 64], a2);
-    a3 = fma(m3, v[r + 96], a3);
-    a4 = fma(m4, v[r + 128], a4);
-    a5 = fma(m5, v[r + 160], a5);
-    a6 = fma(m6, v[r + 192], a6);
-    a7 = fma(m7, v[r + 224], a7);
-  }
-  for (; r + 32 < r1; r += 64) {
-    const double m0 = col[r], m1 = col[r + 32];
-    a0 = fma(m0, v[r], a0);
-    a1 = fma(m1, v[r + 32], a1);
-  }
-  if (r < r1) a2 = fma(col[r], v[r], a2);
-  return warp_sum(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
-}
 
 // Grid-wide barrier for the persistent (cooperatively launched, hence co-resident) panel
 // kernels: one monotonically increasing counter in global memory, zeroed before the launch.
@@ -128,133 +56,74 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 }
 
 // Partial dot of one column against v by ONE WARP of a CTA that streams the column
-// cooperatively: the CTA covers rows contiguously (thread t takes rows t, t + blockDim, ...),
-// 8 loads per thread in flight; the caller stores the per-warp partial and the consumer adds
-// the blockDim/32 partials in fixed order - no block-level barrier in the streaming loop.
+// cooperatively.  The CTA covers the column contiguously; thread t takes the 16-byte pairs
+// t, t + blockDim, ...  The column is staged global -> shared with per-thread cp.async
+// (LDGSTS) 16-byte copies, kAsyncDepth deep, into slots owned by the issuing thread, so no
+// registers are held while the data is in flight (128 KB per SM at 1024 resident threads -
+// the register-staged version was latency-bound at ~47 % DRAM utilisation in ncu) and no
+// block-level barrier is needed.  v comes from L1.  Every lane returns the warp's sum; the
+// caller stores the per-warp partial and the consumer adds the blockDim/32 partials in fixed
+// order.  Falls back to 8-byte loads when col and v do not share 16-byte parity (odd lda).
+constexpr int kAsyncDepth = 8;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ double cta_strided_warp_dot(const double* __restrict__ col, const double* __restrict__ v,
-                                                       int64_t len) {
+                                                       int64_t len, double2* slots /*[kAsyncDepth][blockDim]*/) {
   const int64_t step = blockDim.x;
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
-  int64_t r = threadIdx.x;
-  for (; r + 7 * step < len; r += 8 * step) {
-    const double m0 = col[r], m1 = col[r + step], m2 = col[r + 2 * step], m3 = col[r + 3 * step];
-    const double m4 = col[r + 4 * step], m5 = col[r + 5 * step], m6 = col[r + 6 * step], m7 = col[r + 7 * step];
-    a0 = fma(m0, v[r], a0);
-    a1 = fma(m1, v[r + step], a1);
-    a2 = fma(m2, v[r + 2 * step], a2);
-    a3 = fma(m3, v[r + 3 * step], a3);
-    a4 = fma(m4, v[r + 4 * step], a4);
-    a5 = fma(m5, v[r + 5 * step], a5);
-    a6 = fma(m6, v[r + 6 * step], a6);
-    a7 = fma(m7, v[r + 7 * step], a7);
-  }
-  if (r + 3 * step < len) {
-    const double m0 = col[r], m1 = col[r + step], m2 = col[r + 2 * step], m3 = col[r + 3 * step];
-    a0 = fma(m0, v[r], a0);
-    a1 = fma(m1, v[r + step], a1);
-    a2 = fma(m2, v[r + 2 * step], a2);
-    a3 = fma(m3, v[r + 3 * step], a3);
-    r += 4 * step;
-  }
-  if (r + step < len) {
-    const double m0 = col[r], m1 = col[r + step];
-    a4 = fma(m0, v[r], a4);
-    a5 = fma(m1, v[r + step], a5);
-    r += 2 * step;
-  }
-  if (r < len) a6 = fma(col[r], v[r], a6);
-  if (r + step < len) a7 = fma(col[r + step], v[r + step], a7);
-  return warp_sum(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
-}
-
-// Work split of the streaming phase: `cols` columns of `len` rows are cut into row chunks so
-// that there are about 8 equal units per warp (balanced tail) but no unit is shorter than 512
-// rows.  Partial sums of the (at most kMaxChunks) chunks are added in fixed order by the
-// consumer, so the result does not depend on the scheduling.
-constexpr int kMaxChunks = 16;
-__device__ __forceinline__ void chunk_plan(int64_t len, int64_t cols, int64_t nwarps, int& H, int64_t& L) {
-  int64_t h = cols > 0 ? (8 * nwarps) / cols : 1;
-  const int64_t hmax = (len + 511) / 512;
-  if (h > hmax) h = hmax;
-  if (h > kMaxChunks) h = kMaxChunks;
-  if (h < 1) h = 1;
-  L = ((len + h - 1) / h + 31) / 32 * 32;
-  if (L < 32) L = 32;
-  H = int((len + L - 1) / L);
-  if (H < 1) H = 1;
-}
-
-// out[j] = dot(M[:, j], x) over `rows` rows for up to three column sets sharing x.
-// `skip` (optional device flag): when *skip != 0 the kernel does nothing.
-static __global__ void __launch_bounds__(256)
-dots3_kernel(DotSeg s0, DotSeg s1, DotSeg s2, const double* __restrict__ x, int64_t rows,
-             const int* __restrict__ skip) {
-  if (skip && *skip) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  const int64_t total = s0.ncols + s1.ncols + s2.ncols;
-  for (int64_t j = warp; j < total; j += nwarps) {
-    const double* col;
-    double* out;
-    if (j < s0.ncols) {
-      col = s0.M + j * s0.ld;
-      out = s0.out + j;
-    } else if (j < s0.ncols + s1.ncols) {
-      int64_t jj = j - s0.ncols;
-      col = s1.M + jj * s1.ld;
-      out = s1.out + jj;
-    } else {
-      int64_t jj = j - s0.ncols - s1.ncols;
-      col = s2.M + jj * s2.ld;
-      out = s2.out + jj;
+  const int tid = threadIdx.x;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if ((((uintptr_t)col ^ (uintptr_t)v) & 8) == 0) {
+    const int64_t head = (((uintptr_t)col & 8) && len > 0) ? 1 : 0;
+    const int64_t npairs = (len - head) >> 1;
+    if (tid == 0 && head) a2 = col[0] * v[0];
+    if (tid == 1 && ((len - head) & 1)) a3 = col[len - 1] * v[len - 1];
+    const double2* c2 = reinterpret_cast<const double2*>(col + head);
+    const double2* v2 = reinterpret_cast<const double2*>(v + head);
+    const int64_t K = npairs > tid ? (npairs - tid + step - 1) / step : 0;
+#pragma unroll
+    for (int k = 0; k < kAsyncDepth; ++k) {
+      if (k < K) cp_async16(&slots[k * step + tid], &c2[tid + k * step]);
+      cp_async_commit();
     }
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    int64_t r = lane;
-    for (; r + 96 < rows; r += 128) {
-      double m0 = col[r], m1 = col[r + 32], m2 = col[r + 64], m3 = col[r + 96];
-      a0 = fma(m0, x[r], a0);
-      a1 = fma(m1, x[r + 32], a1);
-      a2 = fma(m2, x[r + 64], a2);
-      a3 = fma(m3, x[r + 96], a3);
+    for (int64_t k = 0; k < K; ++k) {
+      cp_async_wait<kAsyncDepth - 1>();
+      const int slot = int(k % kAsyncDepth);
+      const double2 m = slots[slot * step + tid];
+      const double2 x = v2[tid + k * step];
+      if (k & 1) {
+        a2 = fma(m.x, x.x, a2);
+        a3 = fma(m.y, x.y, a3);
+      } else {
+        a0 = fma(m.x, x.x, a0);
+        a1 = fma(m.y, x.y, a1);
+      }
+      if (k + kAsyncDepth < K) cp_async16(&slots[slot * step + tid], &c2[tid + (k + kAsyncDepth) * step]);
+      cp_async_commit();
     }
-    for (; r < rows; r += 32) a0 = fma(col[r], x[r], a0);
-    double s = warp_sum((a0 + a1) + (a2 + a3));
-    if (lane == 0) *out = s;
-  }
-}
-
-// Householder reflector (LAPACK DLARFG) for the vector [alpha; x] of length len stored
-// contiguously at v: on exit v[0] = 1, v[1:] = x / (alpha - beta), *beta_out = beta,
-// *tau_out = tau.  Single CTA.  `skip` as above.
-static __global__ void __launch_bounds__(1024)
-larfg_kernel(double* __restrict__ v, int64_t len, double* __restrict__ tau_out, double* __restrict__ beta_out,
-             const int* __restrict__ skip) {
-  if (skip && *skip) return;
-  __shared__ double sh[32];
-  double ss = 0.0;
-  for (int64_t r = 1 + threadIdx.x; r < len; r += blockDim.x) ss = fma(v[r], v[r], ss);
-  ss = block_sum(ss, sh);
-  const double alpha = v[0];
-  __syncthreads();
-  double tau, beta, scal;
-  if (len <= 1 || ss == 0.0) {
-    tau = 0.0;
-    beta = alpha;
-    scal = 0.0;
+    cp_async_wait<0>();
   } else {
-    const double xnorm = sqrt(ss);
-    beta = -copysign(hypot(alpha, xnorm), alpha);
-    tau = (beta - alpha) / beta;
-    scal = 1.0 / (alpha - beta);
+    int64_t r = tid;
+    for (; r + 3 * step < len; r += 4 * step) {
+      const double m0 = col[r], m1 = col[r + step], m2 = col[r + 2 * step], m3 = col[r + 3 * step];
+      a0 = fma(m0, v[r], a0);
+      a1 = fma(m1, v[r + step], a1);
+      a2 = fma(m2, v[r + 2 * step], a2);
+      a3 = fma(m3, v[r + 3 * step], a3);
+    }
+    for (; r < len; r += step) a0 = fma(col[r], v[r], a0);
   }
-  if (tau != 0.0)
-    for (int64_t r = 1 + threadIdx.x; r < len; r += blockDim.x) v[r] *= scal;
-  if (threadIdx.x == 0) {
-    v[0] = 1.0;
-    *tau_out = tau;
-    *beta_out = beta;
-  }
+  return warp_sum((a0 + a1) + (a2 + a3));
 }
 
 // T factor of a block reflector H = I - V T V^T (forward, columnwise; LAPACK DLARFT)
@@ -321,6 +190,8 @@ inline int build_t_factor(cublasHandle_t h, cudaStream_t st, const double* V, in
   TQ_LAUNCH_CHECK();
   return TQ_OK;
 }
+
+constexpr int kMaxChunks = 16;  // per-warp partial slots of the panel kernels (512 threads)
 
 inline unsigned dots_grid(int64_t ncols) {
   int64_t blocks = ceil_div(ncols, 8);  // 8 warps per 256-thread CTA
