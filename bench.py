@@ -205,6 +205,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
     torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()

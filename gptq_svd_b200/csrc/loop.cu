@@ -8,17 +8,41 @@
 //               by its dequantised value once quantised, so Wp ends as Q_final[:, perm]
 //   U   k x n   propagation factors U[c,j] = R[c,j]/R[c,c] (rounded as the reference
 //               rounds them, see prep_u_kernel)
-//   E   m x 128 per-block quantisation errors (the GEMM operand of the lazy update)
+//   E   m x 1024 quantisation errors of the current macro block (the GEMM operand of the lazy
+//       updates; TF32 hi / lo halves for the tcgen05 path)
 //   Cp  m x n   uint8 codes (permuted order), optional
 // Per block of 128 permuted columns: gptq_block_kernel (register-resident column loop,
 // one warp per 8 rows, lanes across columns, error broadcast by warp shuffle) then
-// trailing_update_kernel  W[:, c0+128:] -= E . U[c0:c0+128, c0+128:]  (strict-fp32 SIMT
-// GEMM; the tcgen05 3xTF32 variant lives in trailing_tc.cu).
+// the lazy trailing update  W[:, c0+128:] -= E . U[c0:c0+128, c0+128:]: a tcgen05 3xTF32
+// GEMM (trailing_tc.cu) by default, or the strict-fp32 SIMT GEMM below with
+// TQ_LOOP_STRICT_FP32 / when n is not a multiple of 4.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace tq {
 
+struct TrailingTc {
+  CUtensorMap ehi, elo, uhi, ulo;
+  uint32_t idesc;
+};
+int trailing_tc_prepare(TrailingTc* t, const float* E_hi, const float* E_lo, int64_t m, const float* UT_hi,
+                        const float* UT_lo, int64_t kpad, int64_t n);
+int trailing_tc_launch(const TrailingTc* t, float* C, int64_t ldc, int64_t m, int64_t N, int64_t e_col0,
+                       int64_t u_row0, int kcount, int64_t u_col0, cudaStream_t st);
+
+// x = hi + lo with hi, lo representable in TF32 (round to nearest): operands of the 3xTF32 update
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  const float rest = __fsub_rn(x, hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rest));
+  lo = __uint_as_float(l);
+}
+
 constexpr int kBlk = 128;        // columns per block step
+constexpr int kMacro = 1024;     // lazy-batch width of the far trailing update (the reference's block_size scale)
 constexpr int kRowsPerWarp = 8;  // rows interleaved per warp for ILP
 constexpr int kWarpsPerCta = 4;
 
@@ -86,6 +110,28 @@ __global__ void prep_u_kernel(const TR* __restrict__ R, int64_t ldr, int64_t k, 
   if (blockIdx.x == 0 && threadIdx.x == 0) dvec[c] = d;
 }
 
+// UT_hi / UT_lo (n x kpad, zero padded) = TF32 hi / lo split of U^T: the K-major B operand of
+// the tcgen05 trailing update.  32 x 32 tiles through shared memory, coalesced both ways.
+__global__ void split_transpose_u_kernel(const float* __restrict__ U, int64_t k, int64_t n, int64_t kpad,
+                                         float* __restrict__ UT_hi, float* __restrict__ UT_lo) {
+  __shared__ float t[32][33];
+  const int64_t c0 = int64_t(blockIdx.y) * 32, j0 = int64_t(blockIdx.x) * 32;
+  for (int a = threadIdx.y; a < 32; a += blockDim.y) {
+    const int64_t c = c0 + a, j = j0 + threadIdx.x;
+    t[a][threadIdx.x] = (c < k && j < n) ? U[c * n + j] : 0.f;
+  }
+  __syncthreads();
+  for (int a = threadIdx.y; a < 32; a += blockDim.y) {
+    const int64_t j = j0 + a, c = c0 + threadIdx.x;
+    if (j < n && c < kpad) {
+      float hi, lo;
+      split_tf32(t[threadIdx.x][a], hi, lo);
+      UT_hi[j * kpad + c] = hi;
+      UT_lo[j * kpad + c] = lo;
+    }
+  }
+}
+
 __global__ void perm_meta_kernel(const int64_t* __restrict__ perm, int64_t n, int g,
                                  int* __restrict__ invperm, int* __restrict__ gidx,
                                  int* __restrict__ bad) {
@@ -128,8 +174,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 gptq_block_kernel(float* __restrict__ Wp, int64_t n, const float* __restrict__ U,
                   const float* __restrict__ dvec, const float* __restrict__ scale,
                   const float* __restrict__ zero, int ng, const int* __restrict__ gidx, int64_t m,
-                  int64_t c0, int cnt, float min_q, float max_q, float* __restrict__ E,
-                  uint8_t* __restrict__ Cp) {
+                  int64_t c0, int cnt, float min_q, float max_q, float* __restrict__ E /* + column offset */,
+                  float* __restrict__ E_lo /* non-null: E receives the TF32 hi part */, uint8_t* __restrict__ Cp) {
   extern __shared__ float Us[];  // [kBlk][kBlk]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int idx = tid; idx < kBlk * kBlk; idx += blockDim.x) {
@@ -206,7 +252,15 @@ gptq_block_kernel(float* __restrict__ Wp, int64_t n, const float* __restrict__ U
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
       int col = 4 * lane + cc;
-      E[r * kBlk + col] = (col < cnt) ? eo[rr][cc] : 0.f;
+      const float ev = (col < cnt) ? eo[rr][cc] : 0.f;
+      if (E_lo) {
+        float hi, lo;
+        split_tf32(ev, hi, lo);
+        E[r * kMacro + col] = hi;
+        E_lo[r * kMacro + col] = lo;
+      } else {
+        E[r * kMacro + col] = ev;
+      }
       if (col < cnt) {
         Wp[r * n + c0 + col] = w[rr][cc];
         if (Cp) Cp[r * n + c0 + col] = uint8_t((code[rr] >> (8 * cc)) & 0xff);
@@ -352,7 +406,8 @@ extern "C" int tq_gptq_loop_workspace(int64_t m, int64_t n, int64_t k, size_t* b
   size_t b = 0;
   b += ws_bytes_for(size_t(m) * n, 4);     // Wp
   b += ws_bytes_for(size_t(k) * n, 4);     // U
-  b += ws_bytes_for(size_t(m) * kBlk, 4);  // E
+  b += ws_bytes_for(size_t(m) * kMacro, 4) * 2;  // E (hi), E_lo: m x 1024
+  b += ws_bytes_for(size_t(k + 4) * n, 4) * 2; // UT_hi, UT_lo
   b += ws_bytes_for(size_t(m) * n, 1);     // Cp
   b += ws_bytes_for(size_t(n), 4) * 2;     // invperm, gidx
   b += ws_bytes_for(size_t(k) + 1, 4);     // dvec
@@ -375,7 +430,11 @@ extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dt
              "tq_gptq_loop: leading dimension too small");
   TQ_REQUIRE(bits >= 2 && bits <= 8, "tq_gptq_loop: bits=%d outside [2,8]", bits);
   TQ_REQUIRE(r_dtype == TQ_F64 || r_dtype == TQ_F32, "tq_gptq_loop: R must be fp64 or fp32");
+  const bool strict_fp32 = (semantics & TQ_LOOP_STRICT_FP32) != 0;
+  semantics &= ~TQ_LOOP_STRICT_FP32;
   TQ_REQUIRE(semantics == TQ_LOOP_TRITON || semantics == TQ_LOOP_TORCH, "tq_gptq_loop: bad semantics");
+  // the tcgen05 path needs 16-byte row strides for TMA; other shapes take the SIMT fp32 GEMM
+  const bool use_tc = !strict_fp32 && k > 0;
   TQ_REQUIRE(ref_block > 0, "tq_gptq_loop: ref_block must be positive");
   int64_t g = group > 0 ? group : n;
   TQ_REQUIRE(n % g == 0, "tq_gptq_loop: in_features %lld not divisible by group size %lld",
@@ -386,7 +445,11 @@ extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dt
   Workspace wsp(ws, ws_bytes);
   float* Wp = wsp.take<float>(size_t(m) * n);
   float* U = wsp.take<float>(size_t(k) * n);
-  float* E = wsp.take<float>(size_t(m) * kBlk);
+  float* E = wsp.take<float>(size_t(m) * kMacro);
+  float* E_lo = wsp.take<float>(size_t(m) * kMacro);
+  const int64_t kpad = (k + 3) / 4 * 4;
+  float* U_hi = wsp.take<float>(size_t(kpad) * n);   // U^T hi / lo, n x kpad
+  float* U_lo = wsp.take<float>(size_t(kpad) * n);
   uint8_t* Cp = wsp.take<uint8_t>(size_t(m) * n);
   int* invperm = wsp.take<int>(n);
   int* gidx = wsp.take<int>(n);
@@ -416,6 +479,11 @@ extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dt
     else
       prep_u_kernel<float><<<grid, 256, 0, st>>>((const float*)R, ldr, k, n, ref_block, semantics, U, dvec);
     TQ_LAUNCH_CHECK();
+    if (use_tc) {
+      dim3 tg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(kpad, 32));
+      split_transpose_u_kernel<<<tg, dim3(32, 8), 0, st>>>(U, k, n, kpad, U_hi, U_lo);
+      TQ_LAUNCH_CHECK();
+    }
   }
 
   const size_t smem = size_t(kBlk) * kBlk * sizeof(float);
@@ -427,23 +495,37 @@ extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dt
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
+  TrailingTc tc;
+  if (use_tc) TQ_TRY(trailing_tc_prepare(&tc, E, E_lo, m, U_hi, U_lo, kpad, n));
+  TQ_CUDA_CHECK(cudaMemsetAsync(E, 0, sizeof(float) * size_t(m) * kMacro * 2, st));   // E and E_lo are adjacent
   const unsigned row_ctas = (unsigned)ceil_div(m, kRowsPerWarp * kWarpsPerCta);
-  for (int64_t c0 = 0; c0 < k; c0 += kBlk) {
-    int cnt = int(imin(kBlk, k - c0));
-    if (semantics == TQ_LOOP_TRITON)
-      gptq_block_kernel<TQ_LOOP_TRITON><<<row_ctas, kWarpsPerCta * 32, smem, st>>>(
-          Wp, n, U, dvec, scale, zero, ng, gidx, m, c0, cnt, min_q, max_q, E, Cp);
-    else
-      gptq_block_kernel<TQ_LOOP_TORCH><<<row_ctas, kWarpsPerCta * 32, smem, st>>>(
-          Wp, n, U, dvec, scale, zero, ng, gidx, m, c0, cnt, min_q, max_q, E, Cp);
+  // Two-level lazy batching: 128-column block steps update only the rest of their 1024-column
+  // macro block (K = 128); the far columns are updated once per macro block with K = 1024.
+  auto trailing = [&](int64_t j0, int64_t N, int64_t e_col0, int64_t u_row0, int kcount) -> int {
+    if (N <= 0 || kcount <= 0) return TQ_OK;
+    if (use_tc) return trailing_tc_launch(&tc, Wp + j0, n, m, N, e_col0, u_row0, kcount, j0, st);
+    dim3 grid((unsigned)ceil_div(N, kTN), (unsigned)ceil_div(m, kTM));
+    trailing_update_kernel<<<grid, 256, 0, st>>>(Wp + j0, n, E + e_col0, kMacro, U + u_row0 * n + j0, n, m, N, kcount);
     TQ_LAUNCH_CHECK();
-    int64_t j0 = c0 + cnt;
-    if (j0 < n) {
-      int64_t N = n - j0;
-      dim3 grid((unsigned)ceil_div(N, kTN), (unsigned)ceil_div(m, kTM));
-      trailing_update_kernel<<<grid, 256, 0, st>>>(Wp + j0, n, E, kBlk, U + c0 * n + j0, n, m, N, cnt);
+    return TQ_OK;
+  };
+  for (int64_t M0 = 0; M0 < k; M0 += kMacro) {
+    const int64_t M1 = imin(M0 + kMacro, k);
+    for (int64_t c0 = M0; c0 < M1; c0 += kBlk) {
+      const int cnt = int(imin(kBlk, M1 - c0));
+      float* Eb = E + (c0 - M0);
+      float* Elb = use_tc ? E_lo + (c0 - M0) : nullptr;
+      if (semantics == TQ_LOOP_TRITON)
+        gptq_block_kernel<TQ_LOOP_TRITON><<<row_ctas, kWarpsPerCta * 32, smem, st>>>(
+            Wp, n, U, dvec, scale, zero, ng, gidx, m, c0, cnt, min_q, max_q, Eb, Elb, Cp);
+      else
+        gptq_block_kernel<TQ_LOOP_TORCH><<<row_ctas, kWarpsPerCta * 32, smem, st>>>(
+            Wp, n, U, dvec, scale, zero, ng, gidx, m, c0, cnt, min_q, max_q, Eb, Elb, Cp);
       TQ_LAUNCH_CHECK();
+      const int64_t j0 = c0 + cnt;
+      TQ_TRY(trailing(j0, M1 - j0, c0 - M0, c0, cnt));                 // rest of the macro block
     }
+    TQ_TRY(trailing(M1, n - M1, 0, M0, int(M1 - M0)));                 // everything beyond it
   }
   if (k < n) {
     dim3 grid((unsigned)imin(ceil_div(n - k, 256), 64), (unsigned)m);

@@ -246,10 +246,17 @@ class QuantizedLinear:
     rel_error: Optional[float] = None
 
 
+# Lazy trailing update W[:, i2:] -= E @ U: tcgen05 3xTF32 GEMM by default; set to True for the
+# strict-fp32 SIMT GEMM (the reference runs this product with TF32 disabled, gptq_utils.py:474-475).
+TRAILING_STRICT_FP32 = False
+
+
 def gptq_quantize(weight_mat: torch.Tensor, H_inv_sqrt: torch.Tensor, quantizer: Quantizer, perm: torch.Tensor,
                   block_size: int = 128, use_triton: bool = True, R_x: Optional[torch.Tensor] = None,
-                  want_codes: bool = True) -> QuantizedLinear:
+                  want_codes: bool = True, strict_fp32: Optional[bool] = None) -> QuantizedLinear:
     """gptq_fwrd plus the integer codes and grid parameters."""
+    if strict_fp32 is None:
+        strict_fp32 = TRAILING_STRICT_FP32
     _require_cuda(weight_mat, "gptq_fwrd")
     lib = _lib.load()
     m, n = weight_mat.shape
@@ -279,7 +286,8 @@ def gptq_quantize(weight_mat: torch.Tensor, H_inv_sqrt: torch.Tensor, quantizer:
         check(lib.tq_gptq_loop(_ptr(W32), W32.stride(0), _ptr(R), _DTYPE_CODE[R.dtype], R.stride(0) if k else n,
                                k, _ptr(p64), _ptr(quantizer.scale), _ptr(quantizer.zero), m, n, quantizer.w_bits,
                                quantizer.group_size, int(quantizer.sym), int(block_size),
-                               _lib.TQ_LOOP_TRITON if use_triton else _lib.TQ_LOOP_TORCH, _ptr(out), out.stride(0),
+                               (_lib.TQ_LOOP_TRITON if use_triton else _lib.TQ_LOOP_TORCH)
+                               | (_lib.TQ_LOOP_STRICT_FP32 if strict_fp32 else 0), _ptr(out), out.stride(0),
                                _ptr(codes), n, _ptr(ws), ws.numel(), _stream(W32)), "tq_gptq_loop")
     rel = None
     if R_x is not None:

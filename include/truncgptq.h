@@ -57,6 +57,10 @@ extern "C" {
 /* loop arithmetic (gptq_utils.py:507-534) */
 #define TQ_LOOP_TRITON 0 /* Triton kernel semantics: half-up, un-scaled error (:345-386) */
 #define TQ_LOOP_TORCH 1  /* torch fallback semantics: half-even, error / diag (:516-534)  */
+/* OR-ed into `semantics`: run the lazy trailing update as a strict-fp32 SIMT GEMM instead of
+ * the default tcgen05 3xTF32 GEMM (both meet the 99.9 % code-parity bar; the reference runs
+ * this product in fp32 with TF32 disabled, :474-475). */
+#define TQ_LOOP_STRICT_FP32 0x100
 
 int tq_version(void);
 const char* tq_last_error(void);

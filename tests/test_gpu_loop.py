@@ -18,21 +18,26 @@ def G():
     return G
 
 
-def _run(G, W, R, perm, bits, group, sym, block, use_triton, R_x=None):
+def _run(G, W, R, perm, bits, group, sym, block, use_triton, R_x=None, strict=False):
     from gpu_common import to_gpu
     q = G.Quantizer(bits, group, sym)
     res = G.gptq_quantize(to_gpu(W), to_gpu(R), q, to_gpu(perm), block_size=block,
-                          use_triton=use_triton, R_x=None if R_x is None else to_gpu(R_x))
+                          use_triton=use_triton, R_x=None if R_x is None else to_gpu(R_x), strict_fp32=strict)
     torch.cuda.synchronize()
     return q, res
 
 
+# trailing update: tcgen05 3xTF32 GEMM (default product path) and the strict-fp32 SIMT GEMM
+TRAILING = [pytest.param(False, id="tcgen05_3xtf32"), pytest.param(True, id="simt_fp32")]
+
+
+@pytest.mark.parametrize("strict", TRAILING)
 @pytest.mark.parametrize("name", golden_cases())
 @pytest.mark.parametrize("tag", ["triton", "torch"])
-def test_loop_vs_reference_golden(G, name, tag, golden):
+def test_loop_vs_reference_golden(G, name, tag, strict, golden):
     g = golden(name)
     bits, group, sym, block = int(g["bits"]), int(g["group"]), bool(g["sym"]), int(g["block"])
-    q, res = _run(G, g["W"], g["R"], g["perm"], bits, group, sym, block, tag == "triton", g["R_x"])
+    q, res = _run(G, g["W"], g["R"], g["perm"], bits, group, sym, block, tag == "triton", g["R_x"], strict)
     assert res.rank == int(g["k"])
     assert np.array_equal(q.scale.cpu().numpy(), g["scale"])      # bit-exact grid
     assert np.array_equal(q.zero.cpu().numpy(), g["zero"])
@@ -52,7 +57,8 @@ def test_loop_vs_reference_golden(G, name, tag, golden):
     (520, 384, 3, 128, False, 1e-6),       # ragged rows
     (257, 256, 2, -1, False, 1e-3),        # per-channel groups, odd row count
 ])
-def test_loop_vs_oracle(G, m, n, bits, group, sym, eps):
+@pytest.mark.parametrize("strict", TRAILING)
+def test_loop_vs_oracle(G, m, n, bits, group, sym, eps, strict):
     X = O.make_activations(8192, n, seed=7 * n + m, dist="llm").astype(np.float64)
     H = X.T @ X / X.shape[0]
     f = O.process_hessian_alt(H, eps, "energy")
@@ -60,7 +66,8 @@ def test_loop_vs_oracle(G, m, n, bits, group, sym, eps):
     oq = O.Quantizer(bits, group, sym)
     fw_o, k, codes_o = O.gptq_fwrd(W, f.R, oq, f.perm, block_size=1024, use_triton=True, fma=True,
                                    return_codes=True)
-    q, res = _run(G, W, f.R, f.perm, bits, group, sym, 1024, True, f.R_x)
+    q, res = _run(G, W, f.R, f.perm, bits, group, sym, 1024, True, f.R_x, strict)
+    print(f"codes identical to the oracle: {np.mean((res.codes.cpu().numpy().astype(np.int32) + res.min_q) == codes_o):.5%}")
     assert res.rank == k
     assert np.array_equal(q.scale.cpu().numpy(), oq.scale)
     assert np.array_equal(q.zero.cpu().numpy(), oq.zero)
@@ -132,3 +139,8 @@ def test_full_size_properties(G):
     # deterministic
     c = G.gptq_quantize(W, R, G.Quantizer(4, 128, True), perm, block_size=1024)
     assert torch.equal(a.codes, c.codes)
+    # tcgen05 3xTF32 trailing update vs strict-fp32 SIMT trailing update: >= 99.9 % identical codes
+    d = G.gptq_quantize(W, R, G.Quantizer(4, 128, True), perm, block_size=1024, strict_fp32=True)
+    same = float((a.codes == d.codes).float().mean())
+    print(f"tcgen05 3xTF32 vs strict fp32 trailing update: {same:.5%} identical codes")
+    assert same >= 0.999
