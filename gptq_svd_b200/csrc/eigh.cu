@@ -26,23 +26,34 @@ constexpr int kOrmNb = 64;   // back-transform block
 
 
 // ----------------------------------------------------------------------- persistent panel
-// One cooperative launch factors a whole panel of up to kTrdNb columns.  The per-column
-// phases are separated by two grid-wide barriers (grid_barrier) instead of kernel launches:
-//   A  column update A[c:, c] -= V W[c,:]^T + W V[c,:]^T (own rows), partial sum of squares,
-//      d[c]                                                                      | barrier
-//   B  Householder scalars (every CTA, same order).  One CTA per trailing column streams it
-//      against the RAW column u = [alpha; x]; since v = [1; scl x], the per-warp partial is
-//      fixed up as  scl * p + col[0] (1 - scl alpha)  by the warp that owns row 0.  Per-warp
-//      partials of y = A22 v, W^T v, V^T v go to ypart/tmppart (no block barrier while
-//      streaming); v^T y is accumulated on the fly                               | barrier
-//   C  v scaled in place (own rows), w = tau (y - V W^T v - W V^T v) - tau/2 (w.v) v with
-//      w.v = tau (v^T y - 2 (W^T v).(V^T v)) known without another reduction.
+// One cooperative launch (one CTA of 1024 threads per SM) factors a whole panel of up to
+// kTrdNb columns.  The per-column phases are separated by grid-wide barriers (grid_barrier)
+// instead of kernel launches:
+//   A   column update A[c:, c] -= V W[c,:]^T + W V[c,:]^T (own rows), partial sum of squares,
+//       d[c]                                                                      | barrier
+//   B   Householder scalars (every CTA, same order), then y = A22 v streamed against the RAW
+//       column u = [alpha; x] (v = scl u + (1 - scl alpha) e_1 is fixed up afterwards):
+//       * symmetric path (2048 <= len <= 12288, even n): each trailing column is read ONLY
+//         from its diagonal down (half the HBM traffic).  Element A[r,g] contributes
+//         A[r,g] u[r] to the dot of column g (per-warp partials) and A[r,g] u[g] to y[r];
+//         the second kind is accumulated in registers - every thread owns fixed row pairs -
+//         and written once per CTA to ypriv.  cp.async stages the whole column slice.
+//       * full path (small or odd sizes): one CTA per full column, per-warp partials.
+//       The panel columns W^T v and V^T v always take the full path.               | barrier
+//   B2  (symmetric path only) y[r] = sum over CTAs and warps of the partials, 8 lanes per
+//       row in fixed order; v^T y partials                                         | barrier
+//   C   v scaled in place (own rows), w = tau (y - V W^T v - W V^T v) - tau/2 (w.v) v with
+//       w.v = tau (v^T y - 2 (W^T v).(V^T v)) known without another reduction.
 // Row r is always handled by the same thread (r = global thread id + q * total threads), so
 // values a thread wrote for its own rows need no barrier before it reads them again; the one
 // foreign value the next column update needs, W[c+1, i], is recomputed by every CTA.
-constexpr int kPanelThreads = 512;
+constexpr int kPanelThreads = 1024;
 constexpr int kPanelWarps = kPanelThreads / 32;
-constexpr size_t kPanelSmem = size_t(kAsyncDepth) * kPanelThreads * sizeof(double2);
+constexpr int kSymPairs = 6;                       // 16-byte row pairs per thread on the symmetric path
+constexpr int64_t kSymMaxLen = int64_t(kSymPairs) * kPanelThreads * 2;
+constexpr int64_t kSymMinLen = 2048;
+constexpr int kPanelDepth = (kAsyncDepth > kSymPairs) ? kAsyncDepth : kSymPairs;
+constexpr size_t kPanelSmem = size_t(kPanelDepth) * kPanelThreads * sizeof(double2);
 
 struct TrdPanelArgs {
   double* A;
@@ -53,8 +64,10 @@ struct TrdPanelArgs {
   double* d;
   double* e;
   double* tau;
-  double* ypart;   // kPanelWarps x n          per-warp partials of y = A22 v
+  double* ypart;   // kPanelWarps x n          per-warp partials of the column dots
   double* tmppart; // kPanelWarps x 2 kTrdNb   per-warp partials of W^T v | V^T v
+  double* ypriv;   // gridDim.x x n            per-CTA partials of the symmetric path
+  double* ysum;    // n                        y of the symmetric path
   double* part;    // 2 x gridDim.x
   double* scal;    // scalar scratch; [8..15] phase cycle counters when tracing
   unsigned int* bar;
@@ -67,18 +80,20 @@ __device__ __forceinline__ double grid_total(const double* part, int nb, double*
   return block_sum(v, sh);
 }
 
-__global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelArgs a) {
-  extern __shared__ double2 dot_slots[];   // [kAsyncDepth][blockDim] cp.async staging of the streamed column
+__global__ void __launch_bounds__(kPanelThreads, 1) sytrd_panel_kernel(TrdPanelArgs a) {
+  extern __shared__ double2 dot_slots[];   // cp.async staging of the streamed columns
   __shared__ double sh[32];
   __shared__ double tmps[2 * kTrdNb];
   __shared__ double wrow_s;          // W[c, i-1], computed locally at the end of the previous column
   double* const A = a.A;
   double* const W = a.W;
   const int64_t n = a.n, lda = a.n, ldw = a.n, j0 = a.j0;
+  const int tid = threadIdx.x;
   const int64_t gt = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
   const unsigned int nb = gridDim.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t gwarp = gt >> 5, nwarps = nthreads >> 5;
   double* part1 = a.part;
   double* part2 = a.part + nb;
   unsigned int bar_target = 0;
@@ -142,21 +157,100 @@ __global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelA
       scl = 1.0 / (alpha - beta);
     }
     const double fix = 1.0 - scl * alpha;
-    const double* u = A + (c + 1) + c * lda;       // raw column [alpha; x]
-    double vy = 0.0;                               // lane 0 of each warp: sum_j v_j * (this warp's partial of y_j)
-    {
+    const int64_t base = c + 1;
+    const double* ucol = A + c * lda;              // raw reflector by GLOBAL row: u[g] = ucol[g], g >= base
+    const double* u = ucol + base;                 // raw column [alpha; x]
+    const bool sym = (len >= kSymMinLen) && (len <= kSymMaxLen) && ((n & 1) == 0);
+    double vy = 0.0;                               // partial of v^T y (full path: lane 0 of each warp)
+    if (sym) {
+      const int64_t Pbase = base >> 1, Plast = (n - 1) >> 1;
+      double2 yacc[kSymPairs];
+#pragma unroll
+      for (int k = 0; k < kSymPairs; ++k) yacc[k] = make_double2(0.0, 0.0);
+      for (int64_t j = blockIdx.x; j < len; j += gridDim.x) {
+        const int64_t g = base + j;
+        const int64_t Pg = g >> 1;
+        const double* col = A + g * lda;
+        const double ug = ucol[g];
+#pragma unroll
+        for (int k = 0; k < kSymPairs; ++k) {
+          const int64_t P = Pbase + tid + int64_t(k) * kPanelThreads;
+          if (P >= Pg && P <= Plast) cp_async16(&dot_slots[k * kPanelThreads + tid], col + 2 * P);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        double dsum = 0.0;
+#pragma unroll
+        for (int k = 0; k < kSymPairs; ++k) {
+          const int64_t P = Pbase + tid + int64_t(k) * kPanelThreads;
+          if (P >= Pg && P <= Plast) {
+            const double2 m = dot_slots[k * kPanelThreads + tid];
+            const int64_t r0 = 2 * P, r1 = r0 + 1;
+            if (r0 >= g) {                       // r0 == g - 1 only for the pair that straddles the diagonal
+              dsum = fma(m.x, ucol[r0], dsum);
+              if (r0 > g) yacc[k].x = fma(m.x, ug, yacc[k].x);
+            }
+            dsum = fma(m.y, ucol[r1], dsum);
+            if (r1 > g) yacc[k].y = fma(m.y, ug, yacc[k].y);
+          }
+        }
+        dsum = warp_sum(dsum);
+        if (lane == 0) a.ypart[int64_t(wid) * n + g] = dsum;
+      }
+#pragma unroll
+      for (int k = 0; k < kSymPairs; ++k) {
+        const int64_t P = Pbase + tid + int64_t(k) * kPanelThreads;
+        if (P <= Plast) *reinterpret_cast<double2*>(a.ypriv + int64_t(blockIdx.x) * n + 2 * P) = yacc[k];
+      }
+      // panel columns (full length)
+      for (int64_t j = blockIdx.x; j < 2 * i; j += gridDim.x) {
+        const double* col = (j < i) ? W + base + j * ldw : A + base + (j0 + (j - i)) * lda;
+        double* out = a.tmppart + wid * (2 * kTrdNb) + ((j < i) ? j : kTrdNb + (j - i));
+        double p = scl * cta_strided_warp_dot(col, u, len, dot_slots);
+        if (lane == 0) {
+          if (wid == 0) p = fma(col[0], fix, p);
+          *out = p;
+        }
+      }
+      TQ_PHASE(2)
+      grid_barrier(a.bar, bar_target, nb);
+      TQ_PHASE(3)
+      // ---------------- B2: y[g] = scl * (sum of partials) + fix * A[g, base]; 8 lanes per row
+      {
+        const int rsel = lane >> 3, sub = lane & 7;
+        const int64_t ntask = (len + 3) >> 2;
+        for (int64_t wt = gwarp; wt < ntask; wt += nwarps) {
+          const int64_t g = base + 4 * wt + rsel;
+          double s = 0.0;
+          if (g < n) {
+            for (unsigned int b = sub; b < nb; b += 8) s += a.ypriv[int64_t(b) * n + g];
+            for (int w = sub; w < kPanelWarps; w += 8) s += a.ypart[int64_t(w) * n + g];
+          }
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          if (sub == 0 && g < n) {
+            const double y = fma(scl, s, fix * A[g + base * lda]);
+            a.ysum[g] = y;
+            vy = fma(y, (g == base) ? 1.0 : scl * ucol[g], vy);
+          }
+        }
+      }
+      vy = block_sum(vy, sh);
+      if (threadIdx.x == 0) part2[blockIdx.x] = vy;
+    } else {
       const int64_t total = len + 2 * i;
       for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
         const double* col;
         double* out;
         if (j < len) {
-          col = A + (c + 1) + (c + 1 + j) * lda;
-          out = a.ypart + int64_t(wid) * n + (c + 1 + j);
+          col = A + base + (base + j) * lda;
+          out = a.ypart + int64_t(wid) * n + (base + j);
         } else if (j < len + i) {
-          col = W + (c + 1) + (j - len) * ldw;
+          col = W + base + (j - len) * ldw;
           out = a.tmppart + wid * (2 * kTrdNb) + (j - len);
         } else {
-          col = A + (c + 1) + (j0 + (j - len - i)) * lda;
+          col = A + base + (j0 + (j - len - i)) * lda;
           out = a.tmppart + wid * (2 * kTrdNb) + kTrdNb + (j - len - i);
         }
         double p = scl * cta_strided_warp_dot(col, u, len, dot_slots);
@@ -166,10 +260,10 @@ __global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelA
           if (j < len) vy = fma(p, (j == 0) ? 1.0 : scl * u[j], vy);
         }
       }
+      vy = block_sum(lane == 0 ? vy : 0.0, sh);
+      if (threadIdx.x == 0) part2[blockIdx.x] = vy;
+      TQ_PHASE(2)
     }
-    vy = block_sum(lane == 0 ? vy : 0.0, sh);
-    if (threadIdx.x == 0) part2[blockIdx.x] = vy;
-    TQ_PHASE(2)
     grid_barrier(a.bar, bar_target, nb);
     TQ_PHASE(3)
     // ---------------- C
@@ -189,7 +283,11 @@ __global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelA
       const double vr = (r == c + 1) ? 1.0 : scl * A[r + c * lda];
       A[r + c * lda] = vr;
       double y = 0.0;
-      for (int w = 0; w < kPanelWarps; ++w) y += a.ypart[int64_t(w) * n + r];
+      if (sym) {
+        y = a.ysum[r];
+      } else {
+        for (int w = 0; w < kPanelWarps; ++w) y += a.ypart[int64_t(w) * n + r];
+      }
       double s0 = 0.0, s1 = 0.0;
       for (int t = 0; t < i; ++t) {
         s0 = fma(A[r + (j0 + t) * lda], tmps[t], s0);
@@ -204,7 +302,11 @@ __global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelA
     if (threadIdx.x == 0) {            // W[c+1, i] for the next column update (v[c+1] = 1)
       const int64_t r = c + 1;
       double y = 0.0;
-      for (int w = 0; w < kPanelWarps; ++w) y += a.ypart[int64_t(w) * n + r];
+      if (sym) {
+        y = a.ysum[r];
+      } else {
+        for (int w = 0; w < kPanelWarps; ++w) y += a.ypart[int64_t(w) * n + r];
+      }
       double s0 = 0.0, s1 = 0.0;
       for (int t = 0; t < i; ++t) {
         s0 = fma(A[r + (j0 + t) * lda], tmps[t], s0);
@@ -222,8 +324,8 @@ __global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelA
 // d[0:n], e[0:n-1], tau[0:n-1]; reflector c lives in A[c+1:, c] with an explicit unit at
 // A[c+1, c].
 static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double* d, double* e, double* tau,
-                       double* W, double* y /*16 n*/, double* tmp /*16*2*kTrdNb*/, double* part /*2*1024*/, double* scal /*8*/,
-                       unsigned int* bar) {
+                       double* W, double* y /*32 n*/, double* tmp /*32*2*kTrdNb*/, double* ypriv /*SMs x n*/,
+                       double* ysum /*n*/, double* part /*2*1024*/, double* scal /*16*/, unsigned int* bar) {
   const int64_t lda = n, ldw = n;
   const double one = 1.0, mone = -1.0;
   TQ_CUDA_CHECK(cudaMemsetAsync(tau, 0, sizeof(double) * n, st));
@@ -240,13 +342,13 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
       set_error("sytrd: panel kernel cannot be made resident");
       return TQ_ERR_CUDA;
     }
-    coop_blocks = num_sms() * (per_sm > 2 ? 2 : per_sm);
+    coop_blocks = int(imin(num_sms(), 160));   // ypriv holds 160 per-CTA partial vectors
   }
   for (int64_t j0 = 0; j0 < n; j0 += kTrdNb) {
     const int jb = int(imin(kTrdNb, n - j0));
     {
       TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
-      TrdPanelArgs pa{A, n, j0, jb, W, d, e, tau, y, tmp, part, scal, bar, trace_enabled() ? 1 : 0};
+      TrdPanelArgs pa{A, n, j0, jb, W, d, e, tau, y, tmp, ypriv, ysum, part, scal, bar, trace_enabled() ? 1 : 0};
       void* kargs[] = {&pa};
       double bytes = 0.0;      // algorithmic bytes of the panel: every column streams the trailing matrix once
       for (int i = 0; i < jb; ++i) {
@@ -896,7 +998,7 @@ __global__ void copy_sym_kernel(const double* __restrict__ H, int64_t ldh, int64
 size_t eigh_ws_bytes(int64_t n) {
   size_t b = 0;
   b += ws_bytes_for(size_t(n) * n, 8) * 4;                 // A, Zg, Zo, U
-  b += ws_bytes_for(n, 8) * (12 + kMaxChunks) + ws_bytes_for(2 * kTrdNb * kMaxChunks, 8) + ws_bytes_for(n, 4) * 8 + ws_bytes_for(n, sizeof(DcRot));
+  b += ws_bytes_for(n, 8) * (14 + 32 + 160) + ws_bytes_for(2 * kTrdNb * 32, 8) + ws_bytes_for(n, 4) * 8 + ws_bytes_for(n, sizeof(DcRot));
   b += ws_bytes_for(size_t(n) * kTrdNb, 8) * 2;            // W, Vc
   b += ws_bytes_for(size_t(kOrmNb) * n, 8) * 2;            // w1, w2
   b += ws_bytes_for(kTrdNb * kTrdNb, 8) * 2 + ws_bytes_for(4 * kTrdNb, 8);
@@ -909,9 +1011,11 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   double* A = ws.take<double>(size_t(n) * n);
   double* e = ws.take<double>(n);
   double* tau = ws.take<double>(n);
-  double* y = ws.take<double>(size_t(n) * kMaxChunks);
+  double* y = ws.take<double>(size_t(n) * kPanelWarps);
+  double* ypriv = ws.take<double>(size_t(n) * 160);
+  double* ysum = ws.take<double>(n);
   double* W = ws.take<double>(size_t(n) * kTrdNb);
-  double* tmp = ws.take<double>(2 * kTrdNb * kMaxChunks);
+  double* tmp = ws.take<double>(2 * kTrdNb * kPanelWarps);
   double* part = ws.take<double>(2048);
   double* scal = ws.take<double>(16);
   unsigned int* bar = ws.take<unsigned int>(4);
@@ -926,12 +1030,12 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   TQ_LAUNCH_CHECK();
   {
     StageTimer tm(st, "sytrd");
-    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, part, scal, bar));
+    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, ypriv, ysum, part, scal, bar));
     if (trace_enabled()) {
       double hc[16];
       cudaMemcpyAsync(hc, scal, sizeof(hc), cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
-      fprintf(stderr, "[tq-trace] sytrd phase Mcycles (CTA 0): A %.1f  barrier1 %.1f  B(stream) %.1f  barrier2 %.1f  C %.1f\n",
+      fprintf(stderr, "[tq-trace] sytrd phase Mcycles (CTA 0): A %.1f  barrier1 %.1f  B(stream) %.1f  barrier2(+B2) %.1f  C %.1f\n",
               hc[8] * 1e-6, hc[9] * 1e-6, hc[10] * 1e-6, hc[11] * 1e-6, hc[12] * 1e-6);
     }
   }

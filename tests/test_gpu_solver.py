@@ -157,3 +157,17 @@ def test_solver_invariants_medium(G, n, eps):
     if n == 1024:
         fo = O.process_hessian_alt(H, eps, "energy")
         assert np.array_equal(P[:k], fo.perm[:k])
+
+
+@pytest.mark.parametrize("n", [2304, 4096])
+def test_eigh_large_symmetric_path(S, n):
+    """Sizes where the tridiagonal reduction streams only the lower triangle (len >= 2048)."""
+    torch.manual_seed(n)
+    X = torch.randn(2 * n, n, device="cuda", dtype=torch.float64) * torch.logspace(0, -3, n, device="cuda", dtype=torch.float64)
+    H = X.T @ X / X.shape[0]
+    w, V = S.eigh(H)
+    wr = torch.linalg.eigvalsh(H)
+    scale = float(wr.abs().max())
+    assert float((w - wr).abs().max()) <= 1e-12 * scale * n ** 0.5
+    assert float(torch.linalg.norm(H @ V - V * w[None, :])) <= 1e-12 * float(torch.linalg.norm(H)) * n ** 0.5
+    assert float(torch.linalg.norm(V.T @ V - torch.eye(n, device="cuda", dtype=torch.float64))) <= 1e-12 * n
