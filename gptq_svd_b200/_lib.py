@@ -16,6 +16,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "truncgptq.h")
 
 TQ_F16, TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2, 3
 TQ_RANK_ENERGY, TQ_RANK_MEAN_TRIMMED, TQ_RANK_FULL = 0, 1, 2
+TQ_SOLVE_HOUSEHOLDER_QRCP = 0x100
 TQ_LOOP_TRITON, TQ_LOOP_TORCH = 0, 1
 TQ_LOOP_STRICT_FP32 = 0x100
 

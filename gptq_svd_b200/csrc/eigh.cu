@@ -52,7 +52,9 @@ constexpr int kPanelWarps = kPanelThreads / 32;
 constexpr int kSymPairs = 6;                       // 16-byte row pairs per thread on the symmetric path
 constexpr int64_t kSymMaxLen = int64_t(kSymPairs) * kPanelThreads * 2;
 constexpr int64_t kSymMinLen = 2048;
-constexpr int kPanelDepth = (kAsyncDepth > kSymPairs) ? kAsyncDepth : kSymPairs;
+constexpr int kPiecePairs = 2 * kPanelThreads;      // pairs per piece: two per thread (4096 rows)
+constexpr int kRing = 6;                           // pieces in flight per CTA (6 x 32 KB)
+constexpr int kPanelDepth = (kAsyncDepth > 2 * kRing) ? kAsyncDepth : 2 * kRing;
 constexpr size_t kPanelSmem = size_t(kPanelDepth) * kPanelThreads * sizeof(double2);
 
 struct TrdPanelArgs {
@@ -167,39 +169,79 @@ __global__ void __launch_bounds__(kPanelThreads, 1) sytrd_panel_kernel(TrdPanelA
       double2 yacc[kSymPairs];
 #pragma unroll
       for (int k = 0; k < kSymPairs; ++k) yacc[k] = make_double2(0.0, 0.0);
+      // The CTA's columns are cut into pieces of kPieceRows rows (two 16-byte pairs per thread);
+      // the pieces of all its columns form one stream that runs through a kRing-deep cp.async
+      // ring (192 KB in flight per SM), so the pipeline never drains at a column boundary.
+      const int Q = int((Plast - Pbase + kPiecePairs) / kPiecePairs);            // pieces per full column
+      auto first_piece = [&](int64_t jj) { return int((((base + jj) >> 1) - Pbase) / kPiecePairs); };
+      auto issue = [&](int64_t jj, int q, int slot) {
+        if (jj < len) {
+          const int64_t gg = base + jj;
+          const int64_t Pgg = gg >> 1;
+          const double* colp = A + gg * lda;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int64_t P = Pbase + int64_t(q) * kPiecePairs + e * kPanelThreads + tid;
+            if (P >= Pgg && P <= Plast) cp_async16(&dot_slots[(slot * 2 + e) * kPanelThreads + tid], colp + 2 * P);
+          }
+        }
+        cp_async_commit();
+      };
+      int64_t ij = blockIdx.x;                      // issue iterator (column, piece)
+      int iq = (ij < len) ? first_piece(ij) : 0;
+      auto advance_issue = [&]() {
+        if (ij >= len) return;
+        if (++iq >= Q) {
+          ij += gridDim.x;
+          iq = (ij < len) ? first_piece(ij) : 0;
+        }
+      };
+#pragma unroll 1
+      for (int sl = 0; sl < kRing; ++sl) {
+        issue(ij, iq, sl);
+        advance_issue();
+      }
+      int slot = 0;
+      double dsum = 0.0;
       for (int64_t j = blockIdx.x; j < len; j += gridDim.x) {
         const int64_t g = base + j;
         const int64_t Pg = g >> 1;
-        const double* col = A + g * lda;
         const double ug = ucol[g];
+        for (int q = first_piece(j); q < Q; ++q) {
+          cp_async_wait<kRing - 1>();
 #pragma unroll
-        for (int k = 0; k < kSymPairs; ++k) {
-          const int64_t P = Pbase + tid + int64_t(k) * kPanelThreads;
-          if (P >= Pg && P <= Plast) cp_async16(&dot_slots[k * kPanelThreads + tid], col + 2 * P);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-        double dsum = 0.0;
+          for (int e = 0; e < 2; ++e) {
+            const int64_t P = Pbase + int64_t(q) * kPiecePairs + e * kPanelThreads + tid;
+            if (P >= Pg && P <= Plast) {
+              const double2 m = dot_slots[(slot * 2 + e) * kPanelThreads + tid];
+              const int64_t r0 = 2 * P, r1 = r0 + 1;
+              double ax = 0.0, ay = 0.0;
+              if (r0 >= g) {                     // r0 == g - 1 only for the pair that straddles the diagonal
+                dsum = fma(m.x, ucol[r0], dsum);
+                if (r0 > g) ax = m.x * ug;
+              }
+              dsum = fma(m.y, ucol[r1], dsum);
+              if (r1 > g) ay = m.y * ug;
 #pragma unroll
-        for (int k = 0; k < kSymPairs; ++k) {
-          const int64_t P = Pbase + tid + int64_t(k) * kPanelThreads;
-          if (P >= Pg && P <= Plast) {
-            const double2 m = dot_slots[k * kPanelThreads + tid];
-            const int64_t r0 = 2 * P, r1 = r0 + 1;
-            if (r0 >= g) {                       // r0 == g - 1 only for the pair that straddles the diagonal
-              dsum = fma(m.x, ucol[r0], dsum);
-              if (r0 > g) yacc[k].x = fma(m.x, ug, yacc[k].x);
+              for (int qq = 0; qq < kSymPairs / 2; ++qq)
+                if (qq == q) {
+                  yacc[qq * 2 + e].x += ax;
+                  yacc[qq * 2 + e].y += ay;
+                }
             }
-            dsum = fma(m.y, ucol[r1], dsum);
-            if (r1 > g) yacc[k].y = fma(m.y, ug, yacc[k].y);
           }
+          issue(ij, iq, slot);                   // refill the slot just consumed
+          advance_issue();
+          slot = (slot + 1 == kRing) ? 0 : slot + 1;
         }
         dsum = warp_sum(dsum);
         if (lane == 0) a.ypart[int64_t(wid) * n + g] = dsum;
+        dsum = 0.0;
       }
+      cp_async_wait<0>();
 #pragma unroll
       for (int k = 0; k < kSymPairs; ++k) {
-        const int64_t P = Pbase + tid + int64_t(k) * kPanelThreads;
+        const int64_t P = Pbase + int64_t(k >> 1) * kPiecePairs + (k & 1) * kPanelThreads + tid;
         if (P <= Plast) *reinterpret_cast<double2*>(a.ypriv + int64_t(blockIdx.x) * n + 2 * P) = yacc[k];
       }
       // panel columns (full length)

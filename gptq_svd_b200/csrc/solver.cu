@@ -1,6 +1,7 @@
 // Spectral solver glue - replaces process_hessian_alt (reference gptq_utils.py:87-126):
 //   eigh (eigh.cu) -> clamp / sqrt / flip and the retained-rank rule (block prefix scan
-//   built from warp-level scans) -> S = Lambda^1/2 V_k^T -> column-pivoted QR (qr.cu) ->
+//   built from warp-level scans) -> S = Lambda^1/2 V_k^T -> pivot order + R_x (pivoted Cholesky of
+//   S^T S, pchol.cu; or the Householder column-pivoted QR of S, qr.cu) ->
 //   B = Lambda^-1/2 V_k^T[:, perm] -> unpivoted QR -> sign-normalised R_x, R (row-major).
 #include "solver_kernels.cuh"
 
@@ -13,6 +14,9 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
 int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n, int64_t* perm,
                   Workspace& ws);
 size_t qr_stage_ws_bytes(int64_t k, int64_t n);
+size_t pchol_ws_bytes(int64_t n, int64_t k);
+int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64_t k, double* Rx, int64_t ldr,
+                  int64_t* perm64, Workspace& ws);
 __global__ void emit_r_kernel(const double* __restrict__ A, int64_t lda, int64_t k, int64_t n,
                               double* __restrict__ R, int64_t ldr);
 
@@ -145,7 +149,7 @@ static size_t solver_ws_bytes(int64_t n) {
   // V (n^2) + eigh scratch, later overlaid by S/B (n^2) + QR scratch
   size_t a = ws_bytes_for(size_t(n) * n, 8) + ws_bytes_for(n, 8) * 2 + 1024;
   size_t e = eigh_ws_bytes(n);
-  size_t q = ws_bytes_for(size_t(n) * n, 8) + qr_stage_ws_bytes(n, n);
+  size_t q = ws_bytes_for(size_t(n) * n, 8) * 2 + qr_stage_ws_bytes(n, n) + pchol_ws_bytes(n, n);
   return a + (e > q ? e : q) + (size_t(1) << 20);
 }
 
@@ -183,6 +187,8 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
                                  double* Rx, int64_t* perm, double* eigvals, int64_t* k_host, void* ws,
                                  size_t ws_bytes, void* stream) {
   TQ_TRY(check_device());
+  const bool force_householder = (method & TQ_SOLVE_HOUSEHOLDER_QRCP) != 0;
+  method &= ~TQ_SOLVE_HOUSEHOLDER_QRCP;
   TQ_REQUIRE(H && R && Rx && perm && eigvals && k_host, "tq_spectral_solve: null pointer");
   TQ_REQUIRE(n > 0 && ldh >= n && n < (1 << 30), "tq_spectral_solve: bad shape n=%lld", (long long)n);
   cudaStream_t st = (cudaStream_t)stream;
@@ -219,13 +225,34 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
   dim3 tg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(k, 32));
   build_s_kernel<<<tg, dim3(32, 8), 0, st>>>(V, n, k, eigvals, SB);
   TQ_LAUNCH_CHECK();
-  {
+  // R_x and perm: diagonally pivoted Cholesky of G = S^T S (same pivots and factor as the
+  // column-pivoted QR of S, see pchol.cu); Householder DLAQPS on S when asked for or when a
+  // pivot is not positive.
+  bool householder = force_householder;
+  if (!householder) {
     Workspace s2 = sub;
-    StageTimer tm(st, "qrcp");
-    TQ_TRY(qrcp_colmajor(h, st, SB, k, k, n, perm, s2));
+    double* Gm = s2.take<double>(size_t(n) * n);
+    if (s2.overflow) {
+      set_error("tq_spectral_solve: workspace too small for the Gram matrix");
+      return TQ_ERR_WORKSPACE;
+    }
+    StageTimer tm(st, "gram+pchol");
+    const double one = 1.0, zero = 0.0;
+    TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, int(n), int(n), int(k), &one, SB, int(k), SB, int(k),
+                                &zero, Gm, int(n)));
+    const int rc = pchol_pivoted(h, st, Gm, n, k, Rx, n, perm, s2);
+    if (rc == TQ_ERR_NOCONV) householder = true;
+    else if (rc != TQ_OK) return rc;
   }
-  emit_r_kernel<<<tg, dim3(32, 8), 0, st>>>(SB, k, k, n, Rx, n);
-  TQ_LAUNCH_CHECK();
+  if (householder) {
+    {
+      Workspace s2 = sub;
+      StageTimer tm(st, "qrcp");
+      TQ_TRY(qrcp_colmajor(h, st, SB, k, k, n, perm, s2));
+    }
+    emit_r_kernel<<<tg, dim3(32, 8), 0, st>>>(SB, k, k, n, Rx, n);
+    TQ_LAUNCH_CHECK();
+  }
   build_b_kernel<<<tg, dim3(32, 8), 0, st>>>(V, n, k, eigvals, perm, SB);
   TQ_LAUNCH_CHECK();
   {

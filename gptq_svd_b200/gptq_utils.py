@@ -125,9 +125,13 @@ class SpectralFactors:
     k: int
 
 
-def spectral_solve(H: torch.Tensor, threshold: float = 0.0005,
-                   threshold_method: str = "mean_trimmed") -> SpectralFactors:
-    """process_hessian_alt plus the eigenvalues and k (one `tq_spectral_solve` call)."""
+def spectral_solve(H: torch.Tensor, threshold: float = 0.0005, threshold_method: str = "mean_trimmed",
+                   householder_qrcp: bool = False) -> SpectralFactors:
+    """process_hessian_alt plus the eigenvalues and k (one `tq_spectral_solve` call).
+
+    perm / R_x come from the diagonally pivoted Cholesky of S^T S (same pivots and factor as
+    the column-pivoted QR of S, BLAS-3 bound); `householder_qrcp=True` runs the LAPACK-style
+    Householder QRCP of S instead (BLAS-2 bound)."""
     _require_cuda(H, "process_hessian_alt")
     lib = _lib.load()
     n = H.shape[0]
@@ -137,6 +141,8 @@ def spectral_solve(H: torch.Tensor, threshold: float = 0.0005,
     if Hd.stride(1) != 1:
         Hd = Hd.contiguous()
     method = _METHOD_CODE.get(threshold_method, _lib.TQ_RANK_FULL)
+    if householder_qrcp:
+        method |= _lib.TQ_SOLVE_HOUSEHOLDER_QRCP
     dev = H.device
     with torch.cuda.device(dev):
         nbytes = C.c_size_t(0)

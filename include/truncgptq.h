@@ -53,6 +53,10 @@ extern "C" {
 #define TQ_RANK_ENERGY 0
 #define TQ_RANK_MEAN_TRIMMED 1
 #define TQ_RANK_FULL 2
+/* OR-ed into `method` of tq_spectral_solve: obtain perm / R_x from the Householder
+ * column-pivoted QR of S (LAPACK DLAQPS semantics, BLAS-2 bound) instead of the default
+ * diagonally pivoted Cholesky of S^T S (same pivots and factor, BLAS-3 bound). */
+#define TQ_SOLVE_HOUSEHOLDER_QRCP 0x100
 
 /* loop arithmetic (gptq_utils.py:507-534) */
 #define TQ_LOOP_TRITON 0 /* Triton kernel semantics: half-up, un-scaled error (:345-386) */

@@ -116,10 +116,14 @@ def test_qr_r_vs_lapack(S, name):
     assert np.abs(np.tril(R, -1)).max() == 0.0
 
 
+QRCP_PATH = [pytest.param(False, id="pivoted_cholesky"), pytest.param(True, id="householder_qrcp")]
+
+
+@pytest.mark.parametrize("hh", QRCP_PATH)
 @pytest.mark.parametrize("name", golden_cases())
-def test_process_hessian_alt_golden(G, name, golden):
+def test_process_hessian_alt_golden(G, name, hh, golden):
     g = golden(name)
-    f = G.spectral_solve(_gpu(g["H"]), float(g["eps"]), str(g["method"]))
+    f = G.spectral_solve(_gpu(g["H"]), float(g["eps"]), str(g["method"]), householder_qrcp=hh)
     k = int(g["k"])
     assert f.k == k                                                          # retained rank identical
     perm = f.perm.cpu().numpy()
@@ -137,12 +141,13 @@ def test_process_hessian_alt_golden(G, name, golden):
     assert R2.shape == R.shape and p2.dtype == torch.int64 and R2.dtype == torch.float64
 
 
+@pytest.mark.parametrize("hh", QRCP_PATH)
 @pytest.mark.parametrize("n,eps", [(1024, 1e-4), (2048, 1e-6)])
-def test_solver_invariants_medium(G, n, eps):
+def test_solver_invariants_medium(G, n, eps, hh):
     """Oracle-free invariants at Qwen3-0.6B widths, plus the oracle at n=1024."""
     X = O.make_activations(4 * n, n, seed=n, dist="llm").astype(np.float64)
     H = X.T @ X / X.shape[0]
-    f = G.spectral_solve(_gpu(H), eps, "energy")
+    f = G.spectral_solve(_gpu(H), eps, "energy", householder_qrcp=hh)
     k = f.k
     P = f.perm.cpu().numpy()
     L, V = np.linalg.eigh(H)
@@ -171,3 +176,32 @@ def test_eigh_large_symmetric_path(S, n):
     assert float((w - wr).abs().max()) <= 1e-12 * scale * n ** 0.5
     assert float(torch.linalg.norm(H @ V - V * w[None, :])) <= 1e-12 * float(torch.linalg.norm(H)) * n ** 0.5
     assert float(torch.linalg.norm(V.T @ V - torch.eye(n, device="cuda", dtype=torch.float64))) <= 1e-12 * n
+
+
+@pytest.mark.parametrize("n,eps,dist", [(1024, 1e-7, "llm"), (1024, 1e-4, "flat"), (3072, 1e-4, "llm")])
+def test_pivoted_cholesky_matches_householder_qrcp(G, n, eps, dist):
+    """The default perm / R_x path (pivoted Cholesky of S^T S) against the LAPACK-style
+    Householder QRCP of S on the same H: identical pivots (whole permutation), same R_x, same R."""
+    X = O.make_activations(4 * n, n, seed=3 * n, dist=dist).astype(np.float64)
+    H = _gpu(X.T @ X / X.shape[0])
+    a = G.spectral_solve(H, eps, "energy")
+    b = G.spectral_solve(H, eps, "energy", householder_qrcp=True)
+    assert a.k == b.k
+    assert torch.equal(a.perm, b.perm)
+    sx = float(b.R_x.abs().max())
+    assert float((a.R_x - b.R_x).abs().max()) <= 1e-10 * sx
+    assert torch.equal(a.R, b.R) or float((a.R - b.R).abs().max()) <= 1e-12 * float(b.R.abs().max())
+
+
+def test_rank_deficient_falls_back(G):
+    """Exactly rank-deficient H with the full rule (k = n): eigenvalues are clamped at 1e-12; whichever
+    path runs, the factors satisfy the defining identity R_x^T R_x = P^T H_k P."""
+    rng = np.random.RandomState(0)
+    B = rng.standard_normal((96, 24))
+    H = B @ B.T
+    f = G.spectral_solve(_gpu(H), 0.0, "none")
+    assert f.k == 96
+    P = f.perm.cpu().numpy()
+    assert sorted(P.tolist()) == list(range(96))
+    Rx = f.R_x.cpu().numpy()
+    assert np.linalg.norm(Rx.T @ Rx - H[np.ix_(P, P)]) <= 1e-9 * np.linalg.norm(H)
