@@ -26,36 +26,27 @@ constexpr int kOrmNb = 64;   // back-transform block
 
 
 // ----------------------------------------------------------------------- persistent panel
-// One cooperative launch (one CTA of 1024 threads per SM) factors a whole panel of up to
+// One cooperative launch (two CTAs of 512 threads per SM) factors a whole panel of up to
 // kTrdNb columns.  The per-column phases are separated by grid-wide barriers (grid_barrier)
 // instead of kernel launches:
 //   A   column update A[c:, c] -= V W[c,:]^T + W V[c,:]^T (own rows), partial sum of squares,
 //       d[c]                                                                      | barrier
-//   B   Householder scalars (every CTA, same order), then y = A22 v streamed against the RAW
-//       column u = [alpha; x] (v = scl u + (1 - scl alpha) e_1 is fixed up afterwards):
-//       * symmetric path (2048 <= len <= 12288, even n): each trailing column is read ONLY
-//         from its diagonal down (half the HBM traffic).  Element A[r,g] contributes
-//         A[r,g] u[r] to the dot of column g (per-warp partials) and A[r,g] u[g] to y[r];
-//         the second kind is accumulated in registers - every thread owns fixed row pairs -
-//         and written once per CTA to ypriv.  cp.async stages the whole column slice.
-//       * full path (small or odd sizes): one CTA per full column, per-warp partials.
-//       The panel columns W^T v and V^T v always take the full path.               | barrier
-//   B2  (symmetric path only) y[r] = sum over CTAs and warps of the partials, 8 lanes per
-//       row in fixed order; v^T y partials                                         | barrier
+//   B   Householder scalars (every CTA, same order).  One CTA per trailing column streams it
+//       (cp.async staged, see cta_strided_warp_dot) against the RAW column u = [alpha; x];
+//       since v = [1; scl x], the per-warp partial is fixed up as
+//       scl * p + col[0] (1 - scl alpha)  by the warp that owns row 0.  Per-warp partials of
+//       y = A22 v, W^T v, V^T v go to ypart / tmppart; v^T y is accumulated on the fly.
+//       (A variant that reads only the lower triangle - half the DRAM bytes - was measured
+//       slower on B200, 1.58 s vs 1.51 s at n = 12288: it is instruction-bound on the per-column
+//       warp reductions.  A tile-wise symmetric product is the next step, see DESIGN.md.)  | barrier
 //   C   v scaled in place (own rows), w = tau (y - V W^T v - W V^T v) - tau/2 (w.v) v with
 //       w.v = tau (v^T y - 2 (W^T v).(V^T v)) known without another reduction.
 // Row r is always handled by the same thread (r = global thread id + q * total threads), so
 // values a thread wrote for its own rows need no barrier before it reads them again; the one
 // foreign value the next column update needs, W[c+1, i], is recomputed by every CTA.
-constexpr int kPanelThreads = 1024;
+constexpr int kPanelThreads = 512;    // 2 CTAs per SM: measured 1.51 s (n = 12288) vs 1.99 s with 1 x 1024
 constexpr int kPanelWarps = kPanelThreads / 32;
-constexpr int kSymPairs = 6;                       // 16-byte row pairs per thread on the symmetric path
-constexpr int64_t kSymMaxLen = int64_t(kSymPairs) * kPanelThreads * 2;
-constexpr int64_t kSymMinLen = 2048;
-constexpr int kPiecePairs = 2 * kPanelThreads;      // pairs per piece: two per thread (4096 rows)
-constexpr int kRing = 6;                           // pieces in flight per CTA (6 x 32 KB)
-constexpr int kPanelDepth = (kAsyncDepth > 2 * kRing) ? kAsyncDepth : 2 * kRing;
-constexpr size_t kPanelSmem = size_t(kPanelDepth) * kPanelThreads * sizeof(double2);
+constexpr size_t kPanelSmem = size_t(kAsyncDepth) * kPanelThreads * sizeof(double2);
 
 struct TrdPanelArgs {
   double* A;
@@ -68,13 +59,13 @@ struct TrdPanelArgs {
   double* tau;
   double* ypart;   // kPanelWarps x n          per-warp partials of the column dots
   double* tmppart; // kPanelWarps x 2 kTrdNb   per-warp partials of W^T v | V^T v
-  double* ypriv;   // gridDim.x x n            per-CTA partials of the symmetric path
-  double* ysum;    // n                        y of the symmetric path
   double* part;    // 2 x gridDim.x
   double* scal;    // scalar scratch; [8..15] phase cycle counters when tracing
   unsigned int* bar;
   int trace;
 };
+
+__device__ __forceinline__ int64_t imin_d(int64_t a, int64_t b) { return a < b ? a : b; }
 
 __device__ __forceinline__ double grid_total(const double* part, int nb, double* sh) {
   double v = (threadIdx.x < nb) ? part[threadIdx.x] : 0.0;
@@ -82,7 +73,7 @@ __device__ __forceinline__ double grid_total(const double* part, int nb, double*
   return block_sum(v, sh);
 }
 
-__global__ void __launch_bounds__(kPanelThreads, 1) sytrd_panel_kernel(TrdPanelArgs a) {
+__global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelArgs a) {
   extern __shared__ double2 dot_slots[];   // cp.async staging of the streamed columns
   __shared__ double sh[32];
   __shared__ double tmps[2 * kTrdNb];
@@ -96,6 +87,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) sytrd_panel_kernel(TrdPanelA
   const unsigned int nb = gridDim.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t gwarp = gt >> 5, nwarps = nthreads >> 5;
+  const int sub = lane & 7, rsel = lane >> 3;      // row-wise phases: 4 rows per warp, 8 lanes per row
   double* part1 = a.part;
   double* part2 = a.part + nb;
   unsigned int bar_target = 0;
@@ -111,31 +103,31 @@ __global__ void __launch_bounds__(kPanelThreads, 1) sytrd_panel_kernel(TrdPanelA
   }
   for (int i = 0; i < a.jb; ++i) {
     const int64_t c = j0 + i;
-    // ---------------- A
+    // ---------------- A   (8 lanes per row: the panel history t < i is split over the lanes)
     double ss = 0.0;
-    for (int64_t r = gt; r < n; r += nthreads) {
-      if (r < c) continue;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int t = 0;
-      for (; t + 1 < i - 1; t += 2) {          // t, t+1 <= i-2: plain panel entries, 4 loads in flight
-        const double v0 = A[r + (j0 + t) * lda], w0 = W[r + t * ldw];
-        const double v1 = A[r + (j0 + t + 1) * lda], w1 = W[r + (t + 1) * ldw];
-        s0 = fma(v0, W[c + t * ldw], s0);
-        s1 = fma(w0, A[c + (j0 + t) * lda], s1);
-        s2 = fma(v1, W[c + (t + 1) * ldw], s2);
-        s3 = fma(w1, A[c + (j0 + t + 1) * lda], s3);
+    for (int64_t rb = 4 * gwarp; rb < n; rb += 4 * nwarps) {
+      const int64_t r = rb + rsel;
+      const bool act = (r < n) && (r >= c);
+      double s0 = 0.0, s1 = 0.0;
+      if (act) {
+        for (int t = sub; t < i; t += 8) {
+          const double wc = (t == i - 1) ? wrow_s : W[c + t * ldw];
+          const double vc = (t == i - 1) ? 1.0 : A[c + (j0 + t) * lda];   // V[c, i-1] is the unit entry
+          s0 = fma(A[r + (j0 + t) * lda], wc, s0);
+          s1 = fma(W[r + t * ldw], vc, s1);
+        }
       }
-      for (; t < i; ++t) {
-        const double wc = (t == i - 1) ? wrow_s : W[c + t * ldw];
-        const double vc = (t == i - 1) ? 1.0 : A[c + (j0 + t) * lda];   // V[c, i-1] is the unit entry
-        s0 = fma(A[r + (j0 + t) * lda], wc, s0);
-        s1 = fma(W[r + t * ldw], vc, s1);
+      double s = s0 + s1;
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (act && sub == 0) {
+        const double v = A[r + c * lda] - s;
+        A[r + c * lda] = v;
+        if (r == c) a.d[c] = v;
+        if (r == c + 1) a.scal[0] = v;
+        if (r >= c + 2) ss = fma(v, v, ss);
       }
-      const double v = A[r + c * lda] - ((s0 + s1) + (s2 + s3));
-      A[r + c * lda] = v;
-      if (r == c) a.d[c] = v;
-      if (r == c + 1) a.scal[0] = v;
-      if (r >= c + 2) ss = fma(v, v, ss);
     }
     const int64_t len = n - c - 1;
     if (len <= 0) break;               // last column: only the diagonal entry (uniform across the grid)
@@ -162,125 +154,8 @@ __global__ void __launch_bounds__(kPanelThreads, 1) sytrd_panel_kernel(TrdPanelA
     const int64_t base = c + 1;
     const double* ucol = A + c * lda;              // raw reflector by GLOBAL row: u[g] = ucol[g], g >= base
     const double* u = ucol + base;                 // raw column [alpha; x]
-    const bool sym = (len >= kSymMinLen) && (len <= kSymMaxLen) && ((n & 1) == 0);
     double vy = 0.0;                               // partial of v^T y (full path: lane 0 of each warp)
-    if (sym) {
-      const int64_t Pbase = base >> 1, Plast = (n - 1) >> 1;
-      double2 yacc[kSymPairs];
-#pragma unroll
-      for (int k = 0; k < kSymPairs; ++k) yacc[k] = make_double2(0.0, 0.0);
-      // The CTA's columns are cut into pieces of kPieceRows rows (two 16-byte pairs per thread);
-      // the pieces of all its columns form one stream that runs through a kRing-deep cp.async
-      // ring (192 KB in flight per SM), so the pipeline never drains at a column boundary.
-      const int Q = int((Plast - Pbase + kPiecePairs) / kPiecePairs);            // pieces per full column
-      auto first_piece = [&](int64_t jj) { return int((((base + jj) >> 1) - Pbase) / kPiecePairs); };
-      auto issue = [&](int64_t jj, int q, int slot) {
-        if (jj < len) {
-          const int64_t gg = base + jj;
-          const int64_t Pgg = gg >> 1;
-          const double* colp = A + gg * lda;
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int64_t P = Pbase + int64_t(q) * kPiecePairs + e * kPanelThreads + tid;
-            if (P >= Pgg && P <= Plast) cp_async16(&dot_slots[(slot * 2 + e) * kPanelThreads + tid], colp + 2 * P);
-          }
-        }
-        cp_async_commit();
-      };
-      int64_t ij = blockIdx.x;                      // issue iterator (column, piece)
-      int iq = (ij < len) ? first_piece(ij) : 0;
-      auto advance_issue = [&]() {
-        if (ij >= len) return;
-        if (++iq >= Q) {
-          ij += gridDim.x;
-          iq = (ij < len) ? first_piece(ij) : 0;
-        }
-      };
-#pragma unroll 1
-      for (int sl = 0; sl < kRing; ++sl) {
-        issue(ij, iq, sl);
-        advance_issue();
-      }
-      int slot = 0;
-      double dsum = 0.0;
-      for (int64_t j = blockIdx.x; j < len; j += gridDim.x) {
-        const int64_t g = base + j;
-        const int64_t Pg = g >> 1;
-        const double ug = ucol[g];
-        for (int q = first_piece(j); q < Q; ++q) {
-          cp_async_wait<kRing - 1>();
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int64_t P = Pbase + int64_t(q) * kPiecePairs + e * kPanelThreads + tid;
-            if (P >= Pg && P <= Plast) {
-              const double2 m = dot_slots[(slot * 2 + e) * kPanelThreads + tid];
-              const int64_t r0 = 2 * P, r1 = r0 + 1;
-              double ax = 0.0, ay = 0.0;
-              if (r0 >= g) {                     // r0 == g - 1 only for the pair that straddles the diagonal
-                dsum = fma(m.x, ucol[r0], dsum);
-                if (r0 > g) ax = m.x * ug;
-              }
-              dsum = fma(m.y, ucol[r1], dsum);
-              if (r1 > g) ay = m.y * ug;
-#pragma unroll
-              for (int qq = 0; qq < kSymPairs / 2; ++qq)
-                if (qq == q) {
-                  yacc[qq * 2 + e].x += ax;
-                  yacc[qq * 2 + e].y += ay;
-                }
-            }
-          }
-          issue(ij, iq, slot);                   // refill the slot just consumed
-          advance_issue();
-          slot = (slot + 1 == kRing) ? 0 : slot + 1;
-        }
-        dsum = warp_sum(dsum);
-        if (lane == 0) a.ypart[int64_t(wid) * n + g] = dsum;
-        dsum = 0.0;
-      }
-      cp_async_wait<0>();
-#pragma unroll
-      for (int k = 0; k < kSymPairs; ++k) {
-        const int64_t P = Pbase + int64_t(k >> 1) * kPiecePairs + (k & 1) * kPanelThreads + tid;
-        if (P <= Plast) *reinterpret_cast<double2*>(a.ypriv + int64_t(blockIdx.x) * n + 2 * P) = yacc[k];
-      }
-      // panel columns (full length)
-      for (int64_t j = blockIdx.x; j < 2 * i; j += gridDim.x) {
-        const double* col = (j < i) ? W + base + j * ldw : A + base + (j0 + (j - i)) * lda;
-        double* out = a.tmppart + wid * (2 * kTrdNb) + ((j < i) ? j : kTrdNb + (j - i));
-        double p = scl * cta_strided_warp_dot(col, u, len, dot_slots);
-        if (lane == 0) {
-          if (wid == 0) p = fma(col[0], fix, p);
-          *out = p;
-        }
-      }
-      TQ_PHASE(2)
-      grid_barrier(a.bar, bar_target, nb);
-      TQ_PHASE(3)
-      // ---------------- B2: y[g] = scl * (sum of partials) + fix * A[g, base]; 8 lanes per row
-      {
-        const int rsel = lane >> 3, sub = lane & 7;
-        const int64_t ntask = (len + 3) >> 2;
-        for (int64_t wt = gwarp; wt < ntask; wt += nwarps) {
-          const int64_t g = base + 4 * wt + rsel;
-          double s = 0.0;
-          if (g < n) {
-            for (unsigned int b = sub; b < nb; b += 8) s += a.ypriv[int64_t(b) * n + g];
-            for (int w = sub; w < kPanelWarps; w += 8) s += a.ypart[int64_t(w) * n + g];
-          }
-          s += __shfl_xor_sync(0xffffffffu, s, 4);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          if (sub == 0 && g < n) {
-            const double y = fma(scl, s, fix * A[g + base * lda]);
-            a.ysum[g] = y;
-            vy = fma(y, (g == base) ? 1.0 : scl * ucol[g], vy);
-          }
-        }
-      }
-      vy = block_sum(vy, sh);
-      if (threadIdx.x == 0) part2[blockIdx.x] = vy;
-    } else {
+    {
       const int64_t total = len + 2 * i;
       for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
         const double* col;
@@ -320,41 +195,45 @@ __global__ void __launch_bounds__(kPanelThreads, 1) sytrd_panel_kernel(TrdPanelA
     for (int t = 0; t < i; ++t) cross = fma(tmps[t], tmps[kTrdNb + t], cross);
     const double wv = tau * (vtyv - 2.0 * cross);          // w'.v
     const double alpha2 = -0.5 * tau * wv;
-    for (int64_t r = gt; r < n; r += nthreads) {
-      if (r < c + 1) continue;
-      const double vr = (r == c + 1) ? 1.0 : scl * A[r + c * lda];
-      A[r + c * lda] = vr;
-      double y = 0.0;
-      if (sym) {
-        y = a.ysum[r];
-      } else {
-        for (int w = 0; w < kPanelWarps; ++w) y += a.ypart[int64_t(w) * n + r];
+    for (int64_t rb = 4 * gwarp; rb < n; rb += 4 * nwarps) {
+      const int64_t r = rb + rsel;
+      const bool act = (r < n) && (r >= c + 1);
+      double acc = 0.0, s1 = 0.0;
+      if (act) {
+        for (int w = sub; w < kPanelWarps; w += 8) acc += a.ypart[int64_t(w) * n + r];
+        for (int t = sub; t < i; t += 8) {
+          acc = fma(-A[r + (j0 + t) * lda], tmps[t], acc);
+          s1 = fma(-W[r + t * ldw], tmps[kTrdNb + t], s1);
+        }
       }
-      double s0 = 0.0, s1 = 0.0;
-      for (int t = 0; t < i; ++t) {
-        s0 = fma(A[r + (j0 + t) * lda], tmps[t], s0);
-        s1 = fma(W[r + t * ldw], tmps[kTrdNb + t], s1);
+      double ymw = acc + s1;                                  // y - V tmp1 - W tmp2
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 4);
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 2);
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 1);
+      if (act && sub == 0) {
+        const double vr = (r == c + 1) ? 1.0 : scl * A[r + c * lda];
+        A[r + c * lda] = vr;
+        W[r + int64_t(i) * ldw] = fma(alpha2, vr, tau * ymw);
       }
-      W[r + int64_t(i) * ldw] = fma(alpha2, vr, tau * (y - (s0 + s1)));
     }
+    __syncwarp();
     if (gt == 0) {
       a.tau[c] = tau;
       a.e[c] = beta;
     }
-    if (threadIdx.x == 0) {            // W[c+1, i] for the next column update (v[c+1] = 1)
-      const int64_t r = c + 1;
-      double y = 0.0;
-      if (sym) {
-        y = a.ysum[r];
-      } else {
-        for (int w = 0; w < kPanelWarps; ++w) y += a.ypart[int64_t(w) * n + r];
+    if (wid == 0) {                    // W[c+1, i] for the next column update (v[c+1] = 1): every CTA repeats
+      const int64_t r = c + 1;         // the owner's arithmetic (same lane split) so the value is bit-identical
+      double acc = 0.0, s1 = 0.0;
+      for (int w = sub; w < kPanelWarps; w += 8) acc += a.ypart[int64_t(w) * n + r];
+      for (int t = sub; t < i; t += 8) {
+        acc = fma(-A[r + (j0 + t) * lda], tmps[t], acc);
+        s1 = fma(-W[r + t * ldw], tmps[kTrdNb + t], s1);
       }
-      double s0 = 0.0, s1 = 0.0;
-      for (int t = 0; t < i; ++t) {
-        s0 = fma(A[r + (j0 + t) * lda], tmps[t], s0);
-        s1 = fma(W[r + t * ldw], tmps[kTrdNb + t], s1);
-      }
-      wrow_s = fma(alpha2, 1.0, tau * (y - (s0 + s1)));
+      double ymw = acc + s1;
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 4);
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 2);
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 1);
+      if (lane == 0) wrow_s = fma(alpha2, 1.0, tau * ymw);
     }
     __syncthreads();
     TQ_PHASE(4)
@@ -366,8 +245,8 @@ __global__ void __launch_bounds__(kPanelThreads, 1) sytrd_panel_kernel(TrdPanelA
 // d[0:n], e[0:n-1], tau[0:n-1]; reflector c lives in A[c+1:, c] with an explicit unit at
 // A[c+1, c].
 static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double* d, double* e, double* tau,
-                       double* W, double* y /*32 n*/, double* tmp /*32*2*kTrdNb*/, double* ypriv /*SMs x n*/,
-                       double* ysum /*n*/, double* part /*2*1024*/, double* scal /*16*/, unsigned int* bar) {
+                       double* W, double* y /*warps x n*/, double* tmp /*warps*2*kTrdNb*/, double* part /*2*1024*/,
+                       double* scal /*16*/, unsigned int* bar) {
   const int64_t lda = n, ldw = n;
   const double one = 1.0, mone = -1.0;
   TQ_CUDA_CHECK(cudaMemsetAsync(tau, 0, sizeof(double) * n, st));
@@ -384,13 +263,13 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
       set_error("sytrd: panel kernel cannot be made resident");
       return TQ_ERR_CUDA;
     }
-    coop_blocks = int(imin(num_sms(), 160));   // ypriv holds 160 per-CTA partial vectors
+    coop_blocks = num_sms() * (per_sm > 2 ? 2 : per_sm);
   }
   for (int64_t j0 = 0; j0 < n; j0 += kTrdNb) {
     const int jb = int(imin(kTrdNb, n - j0));
     {
       TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
-      TrdPanelArgs pa{A, n, j0, jb, W, d, e, tau, y, tmp, ypriv, ysum, part, scal, bar, trace_enabled() ? 1 : 0};
+      TrdPanelArgs pa{A, n, j0, jb, W, d, e, tau, y, tmp, part, scal, bar, trace_enabled() ? 1 : 0};
       void* kargs[] = {&pa};
       double bytes = 0.0;      // algorithmic bytes of the panel: every column streams the trailing matrix once
       for (int i = 0; i < jb; ++i) {
@@ -1031,16 +910,25 @@ static int ormtr_lower(cublasHandle_t h, cudaStream_t st, const double* A, const
   return TQ_OK;
 }
 
+// A (n x n, both triangles) = the symmetric matrix defined by the LOWER triangle of the
+// row-major H, like torch.linalg.eigh's default UPLO='L' (gptq_utils.py:93).
 __global__ void copy_sym_kernel(const double* __restrict__ H, int64_t ldh, int64_t n, double* __restrict__ A) {
   int64_t c = blockIdx.y;
   for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += int64_t(gridDim.x) * blockDim.x)
-    A[r + c * n] = H[c * ldh + r];   // row-major (c, r) == column-major (r, c) of H^T = H
+    A[r + c * n] = (r >= c) ? H[r * ldh + c] : H[c * ldh + r];
+}
+
+int copy_symmetric_lower(cudaStream_t st, const double* H, int64_t ldh, int64_t n, double* A) {
+  dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)n);
+  copy_sym_kernel<<<grid, 256, 0, st>>>(H, ldh, n, A);
+  TQ_LAUNCH_CHECK();
+  return TQ_OK;
 }
 
 size_t eigh_ws_bytes(int64_t n) {
   size_t b = 0;
   b += ws_bytes_for(size_t(n) * n, 8) * 4;                 // A, Zg, Zo, U
-  b += ws_bytes_for(n, 8) * (14 + 32 + 160) + ws_bytes_for(2 * kTrdNb * 32, 8) + ws_bytes_for(n, 4) * 8 + ws_bytes_for(n, sizeof(DcRot));
+  b += ws_bytes_for(n, 8) * (14 + 32) + ws_bytes_for(2 * kTrdNb * 32, 8) + ws_bytes_for(n, 4) * 8 + ws_bytes_for(n, sizeof(DcRot));
   b += ws_bytes_for(size_t(n) * kTrdNb, 8) * 2;            // W, Vc
   b += ws_bytes_for(size_t(kOrmNb) * n, 8) * 2;            // w1, w2
   b += ws_bytes_for(kTrdNb * kTrdNb, 8) * 2 + ws_bytes_for(4 * kTrdNb, 8);
@@ -1054,8 +942,6 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   double* e = ws.take<double>(n);
   double* tau = ws.take<double>(n);
   double* y = ws.take<double>(size_t(n) * kPanelWarps);
-  double* ypriv = ws.take<double>(size_t(n) * 160);
-  double* ysum = ws.take<double>(n);
   double* W = ws.take<double>(size_t(n) * kTrdNb);
   double* tmp = ws.take<double>(2 * kTrdNb * kPanelWarps);
   double* part = ws.take<double>(2048);
@@ -1072,12 +958,12 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   TQ_LAUNCH_CHECK();
   {
     StageTimer tm(st, "sytrd");
-    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, ypriv, ysum, part, scal, bar));
+    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, part, scal, bar));
     if (trace_enabled()) {
       double hc[16];
       cudaMemcpyAsync(hc, scal, sizeof(hc), cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
-      fprintf(stderr, "[tq-trace] sytrd phase Mcycles (CTA 0): A %.1f  barrier1 %.1f  B(stream) %.1f  barrier2(+B2) %.1f  C %.1f\n",
+      fprintf(stderr, "[tq-trace] sytrd phase Mcycles (CTA 0): A %.1f  barrier1 %.1f  B(stream) %.1f  barrier2 %.1f  C %.1f\n",
               hc[8] * 1e-6, hc[9] * 1e-6, hc[10] * 1e-6, hc[11] * 1e-6, hc[12] * 1e-6);
     }
   }

@@ -10,6 +10,7 @@ namespace tq {
 int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ldh, int64_t n, double* w,
                   double* Zout, Workspace& ws);
 size_t eigh_ws_bytes(int64_t n);
+int copy_symmetric_lower(cudaStream_t st, const double* H, int64_t ldh, int64_t n, double* A);
 int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n, Workspace& ws);
 int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n, int64_t* perm,
                   Workspace& ws);
@@ -109,6 +110,23 @@ rank_select_kernel(const double* __restrict__ w, int64_t n, double thr, int meth
   }
 }
 
+// flags[0] = 1 when a retained eigenvalue was raised by the 1e-12 clamp (then H_k must be built
+// from the clamped spectrum, not as H minus the discarded part)
+__global__ void clamp_flag_kernel(const double* __restrict__ w, int64_t n, const long long* __restrict__ k,
+                                  long long* __restrict__ flags) {
+  const long long kk = *k;
+  flags[0] = (kk > 0 && kk <= n && w[n - kk] < 1e-12) ? 1 : 0;
+}
+
+// Y[:, i] = Z[:, i] * w[i]  (n rows, t columns, column-major ld n)
+__global__ void scale_cols_kernel(const double* __restrict__ Z, const double* __restrict__ w, int64_t n, int64_t t,
+                                  double* __restrict__ Y) {
+  const int64_t i = blockIdx.y;
+  const double wi = w[i];
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += int64_t(gridDim.x) * blockDim.x)
+    Y[r + i * n] = Z[r + i * n] * wi;
+}
+
 // ------------------------------------------------------------------ S and B builders
 // V is row-major: row r = eigenvector of w[r] (ascending).  Descending index i <-> row n-1-i.
 // S (col-major k x n): S[i + j k] = sqrt(e_i) * V[n-1-i][j]              (gptq_utils.py:112)
@@ -195,7 +213,7 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
   Workspace wsp(ws, ws_bytes);
   double* V = wsp.take<double>(size_t(n) * n);
   double* w = wsp.take<double>(n);
-  long long* kd = wsp.take<long long>(1);
+  long long* kd = wsp.take<long long>(2);
   if (wsp.overflow) {
     set_error("tq_spectral_solve: workspace too small (%zu bytes given, %zu needed)", ws_bytes, solver_ws_bytes(n));
     return TQ_ERR_WORKSPACE;
@@ -208,9 +226,13 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
   }
   rank_select_kernel<<<1, 1024, 0, st>>>(w, n, threshold, method, eigvals, kd);
   TQ_LAUNCH_CHECK();
-  long long kh = 0;
-  TQ_CUDA_CHECK(cudaMemcpyAsync(&kh, kd, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  clamp_flag_kernel<<<1, 1, 0, st>>>(w, n, kd, kd + 1);
+  TQ_LAUNCH_CHECK();
+  long long kh2[2] = {0, 0};
+  TQ_CUDA_CHECK(cudaMemcpyAsync(kh2, kd, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
   TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  const long long kh = kh2[0];
+  const bool clamped = kh2[1] != 0;
   *k_host = kh;
   const int64_t k = kh;
   if (k <= 0) return TQ_OK;   // nothing retained (mean_trimmed can return 0): R, Rx are empty
@@ -223,12 +245,14 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
     return TQ_ERR_WORKSPACE;
   }
   dim3 tg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(k, 32));
-  build_s_kernel<<<tg, dim3(32, 8), 0, st>>>(V, n, k, eigvals, SB);
-  TQ_LAUNCH_CHECK();
-  // R_x and perm: diagonally pivoted Cholesky of G = S^T S (same pivots and factor as the
+  // R_x and perm: diagonally pivoted Cholesky of H_k = S^T S (same pivots and factor as the
   // column-pivoted QR of S, see pchol.cu); Householder DLAQPS on S when asked for or when a
-  // pivot is not positive.
+  // pivot is not positive.  H_k is formed with the cheaper of two DGEMMs:
+  //   H_k = S^T S                         (2 n^2 k flop), or
+  //   H_k = H - V_t diag(lambda_t) V_t^T  (2 n^2 (n-k) flop) when fewer pairs are discarded than
+  //   kept and no retained eigenvalue was touched by the 1e-12 clamp.
   bool householder = force_householder;
+  bool have_s = false;
   if (!householder) {
     Workspace s2 = sub;
     double* Gm = s2.take<double>(size_t(n) * n);
@@ -237,14 +261,33 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
       return TQ_ERR_WORKSPACE;
     }
     StageTimer tm(st, "gram+pchol");
-    const double one = 1.0, zero = 0.0;
-    TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, int(n), int(n), int(k), &one, SB, int(k), SB, int(k),
-                                &zero, Gm, int(n)));
+    const double one = 1.0, zero = 0.0, mone = -1.0;
+    const int64_t t = n - k;
+    if (!clamped && t < k) {
+      TQ_TRY(copy_symmetric_lower(st, H, ldh, n, Gm));
+      if (t > 0) {
+        dim3 sg((unsigned)imin(ceil_div(n, 256), 64), (unsigned)t);
+        scale_cols_kernel<<<sg, 256, 0, st>>>(V, w, n, t, SB);          // SB is free until S / B are built
+        TQ_LAUNCH_CHECK();
+        TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(n), int(n), int(t), &mone, SB, int(n), V,
+                                    int(n), &one, Gm, int(n)));
+      }
+    } else {
+      build_s_kernel<<<tg, dim3(32, 8), 0, st>>>(V, n, k, eigvals, SB);
+      TQ_LAUNCH_CHECK();
+      have_s = true;
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, int(n), int(n), int(k), &one, SB, int(k), SB, int(k),
+                                  &zero, Gm, int(n)));
+    }
     const int rc = pchol_pivoted(h, st, Gm, n, k, Rx, n, perm, s2);
     if (rc == TQ_ERR_NOCONV) householder = true;
     else if (rc != TQ_OK) return rc;
   }
   if (householder) {
+    if (!have_s) {
+      build_s_kernel<<<tg, dim3(32, 8), 0, st>>>(V, n, k, eigvals, SB);
+      TQ_LAUNCH_CHECK();
+    }
     {
       Workspace s2 = sub;
       StageTimer tm(st, "qrcp");
