@@ -26,7 +26,7 @@ constexpr int kOrmNb = 64;   // back-transform block
 
 
 // ----------------------------------------------------------------------- persistent panel
-// One cooperative launch (two CTAs of 512 threads per SM) factors a whole panel of up to
+// One cooperative launch (four CTAs of 256 threads per SM) factors a whole panel of up to
 // kTrdNb columns.  The per-column phases are separated by grid-wide barriers (grid_barrier)
 // instead of kernel launches:
 //   A   column update A[c:, c] -= V W[c,:]^T + W V[c,:]^T (own rows), partial sum of squares,
@@ -44,7 +44,7 @@ constexpr int kOrmNb = 64;   // back-transform block
 // Row r is always handled by the same thread (r = global thread id + q * total threads), so
 // values a thread wrote for its own rows need no barrier before it reads them again; the one
 // foreign value the next column update needs, W[c+1, i], is recomputed by every CTA.
-constexpr int kPanelThreads = 512;    // 2 CTAs per SM: measured 1.51 s (n = 12288) vs 1.99 s with 1 x 1024
+constexpr int kPanelThreads = 256;    // 4 CTAs per SM; measured at n = 12288: 1.99 s (1 x 1024), 1.45 s (2 x 512), 1.33 s (4 x 256), 1.38 s (8 x 128)    // 2 CTAs per SM: measured 1.51 s (n = 12288) vs 1.99 s with 1 x 1024
 constexpr int kPanelWarps = kPanelThreads / 32;
 constexpr size_t kPanelSmem = size_t(kAsyncDepth) * kPanelThreads * sizeof(double2);
 
@@ -73,7 +73,7 @@ __device__ __forceinline__ double grid_total(const double* part, int nb, double*
   return block_sum(v, sh);
 }
 
-__global__ void __launch_bounds__(kPanelThreads, 2) sytrd_panel_kernel(TrdPanelArgs a) {
+__global__ void __launch_bounds__(kPanelThreads, 4) sytrd_panel_kernel(TrdPanelArgs a) {
   extern __shared__ double2 dot_slots[];   // cp.async staging of the streamed columns
   __shared__ double sh[32];
   __shared__ double tmps[2 * kTrdNb];
@@ -263,7 +263,7 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
       set_error("sytrd: panel kernel cannot be made resident");
       return TQ_ERR_CUDA;
     }
-    coop_blocks = num_sms() * (per_sm > 2 ? 2 : per_sm);
+    coop_blocks = num_sms() * (per_sm > 4 ? 4 : per_sm);
   }
   for (int64_t j0 = 0; j0 < n; j0 += kTrdNb) {
     const int jb = int(imin(kTrdNb, n - j0));
@@ -944,7 +944,7 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   double* y = ws.take<double>(size_t(n) * kPanelWarps);
   double* W = ws.take<double>(size_t(n) * kTrdNb);
   double* tmp = ws.take<double>(2 * kTrdNb * kPanelWarps);
-  double* part = ws.take<double>(2048);
+  double* part = ws.take<double>(4096);
   double* scal = ws.take<double>(16);
   unsigned int* bar = ws.take<unsigned int>(4);
   double* G = ws.take<double>(kTrdNb * kTrdNb);
