@@ -255,16 +255,23 @@ def main():
         ranks_seen = layer_step(Xs, Ws, False)
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("TQ_BENCH_NO_SMI"):
         sampler.start()
-    lib.tq_profile_begin(4)
+    if not os.environ.get("TQ_BENCH_NO_PROF"):
+        lib.tq_profile_begin(4)
     l0 = lib.tq_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e0.record()
-    for _ in range(args.steps):
+    step_ev[0].record()
+    for si in range(args.steps):
         layer_step(Xs, Ws, False)
+        step_ev[si + 1].record()
     e1.record()
     barrier()
+    if rank == 0:
+        sys.stderr.write("per-step ms: " + ", ".join(f"{step_ev[i].elapsed_time(step_ev[i + 1]):.1f}"
+                                                     for i in range(args.steps)) + "\n")
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     launches = torch.tensor([lib.tq_launch_count() - l0], device=dev, dtype=torch.float64)
     import ctypes as C

@@ -827,15 +827,19 @@ static int stedc(cublasHandle_t h, cudaStream_t st, double* d, const double* e, 
     set_error("stedc: workspace too small");
     return TQ_ERR_WORKSPACE;
   }
-  // pinned host staging (one allocation)
-  const size_t hbytes = sizeof(double) * n * 6 + sizeof(int) * n * 2 + sizeof(DcRot) * n + sizeof(double) * n;
-  char* hbuf = nullptr;
-  TQ_CUDA_CHECK(cudaMallocHost(&hbuf, hbytes));
-  struct Free {
-    char* p;
-    ~Free() { cudaFreeHost(p); }
-  } freer{hbuf};
-  char* hp = hbuf;
+  // pinned host staging: one grow-only buffer per host thread (cudaMallocHost / cudaFreeHost per
+  // call cost 0.1 - 0.9 s at random in the end-to-end runs)
+  const size_t hbytes = sizeof(double) * n * 7 + sizeof(int) * n * 2 + sizeof(DcRot) * n + 4096;
+  static thread_local char* pinned = nullptr;
+  static thread_local size_t pinned_size = 0;
+  if (pinned_size < hbytes) {
+    if (pinned) cudaFreeHost(pinned);
+    pinned = nullptr;
+    pinned_size = 0;
+    TQ_CUDA_CHECK(cudaMallocHost(&pinned, hbytes));
+    pinned_size = hbytes;
+  }
+  char* hp = pinned;
   auto htake = [&](size_t bytes) {
     char* r = hp;
     hp += (bytes + 15) / 16 * 16;
@@ -850,8 +854,8 @@ static int stedc(cublasHandle_t h, cudaStream_t st, double* d, const double* e, 
   B.h_rowpos = (int*)htake(sizeof(int) * n);
   B.h_gidx = (int*)htake(sizeof(int) * n);
   B.h_rot = (DcRot*)htake(sizeof(DcRot) * n);
-  std::vector<double> he(n);
-  TQ_CUDA_CHECK(cudaMemcpyAsync(he.data(), e, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  double* he = (double*)htake(sizeof(double) * n);
+  TQ_CUDA_CHECK(cudaMemcpyAsync(he, e, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
 
   std::vector<DcNode> leaves, merges;
   std::vector<int> cuts, merge_n1;
