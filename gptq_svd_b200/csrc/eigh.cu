@@ -20,7 +20,7 @@ namespace tq {
 
 constexpr int kTrdNb = 64;   // sytrd panel width
 constexpr int kLeaf = 32;    // D&C leaf size (one warp)
-constexpr int kOrmNb = 64;   // back-transform block
+constexpr int kOrmNb = 128;  // back-transform block (rank-128 DGEMM updates run at 30 TF/s, rank-64 at 20: profiles/r01_dgemm_probe.log)
 
 
 
@@ -241,12 +241,25 @@ __global__ void __launch_bounds__(kPanelThreads, 4) sytrd_panel_kernel(TrdPanelA
 #undef TQ_PHASE
 }
 
+// X = [V | W], Y = [W | V]  (s x 2jb each, leading dimension ld)
+__global__ void pack_vw_kernel(const double* __restrict__ V, int64_t ldv, const double* __restrict__ W, int64_t ldw,
+                               int64_t s, int jb, double* __restrict__ X, double* __restrict__ Y, int64_t ld) {
+  const int t = blockIdx.y;
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < s; r += int64_t(gridDim.x) * blockDim.x) {
+    const double v = V[r + int64_t(t) * ldv], w = W[r + int64_t(t) * ldw];
+    X[r + int64_t(t) * ld] = v;
+    X[r + int64_t(jb + t) * ld] = w;
+    Y[r + int64_t(t) * ld] = w;
+    Y[r + int64_t(jb + t) * ld] = v;
+  }
+}
+
 // Reduces A (n x n, symmetric, both triangles valid) to tridiagonal form.  On exit
 // d[0:n], e[0:n-1], tau[0:n-1]; reflector c lives in A[c+1:, c] with an explicit unit at
 // A[c+1, c].
 static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double* d, double* e, double* tau,
                        double* W, double* y /*warps x n*/, double* tmp /*warps*2*kTrdNb*/, double* part /*2*1024*/,
-                       double* scal /*16*/, unsigned int* bar) {
+                       double* scal /*16*/, unsigned int* bar, double* XY /*2 x (n x 2 kTrdNb)*/) {
   const int64_t lda = n, ldw = n;
   const double one = 1.0, mone = -1.0;
   TQ_CUDA_CHECK(cudaMemsetAsync(tau, 0, sizeof(double) * n, st));
@@ -285,11 +298,14 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
     const int64_t r0 = j0 + jb;
     const int64_t s2 = n - r0;
     if (s2 > 0) {
-      // A22 -= V2 W2^T + W2 V2^T   (full square, keeps both triangles valid)
-      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(s2), int(s2), jb, &mone, A + r0 + j0 * lda,
-                                  int(lda), W + r0, int(ldw), &one, A + r0 + r0 * lda, int(lda)));
-      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(s2), int(s2), jb, &mone, W + r0, int(ldw),
-                                  A + r0 + j0 * lda, int(lda), &one, A + r0 + r0 * lda, int(lda)));
+      // A22 -= V2 W2^T + W2 V2^T = [V2 W2] [W2 V2]^T as ONE rank-2jb DGEMM (full square, keeps both
+      // triangles valid): cuBLAS runs a rank-128 update at 30 TF/s, two rank-64 updates at 20.7
+      // (profiles/r01_dgemm_probe.log)
+      dim3 grid((unsigned)imin(ceil_div(s2, 256), 64), (unsigned)jb);
+      pack_vw_kernel<<<grid, 256, 0, st>>>(A + r0 + j0 * lda, lda, W + r0, ldw, s2, jb, XY, XY + size_t(n) * 2 * kTrdNb, n);
+      TQ_LAUNCH_CHECK();
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(s2), int(s2), 2 * jb, &mone, XY, int(n),
+                                  XY + size_t(n) * 2 * kTrdNb, int(n), &one, A + r0 + r0 * lda, int(lda)));
     }
   }
   return TQ_OK;
@@ -933,9 +949,9 @@ size_t eigh_ws_bytes(int64_t n) {
   size_t b = 0;
   b += ws_bytes_for(size_t(n) * n, 8) * 4;                 // A, Zg, Zo, U
   b += ws_bytes_for(n, 8) * (14 + 32) + ws_bytes_for(2 * kTrdNb * 32, 8) + ws_bytes_for(n, 4) * 8 + ws_bytes_for(n, sizeof(DcRot));
-  b += ws_bytes_for(size_t(n) * kTrdNb, 8) * 2;            // W, Vc
+  b += ws_bytes_for(size_t(n) * kTrdNb, 8) * 5 + ws_bytes_for(size_t(n) * kOrmNb, 8);   // W, XY, Vc
   b += ws_bytes_for(size_t(kOrmNb) * n, 8) * 2;            // w1, w2
-  b += ws_bytes_for(kTrdNb * kTrdNb, 8) * 2 + ws_bytes_for(4 * kTrdNb, 8);
+  b += ws_bytes_for(kOrmNb * kOrmNb, 8) * 2 + ws_bytes_for(4 * kTrdNb, 8);
   return b;
 }
 
@@ -947,12 +963,13 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   double* tau = ws.take<double>(n);
   double* y = ws.take<double>(size_t(n) * kPanelWarps);
   double* W = ws.take<double>(size_t(n) * kTrdNb);
+  double* XY = ws.take<double>(size_t(n) * 4 * kTrdNb);
   double* tmp = ws.take<double>(2 * kTrdNb * kPanelWarps);
   double* part = ws.take<double>(4096);
   double* scal = ws.take<double>(16);
   unsigned int* bar = ws.take<unsigned int>(4);
-  double* G = ws.take<double>(kTrdNb * kTrdNb);
-  double* T = ws.take<double>(kTrdNb * kTrdNb);
+  double* G = ws.take<double>(kOrmNb * kOrmNb);
+  double* T = ws.take<double>(kOrmNb * kOrmNb);
   if (ws.overflow) {
     set_error("eigh: workspace too small");
     return TQ_ERR_WORKSPACE;
@@ -962,7 +979,7 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   TQ_LAUNCH_CHECK();
   {
     StageTimer tm(st, "sytrd");
-    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, part, scal, bar));
+    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, part, scal, bar, XY));
     if (trace_enabled()) {
       double hc[16];
       cudaMemcpyAsync(hc, scal, sizeof(hc), cudaMemcpyDeviceToHost, st);

@@ -10,7 +10,12 @@
 //  * qr_r_colmajor: unpivoted blocked Householder QR that never forms Q (the reference
 //    calls torch.linalg.qr and discards Q, gptq_utils.py:120): panel by BLAS-2 kernels,
 //    trailing update by compact-WY DGEMMs.
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 #include "solver_kernels.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace tq {
 
@@ -77,6 +82,9 @@ struct QrcpCtl {
 constexpr int kQrPanelThreads = 512;
 constexpr int kQrPanelWarps = kQrPanelThreads / 32;
 constexpr size_t kQrPanelSmem = size_t(kAsyncDepth) * kQrPanelThreads * sizeof(double2);
+
+__device__ __forceinline__ int64_t imin_d(int64_t a, int64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ int64_t imax_d(int64_t a, int64_t b) { return a > b ? a : b; }
 
 __device__ __forceinline__ double grid_total(const double* part, int nb, double* sh) {
   double v = (threadIdx.x < nb) ? part[threadIdx.x] : 0.0;
@@ -192,6 +200,234 @@ __global__ void __launch_bounds__(kQrPanelThreads, 2) qr_panel_kernel(QrPanelArg
     scl_p = scl;
     grid_barrier(a.bar, bar_target, nb);
   }
+}
+
+
+// ----------------------------------------------------------------------- cluster panel
+// Unpivoted Householder panel held in DISTRIBUTED SHARED MEMORY.  The BLAS-2 panel of a
+// tall matrix is pure latency: per column the grid-wide version above pays two grid barriers
+// (~3 us each across 100+ CTAs) around a few microseconds of L2 traffic - 18.6 us per column
+// measured at k = 11030.  Here ONE thread-block cluster (16 CTAs, non-portable size) owns the
+// panel: CTA q keeps rows [q rpc, (q+1) rpc) x jb columns in its shared memory for the whole
+// panel (<= 213 KB), partial dots are exchanged with DSMEM stores and ONE hardware cluster
+// barrier per column (barrier.cluster, a few hundred ns) replaces the grid barriers.
+// Per column i:
+//   A  raw dots  d[cc] = sum_{g >= i} P[g, i] P[g, cc]  (cc > i), ss = sum_{g > i} P[g, i]^2:
+//      warp w owns columns i + w, i + w + 16, ...; per-CTA partials are stored into EVERY CTA's
+//      xch[parity][source][.]; the owner of panel row i broadcasts that row      | cluster barrier
+//   B  every CTA adds the partials in rank order (bit-identical everywhere), forms the
+//      Householder scalars and w = scl d + P[i, :] (1 - scl alpha), and updates its own rows
+//      P[g, cc] -= tau v_g w[cc]; column i keeps the RAW x, scaled on the way out.
+// On exit A holds R on and above the diagonal and the scaled reflector tails below it.
+constexpr int kQcThreads = 512;
+constexpr int kQcWarps = kQcThreads / 32;
+constexpr int kQcMaxJb = 64;
+constexpr int kQcMaxCluster = 16;
+constexpr int kQcColsPerWarp = kQcMaxJb / kQcWarps;   // 4
+
+struct QcArgs {
+  double* A;
+  int64_t lda, k, j0;
+  int jb;
+  int rpc;       // panel rows per CTA (leading dimension of the shared-memory slab)
+  double* tau;
+  double* beta;
+};
+
+__global__ void __launch_bounds__(kQcThreads, 1) qr_cluster_panel_kernel(QcArgs a) {
+  extern __shared__ double slab[];                         // rpc x jb, column-major
+  __shared__ double xch[2][kQcMaxCluster][kQcMaxJb];        // [parity][source CTA][cc - i]
+  __shared__ double prow[2][kQcMaxJb];                      // panel row i, columns i.. (from its owner)
+  __shared__ double dsum[kQcMaxJb];
+  __shared__ double wv[kQcMaxJb];                           // tau * w, indexed by cc - i
+  __shared__ double scl_s[kQcMaxJb], beta_s[kQcMaxJb];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = int(cluster.block_rank());
+  const int csize = int(cluster.num_blocks());
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int jb = a.jb, ldp = a.rpc;
+  const int64_t s = a.k - a.j0;                             // panel rows
+  const int64_t row0 = int64_t(rank) * a.rpc;               // first panel row of this CTA
+  const int nrows = int(imax_d(0, imin_d(int64_t(a.rpc), s - row0)));
+  double* const Ap = a.A + a.j0 + a.j0 * a.lda;             // panel origin
+  for (int cc = 0; cc < jb; ++cc)
+    for (int rl = tid; rl < nrows; rl += kQcThreads) slab[rl + cc * ldp] = Ap[(row0 + rl) + int64_t(cc) * a.lda];
+  __syncthreads();
+  cluster.sync();                                           // every CTA of the cluster is running
+  for (int i = 0; i < jb; ++i) {
+    const int par = i & 1;
+    const int ncols = jb - i;
+    const int lo = int(imax_d(0, imin_d(int64_t(nrows), int64_t(i) - row0)));   // first local row with g >= i
+    const bool own_diag = (int64_t(i) >= row0) && (int64_t(i) < row0 + nrows);
+    const int rl_diag = int(int64_t(i) - row0);
+    const double* pi = slab + i * ldp;
+    // ---------------- A: raw dots against column i
+    {
+      double acc[kQcColsPerWarp];
+      const double* pc[kQcColsPerWarp];
+#pragma unroll
+      for (int q = 0; q < kQcColsPerWarp; ++q) {
+        acc[q] = 0.0;
+        const int cc = i + wid + q * kQcWarps;
+        pc[q] = slab + (cc < jb ? cc : i) * ldp;
+      }
+      for (int rl = lo + lane; rl < nrows; rl += 32) {
+        const double x = pi[rl];
+#pragma unroll
+        for (int q = 0; q < kQcColsPerWarp; ++q) {
+          double y = pc[q][rl];
+          if (q == 0 && wid == 0 && own_diag && rl == rl_diag) y = 0.0;   // ss excludes the diagonal entry
+          acc[q] = fma(x, y, acc[q]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < kQcColsPerWarp; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+      }
+      if (lane < csize) {
+#pragma unroll
+        for (int q = 0; q < kQcColsPerWarp; ++q) {
+          const int c2 = wid + q * kQcWarps;
+          if (c2 < ncols) *cluster.map_shared_rank(&xch[par][rank][c2], lane) = acc[q];
+        }
+      }
+      if (own_diag) {
+        for (int idx = tid; idx < ncols * csize; idx += kQcThreads) {
+          const int q = idx / ncols, c2 = idx - q * ncols;
+          *cluster.map_shared_rank(&prow[par][c2], q) = slab[rl_diag + (i + c2) * ldp];
+        }
+      }
+    }
+    cluster.sync();
+    // ---------------- B: scalars, w, rank-1 update of the own rows
+    if (tid < ncols) {
+      double t = 0.0;
+      for (int q = 0; q < csize; ++q) t += xch[par][q][tid];
+      dsum[tid] = t;
+    }
+    __syncthreads();
+    const double alpha = prow[par][0];
+    double tau, beta, scl;
+    householder_scalars(alpha, dsum[0], s - i, tau, beta, scl);
+    const double fix = 1.0 - scl * alpha;
+    if (tid >= 1 && tid < ncols) wv[tid] = tau * fma(scl, dsum[tid], prow[par][tid] * fix);
+    if (tid == 0) {
+      scl_s[i] = scl;
+      beta_s[i] = beta;
+      if (rank == 0) {
+        a.tau[a.j0 + i] = tau;
+        a.beta[a.j0 + i] = beta;
+      }
+    }
+    __syncthreads();
+    if (tau != 0.0) {
+      double* pcw[kQcColsPerWarp];
+      double wq[kQcColsPerWarp];
+#pragma unroll
+      for (int q = 0; q < kQcColsPerWarp; ++q) {
+        const int c2 = 1 + wid + q * kQcWarps;
+        pcw[q] = (c2 < ncols) ? slab + (i + c2) * ldp : nullptr;
+        wq[q] = (c2 < ncols) ? wv[c2] : 0.0;
+      }
+      for (int rl = lo + lane; rl < nrows; rl += 32) {
+        const double v = (own_diag && rl == rl_diag) ? 1.0 : scl * pi[rl];
+#pragma unroll
+        for (int q = 0; q < kQcColsPerWarp; ++q)
+          if (pcw[q]) pcw[q][rl] = fma(-v, wq[q], pcw[q][rl]);
+      }
+    }
+    __syncthreads();
+  }
+  // ---------------- write-out: R above / on the diagonal, scaled reflector tails below
+  for (int cc = 0; cc < jb; ++cc) {
+    const double sc = scl_s[cc], be = beta_s[cc];
+    for (int rl = tid; rl < nrows; rl += kQcThreads) {
+      const int64_t g = row0 + rl;
+      double v = slab[rl + cc * ldp];
+      if (g > cc) v *= sc;
+      else if (g == cc) v = be;
+      Ap[g + int64_t(cc) * a.lda] = v;
+    }
+  }
+  cluster.sync();     // no CTA leaves while a sibling could still touch its shared memory
+}
+
+// Cluster geometry for a panel with s rows: the widest of 64 / 32 / 16 columns whose slab fits.
+struct QcPlan {
+  int csize = 0;       // 0: the cluster kernel cannot be used on this device
+  size_t max_dyn = 0;
+};
+
+static int qc_plan(QcPlan** out) {
+  static thread_local QcPlan plan;
+  static thread_local bool done = false;
+  *out = &plan;
+  if (done) return TQ_OK;
+  done = true;
+  const char* env = getenv("TQ_QR_COOP_PANEL");
+  if (env && env[0] && env[0] != '0') return TQ_OK;      // A/B switch: keep the grid-barrier panel
+  int dev = 0, optin = 0;
+  TQ_CUDA_CHECK(cudaGetDevice(&dev));
+  TQ_CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  cudaFuncAttributes fa;
+  TQ_CUDA_CHECK(cudaFuncGetAttributes(&fa, qr_cluster_panel_kernel));
+  const size_t max_dyn = size_t(optin) - fa.sharedSizeBytes - 1024;
+  TQ_CUDA_CHECK(cudaFuncSetAttribute(qr_cluster_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     int(max_dyn)));
+  TQ_CUDA_CHECK(cudaFuncSetAttribute(qr_cluster_panel_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  for (int cs = kQcMaxCluster; cs >= 8; cs >>= 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(kQcThreads);
+    cfg.dynamicSmemBytes = max_dyn;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, qr_cluster_panel_kernel, &cfg) == cudaSuccess && nclusters >= 1) {
+      plan.csize = cs;
+      plan.max_dyn = max_dyn;
+      break;
+    }
+    cudaGetLastError();
+  }
+  return TQ_OK;
+}
+
+// widest cluster panel (64 / 32 / 16 columns) for s rows; 0 when even 16 columns do not fit
+static int qc_width(const QcPlan& plan, int64_t s, int* rpc_out) {
+  if (plan.csize == 0) return 0;
+  const int64_t rpc = (ceil_div(s, plan.csize) + 1) / 2 * 2;
+  for (int jb = kQcMaxJb; jb >= 16; jb >>= 1) {
+    if (size_t(rpc) * jb * sizeof(double) <= plan.max_dyn) {
+      *rpc_out = int(rpc);
+      return jb;
+    }
+  }
+  return 0;
+}
+
+static int qc_launch(cudaStream_t st, const QcPlan& plan, const QcArgs& args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.csize);
+  cfg.blockDim = dim3(kQcThreads);
+  cfg.dynamicSmemBytes = size_t(args.rpc) * args.jb * sizeof(double);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = plan.csize;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  TQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, qr_cluster_panel_kernel, args));
+  ++g_launch_count;
+  return TQ_OK;
 }
 
 struct QrcpPanelArgs {
@@ -420,6 +656,24 @@ __global__ void __launch_bounds__(kQrPanelThreads, 2) qrcp_panel_kernel(QrcpPane
 }
 
 // in place: on exit triu(A[0:k, 0:n]) = R (diagonal sign arbitrary)
+// Two-level blocking: inner panels of 64 / 32 / 16 columns are factored by the cluster kernel
+// (or, when a slab does not fit, by the grid-barrier kernel) and applied only inside the current
+// outer block of kQrOb = 128 columns; the trailing matrix sees ONE compact-WY update per outer
+// block, so its DGEMMs run with K = 128 (30-35 TF/s) instead of K = 64 / 32 (20 / 12 TF/s).
+constexpr int kQrOb = 128;
+
+static int qr_block_update(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t j0, int jb,
+                           int64_t c0, int64_t nc, const double* tau, double* Vc, double* G, double* T, double* w1,
+                           double* w2) {
+  if (nc <= 0) return TQ_OK;
+  const int64_t s = k - j0;
+  dim3 grid((unsigned)imin(ceil_div(s, 256), 256), (unsigned)jb);
+  copy_reflectors_kernel<<<grid, 256, 0, st>>>(A + j0 + j0 * lda, lda, s, jb, Vc, s);
+  TQ_LAUNCH_CHECK();
+  TQ_TRY(build_t_factor(h, st, Vc, s, s, jb, tau + j0, G, T));
+  return apply_block_reflector(h, Vc, s, s, jb, T, jb, /*trans_t=*/true, A + j0 + c0 * lda, lda, nc, w1, w2);
+}
+
 int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n,
                   Workspace& ws) {
   double* tau = ws.take<double>(k);
@@ -428,15 +682,17 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
   double* part = ws.take<double>(1024);
   double* scal = ws.take<double>(8);
   unsigned int* bar = ws.take<unsigned int>(4);
-  double* Vc = ws.take<double>(size_t(k) * kQrNb);
-  double* G = ws.take<double>(kQrNb * kQrNb);
-  double* T = ws.take<double>(kQrNb * kQrNb);
-  double* w1 = ws.take<double>(size_t(kQrNb) * n);
-  double* w2 = ws.take<double>(size_t(kQrNb) * n);
+  double* Vc = ws.take<double>(size_t(k) * kQrOb);
+  double* G = ws.take<double>(kQrOb * kQrOb);
+  double* T = ws.take<double>(kQrOb * kQrOb);
+  double* w1 = ws.take<double>(size_t(kQrOb) * n);
+  double* w2 = ws.take<double>(size_t(kQrOb) * n);
   if (ws.overflow) {
     set_error("qr_r: workspace too small");
     return TQ_ERR_WORKSPACE;
   }
+  QcPlan* plan = nullptr;
+  TQ_TRY(qc_plan(&plan));
   static thread_local int coop_blocks = 0;
   if (!coop_blocks) {
     int per_sm = 0;
@@ -450,33 +706,38 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
     }
     coop_blocks = num_sms() * (per_sm > 2 ? 2 : per_sm);
   }
-  for (int64_t j0 = 0; j0 < k; j0 += kQrNb) {
-    const int jb = int(imin(kQrNb, k - j0));
-    {
-      // a tall-skinny panel does not need the whole machine: fewer CTAs make the barriers cheaper
-      const int64_t rows = k - j0;
-      int blocks = int(imin(coop_blocks, imax(8, ceil_div(rows, kQrPanelThreads) * 4)));
-      TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
-      QrPanelArgs pa{A, lda, k, j0, jb, tau, beta, wdot, part, scal, bar};
-      void* kargs[] = {&pa};
-      TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(blocks), dim3(kQrPanelThreads), kargs,
-                                                kQrPanelSmem, st));
-      ++g_launch_count;
+  for (int64_t j0 = 0; j0 < k; j0 += kQrOb) {
+    const int ob = int(imin(kQrOb, k - j0));
+    const int64_t oend = j0 + ob;
+    int64_t jp = j0;
+    while (jp < oend) {
+      const int64_t rows = k - jp;
+      int rpc = 0;
+      const int cw = qc_width(*plan, rows, &rpc);
+      int jb;
+      if (cw > 0) {
+        jb = int(imin(cw, oend - jp));
+        QcArgs qa{A, lda, k, jp, jb, rpc, tau, beta};
+        TQ_TRY(qc_launch(st, *plan, qa));
+      } else {
+        // a tall-skinny panel does not need the whole machine: fewer CTAs make the barriers cheaper
+        jb = int(imin(kQrNb, oend - jp));
+        int blocks = int(imin(coop_blocks, imax(8, ceil_div(rows, kQrPanelThreads) * 4)));
+        TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
+        QrPanelArgs pa{A, lda, k, jp, jb, tau, beta, wdot, part, scal, bar};
+        void* kargs[] = {&pa};
+        TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(blocks), dim3(kQrPanelThreads),
+                                                  kargs, kQrPanelSmem, st));
+        ++g_launch_count;
+        set_diag_kernel<<<1, kQrNb, 0, st>>>(A, lda, jp, jb, beta);
+        TQ_LAUNCH_CHECK();
+      }
+      // inner update: the rest of the outer block
+      TQ_TRY(qr_block_update(h, st, A, lda, k, jp, jb, jp + jb, oend - (jp + jb), tau, Vc, G, T, w1, w2));
+      jp += jb;
     }
-    const int64_t s = k - j0;
-    const int64_t nc = n - j0 - jb;
-    if (nc > 0) {
-      dim3 grid((unsigned)imin(ceil_div(s, 256), 256), (unsigned)jb);
-      copy_reflectors_kernel<<<grid, 256, 0, st>>>(A + j0 + j0 * lda, lda, s, jb, Vc, s);
-      TQ_LAUNCH_CHECK();
-    }
-    set_diag_kernel<<<1, kQrNb, 0, st>>>(A, lda, j0, jb, beta);
-    TQ_LAUNCH_CHECK();
-    if (nc > 0) {
-      TQ_TRY(build_t_factor(h, st, Vc, s, s, jb, tau + j0, G, T));
-      TQ_TRY(apply_block_reflector(h, Vc, s, s, jb, T, jb, /*trans_t=*/true, A + j0 + (j0 + jb) * lda, lda, nc,
-                                   w1, w2));
-    }
+    // outer update: everything to the right of the outer block, K = ob
+    TQ_TRY(qr_block_update(h, st, A, lda, k, j0, ob, oend, n - oend, tau, Vc, G, T, w1, w2));
   }
   return TQ_OK;
 }
@@ -609,8 +870,8 @@ using namespace tq;
 
 static size_t qr_ws_bytes(int64_t k, int64_t n) {
   size_t b = ws_bytes_for(size_t(k) * n, 8);                       // column-major working copy
-  b += ws_bytes_for(k + 1, 8) * 4 + ws_bytes_for(kQrNb, 8) + ws_bytes_for(size_t(k) * kQrNb, 8);
-  b += ws_bytes_for(kQrNb * kQrNb, 8) * 2 + ws_bytes_for(size_t(kQrNb) * n, 8) * 2;
+  b += ws_bytes_for(k + 1, 8) * 4 + ws_bytes_for(kQrNb, 8) + ws_bytes_for(size_t(k) * kQrOb, 8);
+  b += ws_bytes_for(kQrOb * kQrOb, 8) * 2 + ws_bytes_for(size_t(kQrOb) * n, 8) * 2;
   b += ws_bytes_for(n, 8) * (2 + kMaxChunks) + ws_bytes_for(size_t(n) * kQrcpNb, 8) + ws_bytes_for(2048, 8) * 4;
   return b;
 }

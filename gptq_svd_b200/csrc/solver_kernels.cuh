@@ -163,7 +163,7 @@ static __global__ void copy_reflectors_kernel(const double* __restrict__ A, int6
 
 // C (s x nc) <- (I - V op(T) V^T) C with V s x jb (clean), T jb x jb upper triangular
 // (full storage, zeros below).  Work: jb x nc (x2).  trans_t: use T^T (H^T, as in QR).
-inline int apply_block_reflector(cublasHandle_t h, const double* V, int64_t ldv, int64_t s, int jb,
+static inline int apply_block_reflector(cublasHandle_t h, const double* V, int64_t ldv, int64_t s, int jb,
                                  const double* T, int ldt, bool trans_t, double* C, int64_t ldc, int64_t nc,
                                  double* work1, double* work2) {
   if (s <= 0 || nc <= 0 || jb <= 0) return TQ_OK;
@@ -181,11 +181,16 @@ inline int apply_block_reflector(cublasHandle_t h, const double* V, int64_t ldv,
 }
 
 // G = V^T V and T = larft(G, tau)
-inline int build_t_factor(cublasHandle_t h, cudaStream_t st, const double* V, int64_t ldv, int64_t s, int jb,
+static inline int build_t_factor(cublasHandle_t h, cudaStream_t st, const double* V, int64_t ldv, int64_t s, int jb,
                           const double* tau, double* G, double* T) {
   const double one = 1.0, zero = 0.0;
   TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, jb, jb, int(s), &one, V, int(ldv), V, int(ldv), &zero,
                               G, jb));
+  static thread_local bool big_smem = false;
+  if (!big_smem) {   // jb = 128 needs 128 KB of dynamic shared memory
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8));
+    big_smem = true;
+  }
   larft_kernel<<<1, 128, size_t(jb) * jb * sizeof(double), st>>>(G, jb, tau, jb, T, jb);
   TQ_LAUNCH_CHECK();
   return TQ_OK;
