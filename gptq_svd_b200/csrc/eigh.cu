@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "solver_kernels.cuh"
+#include "tcgen05.cuh"
 
 namespace tq {
 
@@ -241,6 +242,473 @@ __global__ void __launch_bounds__(kPanelThreads, 4) sytrd_panel_kernel(TrdPanelA
 #undef TQ_PHASE
 }
 
+// ----------------------------------------------------------------------- symmetric TMA panel
+// Same panel factorization, but the product y = A22 v reads only the LOWER triangle of the
+// trailing matrix (half the DRAM bytes of the column-dot version above) and the data is staged
+// by TMA instead of per-thread cp.async:
+//   * the lower triangle is cut into tiles of 128 rows x 64 columns (64 KB); thread 0 of each
+//     CTA feeds a 3-stage shared-memory ring with one cp.async.bulk.tensor.2d per tile (fp64
+//     tensor map over A, out-of-bounds rows / columns read as zero), completion on mbarriers,
+//     so 192 KB per SM are in flight without holding a single register;
+//   * every tile element is used twice from shared memory: warp w owns columns 2w, 2w+1 of the
+//     tile, lane l rows l, l+32, l+64, l+96:  yrow[r] += a u[c]  (kept in registers while the
+//     CTA stays in the same 128-row block) and tcol[c] += a u[r] (warp-reduced per tile);
+//     diagonal tiles mask r > c / r >= c;
+//   * tiles are dealt to CTAs in contiguous chunks of the row-block-major order, so a CTA
+//     flushes its row partial once per row block: rowpart[slot][row], slot = CTA - first CTA of
+//     that row block (<= 27 slots per row), colpart[row block][column]; the consumer (phase C)
+//     adds them in a fixed order - the result is deterministic, no atomics;
+//   * W^T v and V^T v (panel history) are two more tiles per row block through the same ring.
+// As above everything is computed against the RAW column u = [alpha; x]:  v = scl u + fix e0,
+// y = scl (A22 u) + fix A22[:, 0],  v^T y = scl^2 u^T(A22 u) + 2 scl fix (A22 u)[0] + fix^2 A22[0, 0].
+// 1 CTA of 1024 threads per SM; two grid barriers per column.
+constexpr int kSymThreads = 1024;
+constexpr int kSymWarps = kSymThreads / 32;
+constexpr int kTileR = 128, kTileC = 64, kSymStages = 3;
+constexpr int kTileElems = kTileR * kTileC;
+constexpr int kRowSlots = 40;
+constexpr size_t kSymSmem = size_t(kSymStages) * kTileElems * 8 + size_t(16) * kTileR * 8 + 128;
+
+struct SymPanelArgs {
+  double* A;
+  int64_t n;
+  int64_t j0;
+  int jb;
+  double* W;        // n x kTrdNb
+  double* d;
+  double* e;
+  double* tau;
+  double* rowpart;  // kRowSlots x n
+  double* colpart;  // ceil(n / 128) x n
+  double* wvpart;   // ceil(n / 128) x 2 kTrdNb   per-row-block partials of W^T u | V^T u
+  double* part;     // 2 x gridDim.x
+  double* scal;
+  unsigned int* bar;
+  int trace;
+  int boxc;         // columns per TMA box (a tile is kTileC / boxc boxes)
+};
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kSymThreads, 1)
+sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
+  extern __shared__ unsigned char sym_smem_raw[];
+  double* const tiles = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sym_smem_raw) + 127) & ~uintptr_t(127));
+  double* const yred = tiles + kSymStages * kTileElems;        // 16 x 128
+  __shared__ uint64_t full[kSymStages];
+  __shared__ double sh[32];
+  __shared__ double tmps[2 * kTrdNb];
+  __shared__ double wrow_s, yraw0_s;
+  double* const A = a.A;
+  double* const W = a.W;
+  const int64_t n = a.n, lda = a.n, ldw = a.n, j0 = a.j0;
+  const int tid = threadIdx.x;
+  const int64_t gt = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  const unsigned int nb = gridDim.x;
+  const int G = int(gridDim.x), bidx = int(blockIdx.x);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t gwarp = gt >> 5, nwarps = nthreads >> 5;
+  const int sub = lane & 7, rsel = lane >> 3;
+  double* part1 = a.part;
+  double* part2 = a.part + nb;
+  unsigned int bar_target = 0;
+  unsigned int use = 0;        // tiles consumed by this CTA so far (ring position, all threads)
+  unsigned int iss = 0;        // tiles issued so far (thread 0)
+  if (tid == 0) {
+    wrow_s = 0.0;
+    for (int s = 0; s < kSymStages; ++s) ptx::mbar_init(&full[s], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  if (a.trace == 10) return;
+  if (a.trace == 30 && j0 > 0) return;
+
+  long long tk = a.trace ? clock64() : 0;
+#define TQ_PHASE(idx)                                   \
+  if (a.trace && gt == 0) {                             \
+    const long long now = clock64();                    \
+    a.scal[8 + (idx)] += double(now - tk);              \
+    tk = now;                                           \
+  }
+  for (int i = 0; i < a.jb; ++i) {
+    const int64_t c = j0 + i;
+    const int64_t len = n - c - 1;
+    const int64_t base = c + 1;
+    // ---- tile list of this column (depends only on len and i)
+    // TMA needs a 16-byte aligned box origin: row blocks start at the EVEN global row base_e = base - dl;
+    // when dl = 1 the first row of row block 0 is row c (not part of the trailing matrix, masked out)
+    const int dl = int(base & 1);
+    const int64_t base_e = base - dl;
+    const int nrb = int((len + dl + kTileR - 1) / kTileR), nstrips = int((len + kTileC - 1) / kTileC);
+    const int TA = nrb > 0 ? nrb * (nrb - 1) + min(2 * nrb, nstrips) : 0;
+    const int T = TA + (i > 0 ? 2 * nrb : 0);
+    const int ch = (T + G - 1) / G > 0 ? (T + G - 1) / G : 1;
+    const int t0 = min(T, bidx * ch), t1 = min(T, t0 + ch);
+    // tile t -> TMA coordinates; A-type tiles only touch the trailing matrix (read-only in this kernel)
+    auto issue_tile = [&](int t) {
+      const int stage = int(iss % kSymStages);
+      double* dst = tiles + stage * kTileElems;
+      ptx::mbar_expect_tx(&full[stage], kTileElems * 8);
+      const CUtensorMap* map;
+      int x, y;
+      if (t < TA) {
+        int rb = int((sqrt(4.0 * double(t) + 1.0) - 1.0) * 0.5);
+        while (rb * (rb + 1) > t) --rb;
+        while ((rb + 1) * (rb + 2) <= t) ++rb;
+        const int cs = t - rb * (rb + 1);
+        map = &tmA;
+        x = int(base_e + int64_t(rb) * kTileR);
+        y = int(base + int64_t(cs) * kTileC);
+      } else if (t < TA + nrb) {
+        map = &tmW;
+        x = int(base_e + int64_t(t - TA) * kTileR);
+        y = 0;
+      } else {
+        map = &tmA;
+        x = int(base_e + int64_t(t - TA - nrb) * kTileR);
+        y = int(j0);
+      }
+      for (int cb = 0; cb < kTileC; cb += a.boxc) ptx::tma_load_2d(dst + cb * kTileR, map, &full[stage], x, y + cb);
+      ++iss;
+    };
+    int issued = 0;
+    if (tid == 0 && !(a.trace & 64))
+      while (issued < kSymStages && t0 + issued < t1 && t0 + issued < TA) issue_tile(t0 + issued++);
+    if (a.trace == 11) {       // debug: wait for the prologue tiles and leave
+      __syncthreads();
+      for (int q = 0; q < kSymStages && t0 + q < t1 && t0 + q < TA; ++q) ptx::mbar_wait(&full[q], 0);
+      return;
+    }
+    // ---------------- A   (8 lanes per row: the panel history t < i is split over the lanes)
+    double ss = 0.0;
+    for (int64_t rb = 4 * gwarp; rb < n; rb += 4 * nwarps) {
+      const int64_t r = rb + rsel;
+      const bool act = (r < n) && (r >= c);
+      double s0 = 0.0, s1 = 0.0;
+      if (act) {
+        for (int t = sub; t < i; t += 8) {
+          const double wc = (t == i - 1) ? wrow_s : W[c + t * ldw];
+          const double vc = (t == i - 1) ? 1.0 : A[c + (j0 + t) * lda];   // V[c, i-1] is the unit entry
+          s0 = fma(A[r + (j0 + t) * lda], wc, s0);
+          s1 = fma(W[r + t * ldw], vc, s1);
+        }
+      }
+      double s = s0 + s1;
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (act && sub == 0) {
+        const double v = A[r + c * lda] - s;
+        A[r + c * lda] = v;
+        if (r == c) a.d[c] = v;
+        if (r == c + 1) a.scal[0] = v;
+        if (r >= c + 2) ss = fma(v, v, ss);
+      }
+    }
+    if (len <= 0) break;               // last column: only the diagonal entry (uniform across the grid)
+    ss = block_sum(ss, sh);
+    if (threadIdx.x == 0) part1[blockIdx.x] = ss;
+    TQ_PHASE(0)
+    grid_barrier(a.bar, bar_target, nb);
+    TQ_PHASE(1)
+    if (a.trace == 12) {
+      __syncthreads();
+      for (int q = 0; q < kSymStages && t0 + q < t1 && t0 + q < TA; ++q) ptx::mbar_wait(&full[q], 0);
+      return;
+    }
+    // ---------------- B
+    if (tid == 0) {
+      fence_proxy_async_all();           // W / V columns written with st by other CTAs -> TMA reads
+      while (issued < kSymStages && t0 + issued < t1) issue_tile(t0 + issued++);
+    }
+    const double sumsq = grid_total(part1, nb, sh);
+    const double alpha = a.scal[0];
+    double tau, beta, scl;
+    if (len <= 1 || sumsq == 0.0) {
+      tau = 0.0;
+      beta = alpha;
+      scl = 0.0;
+    } else {
+      const double xnorm = sqrt(sumsq);
+      beta = -copysign(hypot(alpha, xnorm), alpha);
+      tau = (beta - alpha) / beta;
+      scl = 1.0 / (alpha - beta);
+    }
+    const double fix = 1.0 - scl * alpha;
+    const double* u = A + base + c * lda;          // raw column [alpha; x], u[j], 0 <= j < len
+    // A22[0, 0]: read BEFORE barrier 2 - its owner may already be in phase A of the next column (which
+    // updates exactly this entry) while a slower CTA is still in phase C of this one
+    const double a00 = A[base + base * lda];
+    {
+      double yrow[4] = {0.0, 0.0, 0.0, 0.0}, ur[4] = {0.0, 0.0, 0.0, 0.0};
+      double uy = 0.0;
+      int rb_rows = -1;        // row block whose row partials are being accumulated in yrow
+      int rb_ur = -1;          // row block ur[] belongs to
+      // flush the row partials of row block rb_rows: cross-warp sum in a fixed order
+      auto flush_rows = [&]() {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) uy = fma(yrow[q], ur[q], uy);
+        if (wid >= 16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) yred[(wid - 16) * kTileR + lane + 32 * q] = yrow[q];
+        }
+        __syncthreads();
+        if (wid < 16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) yred[wid * kTileR + lane + 32 * q] += yrow[q];
+        }
+        __syncthreads();
+        if (tid < kTileR) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int w = 0; w < 16; ++w) sacc += yred[w * kTileR + tid];
+          const int64_t rl = int64_t(rb_rows) * kTileR + tid - dl;
+          const int slot = bidx - int((int64_t(rb_rows) * (rb_rows + 1)) / ch);
+          if (rl >= 0 && rl < len) a.rowpart[int64_t(slot) * n + base + rl] = sacc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) yrow[q] = 0.0;
+        rb_rows = -1;
+      };
+      // decode the first tile; afterwards the (rb, cs) pair is advanced incrementally
+      int rb = 0, cs = 0;
+      if (t0 < TA) {
+        rb = int((sqrt(4.0 * double(t0) + 1.0) - 1.0) * 0.5);
+        while (rb * (rb + 1) > t0) --rb;
+        while ((rb + 1) * (rb + 2) <= t0) ++rb;
+        cs = t0 - rb * (rb + 1);
+      }
+      for (int t = t0; t < t1; ++t) {
+        const bool a_tile = t < TA;
+        const int trb = a_tile ? rb : (t < TA + nrb ? t - TA : t - TA - nrb);
+        if (a_tile) {
+          if (rb_rows >= 0 && rb_rows != trb) flush_rows();
+        } else if (rb_rows >= 0) {
+          flush_rows();
+        }
+        if (rb_ur != trb) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int64_t rl = int64_t(trb) * kTileR + lane + 32 * q - dl;
+            ur[q] = (rl >= 0 && rl < len) ? u[rl] : 0.0;
+          }
+          rb_ur = trb;
+        }
+        const int stage = int(use % kSymStages);
+        ptx::mbar_wait(&full[stage], (use / kSymStages) & 1);
+        if (a.trace >= 21 && (a.trace == 22 || !a_tile)) {      // debug: refill the stage with generic loads
+          __syncthreads();
+          double* dstt = tiles + stage * kTileElems;
+          for (int idx = tid; idx < kTileElems; idx += kSymThreads) {
+            const int rr = idx % kTileR, cc = idx / kTileR;
+            const int64_t gr = base_e + int64_t(trb) * kTileR + rr;
+            double v = 0.0;
+            if (gr < n) {
+              if (a_tile) {
+                const int64_t gc = base + int64_t(cs) * kTileC + cc;
+                if (gc < n) v = A[gr + gc * lda];
+              } else if (t < TA + nrb) {
+                v = W[gr + int64_t(cc) * ldw];
+              } else {
+                const int64_t gc = j0 + cc;
+                if (gc < n) v = A[gr + gc * lda];
+              }
+            }
+            dstt[idx] = v;
+          }
+          __syncthreads();
+        }
+        const double* ts = tiles + stage * kTileElems + (2 * wid) * kTileR + lane;
+        double av[2][4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) av[e][q] = ts[e * kTileR + 32 * q];
+        double tcol[2] = {0.0, 0.0};
+        if (a_tile) {
+          rb_rows = trb;
+          const int64_t c0 = int64_t(cs) * kTileC + 2 * wid;        // local column of av[0][.]
+          double uc[2];
+          uc[0] = c0 < len ? u[c0] : 0.0;
+          uc[1] = c0 + 1 < len ? u[c0 + 1] : 0.0;
+          const int64_t r0 = int64_t(trb) * kTileR + lane - dl;     // local row of av[.][0] (-1: row c, masked)
+          if (int64_t(trb) * kTileR - dl >= int64_t(cs + 1) * kTileC) {
+            // whole tile strictly below the diagonal
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                yrow[q] = fma(av[e][q], uc[e], yrow[q]);
+                tcol[e] = fma(av[e][q], ur[q], tcol[e]);
+              }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int64_t rr = r0 + 32 * q, cc = c0 + e;
+                if (rr >= cc) yrow[q] = fma(av[e][q], uc[e], yrow[q]);
+                if (rr > cc) tcol[e] = fma(av[e][q], ur[q], tcol[e]);
+              }
+          }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            tcol[0] += __shfl_xor_sync(0xffffffffu, tcol[0], o);
+            tcol[1] += __shfl_xor_sync(0xffffffffu, tcol[1], o);
+          }
+          if (lane == 0) {
+            if (c0 < len) a.colpart[int64_t(trb) * n + base + c0] = tcol[0];
+            if (c0 + 1 < len) a.colpart[int64_t(trb) * n + base + c0 + 1] = tcol[1];
+            uy = fma(tcol[0], uc[0], uy);
+            uy = fma(tcol[1], uc[1], uy);
+          }
+          if (++cs == min(2 * rb + 2, nstrips)) {
+            ++rb;
+            cs = 0;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tcol[e] = fma(av[e][q], ur[q], tcol[e]);
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            tcol[0] += __shfl_xor_sync(0xffffffffu, tcol[0], o);
+            tcol[1] += __shfl_xor_sync(0xffffffffu, tcol[1], o);
+          }
+          if (lane == 0) {
+            double* out = a.wvpart + int64_t(trb) * (2 * kTrdNb) + (t < TA + nrb ? 0 : kTrdNb) + 2 * wid;
+            out[0] = tcol[0];
+            out[1] = tcol[1];
+          }
+        }
+        __syncthreads();                 // every warp is done with this stage
+        ++use;
+        if (tid == 0 && t + kSymStages < t1) issue_tile(t + kSymStages);
+      }
+      if (rb_rows >= 0) flush_rows();
+      uy = block_sum(uy, sh);
+      if (threadIdx.x == 0) part2[blockIdx.x] = uy;
+      TQ_PHASE(2)
+    }
+    if (a.trace == 13) return;
+    grid_barrier(a.bar, bar_target, nb);
+    TQ_PHASE(3)
+    // ---------------- C
+    // raw product (A22 u)[r - base] for global row r: this lane's share of the partials (8 lanes per row)
+    auto yraw_lane = [&](int64_t r) -> double {
+      const int64_t rl = r - base;
+      if (a.trace == 23) {                               // debug: brute-force row of A22 times u
+        double accb = 0.0;
+        for (int64_t j = sub; j < len; j += 8) accb = fma(A[r + (base + j) * lda], u[j], accb);
+        return accb;
+      }
+      const int rbr = int((rl + dl) / kTileR);           // row block holding this row
+      const int64_t tstart = int64_t(rbr) * (rbr + 1);
+      const int ncs = min(2 * rbr + 2, nstrips);
+      const int b0 = int(tstart / ch), b1 = int((tstart + ncs - 1) / ch);
+      const int rbc = int(rl / kTileC) / 2;              // first row block with a tile over this column
+      const int nslots = b1 - b0 + 1, ncol = nrb - rbc;
+      double acc = 0.0;
+      for (int it = sub; it < nslots + ncol; it += 8)
+        acc += (it < nslots) ? a.rowpart[int64_t(it) * n + r] : a.colpart[int64_t(rbc + it - nslots) * n + r];
+      return acc;
+    };
+    if (a.trace == 30) {                // debug: dump (A22 u) of the very first column into d[] and leave
+      for (int64_t rb4 = 4 * gwarp; rb4 < n; rb4 += 4 * nwarps) {
+        const int64_t r = rb4 + rsel;
+        const bool act = (r < n) && (r >= c + 1);
+        double p = act ? yraw_lane(r) : 0.0;
+        p += __shfl_xor_sync(0xffffffffu, p, 4);
+        p += __shfl_xor_sync(0xffffffffu, p, 2);
+        p += __shfl_xor_sync(0xffffffffu, p, 1);
+        if (act && sub == 0) a.d[r] = p;
+      }
+      return;
+    }
+    double uty = grid_total(part2, nb, sh);
+    if (a.trace == 23) {                // debug: brute-force u^T A22 u
+      double accb = 0.0;
+      for (int64_t e2 = tid; e2 < len * len; e2 += kSymThreads) {
+        const int64_t rr = e2 % len, cc = e2 / len;
+        accb = fma(A[(base + rr) + (base + cc) * lda] * u[cc], u[rr], accb);
+      }
+      uty = block_sum(accb, sh);
+    }
+    if (wid == 0) {                     // (A22 u)[0], by the same lane split as the owner of row `base`
+      double p = yraw_lane(base);
+      p += __shfl_xor_sync(0xffffffffu, p, 4);
+      p += __shfl_xor_sync(0xffffffffu, p, 2);
+      p += __shfl_xor_sync(0xffffffffu, p, 1);
+      if (lane == 0) yraw0_s = p;
+    }
+    if (threadIdx.x < 2 * kTrdNb) {     // tmp1 = W^T v | tmp2 = V^T v: fixed-order sum over the row blocks
+      const int t = threadIdx.x & (kTrdNb - 1);
+      double tsum = 0.0;
+      if (t < i) {
+        for (int q = 0; q < nrb; ++q) tsum += a.wvpart[int64_t(q) * (2 * kTrdNb) + threadIdx.x];
+        const double first = threadIdx.x < kTrdNb ? W[base + t * ldw] : A[base + (j0 + t) * lda];
+        tsum = fma(scl, tsum, fix * first);
+      }
+      tmps[threadIdx.x] = tsum;
+    }
+    __syncthreads();
+    const double vtyv = scl * scl * uty + 2.0 * scl * fix * yraw0_s + fix * fix * a00;
+    double cross = 0.0;
+    for (int t = 0; t < i; ++t) cross = fma(tmps[t], tmps[kTrdNb + t], cross);
+    const double wv = tau * (vtyv - 2.0 * cross);          // w'.v
+    const double alpha2 = -0.5 * tau * wv;
+    for (int64_t rb4 = 4 * gwarp; rb4 < n; rb4 += 4 * nwarps) {
+      const int64_t r = rb4 + rsel;
+      const bool act = (r < n) && (r >= c + 1);
+      double acc = 0.0, s1 = 0.0;
+      if (act) {
+        acc = scl * yraw_lane(r);
+        if (sub == 0) acc = fma(fix, A[r + base * lda], acc);
+        for (int t = sub; t < i; t += 8) {
+          acc = fma(-A[r + (j0 + t) * lda], tmps[t], acc);
+          s1 = fma(-W[r + t * ldw], tmps[kTrdNb + t], s1);
+        }
+      }
+      double ymw = acc + s1;                                  // y - V tmp1 - W tmp2
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 4);
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 2);
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 1);
+      if (act && sub == 0) {
+        const double vr = (r == c + 1) ? 1.0 : scl * A[r + c * lda];
+        A[r + c * lda] = vr;
+        W[r + int64_t(i) * ldw] = fma(alpha2, vr, tau * ymw);
+      }
+    }
+    __syncwarp();
+    if (gt == 0) {
+      a.tau[c] = tau;
+      a.e[c] = beta;
+    }
+    if (wid == 0) {                    // W[c+1, i] for the next column update (v[c+1] = 1): every CTA repeats
+      const int64_t r = c + 1;         // the owner's arithmetic (same lane split) so the value is bit-identical
+      double acc = scl * yraw_lane(r), s1 = 0.0;
+      if (sub == 0) acc = fma(fix, a00, acc);            // r == base: A[r + base * lda] is A22[0, 0]
+      for (int t = sub; t < i; t += 8) {
+        acc = fma(-A[r + (j0 + t) * lda], tmps[t], acc);
+        s1 = fma(-W[r + t * ldw], tmps[kTrdNb + t], s1);
+      }
+      double ymw = acc + s1;
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 4);
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 2);
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 1);
+      if (lane == 0) wrow_s = fma(alpha2, 1.0, tau * ymw);
+    }
+    fence_proxy_async_all();           // this column's V / W entries are read by TMA in the next step
+    __syncthreads();
+    if (a.trace & 128) grid_barrier(a.bar, bar_target, nb);
+    TQ_PHASE(4)
+  }
+#undef TQ_PHASE
+}
+
 // X = [V | W], Y = [W | V]  (s x 2jb each, leading dimension ld)
 __global__ void pack_vw_kernel(const double* __restrict__ V, int64_t ldv, const double* __restrict__ W, int64_t ldw,
                                int64_t s, int jb, double* __restrict__ X, double* __restrict__ Y, int64_t ld) {
@@ -257,9 +725,35 @@ __global__ void pack_vw_kernel(const double* __restrict__ V, int64_t ldv, const 
 // Reduces A (n x n, symmetric, both triangles valid) to tridiagonal form.  On exit
 // d[0:n], e[0:n-1], tau[0:n-1]; reflector c lives in A[c+1:, c] with an explicit unit at
 // A[c+1, c].
+int make_tmap_f64(CUtensorMap* tmap, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                  uint32_t box_rows, uint32_t box_cols);
+
+struct SymBuffers {
+  double* rowpart;
+  double* colpart;
+  double* wvpart;
+};
+
+// largest number of row-partial slots any row block needs for trailing size len with T tiles on G CTAs
+static int sym_max_slots(int64_t len, int dl, bool history, int G) {
+  const int nrb = int((len + dl + kTileR - 1) / kTileR), nstrips = int((len + kTileC - 1) / kTileC);
+  if (nrb <= 0) return 0;
+  const int TA = nrb * (nrb - 1) + std::min(2 * nrb, nstrips);
+  const int T = TA + (history ? 2 * nrb : 0);
+  const int ch = std::max(1, (T + G - 1) / G);
+  int worst = 0;
+  for (int rb = 0; rb < nrb; ++rb) {
+    const int64_t ts = int64_t(rb) * (rb + 1);
+    const int ncs = std::min(2 * rb + 2, nstrips);
+    worst = std::max(worst, int((ts + ncs - 1) / ch - ts / ch + 1));
+  }
+  return worst;
+}
+
 static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double* d, double* e, double* tau,
                        double* W, double* y /*warps x n*/, double* tmp /*warps*2*kTrdNb*/, double* part /*2*1024*/,
-                       double* scal /*16*/, unsigned int* bar, double* XY /*2 x (n x 2 kTrdNb)*/) {
+                       double* scal /*16*/, unsigned int* bar, double* XY /*2 x (n x 2 kTrdNb)*/,
+                       const SymBuffers& sb) {
   const int64_t lda = n, ldw = n;
   const double one = 1.0, mone = -1.0;
   TQ_CUDA_CHECK(cudaMemsetAsync(tau, 0, sizeof(double) * n, st));
@@ -278,9 +772,58 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
     }
     coop_blocks = num_sms() * (per_sm > 4 ? 4 : per_sm);
   }
+  // symmetric TMA panel (half the DRAM bytes) whenever the tensor map can be built: even n (16-byte
+  // row pitch).  TQ_SYTRD_COLDOT=1 keeps the column-dot panel for A/B timing.
+  static thread_local int sym_blocks = -1;
+  if (sym_blocks < 0) {
+    sym_blocks = 0;
+    const char* env = getenv("TQ_SYTRD_COLDOT");
+    if (!(env && env[0] && env[0] != '0')) {
+      int per_sm = 0;
+      TQ_CUDA_CHECK(cudaFuncSetAttribute(sytrd_panel_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(kSymSmem)));
+      TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sytrd_panel_sym_kernel, kSymThreads,
+                                                                  kSymSmem));
+      if (per_sm >= 1) sym_blocks = num_sms();
+    }
+  }
+  const bool use_sym = sym_blocks > 0 && (n % 2 == 0) && n >= 256 && (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(W) % 16 == 0);
+  CUtensorMap tmA, tmW;
+  int boxc = 64;
+  if (const char* bx = getenv("TQ_SYM_BOXC")) boxc = atoi(bx);
+  if (boxc != 64 && boxc != 32 && boxc != 16 && boxc != 8) boxc = 64;
+  if (use_sym) {
+    TQ_TRY(make_tmap_f64(&tmA, A, uint64_t(n), uint64_t(n), uint64_t(n), kTileR, boxc));
+    TQ_TRY(make_tmap_f64(&tmW, W, uint64_t(n), uint64_t(kTrdNb), uint64_t(n), kTileR, boxc));
+    // W is read through TMA before every column of it has been written: keep stale NaNs out of it
+    TQ_CUDA_CHECK(cudaMemsetAsync(W, 0, sizeof(double) * size_t(n) * kTrdNb, st));
+  }
   for (int64_t j0 = 0; j0 < n; j0 += kTrdNb) {
     const int jb = int(imin(kTrdNb, n - j0));
-    {
+    if (use_sym) {
+      for (int i = 0; i < jb; ++i) {
+        if (sym_max_slots(n - (j0 + i) - 1, int((j0 + i + 1) & 1), i > 0, sym_blocks) > kRowSlots) {
+          set_error("sytrd: row-partial slots exceed %d (n=%lld)", kRowSlots, (long long)n);
+          return TQ_ERR_UNSUPPORTED;
+        }
+      }
+      TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
+      const char* dbg = getenv("TQ_SYM_DEBUG");
+      SymPanelArgs pa{A, n, j0, jb, W, d, e, tau, sb.rowpart, sb.colpart, sb.wvpart, part, scal, bar,
+                      dbg ? atoi(dbg) : (trace_enabled() ? 1 : 0), boxc};
+      void* kargs[] = {&pa, &tmA, &tmW};
+      double bytes = 0.0;      // algorithmic bytes: every column streams the LOWER triangle of the trailing matrix once
+      for (int i = 0; i < jb; ++i) {
+        const double len = double(n - (j0 + i) - 1);
+        bytes += len * (0.5 * len + 2.0 * i) * 8.0;
+      }
+      const int pslot = prof_begin_launch(st, bytes);
+      TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sytrd_panel_sym_kernel, dim3(sym_blocks), dim3(kSymThreads),
+                                                kargs, kSymSmem, st));
+      prof_end_launch(st, pslot);
+      ++g_launch_count;
+    } else {
       TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
       TrdPanelArgs pa{A, n, j0, jb, W, d, e, tau, y, tmp, part, scal, bar, trace_enabled() ? 1 : 0};
       void* kargs[] = {&pa};
@@ -950,6 +1493,7 @@ size_t eigh_ws_bytes(int64_t n) {
   b += ws_bytes_for(size_t(n) * n, 8) * 4;                 // A, Zg, Zo, U
   b += ws_bytes_for(n, 8) * (14 + 32) + ws_bytes_for(2 * kTrdNb * 32, 8) + ws_bytes_for(n, 4) * 8 + ws_bytes_for(n, sizeof(DcRot));
   b += ws_bytes_for(size_t(n) * kTrdNb, 8) * 5 + ws_bytes_for(size_t(n) * kOrmNb, 8);   // W, XY, Vc
+  b += ws_bytes_for(size_t(kRowSlots) * n, 8) + ws_bytes_for(size_t((n + kTileR - 1) / kTileR + 1) * n, 8) + ws_bytes_for(size_t((n + kTileR - 1) / kTileR + 1) * 2 * kTrdNb, 8) + 1024;   // symmetric panel partials
   b += ws_bytes_for(size_t(kOrmNb) * n, 8) * 2;            // w1, w2
   b += ws_bytes_for(kOrmNb * kOrmNb, 8) * 2 + ws_bytes_for(4 * kTrdNb, 8);
   return b;
@@ -964,6 +1508,11 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   double* y = ws.take<double>(size_t(n) * kPanelWarps);
   double* W = ws.take<double>(size_t(n) * kTrdNb);
   double* XY = ws.take<double>(size_t(n) * 4 * kTrdNb);
+  const size_t nrb_max = size_t((n + kTileR - 1) / kTileR) + 1;
+  SymBuffers sb;
+  sb.rowpart = ws.take<double>(size_t(kRowSlots) * n);
+  sb.colpart = ws.take<double>(nrb_max * n);
+  sb.wvpart = ws.take<double>(nrb_max * 2 * kTrdNb);
   double* tmp = ws.take<double>(2 * kTrdNb * kPanelWarps);
   double* part = ws.take<double>(4096);
   double* scal = ws.take<double>(16);
@@ -974,18 +1523,29 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
     set_error("eigh: workspace too small");
     return TQ_ERR_WORKSPACE;
   }
-  dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)n);
-  copy_sym_kernel<<<grid, 256, 0, st>>>(H, ldh, n, A);
-  TQ_LAUNCH_CHECK();
+  {
+    StageTimer tm(st, "copy_sym");
+    dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)n);
+    copy_sym_kernel<<<grid, 256, 0, st>>>(H, ldh, n, A);
+    TQ_LAUNCH_CHECK();
+  }
   {
     StageTimer tm(st, "sytrd");
-    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, part, scal, bar, XY));
+    TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, part, scal, bar, XY, sb));
     if (trace_enabled()) {
       double hc[16];
       cudaMemcpyAsync(hc, scal, sizeof(hc), cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
       fprintf(stderr, "[tq-trace] sytrd phase Mcycles (CTA 0): A %.1f  barrier1 %.1f  B(stream) %.1f  barrier2 %.1f  C %.1f\n",
               hc[8] * 1e-6, hc[9] * 1e-6, hc[10] * 1e-6, hc[11] * 1e-6, hc[12] * 1e-6);
+    }
+  }
+  if (const char* dbg = getenv("TQ_SYM_DEBUG")) {
+    if (atoi(dbg) == 30) return TQ_OK;      // debug dump of the first column's product sits in w
+    if (atoi(dbg) & 32) {                   // debug: d in w, e and tau in the first two rows of Zout
+      cudaMemcpyAsync(Zout, e, sizeof(double) * n, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(Zout + n, tau, sizeof(double) * n, cudaMemcpyDeviceToDevice, st);
+      return TQ_OK;
     }
   }
   {

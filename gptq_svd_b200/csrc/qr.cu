@@ -301,10 +301,17 @@ __global__ void __launch_bounds__(kQcThreads, 1) qr_cluster_panel_kernel(QcArgs 
     }
     cluster.sync();
     // ---------------- B: scalars, w, rank-1 update of the own rows
-    if (tid < ncols) {
-      double t = 0.0;
-      for (int q = 0; q < csize; ++q) t += xch[par][q][tid];
-      dsum[tid] = t;
+    // 16 lanes per column add the per-CTA partials in a fixed shuffle tree (deterministic, and the
+    // same in every CTA); the serial 16-term chain cost ~600 cycles per column
+    for (int cb = (tid >> 5) * 2; cb < ncols; cb += kQcThreads / 16) {     // warp-uniform trip count
+      const int c2 = cb + ((tid >> 4) & 1), q = tid & 15;
+      const bool valid = c2 < ncols;
+      double t = (valid && q < csize) ? xch[par][q][c2] : 0.0;
+      t += __shfl_xor_sync(0xffffffffu, t, 8);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      if (valid && q == 0) dsum[c2] = t;
     }
     __syncthreads();
     const double alpha = prow[par][0];

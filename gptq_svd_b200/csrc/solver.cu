@@ -224,13 +224,16 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
     Workspace sub = wsp;
     TQ_TRY(eigh_colmajor(h, st, H, ldh, n, w, V, sub));
   }
-  rank_select_kernel<<<1, 1024, 0, st>>>(w, n, threshold, method, eigvals, kd);
-  TQ_LAUNCH_CHECK();
-  clamp_flag_kernel<<<1, 1, 0, st>>>(w, n, kd, kd + 1);
-  TQ_LAUNCH_CHECK();
   long long kh2[2] = {0, 0};
-  TQ_CUDA_CHECK(cudaMemcpyAsync(kh2, kd, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-  TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  {
+    StageTimer tm(st, "rank");
+    rank_select_kernel<<<1, 1024, 0, st>>>(w, n, threshold, method, eigvals, kd);
+    TQ_LAUNCH_CHECK();
+    clamp_flag_kernel<<<1, 1, 0, st>>>(w, n, kd, kd + 1);
+    TQ_LAUNCH_CHECK();
+    TQ_CUDA_CHECK(cudaMemcpyAsync(kh2, kd, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
   const long long kh = kh2[0];
   const bool clamped = kh2[1] != 0;
   *k_host = kh;
@@ -296,14 +299,20 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
     emit_r_kernel<<<tg, dim3(32, 8), 0, st>>>(SB, k, k, n, Rx, n);
     TQ_LAUNCH_CHECK();
   }
-  build_b_kernel<<<tg, dim3(32, 8), 0, st>>>(V, n, k, eigvals, perm, SB);
-  TQ_LAUNCH_CHECK();
+  {
+    StageTimer tm(st, "build_b");
+    build_b_kernel<<<tg, dim3(32, 8), 0, st>>>(V, n, k, eigvals, perm, SB);
+    TQ_LAUNCH_CHECK();
+  }
   {
     Workspace s2 = sub;
     StageTimer tm(st, "qr_r");
     TQ_TRY(qr_r_colmajor(h, st, SB, k, k, n, s2));
   }
-  emit_r_kernel<<<tg, dim3(32, 8), 0, st>>>(SB, k, k, n, R, n);
-  TQ_LAUNCH_CHECK();
+  {
+    StageTimer tm(st, "emit_r");
+    emit_r_kernel<<<tg, dim3(32, 8), 0, st>>>(SB, k, k, n, R, n);
+    TQ_LAUNCH_CHECK();
+  }
   return TQ_OK;
 }

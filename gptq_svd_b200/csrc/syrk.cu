@@ -279,6 +279,30 @@ int make_tmap_2d(CUtensorMap* tmap, const void* base, int dtype, uint64_t inner,
   return TQ_OK;
 }
 
+// fp64 column-major matrix (rows contiguous), dense box of box_rows x box_cols, no swizzle,
+// out-of-bounds elements read as zero (used by the symmetric SYMV of the tridiagonal reduction)
+int make_tmap_f64(CUtensorMap* tmap, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                  uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return TQ_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {rows, cols};
+  cuuint64_t strides[1] = {ld_elems * 8};
+  cuuint32_t box[2] = {box_rows, box_cols};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (f64) failed with CUresult %d (rows=%llu cols=%llu ld=%llu)", int(r),
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems);
+    return TQ_ERR_CUDA;
+  }
+  return TQ_OK;
+}
+
 }  // namespace tq
 
 using namespace tq;
