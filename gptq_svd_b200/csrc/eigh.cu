@@ -289,6 +289,7 @@ struct SymPanelArgs {
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kSymThreads, 1)
 sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
@@ -298,7 +299,7 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
   __shared__ uint64_t full[kSymStages];
   __shared__ double sh[32];
   __shared__ double tmps[2 * kTrdNb];
-  __shared__ double wrow_s, yraw0_s;
+  __shared__ double wrow_s, yraw0_s, uty_s;
   double* const A = a.A;
   double* const W = a.W;
   const int64_t n = a.n, lda = a.n, ldw = a.n, j0 = a.j0;
@@ -308,13 +309,17 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
   const unsigned int nb = gridDim.x;
   const int G = int(gridDim.x), bidx = int(blockIdx.x);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t gwarp = gt >> 5, nwarps = nthreads >> 5;
+  // row-wise phases: row group g (4 rows) belongs to warp (g / gridDim) of CTA (g % gridDim), so the
+  // active rows r >= c stay spread over ALL SMs as c grows (a CTA-major split leaves the low CTAs idle)
+  const int64_t nwarps = nthreads >> 5;
+  const int64_t gwarp = int64_t(wid) * gridDim.x + blockIdx.x;
   const int sub = lane & 7, rsel = lane >> 3;
   double* part1 = a.part;
   double* part2 = a.part + nb;
   unsigned int bar_target = 0;
   unsigned int use = 0;        // tiles consumed by this CTA so far (ring position, all threads)
-  unsigned int iss = 0;        // tiles issued so far (thread 0)
+  unsigned int iss = 0;        // tiles issued so far (issuing thread only)
+  const bool issuer = (tid == kSymThreads - 32);   // lane 0 of the last warp (rarely owns rows)
   if (tid == 0) {
     wrow_s = 0.0;
     for (int s = 0; s < kSymStages; ++s) ptx::mbar_init(&full[s], 1);
@@ -373,7 +378,7 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       ++iss;
     };
     int issued = 0;
-    if (tid == 0 && !(a.trace & 64))
+    if (issuer && !(a.trace & 64))
       while (issued < kSymStages && t0 + issued < t1 && t0 + issued < TA) issue_tile(t0 + issued++);
     if (a.trace == 11) {       // debug: wait for the prologue tiles and leave
       __syncthreads();
@@ -385,13 +390,30 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
     for (int64_t rb = 4 * gwarp; rb < n; rb += 4 * nwarps) {
       const int64_t r = rb + rsel;
       const bool act = (r < n) && (r >= c);
-      double s0 = 0.0, s1 = 0.0;
+      double s0 = 0.0, s1 = 0.0, acur = 0.0;
       if (act) {
-        for (int t = sub; t < i; t += 8) {
-          const double wc = (t == i - 1) ? wrow_s : W[c + t * ldw];
-          const double vc = (t == i - 1) ? 1.0 : A[c + (j0 + t) * lda];   // V[c, i-1] is the unit entry
-          s0 = fma(A[r + (j0 + t) * lda], wc, s0);
-          s1 = fma(W[r + t * ldw], vc, s1);
+        // every load of this block is independent: one DRAM / L2 round trip for the whole row
+        if (sub == 0) acur = A[r + c * lda];
+        const double* ar = A + r + j0 * lda;
+        const double* wr = W + r;
+        const double* ac = A + c + j0 * lda;      // row c of V (V[c, i-1] is the unit entry)
+        const double* wc = W + c;                 // row c of W (W[c, i-1] was recomputed locally: wrow_s)
+        int t = sub;
+        for (; t + 8 < i; t += 16) {
+          const double x0 = ar[int64_t(t) * lda], x1 = ar[int64_t(t + 8) * lda];
+          const double y0 = wr[int64_t(t) * ldw], y1 = wr[int64_t(t + 8) * ldw];
+          const double w0 = wc[int64_t(t) * ldw], w1 = (t + 8 == i - 1) ? wrow_s : wc[int64_t(t + 8) * ldw];
+          const double v0 = ac[int64_t(t) * lda], v1 = (t + 8 == i - 1) ? 1.0 : ac[int64_t(t + 8) * lda];
+          s0 = fma(x0, w0, s0);
+          s1 = fma(y0, v0, s1);
+          s0 = fma(x1, w1, s0);
+          s1 = fma(y1, v1, s1);
+        }
+        if (t < i) {
+          const double w0 = (t == i - 1) ? wrow_s : wc[int64_t(t) * ldw];
+          const double v0 = (t == i - 1) ? 1.0 : ac[int64_t(t) * lda];
+          s0 = fma(ar[int64_t(t) * lda], w0, s0);
+          s1 = fma(wr[int64_t(t) * ldw], v0, s1);
         }
       }
       double s = s0 + s1;
@@ -399,7 +421,7 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       if (act && sub == 0) {
-        const double v = A[r + c * lda] - s;
+        const double v = acur - s;
         A[r + c * lda] = v;
         if (r == c) a.d[c] = v;
         if (r == c + 1) a.scal[0] = v;
@@ -418,24 +440,10 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       return;
     }
     // ---------------- B
-    if (tid == 0) {
+    if (issuer) {
       fence_proxy_async_all();           // W / V columns written with st by other CTAs -> TMA reads
       while (issued < kSymStages && t0 + issued < t1) issue_tile(t0 + issued++);
     }
-    const double sumsq = grid_total(part1, nb, sh);
-    const double alpha = a.scal[0];
-    double tau, beta, scl;
-    if (len <= 1 || sumsq == 0.0) {
-      tau = 0.0;
-      beta = alpha;
-      scl = 0.0;
-    } else {
-      const double xnorm = sqrt(sumsq);
-      beta = -copysign(hypot(alpha, xnorm), alpha);
-      tau = (beta - alpha) / beta;
-      scl = 1.0 / (alpha - beta);
-    }
-    const double fix = 1.0 - scl * alpha;
     const double* u = A + base + c * lda;          // raw column [alpha; x], u[j], 0 <= j < len
     // A22[0, 0]: read BEFORE barrier 2 - its owner may already be in phase A of the next column (which
     // updates exactly this entry) while a slower CTA is still in phase C of this one
@@ -586,13 +594,29 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
         }
         __syncthreads();                 // every warp is done with this stage
         ++use;
-        if (tid == 0 && t + kSymStages < t1) issue_tile(t + kSymStages);
+        if (issuer && t + kSymStages < t1) issue_tile(t + kSymStages);
       }
       if (rb_rows >= 0) flush_rows();
       uy = block_sum(uy, sh);
       if (threadIdx.x == 0) part2[blockIdx.x] = uy;
-      TQ_PHASE(2)
     }
+    // Householder scalars: not needed by the raw-u products above; part1 / scal[0] must be read before
+    // barrier 2 (a faster CTA rewrites them in phase A of the next column)
+    const double sumsq = grid_total(part1, nb, sh);
+    const double alpha = a.scal[0];
+    double tau, beta, scl;
+    if (len <= 1 || sumsq == 0.0) {
+      tau = 0.0;
+      beta = alpha;
+      scl = 0.0;
+    } else {
+      const double xnorm = sqrt(sumsq);
+      beta = -copysign(hypot(alpha, xnorm), alpha);
+      tau = (beta - alpha) / beta;
+      scl = 1.0 / (alpha - beta);
+    }
+    const double fix = 1.0 - scl * alpha;
+    TQ_PHASE(2)
     if (a.trace == 13) return;
     grid_barrier(a.bar, bar_target, nb);
     TQ_PHASE(3)
@@ -611,10 +635,48 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       const int b0 = int(tstart / ch), b1 = int((tstart + ncs - 1) / ch);
       const int rbc = int(rl / kTileC) / 2;              // first row block with a tile over this column
       const int nslots = b1 - b0 + 1, ncol = nrb - rbc;
-      double acc = 0.0;
-      for (int it = sub; it < nslots + ncol; it += 8)
-        acc += (it < nslots) ? a.rowpart[int64_t(it) * n + r] : a.colpart[int64_t(rbc + it - nslots) * n + r];
-      return acc;
+      // fixed order: lane `sub` takes items sub, sub + 8, ...; four independent accumulators keep the
+      // (L2) loads in flight
+      const double* rp = a.rowpart + r;
+      const double* cp = a.colpart + int64_t(rbc - nslots) * n + r;
+      const int nit = nslots + ncol;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int it = sub;
+      for (; it + 56 < nit; it += 64) {           // 8 independent loads per lane and round
+        double x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = it + 8 * q;
+          x[q] = (j < nslots) ? rp[int64_t(j) * n] : cp[int64_t(j) * n];
+        }
+        a0 += x[0];
+        a1 += x[1];
+        a2 += x[2];
+        a3 += x[3];
+        a0 += x[4];
+        a1 += x[5];
+        a2 += x[6];
+        a3 += x[7];
+      }
+      for (; it + 24 < nit; it += 32) {
+        const double x0 = (it < nslots) ? rp[int64_t(it) * n] : cp[int64_t(it) * n];
+        const double x1 = (it + 8 < nslots) ? rp[int64_t(it + 8) * n] : cp[int64_t(it + 8) * n];
+        const double x2 = (it + 16 < nslots) ? rp[int64_t(it + 16) * n] : cp[int64_t(it + 16) * n];
+        const double x3 = (it + 24 < nslots) ? rp[int64_t(it + 24) * n] : cp[int64_t(it + 24) * n];
+        a0 += x0;
+        a1 += x1;
+        a2 += x2;
+        a3 += x3;
+      }
+      if (it < nit) {                              // up to three more items: independent loads again
+        const double x0 = (it < nslots) ? rp[int64_t(it) * n] : cp[int64_t(it) * n];
+        const double x1 = (it + 8 < nit) ? ((it + 8 < nslots) ? rp[int64_t(it + 8) * n] : cp[int64_t(it + 8) * n]) : 0.0;
+        const double x2 = (it + 16 < nit) ? ((it + 16 < nslots) ? rp[int64_t(it + 16) * n] : cp[int64_t(it + 16) * n]) : 0.0;
+        a0 += x0;
+        a1 += x1;
+        a2 += x2;
+      }
+      return (a0 + a1) + (a2 + a3);
     };
     if (a.trace == 30) {                // debug: dump (A22 u) of the very first column into d[] and leave
       for (int64_t rb4 = 4 * gwarp; rb4 < n; rb4 += 4 * nwarps) {
@@ -628,15 +690,14 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       }
       return;
     }
-    double uty = grid_total(part2, nb, sh);
-    if (a.trace == 23) {                // debug: brute-force u^T A22 u
-      double accb = 0.0;
-      for (int64_t e2 = tid; e2 < len * len; e2 += kSymThreads) {
-        const int64_t rr = e2 % len, cc = e2 / len;
-        accb = fma(A[(base + rr) + (base + cc) * lda] * u[cc], u[rr], accb);
-      }
-      uty = block_sum(accb, sh);
+    if (wid == 1) {                     // u^T (A22 u): per-CTA partials, fixed order
+      double p = 0.0;
+      for (int q = lane; q < int(nb); q += 32) p += part2[q];
+      p = warp_sum(p);
+      if (lane == 0) uty_s = p;
     }
+    double ybase_lane = 0.0;            // last warp: its share of (A22 u)[0] for W[c+1, i] below
+    if (wid == kSymWarps - 1) ybase_lane = yraw_lane(base);
     if (wid == 0) {                     // (A22 u)[0], by the same lane split as the owner of row `base`
       double p = yraw_lane(base);
       p += __shfl_xor_sync(0xffffffffu, p, 4);
@@ -644,64 +705,109 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       p += __shfl_xor_sync(0xffffffffu, p, 1);
       if (lane == 0) yraw0_s = p;
     }
-    if (threadIdx.x < 2 * kTrdNb) {     // tmp1 = W^T v | tmp2 = V^T v: fixed-order sum over the row blocks
-      const int t = threadIdx.x & (kTrdNb - 1);
-      double tsum = 0.0;
+    {   // tmp1 = W^T v | tmp2 = V^T v: 8 threads per entry add the row-block partials (fixed tree)
+      const int o = tid >> 3, part = tid & 7;
+      const int t = o & (kTrdNb - 1);
+      double t0s = 0.0, t1s = 0.0;
       if (t < i) {
-        for (int q = 0; q < nrb; ++q) tsum += a.wvpart[int64_t(q) * (2 * kTrdNb) + threadIdx.x];
-        const double first = threadIdx.x < kTrdNb ? W[base + t * ldw] : A[base + (j0 + t) * lda];
-        tsum = fma(scl, tsum, fix * first);
+        const double* wp = a.wvpart + o;
+        for (int q0 = part; q0 < nrb; q0 += 64) {      // 8 independent loads per thread and round
+          double x[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[q] = (q0 + 8 * q < nrb) ? wp[int64_t(q0 + 8 * q) * (2 * kTrdNb)] : 0.0;
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) {
+            t0s += x[q];
+            t1s += x[q + 1];
+          }
+        }
       }
-      tmps[threadIdx.x] = tsum;
+      double tsum = t0s + t1s;
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, 4);
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
+      if (part == 0) {
+        if (t < i) {
+          const double first = o < kTrdNb ? W[base + t * ldw] : A[base + (j0 + t) * lda];
+          tsum = fma(scl, tsum, fix * first);
+        }
+        tmps[o] = tsum;
+      }
     }
     __syncthreads();
-    const double vtyv = scl * scl * uty + 2.0 * scl * fix * yraw0_s + fix * fix * a00;
+    TQ_PHASE(5)
+    // acc -= V[r, :] tmp1, s1 -= W[r, :] tmp2 over this lane's share of the panel history
+    auto history = [&](int64_t r, double& acc, double& s1) {
+      const double* ar = A + r + j0 * lda;
+      const double* wr = W + r;
+      int t = sub;
+      for (; t + 24 < i; t += 32) {
+        const double x0 = ar[int64_t(t) * lda], x1 = ar[int64_t(t + 8) * lda], x2 = ar[int64_t(t + 16) * lda],
+                     x3 = ar[int64_t(t + 24) * lda];
+        const double y0 = wr[int64_t(t) * ldw], y1 = wr[int64_t(t + 8) * ldw], y2 = wr[int64_t(t + 16) * ldw],
+                     y3 = wr[int64_t(t + 24) * ldw];
+        acc = fma(-x0, tmps[t], acc);
+        s1 = fma(-y0, tmps[kTrdNb + t], s1);
+        acc = fma(-x1, tmps[t + 8], acc);
+        s1 = fma(-y1, tmps[kTrdNb + t + 8], s1);
+        acc = fma(-x2, tmps[t + 16], acc);
+        s1 = fma(-y2, tmps[kTrdNb + t + 16], s1);
+        acc = fma(-x3, tmps[t + 24], acc);
+        s1 = fma(-y3, tmps[kTrdNb + t + 24], s1);
+      }
+      for (; t < i; t += 8) {
+        acc = fma(-ar[int64_t(t) * lda], tmps[t], acc);
+        s1 = fma(-wr[int64_t(t) * ldw], tmps[kTrdNb + t], s1);
+      }
+    };
+    const double vtyv = scl * scl * uty_s + 2.0 * scl * fix * yraw0_s + fix * fix * a00;
     double cross = 0.0;
     for (int t = 0; t < i; ++t) cross = fma(tmps[t], tmps[kTrdNb + t], cross);
     const double wv = tau * (vtyv - 2.0 * cross);          // w'.v
     const double alpha2 = -0.5 * tau * wv;
-    for (int64_t rb4 = 4 * gwarp; rb4 < n; rb4 += 4 * nwarps) {
-      const int64_t r = rb4 + rsel;
-      const bool act = (r < n) && (r >= c + 1);
-      double acc = 0.0, s1 = 0.0;
-      if (act) {
-        acc = scl * yraw_lane(r);
-        if (sub == 0) acc = fma(fix, A[r + base * lda], acc);
-        for (int t = sub; t < i; t += 8) {
-          acc = fma(-A[r + (j0 + t) * lda], tmps[t], acc);
-          s1 = fma(-W[r + t * ldw], tmps[kTrdNb + t], s1);
-        }
-      }
-      double ymw = acc + s1;                                  // y - V tmp1 - W tmp2
-      ymw += __shfl_xor_sync(0xffffffffu, ymw, 4);
-      ymw += __shfl_xor_sync(0xffffffffu, ymw, 2);
-      ymw += __shfl_xor_sync(0xffffffffu, ymw, 1);
-      if (act && sub == 0) {
-        const double vr = (r == c + 1) ? 1.0 : scl * A[r + c * lda];
-        A[r + c * lda] = vr;
-        W[r + int64_t(i) * ldw] = fma(alpha2, vr, tau * ymw);
-      }
-    }
-    __syncwarp();
-    if (gt == 0) {
-      a.tau[c] = tau;
-      a.e[c] = beta;
-    }
-    if (wid == 0) {                    // W[c+1, i] for the next column update (v[c+1] = 1): every CTA repeats
+    // (the last warp rarely owns rows: it starts on the next column's W[c+1, i] right away)
+    if (wid == kSymWarps - 1) {        // W[c+1, i] for the next column update (v[c+1] = 1): every CTA repeats
       const int64_t r = c + 1;         // the owner's arithmetic (same lane split) so the value is bit-identical
-      double acc = scl * yraw_lane(r), s1 = 0.0;
+      double acc = scl * ybase_lane, s1 = 0.0;
       if (sub == 0) acc = fma(fix, a00, acc);            // r == base: A[r + base * lda] is A22[0, 0]
-      for (int t = sub; t < i; t += 8) {
-        acc = fma(-A[r + (j0 + t) * lda], tmps[t], acc);
-        s1 = fma(-W[r + t * ldw], tmps[kTrdNb + t], s1);
-      }
+      history(r, acc, s1);
       double ymw = acc + s1;
       ymw += __shfl_xor_sync(0xffffffffu, ymw, 4);
       ymw += __shfl_xor_sync(0xffffffffu, ymw, 2);
       ymw += __shfl_xor_sync(0xffffffffu, ymw, 1);
       if (lane == 0) wrow_s = fma(alpha2, 1.0, tau * ymw);
     }
-    fence_proxy_async_all();           // this column's V / W entries are read by TMA in the next step
+    for (int64_t rb4 = 4 * gwarp; rb4 < n; rb4 += 4 * nwarps) {
+      const int64_t r = rb4 + rsel;
+      const bool act = (r < n) && (r >= c + 1);
+      double acc = 0.0, s1 = 0.0, ucur = 0.0;
+      if (act) {
+        double a0v = 0.0;
+        if (sub == 0) {                 // independent of the partial sums below: issue first
+          ucur = A[r + c * lda];
+          a0v = A[r + base * lda];
+        }
+        acc = scl * yraw_lane(r);
+        acc = fma(fix, a0v, acc);
+        history(r, acc, s1);
+      }
+      double ymw = acc + s1;                                  // y - V tmp1 - W tmp2
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 4);
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 2);
+      ymw += __shfl_xor_sync(0xffffffffu, ymw, 1);
+      if (act && sub == 0) {
+        const double vr = (r == c + 1) ? 1.0 : scl * ucur;
+        A[r + c * lda] = vr;
+        W[r + int64_t(i) * ldw] = fma(alpha2, vr, tau * ymw);
+        fence_proxy_async_global();      // these two entries are read by TMA (async proxy) in later columns
+      }
+    }
+    __syncwarp();
+    TQ_PHASE(6)
+    if (gt == 0) {
+      a.tau[c] = tau;
+      a.e[c] = beta;
+    }
     __syncthreads();
     if (a.trace & 128) grid_barrier(a.bar, bar_target, nb);
     TQ_PHASE(4)
@@ -1536,8 +1642,8 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
       double hc[16];
       cudaMemcpyAsync(hc, scal, sizeof(hc), cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
-      fprintf(stderr, "[tq-trace] sytrd phase Mcycles (CTA 0): A %.1f  barrier1 %.1f  B(stream) %.1f  barrier2 %.1f  C %.1f\n",
-              hc[8] * 1e-6, hc[9] * 1e-6, hc[10] * 1e-6, hc[11] * 1e-6, hc[12] * 1e-6);
+      fprintf(stderr, "[tq-trace] sytrd phase Mcycles (CTA 0): A %.1f  barrier1 %.1f  B(stream) %.1f  barrier2 %.1f  C %.1f (C1 %.1f C2 %.1f)\n",
+              hc[8] * 1e-6, hc[9] * 1e-6, hc[10] * 1e-6, hc[11] * 1e-6, (hc[12] + hc[13] + hc[14]) * 1e-6, hc[13] * 1e-6, hc[14] * 1e-6);
     }
   }
   if (const char* dbg = getenv("TQ_SYM_DEBUG")) {
