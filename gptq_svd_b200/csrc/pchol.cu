@@ -16,34 +16,47 @@
 // Cholesky touches only O(n nb) data per step (the 64-row block history, L2 resident) and does
 // the rest as DGEMM:  ~0.2 s at n = 12288.
 //
-// Layout: nothing is ever swapped in memory.  G stays in original index order; row j of the
-// factor is stored by ORIGINAL column (Rorig[j, c]); `perm` (position -> original column)
+// Layout: nothing is swapped per step.  The Gram matrix lives in a COMPACT index space that holds
+// the not-yet-pivoted columns (plus the few pivoted since the last compaction): row j of the factor
+// is computed for every compact column (panel buffer Rp[t, a], used by the in-panel history and by
+// the trailing DGEMM) and scattered to Rorig[j, original column]; `perm` (position -> compact index)
 // carries LAPACK's swap semantics so that ties break on the first POSITION like IDAMAX.
-// One cooperative launch per 64-step panel, ONE grid barrier per step:
+// One cooperative launch per 128-step panel, ONE grid barrier per step:
 //   P0  every CTA: argmax over positions p >= j of d[perm[p]] (value desc, position asc) using a
 //       CTA-private copy of perm in shared memory; swap perm[j] <-> perm[pvt] in the private copy
-//   P1  thread per original column c (not yet pivoted):
-//         Rorig[j, c] = (G[c, cj] - sum_{t in block} Rorig[t, cj] Rorig[t, c]) / sqrt(d[cj])
-//         d[c] = max(d[c] - Rorig[j, c]^2, 0)                                      | barrier
-// and after the panel  G -= Rblk^T Rblk  (DGEMM).  If a pivot is not positive (numerical rank
-// below k) the kernel raises a flag and the caller falls back to the Householder QRCP.
+//   P1  four threads per compact column a (not yet pivoted):
+//         r = (G[a, cj] - sum_{t in panel} Rp[t, cj] Rp[t, a]) / sqrt(d[cj])
+//         d[a] = max(d[a] - r^2, 0)                                               | barrier
+// after the panel  G -= Rp^T Rp  as ONE rank-128 DGEMM (30 TF/s; rank-64 updates run at 20), and
+// every 512 pivots the matrix is COMPACTED (gather of the live rows / columns into the other
+// buffer) so the DGEMM only touches live x live entries: 2/3 (n^3 - (n-k)^3) flop in total instead
+// of 2 n^2 k.  If a pivot is not positive (numerical rank below k) the kernel raises a flag and the
+// caller falls back to the Householder QRCP.
 #include <cmath>
+#include <utility>
 
 #include "solver_kernels.cuh"
 
 namespace tq {
 
-constexpr int kPcNb = 64;
+constexpr int kPcNb = 128;
 constexpr int kPcThreads = 1024;
+constexpr int kPcTpc = 4;              // threads per column in P1
+constexpr int kPcCompactEvery = 512;   // pivots between compactions
 
 struct PcholArgs {
-  const double* G;   // n x n symmetric, both triangles valid
-  int64_t n;
+  const double* G;   // ncur x ncur symmetric (both triangles valid), leading dimension ldg
+  int64_t ldg;
+  int64_t ncur;      // compact columns
+  int64_t n;         // original size (leading dimension of Rp / Rorig, length of perm)
   int64_t j0;
   int jb;
-  double* Rorig;     // k x n row-major (ld n), columns in ORIGINAL order
-  double* d;         // n: Schur-complement diagonal by original column; -inf once pivoted
-  int* perm;         // n: position -> original column (global copy, read at entry, written at exit)
+  double* Rp;        // kPcNb x n row-major: this panel's factor rows by COMPACT column
+  double* Rorig;     // k x n row-major (zero-initialised): factor rows by ORIGINAL column
+  double* d;         // ncur: Schur-complement diagonal by compact column; -inf once pivoted
+  const int* orig_of;  // ncur: compact -> original column
+  int* perm;         // n: position -> compact column for positions >= j0 (read at entry, written at exit)
+  int64_t* perm64;   // n: position -> original column, filled for pivoted positions
   unsigned int* bar;
   int* fail;
 };
@@ -55,15 +68,15 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
   __shared__ double hs[kPcNb];
   __shared__ int spvt;
   __shared__ double sdj;
-  const int64_t n = a.n, j0 = a.j0;
+  const int64_t n = a.n, ncur = a.ncur, j0 = a.j0, ldg = a.ldg;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t gt = int64_t(blockIdx.x) * blockDim.x + tid;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
   const unsigned int nb = gridDim.x;
+  const int q4 = tid & (kPcTpc - 1);
   unsigned int bar_target = 0;
-  for (int64_t p = tid; p < n; p += blockDim.x) perm_s[p] = a.perm[p];
+  for (int64_t p = j0 + tid; p < n; p += blockDim.x) perm_s[p] = a.perm[p];
   __syncthreads();
-  int done_steps = 0;
   for (int i = 0; i < a.jb; ++i) {
     const int64_t j = j0 + i;
     // ---------------- P0: pivot
@@ -119,86 +132,186 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
     if (tid == 0) {
       perm_s[pvt] = perm_s[j];
       perm_s[j] = cj;
+      if (blockIdx.x == 0) a.perm64[j] = a.orig_of[cj];
     }
-    if (tid < i) hs[tid] = a.Rorig[(j0 + tid) * n + cj];
+    if (tid < i) hs[tid] = a.Rp[int64_t(tid) * n + cj];
     __syncthreads();
     const double rjj = sqrt(dj);
     const double inv = 1.0 / rjj;
-    // ---------------- P1: row j of the factor, downdate of the diagonal
+    // ---------------- P1: row j of the factor, downdate of the diagonal (kPcTpc threads per column)
+    double* Rpi = a.Rp + int64_t(i) * n;
     double* Rj = a.Rorig + j * n;
-    const double* Gc = a.G + int64_t(cj) * n;     // column cj of G = row cj (symmetric)
-    for (int64_t c = gt; c < n; c += nthreads) {
-      const double dc = a.d[c];
-      if (c == cj) {
-        Rj[c] = rjj;
-        a.d[c] = -INFINITY;
-      } else if (dc == -INFINITY) {
-        Rj[c] = 0.0;
-      } else {
-        double s0 = Gc[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        const double* Rh = a.Rorig + j0 * n + c;
-        int t = 0;
-        for (; t + 7 < i; t += 8) {                 // 8 independent loads in flight (block history, L2)
-          const double r0 = Rh[int64_t(t) * n], r1 = Rh[int64_t(t + 1) * n], r2 = Rh[int64_t(t + 2) * n],
-                       r3 = Rh[int64_t(t + 3) * n], r4 = Rh[int64_t(t + 4) * n], r5 = Rh[int64_t(t + 5) * n],
-                       r6 = Rh[int64_t(t + 6) * n], r7 = Rh[int64_t(t + 7) * n];
+    const double* Gc = a.G + int64_t(cj) * ldg;     // column cj of G = row cj (symmetric)
+    for (int64_t c0 = gt / kPcTpc; c0 < (ncur + 7) / 8 * 8; c0 += nthreads / kPcTpc) {   // warp-uniform trips
+      const int64_t c = c0;
+      const bool inr = c < ncur;
+      const double dc = inr ? a.d[c] : -INFINITY;
+      const bool live = inr && c != cj && dc != -INFINITY;
+      double s0 = 0.0, s1 = 0.0;
+      if (live) {
+        if (q4 == 0) s0 = Gc[c];
+        const double* Rh = a.Rp + c;
+        int t = q4;
+        for (; t + 3 * kPcTpc < i; t += 4 * kPcTpc) {     // 4 independent loads in flight (panel history, L2)
+          const double r0 = Rh[int64_t(t) * n], r1 = Rh[int64_t(t + kPcTpc) * n],
+                       r2 = Rh[int64_t(t + 2 * kPcTpc) * n], r3 = Rh[int64_t(t + 3 * kPcTpc) * n];
           s0 = fma(-hs[t], r0, s0);
-          s1 = fma(-hs[t + 1], r1, s1);
-          s2 = fma(-hs[t + 2], r2, s2);
-          s3 = fma(-hs[t + 3], r3, s3);
-          s0 = fma(-hs[t + 4], r4, s0);
-          s1 = fma(-hs[t + 5], r5, s1);
-          s2 = fma(-hs[t + 6], r6, s2);
-          s3 = fma(-hs[t + 7], r7, s3);
+          s1 = fma(-hs[t + kPcTpc], r1, s1);
+          s0 = fma(-hs[t + 2 * kPcTpc], r2, s0);
+          s1 = fma(-hs[t + 3 * kPcTpc], r3, s1);
         }
-        for (; t < i; ++t) s0 = fma(-hs[t], Rh[int64_t(t) * n], s0);
-        const double r = ((s0 + s1) + (s2 + s3)) * inv;
-        Rj[c] = r;
-        a.d[c] = fmax(fma(-r, r, dc), 0.0);
+        for (; t < i; t += kPcTpc) s0 = fma(-hs[t], Rh[int64_t(t) * n], s0);
+      }
+      double sacc = s0 + s1;
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+      if (inr && q4 == 0) {
+        if (c == cj) {
+          Rpi[c] = rjj;
+          Rj[a.orig_of[c]] = rjj;
+          a.d[c] = -INFINITY;
+        } else if (!live) {
+          Rpi[c] = 0.0;
+        } else {
+          const double r = sacc * inv;
+          Rpi[c] = r;
+          Rj[a.orig_of[c]] = r;
+          a.d[c] = fmax(fma(-r, r, dc), 0.0);
+        }
       }
     }
-    ++done_steps;
     grid_barrier(a.bar, bar_target, nb);
   }
-  (void)done_steps;
   if (blockIdx.x == 0)
-    for (int64_t p = tid; p < n; p += blockDim.x) a.perm[p] = perm_s[p];
+    for (int64_t p = j0 + tid; p < n; p += blockDim.x) a.perm[p] = perm_s[p];
 }
 
 __global__ void pchol_init_kernel(const double* __restrict__ G, int64_t n, double* __restrict__ d,
-                                  int* __restrict__ perm) {
+                                  int* __restrict__ perm, int* __restrict__ orig_of) {
   int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (c < n) {
     d[c] = fmax(G[c + c * n], 0.0);
     perm[c] = int(c);
+    orig_of[c] = int(c);
   }
 }
 
-// Rx (row-major k x n, ld ldr)[t, p] = Rorig[t, perm[p]] for p >= t, 0 left of the diagonal;
-// perm64 = perm.
-__global__ void pchol_emit_kernel(const double* __restrict__ Rorig, int64_t n, int64_t k,
-                                  const int* __restrict__ perm, double* __restrict__ Rx, int64_t ldr,
-                                  int64_t* __restrict__ perm64) {
-  const int64_t t = blockIdx.y;
-  for (int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; p < n; p += int64_t(gridDim.x) * blockDim.x) {
-    Rx[t * ldr + p] = (p >= t) ? Rorig[t * n + perm[p]] : 0.0;
-    if (t == 0) perm64[p] = perm[p];
+// Compaction, step 1 (single CTA): keep[a'] = old compact index of the a'-th live column,
+// newidx[a] = a' (or -1), in increasing order of a; d / orig_of are rewritten through a scratch copy.
+__global__ void __launch_bounds__(1024)
+pchol_compact_index_kernel(int64_t ncur, const double* __restrict__ d, const int* __restrict__ orig_of,
+                           int* __restrict__ keep, int* __restrict__ newidx, double* __restrict__ d_new,
+                           int* __restrict__ orig_new, int* __restrict__ nnew_out) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < ncur; base += blockDim.x) {
+    const int64_t a = base + tid;
+    const int live = (a < ncur && d[a] != -INFINITY) ? 1 : 0;
+    int v = live;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) wsum[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+      int t = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += u;
+      }
+      wsum[lane] = t;
+    }
+    __syncthreads();
+    const int pos = carry + (wid ? wsum[wid - 1] : 0) + v - live;    // exclusive prefix
+    if (a < ncur) {
+      newidx[a] = live ? pos : -1;
+      if (live) {
+        keep[pos] = int(a);
+        d_new[pos] = d[a];
+        orig_new[pos] = orig_of[a];
+      }
+    }
+    __syncthreads();
+    if (tid == blockDim.x - 1) carry = pos + live;
+    __syncthreads();
   }
+  if (tid == 0) *nnew_out = carry;
+}
+
+// Compaction, step 2: Gnew (nnew x nnew, ld nnew) = Gold[keep, keep]; perm (positions >= j) remapped.
+__global__ void pchol_compact_gather_kernel(const double* __restrict__ Gold, int64_t ldo, const int* __restrict__ keep,
+                                            int64_t nnew, double* __restrict__ Gnew) {
+  const int64_t b = blockIdx.y;
+  const double* src = Gold + int64_t(keep[b]) * ldo;
+  double* dst = Gnew + b * nnew;
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < nnew; r += int64_t(gridDim.x) * blockDim.x)
+    dst[r] = src[keep[r]];
+}
+
+// In-place row gather of the panel buffer: Rp[t, a'] = Rp[t, keep[a']].  keep[] is increasing
+// (a' <= keep[a']), so reading through shared-memory staging chunk by chunk in ascending order never
+// reads an element that was already overwritten: one CTA per row, chunks of 1024 with a barrier
+// between the read and the write.
+__global__ void __launch_bounds__(1024)
+pchol_gather_rows_kernel(double* __restrict__ Rp, int64_t ld, const int* __restrict__ keep, int64_t nnew) {
+  double* row = Rp + int64_t(blockIdx.x) * ld;
+  for (int64_t base = 0; base < nnew; base += blockDim.x) {
+    const int64_t a = base + threadIdx.x;
+    const double v = (a < nnew) ? row[keep[a]] : 0.0;
+    __syncthreads();
+    if (a < nnew) row[a] = v;
+    __syncthreads();
+  }
+}
+
+__global__ void pchol_remap_perm_kernel(int* __restrict__ perm, int64_t j, int64_t n, const int* __restrict__ newidx) {
+  const int64_t p = j + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p < n) perm[p] = newidx[perm[p]];
+}
+
+// perm64[p] = original column of position p for the un-pivoted tail p >= k
+__global__ void pchol_tail_perm_kernel(const int* __restrict__ perm, const int* __restrict__ orig_of, int64_t k,
+                                       int64_t n, int64_t* __restrict__ perm64) {
+  const int64_t p = k + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p < n) perm64[p] = orig_of[perm[p]];
+}
+
+// Rx (row-major k x n, ld ldr)[t, p] = Rorig[t, perm64[p]] for p >= t, 0 left of the diagonal
+__global__ void pchol_emit_kernel(const double* __restrict__ Rorig, int64_t n, int64_t k,
+                                  const int64_t* __restrict__ perm64, double* __restrict__ Rx, int64_t ldr) {
+  const int64_t t = blockIdx.y;
+  for (int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; p < n; p += int64_t(gridDim.x) * blockDim.x)
+    Rx[t * ldr + p] = (p >= t) ? Rorig[t * n + perm64[p]] : 0.0;
 }
 
 size_t pchol_ws_bytes(int64_t n, int64_t k) {
-  return ws_bytes_for(size_t(k) * n, 8) + ws_bytes_for(n, 8) + ws_bytes_for(n, 4) + ws_bytes_for(8, 4) * 2;
+  return ws_bytes_for(size_t(k) * n, 8) + ws_bytes_for(size_t(kPcNb) * n, 8) + ws_bytes_for(n, 8) * 2 +
+         ws_bytes_for(n, 4) * 6 + ws_bytes_for(8, 4) * 3;
 }
 
 // G (n x n col-major == row-major, symmetric, DESTROYED) -> Rx (k x n row-major, ld ldr), perm (n int64).
+// `alt` / alt_elems: a second buffer the compacted matrix ping-pongs into (also destroyed).
 // Returns TQ_ERR_NOCONV when a pivot is not positive before step k (caller falls back).
 int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64_t k, double* Rx, int64_t ldr,
-                  int64_t* perm64, Workspace& ws) {
+                  int64_t* perm64, double* alt, size_t alt_elems, Workspace& ws) {
   double* Rorig = ws.take<double>(size_t(k) * n);
+  double* Rp = ws.take<double>(size_t(kPcNb) * n);
   double* d = ws.take<double>(n);
+  double* d2 = ws.take<double>(n);
   int* perm = ws.take<int>(n);
+  int* orig_of = ws.take<int>(n);
+  int* orig2 = ws.take<int>(n);
+  int* keep = ws.take<int>(n);
+  int* newidx = ws.take<int>(n);
   unsigned int* bar = ws.take<unsigned int>(4);
   int* fail = ws.take<int>(4);
+  int* nnew_d = ws.take<int>(4);
   if (ws.overflow) {
     set_error("pchol: workspace too small");
     return TQ_ERR_WORKSPACE;
@@ -219,26 +332,52 @@ int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64
     set_error("pchol: panel kernel cannot be made resident");
     return TQ_ERR_CUDA;
   }
-  // a thread per column: more CTAs than ceil(n / 1024) only make the barrier slower
-  const int blocks = int(imax(1, imin(num_sms(), ceil_div(n, kPcThreads) * 4)));
   TQ_CUDA_CHECK(cudaMemsetAsync(fail, 0, sizeof(int), st));
-  pchol_init_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(G, n, d, perm);
+  TQ_CUDA_CHECK(cudaMemsetAsync(Rorig, 0, sizeof(double) * size_t(k) * n, st));
+  pchol_init_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(G, n, d, perm, orig_of);
   TQ_LAUNCH_CHECK();
   const double one = 1.0, mone = -1.0;
+  double* Gc = G;            // current compact matrix (ld = ncur) and the other buffer
+  double* Go = alt;
+  size_t cap_c = size_t(n) * n, cap_o = alt ? alt_elems : 0;
+  int64_t ncur = n;
+  int64_t dead = 0;          // pivoted columns still inside the compact set
   for (int64_t j0 = 0; j0 < k; j0 += kPcNb) {
     const int jb = int(imin(kPcNb, k - j0));
+    // kPcTpc threads per column: more CTAs than that only make the barrier slower
+    const int blocks = int(imax(1, imin(num_sms(), ceil_div(ncur * kPcTpc, kPcThreads))));
     TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
-    PcholArgs pa{G, n, j0, jb, Rorig, d, perm, bar, fail};
+    PcholArgs pa{Gc, ncur, ncur, n, j0, jb, Rp, Rorig, d, orig_of, perm, perm64, bar, fail};
     void* kargs[] = {&pa};
     TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)pchol_panel_kernel, dim3(blocks), dim3(kPcThreads), kargs,
                                               smem, st));
     ++g_launch_count;
-    if (j0 + jb < k) {
-      // G -= Rblk^T Rblk: Rblk (jb x n row-major, ld n) is the column-major n x jb matrix Rblk^T
-      const double* Rt = Rorig + j0 * n;
-      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(n), int(n), jb, &mone, Rt, int(n), Rt, int(n),
-                                  &one, G, int(n)));
+    dead += jb;
+    if (j0 + jb >= k) break;
+    const int64_t nlive = ncur - dead;
+    if (dead >= kPcCompactEvery && size_t(nlive) * size_t(nlive) <= cap_o) {
+      // compact FIRST (the panel's rows shrink with it), then update only live x live entries
+      pchol_compact_index_kernel<<<1, 1024, 0, st>>>(ncur, d, orig_of, keep, newidx, d2, orig2, nnew_d);
+      TQ_LAUNCH_CHECK();
+      dim3 gg((unsigned)imin(ceil_div(nlive, 256), 64), (unsigned)nlive);
+      pchol_compact_gather_kernel<<<gg, 256, 0, st>>>(Gc, ncur, keep, nlive, Go);
+      TQ_LAUNCH_CHECK();
+      // the panel rows in the new index space: Rp2[t, a'] = Rp[t, keep[a']] (reuse the gather on an n x jb view)
+      pchol_remap_perm_kernel<<<(unsigned)ceil_div(n - (j0 + jb), 256), 256, 0, st>>>(perm, j0 + jb, n, newidx);
+      TQ_LAUNCH_CHECK();
+      // the panel rows move to the new index space as well (in place, see pchol_gather_rows_kernel)
+      pchol_gather_rows_kernel<<<jb, 1024, 0, st>>>(Rp, n, keep, nlive);
+      TQ_LAUNCH_CHECK();
+      std::swap(Gc, Go);
+      std::swap(cap_c, cap_o);
+      std::swap(d, d2);
+      std::swap(orig_of, orig2);
+      ncur = nlive;
+      dead = 0;
     }
+    // G -= Rp^T Rp: Rp (jb x n row-major, ld n) is the column-major ncur x jb matrix Rp^T
+    TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(ncur), int(ncur), jb, &mone, Rp, int(n), Rp, int(n),
+                                &one, Gc, int(ncur)));
   }
   int hfail = 0;
   TQ_CUDA_CHECK(cudaMemcpyAsync(&hfail, fail, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -247,8 +386,12 @@ int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64
     set_error("pchol: non-positive pivot before step k (numerical rank below k)");
     return TQ_ERR_NOCONV;
   }
+  if (k < n) {
+    pchol_tail_perm_kernel<<<(unsigned)ceil_div(n - k, 256), 256, 0, st>>>(perm, orig_of, k, n, perm64);
+    TQ_LAUNCH_CHECK();
+  }
   dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)k);
-  pchol_emit_kernel<<<grid, 256, 0, st>>>(Rorig, n, k, perm, Rx, ldr, perm64);
+  pchol_emit_kernel<<<grid, 256, 0, st>>>(Rorig, n, k, perm64, Rx, ldr);
   TQ_LAUNCH_CHECK();
   return TQ_OK;
 }

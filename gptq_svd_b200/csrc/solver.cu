@@ -17,7 +17,7 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
 size_t qr_stage_ws_bytes(int64_t k, int64_t n);
 size_t pchol_ws_bytes(int64_t n, int64_t k);
 int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64_t k, double* Rx, int64_t ldr,
-                  int64_t* perm64, Workspace& ws);
+                  int64_t* perm64, double* alt, size_t alt_elems, Workspace& ws);
 __global__ void emit_r_kernel(const double* __restrict__ A, int64_t lda, int64_t k, int64_t n,
                               double* __restrict__ R, int64_t ldr);
 
@@ -282,7 +282,9 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
       TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, int(n), int(n), int(k), &one, SB, int(k), SB, int(k),
                                   &zero, Gm, int(n)));
     }
-    const int rc = pchol_pivoted(h, st, Gm, n, k, Rx, n, perm, s2);
+    // SB (k x n) is free until S / B are built: the compacted Gram matrix ping-pongs into it
+    const int rc = pchol_pivoted(h, st, Gm, n, k, Rx, n, perm, SB, size_t(k) * n, s2);
+    have_s = false;
     if (rc == TQ_ERR_NOCONV) householder = true;
     else if (rc != TQ_OK) return rc;
   }
