@@ -5,5 +5,7 @@ from .gptq_utils import (HessianAccumulator, Quantizer, QuantizedLinear, Spectra
                          gptq_fwrd, gptq_quantize, log_quantization_error, pack_codes,
                          process_hessian_alt, spectral_solve)
 
-__all__ = ["HessianAccumulator", "Quantizer", "QuantizedLinear", "SpectralFactors", "gptq_fwrd",
+from .frontends import Sketcher, process_hessian, process_sketch  # noqa: F401,E402
+
+__all__ = ["Sketcher", "process_hessian", "process_sketch", "HessianAccumulator", "Quantizer", "QuantizedLinear", "SpectralFactors", "gptq_fwrd",
            "gptq_quantize", "log_quantization_error", "pack_codes", "process_hessian_alt", "spectral_solve"]

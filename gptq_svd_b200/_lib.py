@@ -44,6 +44,11 @@ SIGNATURES = {
                      _i32, _vp, _i64, _vp, _i64, _vp, _sz, _vp],
     "tq_pack_codes": [_vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp],
     "tq_quant_error_workspace": [_i64, _i64, _i64, C.POINTER(_sz)],
+    "tq_cholesky_workspace": [_i64, C.POINTER(_sz)],
+    "tq_cholesky_solve": [_vp, _i64, _i64, _vp, _dbl, _vp, _i64, C.POINTER(_i32), _vp, _sz, _vp],
+    "tq_sketch_accum": [_vp, _i64, _vp, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _sz, _vp],
+    "tq_sketch_workspace": [_i64, _i64, C.POINTER(_sz)],
+    "tq_sketch_solve": [_vp, _i64, _i64, _i64, _dbl, _i32, _vp, _vp, C.POINTER(_i64), _vp, _sz, _vp],
     "tq_quant_error": [_vp, _i64, _vp, _i64, _vp, _i32, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _sz, _vp],
 }
 _RESTYPES = {"tq_last_error": C.c_char_p, "tq_launch_count": C.c_int64}

@@ -286,6 +286,7 @@ struct SymPanelArgs {
   unsigned int* bar;
   int trace;
   int boxc;         // columns per TMA box (a tile is kTileC / boxc boxes)
+  int align;        // row blocks start at multiples of `align` rows (TMA needs 16 bytes; 32 rows = one 256-byte L2 block)
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -341,9 +342,11 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
     const int64_t len = n - c - 1;
     const int64_t base = c + 1;
     // ---- tile list of this column (depends only on len and i)
-    // TMA needs a 16-byte aligned box origin: row blocks start at the EVEN global row base_e = base - dl;
-    // when dl = 1 the first row of row block 0 is row c (not part of the trailing matrix, masked out)
-    const int dl = int(base & 1);
+    // TMA needs a 16-byte aligned box origin, and a 1 KB column chunk that starts on a 256-byte boundary
+    // costs exactly four 256-byte L2 blocks (a misaligned one five): row blocks start at the global row
+    // base_e = base - dl, a multiple of `align` (32 when the matrix allows it, else 2); the dl rows above
+    // the trailing matrix that fall into row block 0 are masked out
+    const int dl = int(base % a.align);
     const int64_t base_e = base - dl;
     const int nrb = int((len + dl + kTileR - 1) / kTileR), nstrips = int((len + kTileC - 1) / kTileC);
     const int TA = nrb > 0 ? nrb * (nrb - 1) + min(2 * nrb, nstrips) : 0;
@@ -841,7 +844,7 @@ struct SymBuffers {
 };
 
 // largest number of row-partial slots any row block needs for trailing size len with T tiles on G CTAs
-static int sym_max_slots(int64_t len, int dl, bool history, int G) {
+static int sym_max_slots(int64_t len, int dl, bool history, int G) {   // dl = (c + 1) % align
   const int nrb = int((len + dl + kTileR - 1) / kTileR), nstrips = int((len + kTileC - 1) / kTileC);
   if (nrb <= 0) return 0;
   const int TA = nrb * (nrb - 1) + std::min(2 * nrb, nstrips);
@@ -899,6 +902,8 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
   int boxc = 64;
   if (const char* bx = getenv("TQ_SYM_BOXC")) boxc = atoi(bx);
   if (boxc != 64 && boxc != 32 && boxc != 16 && boxc != 8) boxc = 64;
+  int align = (n % 32 == 0 && reinterpret_cast<uintptr_t>(A) % 256 == 0 && reinterpret_cast<uintptr_t>(W) % 256 == 0) ? 32 : 2;
+  if (const char* al = getenv("TQ_SYM_ALIGN")) align = atoi(al) == 2 ? 2 : align;
   if (use_sym) {
     TQ_TRY(make_tmap_f64(&tmA, A, uint64_t(n), uint64_t(n), uint64_t(n), kTileR, boxc));
     TQ_TRY(make_tmap_f64(&tmW, W, uint64_t(n), uint64_t(kTrdNb), uint64_t(n), kTileR, boxc));
@@ -909,7 +914,7 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
     const int jb = int(imin(kTrdNb, n - j0));
     if (use_sym) {
       for (int i = 0; i < jb; ++i) {
-        if (sym_max_slots(n - (j0 + i) - 1, int((j0 + i + 1) & 1), i > 0, sym_blocks) > kRowSlots) {
+        if (sym_max_slots(n - (j0 + i) - 1, int((j0 + i + 1) % align), i > 0, sym_blocks) > kRowSlots) {
           set_error("sytrd: row-partial slots exceed %d (n=%lld)", kRowSlots, (long long)n);
           return TQ_ERR_UNSUPPORTED;
         }
@@ -917,7 +922,7 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
       TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
       const char* dbg = getenv("TQ_SYM_DEBUG");
       SymPanelArgs pa{A, n, j0, jb, W, d, e, tau, sb.rowpart, sb.colpart, sb.wvpart, part, scal, bar,
-                      dbg ? atoi(dbg) : (trace_enabled() ? 1 : 0), boxc};
+                      dbg ? atoi(dbg) : (trace_enabled() ? 1 : 0), boxc, align};
       void* kargs[] = {&pa, &tmA, &tmW};
       double bytes = 0.0;      // algorithmic bytes: every column streams the LOWER triangle of the trailing matrix once
       for (int i = 0; i < jb; ++i) {
@@ -1599,7 +1604,7 @@ size_t eigh_ws_bytes(int64_t n) {
   b += ws_bytes_for(size_t(n) * n, 8) * 4;                 // A, Zg, Zo, U
   b += ws_bytes_for(n, 8) * (14 + 32) + ws_bytes_for(2 * kTrdNb * 32, 8) + ws_bytes_for(n, 4) * 8 + ws_bytes_for(n, sizeof(DcRot));
   b += ws_bytes_for(size_t(n) * kTrdNb, 8) * 5 + ws_bytes_for(size_t(n) * kOrmNb, 8);   // W, XY, Vc
-  b += ws_bytes_for(size_t(kRowSlots) * n, 8) + ws_bytes_for(size_t((n + kTileR - 1) / kTileR + 1) * n, 8) + ws_bytes_for(size_t((n + kTileR - 1) / kTileR + 1) * 2 * kTrdNb, 8) + 1024;   // symmetric panel partials
+  b += ws_bytes_for(size_t(kRowSlots) * n, 8) + ws_bytes_for(size_t((n + kTileR - 1) / kTileR + 2) * n, 8) + ws_bytes_for(size_t((n + kTileR - 1) / kTileR + 2) * 2 * kTrdNb, 8) + 1024;   // symmetric panel partials
   b += ws_bytes_for(size_t(kOrmNb) * n, 8) * 2;            // w1, w2
   b += ws_bytes_for(kOrmNb * kOrmNb, 8) * 2 + ws_bytes_for(4 * kTrdNb, 8);
   return b;
@@ -1614,7 +1619,7 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   double* y = ws.take<double>(size_t(n) * kPanelWarps);
   double* W = ws.take<double>(size_t(n) * kTrdNb);
   double* XY = ws.take<double>(size_t(n) * 4 * kTrdNb);
-  const size_t nrb_max = size_t((n + kTileR - 1) / kTileR) + 1;
+  const size_t nrb_max = size_t((n + kTileR - 1) / kTileR) + 2;
   SymBuffers sb;
   sb.rowpart = ws.take<double>(size_t(kRowSlots) * n);
   sb.colpart = ws.take<double>(nrb_max * n);

@@ -38,7 +38,9 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
 //   otherwise:     k = n
 __global__ void __launch_bounds__(1024)
 rank_select_kernel(const double* __restrict__ w, int64_t n, double thr, int method, double* __restrict__ eig_desc,
-                   long long* __restrict__ k_out) {
+                   long long* __restrict__ k_out, int64_t nvals, int64_t min_rank) {
+  // nvals <= n: only the leading nvals values take part in the rule (process_sketch: the sketch has
+  // min(rank, n) singular values, gptq_utils.py:49-64); the result is clamped to [min_rank, nvals]
   __shared__ double wsum[32];
   __shared__ double carry_s, total_s, ref_s;
   __shared__ unsigned long long count_s;
@@ -50,22 +52,27 @@ rank_select_kernel(const double* __restrict__ w, int64_t n, double thr, int meth
   }
   __syncthreads();
   if (method == TQ_RANK_FULL) {
-    if (tid == 0) *k_out = (long long)n;
+    if (tid == 0) *k_out = (long long)nvals;
     return;
   }
   if (method == TQ_RANK_MEAN_TRIMMED) {
     if (tid == 0) {
-      const int64_t ref_k = n < 33 ? n : 33;
+      const int64_t ref_k = nvals < 33 ? nvals : 33;
       double s = 0.0;
       for (int64_t i = 1; i < ref_k; ++i) s += sqrt(eig_desc[i]);
-      ref_s = n > 1 ? s / double(ref_k - 1) : sqrt(eig_desc[0]);
+      ref_s = nvals > 1 ? s / double(ref_k - 1) : sqrt(eig_desc[0]);
     }
     __syncthreads();
     unsigned long long c = 0;
-    for (int64_t i = tid; i < n; i += blockDim.x) c += (sqrt(eig_desc[i]) > thr * ref_s) ? 1ull : 0ull;
+    for (int64_t i = tid; i < nvals; i += blockDim.x) c += (sqrt(eig_desc[i]) > thr * ref_s) ? 1ull : 0ull;
     atomicAdd(&count_s, c);
     __syncthreads();
-    if (tid == 0) *k_out = (long long)count_s;
+    if (tid == 0) {
+      long long k = (long long)count_s;
+      if (k > nvals) k = nvals;
+      if (k < min_rank) k = min_rank;
+      *k_out = k;
+    }
     return;
   }
   // energy: pass 1 total (fixed order: chunked block scan), pass 2 count
@@ -74,10 +81,10 @@ rank_select_kernel(const double* __restrict__ w, int64_t n, double thr, int meth
     __syncthreads();
     const double target = pass ? (1.0 - thr) * total_s : 0.0;
     unsigned long long c = 0;
-    for (int64_t base = 0; base < n; base += blockDim.x) {
+    for (int64_t base = 0; base < nvals; base += blockDim.x) {
       const int64_t i = base + tid;
       double en = 0.0;
-      if (i < n) {
+      if (i < nvals) {
         const double s = sqrt(eig_desc[i]);
         en = s * s;
       }
@@ -91,7 +98,7 @@ rank_select_kernel(const double* __restrict__ w, int64_t n, double thr, int meth
       }
       __syncthreads();
       const double prefix = carry_s + (wid ? wsum[wid - 1] : 0.0) + v;
-      if (pass && i < n && prefix <= target) ++c;
+      if (pass && i < nvals && prefix <= target) ++c;
       __syncthreads();
       if (tid == blockDim.x - 1) carry_s = prefix;
       __syncthreads();
@@ -105,7 +112,8 @@ rank_select_kernel(const double* __restrict__ w, int64_t n, double thr, int meth
   }
   if (tid == 0) {
     long long k = (long long)count_s;
-    if (k < n) k += 1;
+    if (k < nvals) k += 1;
+    if (k < min_rank) k = min_rank;
     *k_out = k;
   }
 }
@@ -192,7 +200,7 @@ extern "C" int tq_rank_select(const double* w_asc, int64_t n, double threshold, 
     set_error("tq_rank_select: workspace too small");
     return TQ_ERR_WORKSPACE;
   }
-  rank_select_kernel<<<1, 1024, 0, st>>>(w_asc, n, threshold, method, eig_desc, kd);
+  rank_select_kernel<<<1, 1024, 0, st>>>(w_asc, n, threshold, method, eig_desc, kd, n, 0);
   TQ_LAUNCH_CHECK();
   long long kh = 0;
   TQ_CUDA_CHECK(cudaMemcpyAsync(&kh, kd, sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -201,9 +209,9 @@ extern "C" int tq_rank_select(const double* w_asc, int64_t n, double threshold, 
   return TQ_OK;
 }
 
-extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double threshold, int method, double* R,
-                                 double* Rx, int64_t* perm, double* eigvals, int64_t* k_host, void* ws,
-                                 size_t ws_bytes, void* stream) {
+static int spectral_solve_impl(const double* H, int64_t ldh, int64_t n, double threshold, int method, int64_t nvals,
+                               int64_t min_rank, double* R, double* Rx, int64_t* perm, double* eigvals,
+                               int64_t* k_host, void* ws, size_t ws_bytes, void* stream) {
   TQ_TRY(check_device());
   const bool force_householder = (method & TQ_SOLVE_HOUSEHOLDER_QRCP) != 0;
   method &= ~TQ_SOLVE_HOUSEHOLDER_QRCP;
@@ -227,7 +235,7 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
   long long kh2[2] = {0, 0};
   {
     StageTimer tm(st, "rank");
-    rank_select_kernel<<<1, 1024, 0, st>>>(w, n, threshold, method, eigvals, kd);
+    rank_select_kernel<<<1, 1024, 0, st>>>(w, n, threshold, method, eigvals, kd, nvals, min_rank);
     TQ_LAUNCH_CHECK();
     clamp_flag_kernel<<<1, 1, 0, st>>>(w, n, kd, kd + 1);
     TQ_LAUNCH_CHECK();
@@ -317,4 +325,112 @@ extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double
     TQ_LAUNCH_CHECK();
   }
   return TQ_OK;
+}
+
+extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double threshold, int method, double* R,
+                                 double* Rx, int64_t* perm, double* eigvals, int64_t* k_host, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  return spectral_solve_impl(H, ldh, n, threshold, method, n, 0, R, Rx, perm, eigvals, k_host, ws, ws_bytes, stream);
+}
+
+// ------------------------------------------------------------------ sketch path (gptq_utils.py:33-84, 171-211)
+namespace tq {
+__global__ void f32_to_f64_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int64_t n,
+                                  double* __restrict__ dst) {
+  const int64_t total = rows * n;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / n, c = idx - r * n;
+    dst[idx] = double(src[r * lds + c]);
+  }
+}
+__global__ void any_to_f32_kernel(const void* __restrict__ src, int dtype, int64_t lds, int64_t rows, int64_t n,
+                                  float* __restrict__ dst) {
+  const int64_t total = rows * n;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / n, c = idx - r * n;
+    float v;
+    if (dtype == TQ_F16) v = __half2float(reinterpret_cast<const __half*>(src)[r * lds + c]);
+    else if (dtype == TQ_BF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[r * lds + c]);
+    else if (dtype == TQ_F64) v = float(reinterpret_cast<const double*>(src)[r * lds + c]);
+    else v = reinterpret_cast<const float*>(src)[r * lds + c];
+    dst[idx] = v;
+  }
+}
+}  // namespace tq
+
+/* Y (rank x n fp32) += Rb (rank x rows fp32) @ float32(X) (rows x n): Sketcher.hook_fn, gptq_utils.py:185-203.
+ * Plain fp32 SGEMM (TF32 off, like torch's default for addmm_).  ws: rows * n floats when X is not fp32. */
+extern "C" int tq_sketch_accum(float* Y, int64_t ldy, const float* Rb, int64_t ldr, const void* X, int x_dtype,
+                               int64_t ldx, int64_t rank, int64_t rows, int64_t n, void* ws, size_t ws_bytes,
+                               void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(Y && Rb && X && rank > 0 && rows > 0 && n > 0 && ldy >= n && ldr >= rows && ldx >= n,
+             "tq_sketch_accum: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  cublasHandle_t h;
+  TQ_TRY(get_cublas(&h, st));
+  const float* Xf = reinterpret_cast<const float*>(X);
+  int64_t ldxf = ldx;
+  if (x_dtype != TQ_F32) {
+    Workspace wsp(ws, ws_bytes);
+    float* tmp = wsp.take<float>(size_t(rows) * n);
+    if (wsp.overflow) {
+      set_error("tq_sketch_accum: workspace too small (need rows * n floats)");
+      return TQ_ERR_WORKSPACE;
+    }
+    any_to_f32_kernel<<<(unsigned)imin(ceil_div(rows * n, 256), 65535), 256, 0, st>>>(X, x_dtype, ldx, rows, n, tmp);
+    TQ_LAUNCH_CHECK();
+    Xf = tmp;
+    ldxf = n;
+  }
+  const float one = 1.0f;
+  // row-major Y += Rb X  ==  column-major Y^T (n x rank) += X^T (n x rows) Rb^T (rows x rank)
+  TQ_CUBLAS_CHECK(cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH));
+  cublasStatus_t cs = cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, int(n), int(rank), int(rows), &one, Xf, int(ldxf), Rb,
+                                  int(ldr), &one, Y, int(ldy));
+  cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
+  if (cs != CUBLAS_STATUS_SUCCESS) {
+    set_error("tq_sketch_accum: cublasSgemm failed with status %d", int(cs));
+    return TQ_ERR_CUDA;
+  }
+  return TQ_OK;
+}
+
+extern "C" int tq_sketch_workspace(int64_t rank, int64_t n, size_t* bytes) {
+  TQ_REQUIRE(bytes && n > 0 && rank > 0, "tq_sketch_workspace: bad arguments");
+  *bytes = solver_ws_bytes(n) + ws_bytes_for(size_t(n) * n, 8) * 2 + ws_bytes_for(size_t(rank) * n, 8) +
+           ws_bytes_for(n, 8) + 4096;
+  return TQ_OK;
+}
+
+/* process_sketch (gptq_utils.py:33-84) on the scaled sketch Y (rank x n fp32): the reference takes
+ * the singular values / right vectors of the sketch (geqrf + svd); they are the square roots of the
+ * eigenvalues / the eigenvectors of Y^T Y, so the spectral solver runs on G = Y^T Y (fp64) with the
+ * rule restricted to min(rank, n) values and a floor of 1 (:64).  Returns R (k x n) and perm. */
+extern "C" int tq_sketch_solve(const float* Y, int64_t ldy, int64_t rank, int64_t n, double threshold, int method,
+                               double* R, int64_t* perm, int64_t* k_host, void* ws, size_t ws_bytes, void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(Y && R && perm && k_host && rank > 0 && n > 0 && ldy >= n, "tq_sketch_solve: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace wsp(ws, ws_bytes);
+  double* G = wsp.take<double>(size_t(n) * n);
+  double* Rx = wsp.take<double>(size_t(n) * n);
+  double* eig = wsp.take<double>(n);
+  double* Yd = wsp.take<double>(size_t(rank) * n);
+  if (wsp.overflow) {
+    set_error("tq_sketch_solve: workspace too small (see tq_sketch_workspace)");
+    return TQ_ERR_WORKSPACE;
+  }
+  cublasHandle_t h;
+  TQ_TRY(get_cublas(&h, st));
+  f32_to_f64_kernel<<<(unsigned)imin(ceil_div(rank * n, 256), 65535), 256, 0, st>>>(Y, ldy, rank, n, Yd);
+  TQ_LAUNCH_CHECK();
+  const double one = 1.0, zero = 0.0;
+  // row-major Yd (rank x n) is column-major n x rank: G = Yd^T Yd = (col-major Yd)(col-major Yd)^T
+  TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(n), int(n), int(rank), &one, Yd, int(n), Yd, int(n),
+                              &zero, G, int(n)));
+  const int64_t nvals = rank < n ? rank : n;
+  const size_t used = wsp.off;
+  return spectral_solve_impl(G, n, n, threshold, method, nvals, 1, R, Rx, perm, eig, k_host,
+                             static_cast<char*>(ws) + align_up(used, 256), ws_bytes - align_up(used, 256), stream);
 }

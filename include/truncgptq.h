@@ -176,6 +176,44 @@ int tq_quant_error(const float* W, int64_t ldw, const float* Wq, int64_t ldq, co
                    double* out2, void* ws, size_t ws_bytes, void* stream);
 
 /* --------------------------------------------------------------------------
+ * (4) Callers either side of the hot path: the two other
+ *     front ends of the reference that end in the same gptq_fwrd loop.
+ * -------------------------------------------------------------------------- */
+
+int tq_cholesky_workspace(int64_t n, size_t* bytes);
+
+/* Reference-GPTQ factor - replaces process_hessian (gptq_utils.py:129-165).
+ *   H          n x n symmetric fp64 (row-major, ldh);
+ *   perm       optional n int64: act-order permutation (argsort of diag(H), descending,
+ *              :137-139, computed by the caller); the factor is taken of H[perm][:, perm];
+ *   damp_percent  damping ladder damp = 10^e * damp_percent, e = 0..4 (:148-160): the first e for
+ *              which both Cholesky factorizations succeed wins; *damp_exp_host = e, or -1 when all
+ *              five fail and the identity is returned (:161-163);
+ *   Hinv_chol  n x n row-major UPPER factor U with U^T U = (H + damp mean(diag H) I)^-1.
+ * Host synchronisation: one flag read-back per factorization. */
+int tq_cholesky_solve(const double* H, int64_t ldh, int64_t n, const int64_t* perm, double damp_percent,
+                      double* Hinv_chol, int64_t ldo, int* damp_exp_host, void* ws, size_t ws_bytes,
+                      void* stream);
+
+/* Sketch accumulation - replaces the GEMM of Sketcher.hook_fn (gptq_utils.py:185-203):
+ * Y (rank x n fp32) += Rb (rank x rows fp32, the caller's Gaussian block) @ float32(X) with X
+ * rows x n (TQ_F16 / TQ_BF16 / TQ_F32 / TQ_F64).  Strict fp32 SGEMM (no TF32).
+ * ws: rows * n floats when X is not fp32 (may be NULL otherwise). */
+int tq_sketch_accum(float* Y, int64_t ldy, const float* Rb, int64_t ldr, const void* X, int x_dtype,
+                    int64_t ldx, int64_t rank, int64_t rows, int64_t n, void* ws, size_t ws_bytes,
+                    void* stream);
+
+int tq_sketch_workspace(int64_t rank, int64_t n, size_t* bytes);
+
+/* Sketch solver - replaces process_sketch (gptq_utils.py:33-84) on the scaled sketch Y
+ * (rank x n fp32).  The singular values / right singular vectors the reference takes from
+ * geqrf + svd are obtained as the eigen-decomposition of Y^T Y (fp64); the rank rule runs over
+ * min(rank, n) values with a floor of 1 (:49-64); the pivot order and R then follow the same
+ * stages as tq_spectral_solve.  R: n x n row-major buffer, rows [0, k) written. */
+int tq_sketch_solve(const float* Y, int64_t ldy, int64_t rank, int64_t n, double threshold, int method,
+                    double* R, int64_t* perm, int64_t* k_host, void* ws, size_t ws_bytes, void* stream);
+
+/* --------------------------------------------------------------------------
  * Diagnostics (measurement only; no effect on results).
  * -------------------------------------------------------------------------- */
 
