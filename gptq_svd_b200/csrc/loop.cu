@@ -43,8 +43,8 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 constexpr int kBlk = 128;        // columns per block step
 constexpr int kMacro = 1024;     // lazy-batch width of the far trailing update (the reference's block_size scale)
-constexpr int kRowsPerWarp = 8;  // rows interleaved per warp for ILP
-constexpr int kWarpsPerCta = 4;
+constexpr int kRowsPerWarp = 2;  // rows interleaved per warp (8 rows x 4 warps left one warp per SM sub-partition:
+constexpr int kWarpsPerCta = 16; // 1.5 us per column, latency-bound); 16 warps x 2 rows keep the 32-row CTA
 
 // ------------------------------------------------------------------ find_params
 // One warp per (row, group).  Bit-exact with torch: amin/amax, (mx-mn).clamp(1e-5)/max_q,
@@ -165,9 +165,9 @@ __device__ __forceinline__ void quantize(float w, float s, float z, float min_q,
 }
 
 // ------------------------------------------------------------------ in-block column loop
-// CTA = 4 warps x 8 rows.  Lane L owns block columns 4L..4L+3 of its 8 rows in
+// CTA = 16 warps x 2 rows.  Lane L owns block columns 4L..4L+3 of its rows in
 // registers; the 128 x 128 diagonal block of U sits in shared memory.  For column c
-// the owner lane quantises 8 rows (independent chains -> ILP), the errors are
+// the owner lane quantises its rows (independent chains -> ILP), the errors are
 // broadcast with __shfl_sync and every lane applies the rank-1 update to its columns > c.
 template <int SEM>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)

@@ -1,7 +1,11 @@
 // Per-layer output reconstruction error  ||(W-Q)[:,perm] Rx^T||_F / ||W[:,perm] Rx^T||_F
-// (reference log_quantization_error, gptq_utils.py:275-291).  fp32 GEMMs (TF32 off, as
-// the reference runs them inside gptq_fwrd, :474-475) through cuBLAS - a plain library
-// GEMM - with the squared Frobenius norms accumulated in fp64.
+// (reference log_quantization_error, gptq_utils.py:275-291): a logged diagnostic, two plain
+// library GEMMs through cuBLAS with the squared Frobenius norms accumulated in fp64.  The
+// reference runs them in fp32 with TF32 off (:474-475); as SIMT SGEMMs they were 47 % of a
+// down_proj gptq_fwrd call (profiles/r01_launches_loop_down.txt), so they run on the tensor
+// cores with TF32 inputs and fp32 accumulation by default (the ratio moves by < 1e-4 relative,
+// bar 1 %); TQ_METRIC_STRICT_FP32=1 restores the strict-fp32 SGEMM.
+#include <cstdlib>
 #include "blas.cuh"
 #include "common.cuh"
 
@@ -103,9 +107,26 @@ extern "C" int tq_quant_error(const float* W, int64_t ldw, const float* Wq, int6
   const float one = 1.f, zero = 0.f;
   // row-major Y (m x k) = A (m x n) . R32^T  <=>  col-major Y^T (k x m) = R32 . A^T
   const float* srcs[2] = {D, Wo};
+  static int strict = -1;
+  if (strict < 0) {
+    const char* e = getenv("TQ_METRIC_STRICT_FP32");
+    strict = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
   for (int i = 0; i < 2; ++i) {
-    TQ_CUBLAS_CHECK(cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, int(k), int(m), int(n), &one, R32, int(n), srcs[i],
-                                int(n), &zero, Y, int(k)));
+    if (strict) {
+      TQ_CUBLAS_CHECK(cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, int(k), int(m), int(n), &one, R32, int(n), srcs[i],
+                                  int(n), &zero, Y, int(k)));
+    } else {
+      cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
+      cublasStatus_t cs = cublasGemmEx(h, CUBLAS_OP_T, CUBLAS_OP_N, int(k), int(m), int(n), &one, R32, CUDA_R_32F,
+                                       int(n), srcs[i], CUDA_R_32F, int(n), &zero, Y, CUDA_R_32F, int(k),
+                                       CUBLAS_COMPUTE_32F_FAST_TF32, CUBLAS_GEMM_DEFAULT);
+      cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
+      if (cs != CUBLAS_STATUS_SUCCESS) {
+        set_error("tq_quant_error: cublasGemmEx failed with status %d", int(cs));
+        return TQ_ERR_CUDA;
+      }
+    }
     sumsq_kernel<<<296, 256, 0, st>>>(Y, m * k, out2 + i);
     TQ_LAUNCH_CHECK();
   }

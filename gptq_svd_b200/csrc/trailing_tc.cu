@@ -136,13 +136,18 @@ trailing_tc_kernel(const __grid_constant__ CUtensorMap map_ehi, const __grid_con
       __syncwarp();
       const int64_t col = cbase + lane;
       if (col < N) {
-#pragma unroll 4
+        // all 32 row loads of the 32 x 32 sub-tile are issued before the first use: the loop was
+        // latency-bound (4 loads in flight per warp, 130 us per tile; profiles/r01_launches_loop_down.txt)
+        float cv[32];
+#pragma unroll
         for (int rr = 0; rr < 32; ++rr) {
           const int64_t row = rbase + rr;
-          if (row < m) {
-            float* p = C + row * ldc + col;
-            *p = __fsub_rn(*p, mytr[rr * 33 + lane]);
-          }
+          cv[rr] = (row < m) ? C[row * ldc + col] : 0.f;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          const int64_t row = rbase + rr;
+          if (row < m) C[row * ldc + col] = __fsub_rn(cv[rr], mytr[rr * 33 + lane]);
         }
       }
       __syncwarp();

@@ -1,0 +1,22 @@
+"""gptq_fwrd alone on one Linear shape (for an ncu launch list of the loop kernels).
+Usage: python scripts/loop_probe.py [m n]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import gptq_svd_b200 as G
+m = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 12288
+k = int(n * 0.9)
+g = torch.Generator(device="cuda").manual_seed(0)
+R = torch.triu(torch.randn(k, n, device="cuda", dtype=torch.float64, generator=g)) * 0.05
+R += torch.eye(k, n, device="cuda", dtype=torch.float64) * 2
+Rx = R.clone()
+perm = torch.randperm(n, device="cuda", generator=g)
+W = (torch.randn(m, n, device="cuda", generator=g) * 0.02).half()
+def run():
+    q = G.Quantizer(4, 128, True)
+    return G.gptq_fwrd(W, R, q, perm, block_size=1024, use_triton=True, R_x=Rx)
+run(); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); run(); e1.record(); torch.cuda.synchronize()
+print(f"gptq_fwrd m={m} n={n} k={k}: {e0.elapsed_time(e1):.2f} ms")
