@@ -313,9 +313,20 @@ def main():
     if rank == 0:
         peak, which = _peaks()
         achieved = (pb.value / 1e9) / (pms.value / 1e3) if pms.value > 0 else None
-        roof = {"bound": "hbm", "kernel": "sytrd_panel_kernel + qrcp_panel_kernel (persistent panels: trailing matrix x reflector per column)",
+        traffic, traffic_note = None, None
+        try:        # DRAM bytes of ONE captured launch (ncu --set full), committed with the profile
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_sytrd_sym.json")) as f:
+                cap = json.load(f)
+            traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+            traffic_note = (f"ncu capture of panel {cap['panel']} at n={cap['n']}: {traffic / 1e9:.1f} GB DRAM for "
+                            f"{cap['alg_bytes'] / 1e9:.1f} GB algorithmic in that launch")
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": "sytrd_panel_sym_kernel (tridiagonal reduction: lower triangle of the trailing "
+                                          "matrix x reflector per column, TMA-staged, one cooperative launch per 64 columns)",
                 "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_note": traffic_note,
+                "algorithmic_bytes": "sum over the panel's columns of len * (len / 2 + 2 i) * 8 (DESIGN.md 3.2)",
                 "sampled_launches": int(psamp.value), "total_launches": int(ptot.value),
                 "avg_launch_ms": (pms.value / psamp.value) if psamp.value else None,
                 "avg_alg_bytes": (pb.value / psamp.value) if psamp.value else None}
