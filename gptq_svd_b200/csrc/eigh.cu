@@ -300,6 +300,7 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
   __shared__ uint64_t full[kSymStages];
   __shared__ double sh[32];
   __shared__ double tmps[2 * kTrdNb];
+  __shared__ double crow[2 * kTrdNb];   // W[c, t] | V[c, t], t < i: staged during phase C of the previous column
   __shared__ double wrow_s, yraw0_s, uty_s;
   double* const A = a.A;
   double* const W = a.W;
@@ -321,6 +322,7 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
   unsigned int use = 0;        // tiles consumed by this CTA so far (ring position, all threads)
   unsigned int iss = 0;        // tiles issued so far (issuing thread only)
   const bool issuer = (tid == kSymThreads - 32);   // lane 0 of the last warp (rarely owns rows)
+  const uint64_t l2_first = ptx::l2_policy_evict_first();
   if (tid == 0) {
     wrow_s = 0.0;
     for (int s = 0; s < kSymStages; ++s) ptx::mbar_init(&full[s], 1);
@@ -331,8 +333,9 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
   if (a.trace == 30 && j0 > 0) return;
 
   long long tk = a.trace ? clock64() : 0;
+  const bool tracer = (blockIdx.x == 0 && tid == 20 * 32);   // a warp that owns rows until c ~ 11840
 #define TQ_PHASE(idx)                                   \
-  if (a.trace && gt == 0) {                             \
+  if (a.trace && tracer) {                              \
     const long long now = clock64();                    \
     a.scal[8 + (idx)] += double(now - tk);              \
     tk = now;                                           \
@@ -354,6 +357,7 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
     const int ch = (T + G - 1) / G > 0 ? (T + G - 1) / G : 1;
     const int t0 = min(T, bidx * ch), t1 = min(T, t0 + ch);
     // tile t -> TMA coordinates; A-type tiles only touch the trailing matrix (read-only in this kernel)
+    const bool stream_hint = (len > 5000) && !(a.trace & 256);      // lower triangle > 100 MB
     auto issue_tile = [&](int t) {
       const int stage = int(iss % kSymStages);
       double* dst = tiles + stage * kTileElems;
@@ -377,12 +381,17 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
         x = int(base_e + int64_t(t - TA - nrb) * kTileR);
         y = int(j0);
       }
-      for (int cb = 0; cb < kTileC; cb += a.boxc) ptx::tma_load_2d(dst + cb * kTileR, map, &full[stage], x, y + cb);
+      // a trailing matrix far larger than L2 is never re-used from it: stream it with evict_first so the
+      // partial sums and the panel history (phases A / C) stay resident
+      if (stream_hint) {
+        for (int cb = 0; cb < kTileC; cb += a.boxc)
+          ptx::tma_load_2d_hint(dst + cb * kTileR, map, &full[stage], x, y + cb, l2_first);
+      } else {
+        for (int cb = 0; cb < kTileC; cb += a.boxc) ptx::tma_load_2d(dst + cb * kTileR, map, &full[stage], x, y + cb);
+      }
       ++iss;
     };
     int issued = 0;
-    if (issuer && !(a.trace & 64))
-      while (issued < kSymStages && t0 + issued < t1 && t0 + issued < TA) issue_tile(t0 + issued++);
     if (a.trace == 11) {       // debug: wait for the prologue tiles and leave
       __syncthreads();
       for (int q = 0; q < kSymStages && t0 + q < t1 && t0 + q < TA; ++q) ptx::mbar_wait(&full[q], 0);
@@ -395,28 +404,25 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       const bool act = (r < n) && (r >= c);
       double s0 = 0.0, s1 = 0.0, acur = 0.0;
       if (act) {
-        // every load of this block is independent: one DRAM / L2 round trip for the whole row
+        // every load of this block is independent (i <= 64: at most 8 history entries per lane): ONE
+        // DRAM / L2 round trip for the whole row; row c of the history comes from shared memory
         if (sub == 0) acur = A[r + c * lda];
-        const double* ar = A + r + j0 * lda;
-        const double* wr = W + r;
-        const double* ac = A + c + j0 * lda;      // row c of V (V[c, i-1] is the unit entry)
-        const double* wc = W + c;                 // row c of W (W[c, i-1] was recomputed locally: wrow_s)
-        int t = sub;
-        for (; t + 8 < i; t += 16) {
-          const double x0 = ar[int64_t(t) * lda], x1 = ar[int64_t(t + 8) * lda];
-          const double y0 = wr[int64_t(t) * ldw], y1 = wr[int64_t(t + 8) * ldw];
-          const double w0 = wc[int64_t(t) * ldw], w1 = (t + 8 == i - 1) ? wrow_s : wc[int64_t(t + 8) * ldw];
-          const double v0 = ac[int64_t(t) * lda], v1 = (t + 8 == i - 1) ? 1.0 : ac[int64_t(t + 8) * lda];
-          s0 = fma(x0, w0, s0);
-          s1 = fma(y0, v0, s1);
-          s0 = fma(x1, w1, s0);
-          s1 = fma(y1, v1, s1);
+        const double* ar = A + r + (j0 + sub) * lda;
+        const double* wr = W + r + int64_t(sub) * ldw;
+        double x[8], y[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const bool ok = sub + 8 * q < i;
+          x[q] = ok ? ar[int64_t(8 * q) * lda] : 0.0;
+          y[q] = ok ? wr[int64_t(8 * q) * ldw] : 0.0;
         }
-        if (t < i) {
-          const double w0 = (t == i - 1) ? wrow_s : wc[int64_t(t) * ldw];
-          const double v0 = (t == i - 1) ? 1.0 : ac[int64_t(t) * lda];
-          s0 = fma(ar[int64_t(t) * lda], w0, s0);
-          s1 = fma(wr[int64_t(t) * ldw], v0, s1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int t = sub + 8 * q;
+          if (t < i) {
+            s0 = fma(x[q], crow[t], s0);
+            s1 = fma(y[q], crow[kTrdNb + t], s1);
+          }
         }
       }
       double s = s0 + s1;
@@ -432,6 +438,11 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       }
     }
     if (len <= 0) break;               // last column: only the diagonal entry (uniform across the grid)
+    // prefetch the first tiles of this column's product only now: issued at the top of the step, their
+    // 28 MB (3 stages x 148 SMs) queue in front of the small phase-A loads, which then take 4 us
+    if (issuer && !(a.trace & 64))
+      while (issued < kSymStages && t0 + issued < t1 && t0 + issued < TA) issue_tile(t0 + issued++);
+    TQ_PHASE(7)
     ss = block_sum(ss, sh);
     if (threadIdx.x == 0) part1[blockIdx.x] = ss;
     TQ_PHASE(0)
@@ -741,26 +752,22 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
     TQ_PHASE(5)
     // acc -= V[r, :] tmp1, s1 -= W[r, :] tmp2 over this lane's share of the panel history
     auto history = [&](int64_t r, double& acc, double& s1) {
-      const double* ar = A + r + j0 * lda;
-      const double* wr = W + r;
-      int t = sub;
-      for (; t + 24 < i; t += 32) {
-        const double x0 = ar[int64_t(t) * lda], x1 = ar[int64_t(t + 8) * lda], x2 = ar[int64_t(t + 16) * lda],
-                     x3 = ar[int64_t(t + 24) * lda];
-        const double y0 = wr[int64_t(t) * ldw], y1 = wr[int64_t(t + 8) * ldw], y2 = wr[int64_t(t + 16) * ldw],
-                     y3 = wr[int64_t(t + 24) * ldw];
-        acc = fma(-x0, tmps[t], acc);
-        s1 = fma(-y0, tmps[kTrdNb + t], s1);
-        acc = fma(-x1, tmps[t + 8], acc);
-        s1 = fma(-y1, tmps[kTrdNb + t + 8], s1);
-        acc = fma(-x2, tmps[t + 16], acc);
-        s1 = fma(-y2, tmps[kTrdNb + t + 16], s1);
-        acc = fma(-x3, tmps[t + 24], acc);
-        s1 = fma(-y3, tmps[kTrdNb + t + 24], s1);
+      const double* ar = A + r + (j0 + sub) * lda;
+      const double* wr = W + r + int64_t(sub) * ldw;
+      double x[8], y[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {            // i <= 64: at most 8 entries per lane, all loads independent
+        const bool ok = sub + 8 * q < i;
+        x[q] = ok ? ar[int64_t(8 * q) * lda] : 0.0;
+        y[q] = ok ? wr[int64_t(8 * q) * ldw] : 0.0;
       }
-      for (; t < i; t += 8) {
-        acc = fma(-ar[int64_t(t) * lda], tmps[t], acc);
-        s1 = fma(-wr[int64_t(t) * ldw], tmps[kTrdNb + t], s1);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int t = sub + 8 * q;
+        if (t < i) {
+          acc = fma(-x[q], tmps[t], acc);
+          s1 = fma(-y[q], tmps[kTrdNb + t], s1);
+        }
       }
     };
     const double vtyv = scl * scl * uty_s + 2.0 * scl * fix * yraw0_s + fix * fix * a00;
@@ -769,6 +776,15 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
     const double wv = tau * (vtyv - 2.0 * cross);          // w'.v
     const double alpha2 = -0.5 * tau * wv;
     // (the last warp rarely owns rows: it starts on the next column's W[c+1, i] right away)
+    if (wid >= kSymWarps - 3 && wid < kSymWarps - 1) {     // row c+1 of the panel history for the next phase A
+      const int t = (wid - (kSymWarps - 3)) * 32 + lane;   // 64 lanes <-> t
+      if (t < i) {
+        crow[t] = W[(c + 1) + t * ldw];
+        crow[kTrdNb + t] = A[(c + 1) + (j0 + t) * lda];
+      } else if (t == i) {
+        crow[kTrdNb + t] = 1.0;                             // V[c+1, i] is the unit entry; W[c+1, i] = wrow_s below
+      }
+    }
     if (wid == kSymWarps - 1) {        // W[c+1, i] for the next column update (v[c+1] = 1): every CTA repeats
       const int64_t r = c + 1;         // the owner's arithmetic (same lane split) so the value is bit-identical
       double acc = scl * ybase_lane, s1 = 0.0;
@@ -778,7 +794,10 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       ymw += __shfl_xor_sync(0xffffffffu, ymw, 4);
       ymw += __shfl_xor_sync(0xffffffffu, ymw, 2);
       ymw += __shfl_xor_sync(0xffffffffu, ymw, 1);
-      if (lane == 0) wrow_s = fma(alpha2, 1.0, tau * ymw);
+      if (lane == 0) {
+        wrow_s = fma(alpha2, 1.0, tau * ymw);
+        crow[i] = wrow_s;
+      }
     }
     for (int64_t rb4 = 4 * gwarp; rb4 < n; rb4 += 4 * nwarps) {
       const int64_t r = rb4 + rsel;
@@ -1647,8 +1666,8 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
       double hc[16];
       cudaMemcpyAsync(hc, scal, sizeof(hc), cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
-      fprintf(stderr, "[tq-trace] sytrd phase Mcycles (CTA 0): A %.1f  barrier1 %.1f  B(stream) %.1f  barrier2 %.1f  C %.1f (C1 %.1f C2 %.1f)\n",
-              hc[8] * 1e-6, hc[9] * 1e-6, hc[10] * 1e-6, hc[11] * 1e-6, (hc[12] + hc[13] + hc[14]) * 1e-6, hc[13] * 1e-6, hc[14] * 1e-6);
+      fprintf(stderr, "[tq-trace] sytrd phase Mcycles (CTA 0): A %.1f  barrier1 %.1f  B(stream) %.1f  barrier2 %.1f  C %.1f (C1 %.1f C2 %.1f)  [A row loop %.1f]\n",
+              (hc[8] + hc[15]) * 1e-6, hc[9] * 1e-6, hc[10] * 1e-6, hc[11] * 1e-6, (hc[12] + hc[13] + hc[14]) * 1e-6, hc[13] * 1e-6, hc[14] * 1e-6, hc[15] * 1e-6);
     }
   }
   if (const char* dbg = getenv("TQ_SYM_DEBUG")) {
