@@ -59,6 +59,8 @@ struct PcholArgs {
   int64_t* perm64;   // n: position -> original column, filled for pivoted positions
   unsigned int* bar;
   int* fail;
+  double* slots;     // 2 x gridDim x 2: per-CTA pivot candidates (value, position), double-buffered by step parity
+  int local;         // 1: every column quad keeps its diagonal entry and position in registers (see P0)
 };
 
 __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a) {
@@ -77,35 +79,57 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
   unsigned int bar_target = 0;
   for (int64_t p = j0 + tid; p < n; p += blockDim.x) perm_s[p] = a.perm[p];
   __syncthreads();
-  for (int i = 0; i < a.jb; ++i) {
-    const int64_t j = j0 + i;
-    // ---------------- P0: pivot
-    double best = -INFINITY;
-    int bidx = int(n);
-    for (int64_t p = j + tid; p < n; p += blockDim.x) {
-      const double v = a.d[perm_s[p]];
-      if (v > best) {
-        best = v;
-        bidx = int(p);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (ov > best || (ov == best && oi < bidx)) {
-        best = ov;
-        bidx = oi;
-      }
-    }
-    if (lane == 0) {
-      sval[wid] = best;
-      sidx[wid] = bidx;
+  // local mode: the grid has one quad of threads per compact column for the whole launch, so the quad keeps
+  // its column's Schur diagonal (dcr) and current position (posr) in registers: the pivot search becomes a
+  // CTA-local reduction plus ONE load of the per-CTA candidates, instead of a gather of all d[perm[p]]
+  // from L2 (three dependent rounds per step)
+  const int64_t cown = gt / kPcTpc;
+  double dcr = -INFINITY;
+  int posr = int(n);
+  if (a.local) {
+    int* inv_s = perm_s + n;                 // compact column -> position (only needed here)
+    for (int64_t p = j0 + tid; p < n; p += blockDim.x) inv_s[perm_s[p]] = int(p);
+    __syncthreads();
+    if (cown < ncur) {
+      dcr = a.d[cown];
+      if (dcr != -INFINITY) posr = inv_s[cown];
     }
     __syncthreads();
-    if (wid == 0) {
-      best = sval[lane];
-      bidx = sidx[lane];
+  }
+  for (int i = 0; i < a.jb; ++i) {
+    const int64_t j = j0 + i;
+    // ---------------- P0: pivot (value desc, position asc)
+    double best = -INFINITY;
+    int bidx = int(n);
+    if (a.local) {
+      if (q4 == 0 && dcr != -INFINITY) {
+        best = dcr;
+        bidx = posr;
+      }
+    } else {
+      for (int64_t p = j + tid; p < n; p += blockDim.x) {
+        const double v = a.d[perm_s[p]];
+        if (v > best) {
+          best = v;
+          bidx = int(p);
+        }
+      }
+    }
+    for (int round = 0; round < (a.local ? 2 : 1); ++round) {
+      if (round == 1) {                       // second round: reduce the per-CTA candidates (after the barrier)
+        double* sl = a.slots + size_t(i & 1) * 2 * nb;
+        if (tid == 0) {
+          sl[2 * blockIdx.x] = sdj;
+          sl[2 * blockIdx.x + 1] = double(spvt);
+        }
+        grid_barrier(a.bar, bar_target, nb);
+        best = -INFINITY;
+        bidx = int(n);
+        if (tid < int(nb)) {
+          best = sl[2 * tid];
+          bidx = int(sl[2 * tid + 1]);
+        }
+      }
 #pragma unroll
       for (int o = 16; o; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -115,12 +139,31 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
           bidx = oi;
         }
       }
+      __syncthreads();                        // sval / sidx / spvt of the previous round have been read
       if (lane == 0) {
-        spvt = bidx;
-        sdj = best;
+        sval[wid] = best;
+        sidx[wid] = bidx;
       }
+      __syncthreads();
+      if (wid == 0) {
+        best = sval[lane];
+        bidx = sidx[lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+          if (ov > best || (ov == best && oi < bidx)) {
+            best = ov;
+            bidx = oi;
+          }
+        }
+        if (lane == 0) {
+          spvt = bidx;
+          sdj = best;
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
     const int pvt = spvt;
     const double dj = sdj;
     if (!(dj > 0.0) || pvt >= n) {          // numerically rank deficient before step k (same in every CTA)
@@ -128,12 +171,14 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
       break;
     }
     const int cj = perm_s[pvt];
+    const int cq = perm_s[j];                 // the column that moves from position j to position pvt
     __syncthreads();
     if (tid == 0) {
-      perm_s[pvt] = perm_s[j];
+      perm_s[pvt] = cq;
       perm_s[j] = cj;
       if (blockIdx.x == 0) a.perm64[j] = a.orig_of[cj];
     }
+    if (a.local && cown == cq) posr = pvt;
     if (tid < i) hs[tid] = a.Rp[int64_t(tid) * n + cj];
     __syncthreads();
     const double rjj = sqrt(dj);
@@ -145,43 +190,62 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
     for (int64_t c0 = gt / kPcTpc; c0 < (ncur + 7) / 8 * 8; c0 += nthreads / kPcTpc) {   // warp-uniform trips
       const int64_t c = c0;
       const bool inr = c < ncur;
-      const double dc = inr ? a.d[c] : -INFINITY;
+      const double dc = a.local ? dcr : (inr ? a.d[c] : -INFINITY);
       const bool live = inr && c != cj && dc != -INFINITY;
       double s0 = 0.0, s1 = 0.0;
       if (live) {
         if (q4 == 0) s0 = Gc[c];
         const double* Rh = a.Rp + c;
         int t = q4;
-        for (; t + 3 * kPcTpc < i; t += 4 * kPcTpc) {     // 4 independent loads in flight (panel history, L2)
-          const double r0 = Rh[int64_t(t) * n], r1 = Rh[int64_t(t + kPcTpc) * n],
-                       r2 = Rh[int64_t(t + 2 * kPcTpc) * n], r3 = Rh[int64_t(t + 3 * kPcTpc) * n];
-          s0 = fma(-hs[t], r0, s0);
-          s1 = fma(-hs[t + kPcTpc], r1, s1);
-          s0 = fma(-hs[t + 2 * kPcTpc], r2, s0);
-          s1 = fma(-hs[t + 3 * kPcTpc], r3, s1);
+        for (; t + 7 * kPcTpc < i; t += 8 * kPcTpc) {     // 8 independent loads in flight (panel history, L2)
+          double r[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) r[q] = Rh[int64_t(t + q * kPcTpc) * n];
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) {
+            s0 = fma(-hs[t + q * kPcTpc], r[q], s0);
+            s1 = fma(-hs[t + (q + 1) * kPcTpc], r[q + 1], s1);
+          }
+        }
+        if (t < i) {                                        // up to 7 more, again all issued before the first use
+          double r[7];
+#pragma unroll
+          for (int q = 0; q < 7; ++q) r[q] = (t + q * kPcTpc < i) ? Rh[int64_t(t + q * kPcTpc) * n] : 0.0;
+#pragma unroll
+          for (int q = 0; q < 7; ++q)
+            if (t + q * kPcTpc < i) s0 = fma(-hs[t + q * kPcTpc], r[q], s0);
+          t = i;
         }
         for (; t < i; t += kPcTpc) s0 = fma(-hs[t], Rh[int64_t(t) * n], s0);
       }
       double sacc = s0 + s1;
       sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
       sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-      if (inr && q4 == 0) {
+      if (inr) {
+        double dnew = dc;
         if (c == cj) {
-          Rpi[c] = rjj;
-          Rj[a.orig_of[c]] = rjj;
-          a.d[c] = -INFINITY;
+          dnew = -INFINITY;
+          if (q4 == 0) {
+            Rpi[c] = rjj;
+            Rj[a.orig_of[c]] = rjj;
+          }
         } else if (!live) {
-          Rpi[c] = 0.0;
+          if (q4 == 0) Rpi[c] = 0.0;
         } else {
           const double r = sacc * inv;
-          Rpi[c] = r;
-          Rj[a.orig_of[c]] = r;
-          a.d[c] = fmax(fma(-r, r, dc), 0.0);
+          dnew = fmax(fma(-r, r, dc), 0.0);
+          if (q4 == 0) {
+            Rpi[c] = r;
+            Rj[a.orig_of[c]] = r;
+          }
         }
+        if (a.local) dcr = dnew;                       // every thread of the quad tracks it
+        else if (q4 == 0) a.d[c] = dnew;
       }
     }
-    grid_barrier(a.bar, bar_target, nb);
+    if (!a.local) grid_barrier(a.bar, bar_target, nb);
   }
+  if (a.local && cown < ncur && q4 == 0) a.d[cown] = dcr;
   if (blockIdx.x == 0)
     for (int64_t p = j0 + tid; p < n; p += blockDim.x) a.perm[p] = perm_s[p];
 }
@@ -291,7 +355,7 @@ __global__ void pchol_emit_kernel(const double* __restrict__ Rorig, int64_t n, i
 }
 
 size_t pchol_ws_bytes(int64_t n, int64_t k) {
-  return ws_bytes_for(size_t(k) * n, 8) + ws_bytes_for(size_t(kPcNb) * n, 8) + ws_bytes_for(n, 8) * 2 +
+  return ws_bytes_for(size_t(k) * n, 8) + ws_bytes_for(size_t(kPcNb) * n, 8) + ws_bytes_for(n, 8) * 2 + ws_bytes_for(4 * 1024, 8) +
          ws_bytes_for(n, 4) * 6 + ws_bytes_for(8, 4) * 3;
 }
 
@@ -312,11 +376,15 @@ int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64
   unsigned int* bar = ws.take<unsigned int>(4);
   int* fail = ws.take<int>(4);
   int* nnew_d = ws.take<int>(4);
+  double* slots = ws.take<double>(4 * 1024);
   if (ws.overflow) {
     set_error("pchol: workspace too small");
     return TQ_ERR_WORKSPACE;
   }
-  const size_t smem = size_t(n) * sizeof(int);
+  // local pivot search needs the inverse permutation next to perm in shared memory (2 n ints) and one
+  // quad of threads per column on at most one CTA per SM
+  const bool local = size_t(n) * 8 <= 200 * 1024 && ceil_div(n * kPcTpc, kPcThreads) <= num_sms();
+  const size_t smem = size_t(n) * sizeof(int) * (local ? 2 : 1);
   if (smem > 200 * 1024) {
     set_error("pchol: n = %lld too large for the shared-memory permutation", (long long)n);
     return TQ_ERR_UNSUPPORTED;
@@ -347,7 +415,7 @@ int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64
     // kPcTpc threads per column: more CTAs than that only make the barrier slower
     const int blocks = int(imax(1, imin(num_sms(), ceil_div(ncur * kPcTpc, kPcThreads))));
     TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
-    PcholArgs pa{Gc, ncur, ncur, n, j0, jb, Rp, Rorig, d, orig_of, perm, perm64, bar, fail};
+    PcholArgs pa{Gc, ncur, ncur, n, j0, jb, Rp, Rorig, d, orig_of, perm, perm64, bar, fail, slots, local ? 1 : 0};
     void* kargs[] = {&pa};
     TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)pchol_panel_kernel, dim3(blocks), dim3(kPcThreads), kargs,
                                               smem, st));
