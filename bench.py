@@ -159,7 +159,9 @@ def _config(args, k_list):
             "bits": args.bits, "sym": bool(args.sym), "group_size": 128, "eps": args.eps, "threshold_method": "energy",
             "block_size": 1024, "activations": f"randn @ A^T, column scales logspace(0,{args.decay}), 8 outlier channels x30",
             "retained_rank": k_list, "l2": "inputs per step (12.9 GB) exceed the 126 MB L2; no explicit flush",
-            "parallelism": f"layers sharded over {args.gpus} rank(s), no collective"}
+            "parallelism": f"layers sharded over {args.gpus} rank(s), no collective",
+            "solves": ("the three n=4096 Hessians of a layer side by side (SM budget 49 each), n=12288 alone"
+                       if args.concurrent_solves else "one after another")}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -187,6 +189,8 @@ def main():
     ap.add_argument("--tiny", action="store_true", help="small shapes (functional check only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--concurrent-solves", type=int, default=1,
+                    help="solve the n <= 8192 Hessians of a layer side by side on one GPU (0: one after another)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -222,6 +226,10 @@ def main():
     ranks_seen = []
 
     copy_stream = torch.cuda.Stream(device=dev)
+    pool = None
+    if args.concurrent_solves:
+        from gptq_svd_b200.concurrent import SolverPool
+        pool = SolverPool(workers=3, device=dev)
     staging = {}          # device staging buffers of the e2e leg (allocated once, reused every step)
 
     def layer_step(x_src, w_src, host: bool, sink=None):
@@ -250,6 +258,8 @@ def main():
                         staging[key].copy_(w_src[gi][li], non_blocking=True)
                         events[key] = torch.cuda.Event()
                         events[key].record(copy_stream)
+        # 1. Hessians of the four groups
+        Hs = []
         for gi, (n, outs) in enumerate(groups):
             acc = G.HessianAccumulator(n, dev)
             for c in range(0, tokens, chunk):
@@ -259,8 +269,21 @@ def main():
                 else:
                     xb = x_src[gi][c:c + chunk]
                 acc.add_batch(xb.view(-1, 2048, n) if (xb.shape[0] % 2048 == 0) else xb)
-            H = acc.get_hessian()
-            R, R_x, perm = G.process_hessian_alt(H, args.eps, "energy")
+            Hs.append(acc.get_hessian())
+            del acc
+        # 2. spectral solves: the latency-bound n <= 8192 ones side by side (one host thread, stream and SM
+        #    budget each, gptq_svd_b200/concurrent.py), the bandwidth-bound wide one alone on the whole GPU
+        facs = [None] * len(groups)
+        small = [gi for gi, (n, _) in enumerate(groups) if n <= 8192] if pool is not None else []
+        if len(small) > 1:
+            for gi, f in zip(small, pool.process_hessian_alt_many([Hs[gi] for gi in small], args.eps, "energy")):
+                facs[gi] = f
+        for gi in range(len(groups)):
+            if facs[gi] is None:
+                facs[gi] = G.process_hessian_alt(Hs[gi], args.eps, "energy")
+        # 3. grid + loop of the seven Linears
+        for gi, (n, outs) in enumerate(groups):
+            R, R_x, perm = facs[gi]
             ks.append(int(R.shape[0]))
             for li, m in enumerate(outs):
                 if host:
@@ -272,7 +295,7 @@ def main():
                 fw, k = G.gptq_fwrd(W, R, q, perm, block_size=1024, use_triton=True, R_x=R_x)
                 if host:
                     sink[gi][li].copy_(fw, non_blocking=True)
-            del acc, H, R, R_x, perm
+        del Hs, facs
         return ks
 
     def barrier():
@@ -288,7 +311,7 @@ def main():
         sampler.start()
     if not os.environ.get("TQ_BENCH_NO_PROF"):
         lib.tq_profile_begin(4)
-    l0 = lib.tq_launch_count()
+    l0 = lib.tq_launch_count() + (pool.launch_count() if pool else 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e0.record()
@@ -302,7 +325,8 @@ def main():
         sys.stderr.write("per-step ms: " + ", ".join(f"{step_ev[i].elapsed_time(step_ev[i + 1]):.1f}"
                                                      for i in range(args.steps)) + "\n")
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    launches = torch.tensor([lib.tq_launch_count() - l0], device=dev, dtype=torch.float64)
+    launches = torch.tensor([lib.tq_launch_count() + (pool.launch_count() if pool else 0) - l0], device=dev,
+                            dtype=torch.float64)
     import ctypes as C
     pb, pms, psamp, ptot = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_int64(0)
     lib.tq_profile_end(C.byref(pb), C.byref(pms), C.byref(psamp), C.byref(ptot))
@@ -372,6 +396,8 @@ def main():
                "dtype": "f64 solver / f32 loop / f16 SYRK inputs", "data": "synthetic", "config": _config(args, ranks_seen),
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()), "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(out))
+    if pool is not None:
+        pool.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -26,6 +26,7 @@ _i64, _i32, _vp, _sz, _dbl = C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_dou
 SIGNATURES = {
     "tq_version": [],
     "tq_launch_count": [],
+    "tq_set_sm_budget": [_i32],
     "tq_profile_begin": [_i32],
     "tq_profile_end": [C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_i64), C.POINTER(_i64)],
     "tq_last_error": [],

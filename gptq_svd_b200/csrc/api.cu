@@ -93,13 +93,18 @@ StageTimer::~StageTimer() {
   }
 }
 
+static thread_local int g_sm_budget = 0;
+
+// SMs the calling thread's persistent (co-resident) kernels may occupy: the device's count, or the
+// budget set with tq_set_sm_budget so that several solves can be in flight on one GPU.
 int num_sms() {
   static thread_local int cached = 0;
-  if (cached) return cached;
-  int dev = 0, n = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  cached = n;
-  return n;
+  if (!cached) {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached = n;
+  }
+  return (g_sm_budget > 0 && g_sm_budget < cached) ? g_sm_budget : cached;
 }
 
 }  // namespace tq
@@ -137,6 +142,11 @@ extern "C" int tq_profile_end(double* alg_bytes, double* ms, int64_t* sampled, i
   if (total) *total = g_prof_seen;
   g_prof_slots.clear();
   g_prof_on = false;
+  return TQ_OK;
+}
+
+extern "C" int tq_set_sm_budget(int sms) {
+  tq::g_sm_budget = sms > 0 ? sms : 0;
   return TQ_OK;
 }
 

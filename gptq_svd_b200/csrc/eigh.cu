@@ -887,8 +887,8 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
   TQ_CUDA_CHECK(cudaMemsetAsync(tau, 0, sizeof(double) * n, st));
   TQ_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 16, st));
   TQ_CUDA_CHECK(cudaMemsetAsync(e, 0, sizeof(double) * n, st));
-  static thread_local int coop_blocks = 0;
-  if (!coop_blocks) {
+  static thread_local int coop_per_sm = 0;
+  if (!coop_per_sm) {
     int per_sm = 0;
     TQ_CUDA_CHECK(cudaFuncSetAttribute(sytrd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        int(kPanelSmem)));
@@ -898,13 +898,14 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
       set_error("sytrd: panel kernel cannot be made resident");
       return TQ_ERR_CUDA;
     }
-    coop_blocks = num_sms() * (per_sm > 4 ? 4 : per_sm);
+    coop_per_sm = per_sm > 4 ? 4 : per_sm;
   }
+  const int coop_blocks = num_sms() * coop_per_sm;      // num_sms() honours tq_set_sm_budget
   // symmetric TMA panel (half the DRAM bytes) whenever the tensor map can be built: even n (16-byte
   // row pitch).  TQ_SYTRD_COLDOT=1 keeps the column-dot panel for A/B timing.
-  static thread_local int sym_blocks = -1;
-  if (sym_blocks < 0) {
-    sym_blocks = 0;
+  static thread_local int sym_ok = -1;
+  if (sym_ok < 0) {
+    sym_ok = 0;
     const char* env = getenv("TQ_SYTRD_COLDOT");
     if (!(env && env[0] && env[0] != '0')) {
       int per_sm = 0;
@@ -912,9 +913,10 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
                                          int(kSymSmem)));
       TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sytrd_panel_sym_kernel, kSymThreads,
                                                                   kSymSmem));
-      if (per_sm >= 1) sym_blocks = num_sms();
+      if (per_sm >= 1) sym_ok = 1;
     }
   }
+  const int sym_blocks = sym_ok ? num_sms() : 0;
   const bool use_sym = sym_blocks > 0 && (n % 2 == 0) && n >= 256 && (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(W) % 16 == 0);
   CUtensorMap tmA, tmW;

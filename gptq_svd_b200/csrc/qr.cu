@@ -700,8 +700,8 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
   }
   QcPlan* plan = nullptr;
   TQ_TRY(qc_plan(&plan));
-  static thread_local int coop_blocks = 0;
-  if (!coop_blocks) {
+  static thread_local int coop_per_sm = 0;
+  if (!coop_per_sm) {
     int per_sm = 0;
     TQ_CUDA_CHECK(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        int(kQrPanelSmem)));
@@ -711,8 +711,9 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
       set_error("qr_r: panel kernel cannot be made resident");
       return TQ_ERR_CUDA;
     }
-    coop_blocks = num_sms() * (per_sm > 2 ? 2 : per_sm);
+    coop_per_sm = per_sm > 2 ? 2 : per_sm;
   }
+  const int coop_blocks = num_sms() * coop_per_sm;      // num_sms() honours tq_set_sm_budget
   for (int64_t j0 = 0; j0 < k; j0 += kQrOb) {
     const int ob = int(imin(kQrOb, k - j0));
     const int64_t oend = j0 + ob;
@@ -804,8 +805,8 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
   const double eps = 1.1102230246251565e-16;   // dlamch('Epsilon')
   const double tol3z = sqrt(eps);
   const int64_t ldf = n;
-  static thread_local int coop_blocks = 0;
-  if (!coop_blocks) {
+  static thread_local int coop_per_sm = 0;
+  if (!coop_per_sm) {
     int per_sm = 0;
     TQ_CUDA_CHECK(cudaFuncSetAttribute(qrcp_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        int(kQrPanelSmem)));
@@ -815,8 +816,9 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
       set_error("qrcp: panel kernel cannot be made resident");
       return TQ_ERR_CUDA;
     }
-    coop_blocks = num_sms() * (per_sm > 2 ? 2 : per_sm);
+    coop_per_sm = per_sm > 2 ? 2 : per_sm;
   }
+  const int coop_blocks = num_sms() * coop_per_sm;      // num_sms() honours tq_set_sm_budget
   TQ_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 16, st));
   init_perm_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(perm, n);
   TQ_LAUNCH_CHECK();

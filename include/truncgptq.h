@@ -69,6 +69,13 @@ extern "C" {
 int tq_version(void);
 const char* tq_last_error(void);
 
+/* Cap the number of SMs the calling thread's persistent (co-resident) kernels occupy; 0 = all.
+ * The panel kernels of the solver are cooperative launches sized to this budget, so several
+ * solves - one host thread and one stream each - can be in flight on one GPU
+ * (gptq_svd_b200/concurrent.py).  Partial sums are added in a fixed, grid-dependent order: results are
+ * reproducible for a given budget and agree across budgets to rounding (R within 2e-12 relative). */
+int tq_set_sm_budget(int sms);
+
 /* --------------------------------------------------------------------------
  * (1) Hessian accumulation - replaces HessianAccumulator.add_batch / get_hessian
  *     (gptq_utils.py:218-228).

@@ -145,3 +145,35 @@ def test_pipeline_tiny_qwen3(G, mode):
     assert err_q < 0.5
     if mode != "svd":      # a rank-n Gaussian sketch of 2048 tokens is a noisy Hessian estimate: parity is checked above
         assert err_q < err_r * 1.05, (err_q, err_r)
+
+
+def test_solver_pool_matches_sequential(G):
+    """Three solves in flight (one thread, stream and SM budget each) agree with the one-at-a-time call:
+    same k, same pivots, factors to rounding (the partial-sum order depends on the grid size)."""
+    from gptq_svd_b200.concurrent import SolverPool
+    Hs = []
+    for seed in range(3):
+        X = O.make_activations(2048, 512, seed=40 + seed, dist="llm").astype(np.float64)
+        Hs.append(_gpu(X.T @ X / X.shape[0]))
+    seq = [G.spectral_solve(H, 1e-4, "energy") for H in Hs]
+    pool = SolverPool(workers=3)
+    try:
+        for budget in (None, 20):
+            res = pool.spectral_solve_many(Hs, 1e-4, "energy", sm_budget=budget)
+            for r, q in zip(res, seq):
+                assert r.k == q.k
+                assert torch.equal(r.perm[:r.k], q.perm[:q.k])
+                assert float((r.R - q.R).abs().max() / q.R.abs().max()) <= 1e-9
+                assert float((r.R_x - q.R_x).abs().max() / q.R_x.abs().max()) <= 1e-10
+        again = pool.spectral_solve_many(Hs, 1e-4, "energy", sm_budget=20)
+        for r, q in zip(again, res):
+            assert torch.equal(r.R, q.R)                      # reproducible for a given budget
+        out = pool.process_hessian_alt_many(Hs[:2], 1e-4, "energy")
+        assert len(out) == 2 and out[0][0].shape == seq[0].R.shape
+        with pytest.raises(RuntimeError):
+            pool.spectral_solve_many([torch.eye(4, dtype=torch.float64)], 1e-4, "energy")   # CPU tensor: no fallback
+    finally:
+        pool.close()
+    _ = G  # the main thread's budget is untouched
+    f = G.spectral_solve(Hs[0], 1e-4, "energy")
+    assert torch.equal(f.R, seq[0].R)
