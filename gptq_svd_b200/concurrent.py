@@ -63,20 +63,22 @@ class SolverPool:
 
     def map(self, fns, sm_budget: Optional[int] = None):
         """Run the callables concurrently (at most `workers` at a time); returns their results.  The
-        caller's current stream waits for every result before it can use it."""
+        caller's current stream waits for every result before it can use it.  `sm_budget`: one value for
+        all jobs or one per job (default: the SMs split evenly)."""
         n = len(fns)
         if n == 0:
             return []
         if sm_budget is None:
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
             sm_budget = max(8, sms // min(n, self.workers))
+        budgets = list(sm_budget) if isinstance(sm_budget, (list, tuple)) else [sm_budget] * n
         cur = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(cur)
         out: List = [None] * n
         done = threading.Semaphore(0)
         for i, fn in enumerate(fns):
-            self._jobs.put((fn, sm_budget, ready, done, out, i))
+            self._jobs.put((fn, budgets[i], ready, done, out, i))
         for _ in range(n):
             done.acquire()
         res = []

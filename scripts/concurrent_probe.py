@@ -32,3 +32,22 @@ for budget in (None, 148, 74, 49, 36):
     print(f"n={n} x{cnt}: sequential {t_seq*1e3:.1f} ms, concurrent (budget {budget}) {t_con*1e3:.1f} ms, "
           f"k equal {same_k}, perm[:k] equal {same_p}, max rel dR {dR:.2e} dRx {dRx:.2e} deig {de:.2e}", flush=True)
 pool.close()
+
+# one wide solve next to the narrow ones: does the bandwidth-bound solve hide the latency-bound ones?
+if len(sys.argv) > 3:
+    nb = int(sys.argv[3])
+    Hb = make_h(nb, seed=9)
+    G.spectral_solve(Hb, 1e-4, "energy")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); G.spectral_solve(Hb, 1e-4, "energy"); torch.cuda.synchronize()
+    t_big = time.perf_counter() - t0
+    pool = SolverPool(workers=cnt + 1)
+    for small_b, big_b in ((16, 100), (12, 112), (24, 76), (8, 124)):
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pool.spectral_solve_many([Hb] + Hs, 1e-4, "energy", sm_budget=[big_b] + [small_b] * cnt)
+            torch.cuda.synchronize()
+            t_all = time.perf_counter() - t0
+        print(f"wide n={nb} alone {t_big*1e3:.0f} ms; wide ({big_b} SMs) + {cnt} x n={n} ({small_b} SMs each) together {t_all*1e3:.0f} ms", flush=True)
+    pool.close()
