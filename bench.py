@@ -258,9 +258,18 @@ def main():
                         staging[key].copy_(w_src[gi][li], non_blocking=True)
                         events[key] = torch.cuda.Event()
                         events[key].record(copy_stream)
-        # 1. Hessians of the four groups
-        Hs = []
-        for gi, (n, outs) in enumerate(groups):
+        # 1 + 2. Hessians and spectral solves.  The latency-bound n <= 8192 solves run side by side (one host
+        #    thread, stream and SM budget each, gptq_svd_b200/concurrent.py) and start as soon as their H is
+        #    accumulated; the bandwidth-bound wide one runs alone on the whole GPU afterwards.
+        small = [gi for gi, (n, _) in enumerate(groups) if n <= 8192] if pool is not None else []
+        if len(small) < 2:
+            small = []
+        order = small + [gi for gi in range(len(groups)) if gi not in small]
+        budget = max(8, 148 // max(1, len(small)))
+        facs = [None] * len(groups)
+        pending = {}
+        for gi in order:
+            n, outs = groups[gi]
             acc = G.HessianAccumulator(n, dev)
             for c in range(0, tokens, chunk):
                 if host:
@@ -269,18 +278,20 @@ def main():
                 else:
                     xb = x_src[gi][c:c + chunk]
                 acc.add_batch(xb.view(-1, 2048, n) if (xb.shape[0] % 2048 == 0) else xb)
-            Hs.append(acc.get_hessian())
+            H = acc.get_hessian()
             del acc
-        # 2. spectral solves: the latency-bound n <= 8192 ones side by side (one host thread, stream and SM
-        #    budget each, gptq_svd_b200/concurrent.py), the bandwidth-bound wide one alone on the whole GPU
-        facs = [None] * len(groups)
-        small = [gi for gi, (n, _) in enumerate(groups) if n <= 8192] if pool is not None else []
-        if len(small) > 1:
-            for gi, f in zip(small, pool.process_hessian_alt_many([Hs[gi] for gi in small], args.eps, "energy")):
-                facs[gi] = f
-        for gi in range(len(groups)):
-            if facs[gi] is None:
-                facs[gi] = G.process_hessian_alt(Hs[gi], args.eps, "energy")
+            if gi in small:
+                def solve(H=H):
+                    H.record_stream(torch.cuda.current_stream(dev))     # read on the worker's stream
+                    return G.process_hessian_alt(H, args.eps, "energy")
+                pending[gi] = pool.submit(solve, budget)
+            else:
+                for gj in list(pending):                 # the wide solve wants the GPU for itself
+                    facs[gj] = pool.result(pending.pop(gj))
+                facs[gi] = G.process_hessian_alt(H, args.eps, "energy")
+            del H
+        for gj in list(pending):
+            facs[gj] = pool.result(pending.pop(gj))
         # 3. grid + loop of the seven Linears
         for gi, (n, outs) in enumerate(groups):
             R, R_x, perm = facs[gi]
@@ -295,7 +306,7 @@ def main():
                 fw, k = G.gptq_fwrd(W, R, q, perm, block_size=1024, use_triton=True, R_x=R_x)
                 if host:
                     sink[gi][li].copy_(fw, non_blocking=True)
-        del Hs, facs
+        del facs
         return ks
 
     def barrier():

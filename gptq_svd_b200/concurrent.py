@@ -61,6 +61,36 @@ class SolverPool:
                 self.launches[idx] = int(lib.tq_launch_count())
                 done.release()
 
+    def submit(self, fn, sm_budget: Optional[int] = None):
+        """Start `fn()` on a worker (its stream first waits for everything enqueued so far on the caller's
+        current stream) and return a handle for `result()`.  Tensors `fn` reads must stay alive until
+        `result()` returns, or be `record_stream`-ed inside `fn` (it runs under the worker's stream)."""
+        if sm_budget is None:
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            sm_budget = max(8, sms // self.workers)
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        out: List = [None]
+        done = threading.Semaphore(0)
+        self._jobs.put((fn, sm_budget, ready, done, out, 0))
+        return (out, done)
+
+    def result(self, handle):
+        """Wait for a submitted job; the caller's current stream waits for the worker's stream."""
+        out, done = handle
+        done.acquire()
+        done.release()                                        # result() may be called again
+        r = out[0]
+        if isinstance(r, BaseException):
+            raise r
+        val, ev, stream = r
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in _tensors(val):
+            t.record_stream(cur)                              # allocated on the worker's stream, used on ours
+        return val
+
     def map(self, fns, sm_budget: Optional[int] = None):
         """Run the callables concurrently (at most `workers` at a time); returns their results.  The
         caller's current stream waits for every result before it can use it.  `sm_budget`: one value for
@@ -72,25 +102,8 @@ class SolverPool:
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
             sm_budget = max(8, sms // min(n, self.workers))
         budgets = list(sm_budget) if isinstance(sm_budget, (list, tuple)) else [sm_budget] * n
-        cur = torch.cuda.current_stream(self.device)
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        out: List = [None] * n
-        done = threading.Semaphore(0)
-        for i, fn in enumerate(fns):
-            self._jobs.put((fn, budgets[i], ready, done, out, i))
-        for _ in range(n):
-            done.acquire()
-        res = []
-        for r in out:
-            if isinstance(r, BaseException):
-                raise r
-            val, ev, stream = r
-            cur.wait_event(ev)
-            for t in _tensors(val):
-                t.record_stream(cur)                          # allocated on the worker's stream, used on ours
-            res.append(val)
-        return res
+        handles = [self.submit(fn, b) for fn, b in zip(fns, budgets)]
+        return [self.result(h) for h in handles]
 
     def spectral_solve_many(self, Hs: Sequence[torch.Tensor], threshold: float = 0.0005,
                             threshold_method: str = "mean_trimmed",
