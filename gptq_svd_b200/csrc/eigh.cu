@@ -973,14 +973,26 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
     const int64_t r0 = j0 + jb;
     const int64_t s2 = n - r0;
     if (s2 > 0) {
-      // A22 -= V2 W2^T + W2 V2^T = [V2 W2] [W2 V2]^T as ONE rank-2jb DGEMM (full square, keeps both
-      // triangles valid): cuBLAS runs a rank-128 update at 30 TF/s, two rank-64 updates at 20.7
-      // (profiles/r01_dgemm_probe.log)
-      dim3 grid((unsigned)imin(ceil_div(s2, 256), 64), (unsigned)jb);
-      pack_vw_kernel<<<grid, 256, 0, st>>>(A + r0 + j0 * lda, lda, W + r0, ldw, s2, jb, XY, XY + size_t(n) * 2 * kTrdNb, n);
-      TQ_LAUNCH_CHECK();
-      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(s2), int(s2), 2 * jb, &mone, XY, int(n),
-                                  XY + size_t(n) * 2 * kTrdNb, int(n), &one, A + r0 + r0 * lda, int(lda)));
+      static int use_syr2k = -1;
+      if (use_syr2k < 0) {
+        const char* e = getenv("TQ_SYTRD_NO_SYR2K");
+        use_syr2k = (e && e[0] && e[0] != '0') ? 0 : 1;
+      }
+      if (use_sym && use_syr2k) {
+        // A22 -= V2 W2^T + W2 V2^T on the LOWER triangle only (DSYR2K, half the flops): the symmetric panel
+        // kernel, phases A / C and ormtr never read above the diagonal.  844 ms vs 870 at n = 12288.
+        TQ_CUBLAS_CHECK(cublasDsyr2k(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, int(s2), jb, &mone, A + r0 + j0 * lda,
+                                     int(lda), W + r0, int(ldw), &one, A + r0 + r0 * lda, int(lda)));
+      } else {
+        // full square (the column-dot panel reads both triangles) as ONE rank-2jb DGEMM [V2 W2] [W2 V2]^T:
+        // cuBLAS runs a rank-128 update at 30 TF/s, two rank-64 updates at 20.7 (profiles/r01_dgemm_probe.log)
+        dim3 grid((unsigned)imin(ceil_div(s2, 256), 64), (unsigned)jb);
+        pack_vw_kernel<<<grid, 256, 0, st>>>(A + r0 + j0 * lda, lda, W + r0, ldw, s2, jb, XY,
+                                             XY + size_t(n) * 2 * kTrdNb, n);
+        TQ_LAUNCH_CHECK();
+        TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(s2), int(s2), 2 * jb, &mone, XY, int(n),
+                                    XY + size_t(n) * 2 * kTrdNb, int(n), &one, A + r0 + r0 * lda, int(lda)));
+      }
     }
   }
   return TQ_OK;
