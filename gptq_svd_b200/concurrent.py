@@ -30,18 +30,26 @@ from .gptq_utils import SpectralFactors, spectral_solve
 
 class SolverPool:
     def __init__(self, workers: int = 3, device=None):
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        dev = torch.device("cuda") if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"SolverPool: {dev} is not a CUDA device (there is no CPU path)")
+        self.device = torch.device("cuda", torch.cuda.current_device() if dev.index is None else dev.index)
         self.workers = max(1, int(workers))
         self._jobs: "queue.Queue" = queue.Queue()
         self._threads = [threading.Thread(target=self._run, args=(i,), daemon=True) for i in range(self.workers)]
         self.launches = [0] * self.workers          # libtruncgptq kernel launches per worker thread
+        self._broken: Optional[BaseException] = None
         for t in self._threads:
             t.start()
 
     def _run(self, idx: int):
-        torch.cuda.set_device(self.device)
-        stream = torch.cuda.Stream(device=self.device)
-        lib = _lib.load()
+        try:
+            torch.cuda.set_device(self.device)
+            stream = torch.cuda.Stream(device=self.device)
+            lib = _lib.load()
+        except BaseException as ex:               # a worker that cannot start must not leave callers waiting
+            self._broken = ex
+            return
         while True:
             job = self._jobs.get()
             if job is None:
@@ -79,7 +87,9 @@ class SolverPool:
     def result(self, handle):
         """Wait for a submitted job; the caller's current stream waits for the worker's stream."""
         out, done = handle
-        done.acquire()
+        while not done.acquire(timeout=0.5):                  # never wait on a pool whose workers are gone
+            if self._broken is not None or not any(t.is_alive() for t in self._threads):
+                raise RuntimeError(f"SolverPool: worker threads are not running ({self._broken!r})")
         done.release()                                        # result() may be called again
         r = out[0]
         if isinstance(r, BaseException):

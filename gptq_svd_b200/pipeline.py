@@ -119,8 +119,13 @@ def quantize_model(model: nn.Module, input_ids_list: List[torch.Tensor], *, mode
                    threshold_method: str = "energy", adaptive_eps: bool = False, batch_size: int = 32,
                    device="cuda", actorder: bool = False, damp_percent: float = 0.01,
                    sketch_ratio: float = 1.0, keep_packed: bool = False,
-                   offload_layers: bool = False) -> Dict[str, Any]:
+                   offload_layers: bool = False, true_sequential: bool = True) -> Dict[str, Any]:
     """Quantize every decoder Linear of `model` in place (quantize.py:103-252).
+
+    `true_sequential=True` is the reference's order: the groups of a layer are captured and quantized one
+    after another, each seeing the groups before it already quantized.  `true_sequential=False` (the usual
+    GPTQ option of that name; mode "eigh" only) captures the four Hessians of a layer in ONE forward pass of
+    the un-quantized layer and solves the narrow ones side by side on the GPU (`concurrent.SolverPool`).
 
     Returns {"layer_stats": [...], "total_time": s, "packed": {...}}; with `keep_packed` the
     integer codes / scales / zeros / packed words of every Linear are kept (new: the reference
@@ -142,9 +147,67 @@ def quantize_model(model: nn.Module, input_ids_list: List[torch.Tensor], *, mode
         kwargs["use_cache"] = False
         return layer(inps[lo:lo + batch_size], **kwargs)
 
+    pool = None
+    if not true_sequential:
+        if mode != "eigh":
+            raise ValueError("true_sequential=False is implemented for mode='eigh'")
+        from .concurrent import SolverPool
+        pool = SolverPool(workers=3, device=device)
+
+    def quantize_group(li, layer, group, R, R_x, perm):
+        for name in group:
+            sub = get_submodule(layer, name)
+            W = sub.weight.data.float()
+            q = Quantizer(w_bits=w_bits, group_size=group_size, sym=sym)
+            t0 = time.time()
+            use_triton = mode != "gptq"                      # quantize.py:211-229
+            if keep_packed:
+                ql = gptq_quantize(W, R, q, perm, block_size=1024, use_triton=use_triton, R_x=R_x)
+                final_W, rank = ql.final_W, ql.rank
+                packed[f"layer_{li}.{name}"] = {"qweight": pack_codes(ql.codes, w_bits), "scale": ql.scale,
+                                                "zero": ql.zero, "bits": w_bits, "group_size": group_size,
+                                                "sym": sym}
+            else:
+                final_W, rank = gptq_fwrd(W, R, q, perm, block_size=1024, use_triton=use_triton, R_x=R_x)
+            sub.weight.copy_(final_W)
+            torch.cuda.synchronize(device)
+            stats.append({"name": f"layer_{li}.{name}", "rank": rank if mode != "gptq" else "N/A",
+                          "time": time.time() - t0})
+            logging.info(f"   {name: <15} | Rank: {stats[-1]['rank']!s: <4} | Time: {stats[-1]['time']:.2f}s")
+
     for li, layer in enumerate(layers):
         layer = layer.to(device)
-        for group in get_sequenced_groups(layer):
+        if pool is not None:
+            groups = get_sequenced_groups(layer)
+            accs, handles = [], []
+            for group in groups:
+                first = get_submodule(layer, group[0])
+                acc = HessianAccumulator(first.weight.shape[1], device=device)
+                accs.append(acc)
+                handles.append(first.register_forward_hook(
+                    lambda mod, inp, out, acc=acc: acc.add_batch(inp[0].detach())))
+            try:
+                for lo in range(0, n_samples, batch_size):
+                    run_layer(layer, lo)
+            finally:
+                for h in handles:
+                    h.remove()
+            Hs = [acc.get_hessian() for acc in accs]
+            epss = [get_adaptive_eps(g[0], eps) if adaptive_eps else eps for g in groups]
+            narrow = [gi for gi, H in enumerate(Hs) if H.shape[0] <= 8192]
+            pending = {}
+            if len(narrow) > 1:
+                for gi in narrow:
+                    pending[gi] = pool.submit(lambda H=Hs[gi], e=epss[gi]: process_hessian_alt(H, e, threshold_method),
+                                              max(8, 148 // len(narrow)))
+            facs = {gi: pool.result(h) for gi, h in pending.items()}
+            for gi in range(len(groups)):
+                if gi not in facs:
+                    facs[gi] = process_hessian_alt(Hs[gi], epss[gi], threshold_method)
+            for gi, group in enumerate(groups):
+                quantize_group(li, layer, group, *facs[gi])
+            del Hs, facs, accs
+        for group in (get_sequenced_groups(layer) if pool is None else []):
             first = get_submodule(layer, group[0])
             in_features = first.weight.shape[1]
             cur_eps = get_adaptive_eps(group[0], eps) if adaptive_eps else eps
@@ -167,25 +230,7 @@ def quantize_model(model: nn.Module, input_ids_list: List[torch.Tensor], *, mode
             else:
                 R, R_x, perm = process_hessian_alt(acc.get_hessian(), cur_eps, threshold_method)
             del acc
-            for name in group:
-                sub = get_submodule(layer, name)
-                W = sub.weight.data.float()
-                q = Quantizer(w_bits=w_bits, group_size=group_size, sym=sym)
-                t0 = time.time()
-                use_triton = mode != "gptq"                      # quantize.py:211-229
-                if keep_packed:
-                    ql = gptq_quantize(W, R, q, perm, block_size=1024, use_triton=use_triton, R_x=R_x)
-                    final_W, rank = ql.final_W, ql.rank
-                    packed[f"layer_{li}.{name}"] = {"qweight": pack_codes(ql.codes, w_bits), "scale": ql.scale,
-                                                    "zero": ql.zero, "bits": w_bits, "group_size": group_size,
-                                                    "sym": sym}
-                else:
-                    final_W, rank = gptq_fwrd(W, R, q, perm, block_size=1024, use_triton=use_triton, R_x=R_x)
-                sub.weight.copy_(final_W)
-                torch.cuda.synchronize(device)
-                stats.append({"name": f"layer_{li}.{name}", "rank": rank if mode != "gptq" else "N/A",
-                              "time": time.time() - t0})
-                logging.info(f"   {name: <15} | Rank: {stats[-1]['rank']!s: <4} | Time: {stats[-1]['time']:.2f}s")
+            quantize_group(li, layer, group, R, R_x, perm)
             del R, R_x, perm
         for lo in range(0, n_samples, batch_size):                # propagate with the quantized layer
             out = run_layer(layer, lo)
@@ -195,4 +240,6 @@ def quantize_model(model: nn.Module, input_ids_list: List[torch.Tensor], *, mode
         inps, outs = outs, inps
         if offload_layers:
             layer.to("cpu")
+    if pool is not None:
+        pool.close()
     return {"layer_stats": stats, "total_time": time.time() - t_start, "packed": packed}

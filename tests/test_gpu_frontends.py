@@ -105,7 +105,7 @@ def _tiny_qwen3(seed=0):
     return model
 
 
-@pytest.mark.parametrize("mode", ["eigh", "gptq", "svd"])
+@pytest.mark.parametrize("mode", ["eigh", "gptq", "svd", "eigh-parallel-groups"])
 def test_pipeline_tiny_qwen3(G, mode):
     """quantize.main's loop on a random-init Qwen3: every decoder Linear ends on its grid, the
     model still runs, and GPTQ-style error compensation beats plain round-to-nearest."""
@@ -115,8 +115,11 @@ def test_pipeline_tiny_qwen3(G, mode):
     rtn = _tiny_qwen3()
     g = torch.Generator().manual_seed(1)
     ids = [torch.randint(0, 512, (1, 128), generator=g) for _ in range(16)]
+    true_seq = mode != "eigh-parallel-groups"       # False: one capture pass per layer, solves side by side
+    mode = mode.split("-")[0]
     out = quantize_model(model, ids, mode=mode, w_bits=4, group_size=128, sym=False, eps=1e-4,
-                         threshold_method="energy", batch_size=8, device="cuda", keep_packed=True)
+                         threshold_method="energy", batch_size=8, device="cuda", keep_packed=True,
+                         true_sequential=true_seq)
     assert len(out["layer_stats"]) == 2 * 7
     for li, (layer, layer0, layer_r) in enumerate(zip(get_layers(model), get_layers(ref), get_layers(rtn))):
         for group in get_sequenced_groups(layer):

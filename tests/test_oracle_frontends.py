@@ -98,3 +98,15 @@ def test_pipeline_host_helpers():
         G.process_hessian(torch.eye(4, dtype=torch.float64))
     with pytest.raises(RuntimeError):
         G.process_sketch(torch.ones(4, 4))
+
+
+def test_solver_pool_fails_loudly_without_gpu():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from gptq_svd_b200.concurrent import SolverPool
+    with pytest.raises(RuntimeError):
+        pool = SolverPool(workers=2, device="cuda")
+        pool.result(pool.submit(lambda: 1))
+    with pytest.raises(RuntimeError):
+        SolverPool(workers=1, device="cpu")
