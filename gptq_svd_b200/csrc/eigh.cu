@@ -329,8 +329,6 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
     ptx::fence_barrier_init();
   }
   __syncthreads();
-  if (a.trace == 10) return;
-  if (a.trace == 30 && j0 > 0) return;
 
   long long tk = a.trace ? clock64() : 0;
   const bool tracer = (blockIdx.x == 0 && tid == 20 * 32);   // a warp that owns rows until c ~ 11840
@@ -357,7 +355,7 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
     const int ch = (T + G - 1) / G > 0 ? (T + G - 1) / G : 1;
     const int t0 = min(T, bidx * ch), t1 = min(T, t0 + ch);
     // tile t -> TMA coordinates; A-type tiles only touch the trailing matrix (read-only in this kernel)
-    const bool stream_hint = (len > 5000) && !(a.trace & 256);      // lower triangle > 100 MB
+    const bool stream_hint = len > 5000;      // lower triangle > 100 MB
     auto issue_tile = [&](int t) {
       const int stage = int(iss % kSymStages);
       double* dst = tiles + stage * kTileElems;
@@ -392,11 +390,6 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       ++iss;
     };
     int issued = 0;
-    if (a.trace == 11) {       // debug: wait for the prologue tiles and leave
-      __syncthreads();
-      for (int q = 0; q < kSymStages && t0 + q < t1 && t0 + q < TA; ++q) ptx::mbar_wait(&full[q], 0);
-      return;
-    }
     // ---------------- A   (8 lanes per row: the panel history t < i is split over the lanes)
     double ss = 0.0;
     for (int64_t rb = 4 * gwarp; rb < n; rb += 4 * nwarps) {
@@ -440,7 +433,7 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
     if (len <= 0) break;               // last column: only the diagonal entry (uniform across the grid)
     // prefetch the first tiles of this column's product only now: issued at the top of the step, their
     // 28 MB (3 stages x 148 SMs) queue in front of the small phase-A loads, which then take 4 us
-    if (issuer && !(a.trace & 64))
+    if (issuer)
       while (issued < kSymStages && t0 + issued < t1 && t0 + issued < TA) issue_tile(t0 + issued++);
     TQ_PHASE(7)
     ss = block_sum(ss, sh);
@@ -448,11 +441,6 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
     TQ_PHASE(0)
     grid_barrier(a.bar, bar_target, nb);
     TQ_PHASE(1)
-    if (a.trace == 12) {
-      __syncthreads();
-      for (int q = 0; q < kSymStages && t0 + q < t1 && t0 + q < TA; ++q) ptx::mbar_wait(&full[q], 0);
-      return;
-    }
     // ---------------- B
     if (issuer) {
       fence_proxy_async_all();           // W / V columns written with st by other CTAs -> TMA reads
@@ -520,28 +508,6 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
         }
         const int stage = int(use % kSymStages);
         ptx::mbar_wait(&full[stage], (use / kSymStages) & 1);
-        if (a.trace >= 21 && (a.trace == 22 || !a_tile)) {      // debug: refill the stage with generic loads
-          __syncthreads();
-          double* dstt = tiles + stage * kTileElems;
-          for (int idx = tid; idx < kTileElems; idx += kSymThreads) {
-            const int rr = idx % kTileR, cc = idx / kTileR;
-            const int64_t gr = base_e + int64_t(trb) * kTileR + rr;
-            double v = 0.0;
-            if (gr < n) {
-              if (a_tile) {
-                const int64_t gc = base + int64_t(cs) * kTileC + cc;
-                if (gc < n) v = A[gr + gc * lda];
-              } else if (t < TA + nrb) {
-                v = W[gr + int64_t(cc) * ldw];
-              } else {
-                const int64_t gc = j0 + cc;
-                if (gc < n) v = A[gr + gc * lda];
-              }
-            }
-            dstt[idx] = v;
-          }
-          __syncthreads();
-        }
         const double* ts = tiles + stage * kTileElems + (2 * wid) * kTileR + lane;
         double av[2][4];
 #pragma unroll
@@ -631,18 +597,12 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
     }
     const double fix = 1.0 - scl * alpha;
     TQ_PHASE(2)
-    if (a.trace == 13) return;
     grid_barrier(a.bar, bar_target, nb);
     TQ_PHASE(3)
     // ---------------- C
     // raw product (A22 u)[r - base] for global row r: this lane's share of the partials (8 lanes per row)
     auto yraw_lane = [&](int64_t r) -> double {
       const int64_t rl = r - base;
-      if (a.trace == 23) {                               // debug: brute-force row of A22 times u
-        double accb = 0.0;
-        for (int64_t j = sub; j < len; j += 8) accb = fma(A[r + (base + j) * lda], u[j], accb);
-        return accb;
-      }
       const int rbr = int((rl + dl) / kTileR);           // row block holding this row
       const int64_t tstart = int64_t(rbr) * (rbr + 1);
       const int ncs = min(2 * rbr + 2, nstrips);
@@ -692,18 +652,6 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       }
       return (a0 + a1) + (a2 + a3);
     };
-    if (a.trace == 30) {                // debug: dump (A22 u) of the very first column into d[] and leave
-      for (int64_t rb4 = 4 * gwarp; rb4 < n; rb4 += 4 * nwarps) {
-        const int64_t r = rb4 + rsel;
-        const bool act = (r < n) && (r >= c + 1);
-        double p = act ? yraw_lane(r) : 0.0;
-        p += __shfl_xor_sync(0xffffffffu, p, 4);
-        p += __shfl_xor_sync(0xffffffffu, p, 2);
-        p += __shfl_xor_sync(0xffffffffu, p, 1);
-        if (act && sub == 0) a.d[r] = p;
-      }
-      return;
-    }
     if (wid == 1) {                     // u^T (A22 u): per-CTA partials, fixed order
       double p = 0.0;
       for (int q = lane; q < int(nb); q += 32) p += part2[q];
@@ -831,7 +779,6 @@ sytrd_panel_sym_kernel(SymPanelArgs a, const __grid_constant__ CUtensorMap tmA, 
       a.e[c] = beta;
     }
     __syncthreads();
-    if (a.trace & 128) grid_barrier(a.bar, bar_target, nb);
     TQ_PHASE(4)
   }
 #undef TQ_PHASE
@@ -941,9 +888,8 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
         }
       }
       TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
-      const char* dbg = getenv("TQ_SYM_DEBUG");
       SymPanelArgs pa{A, n, j0, jb, W, d, e, tau, sb.rowpart, sb.colpart, sb.wvpart, part, scal, bar,
-                      dbg ? atoi(dbg) : (trace_enabled() ? 1 : 0), boxc, align};
+                      trace_enabled() ? 1 : 0, boxc, align};
       void* kargs[] = {&pa, &tmA, &tmW};
       double bytes = 0.0;      // algorithmic bytes: every column streams the LOWER triangle of the trailing matrix once
       for (int i = 0; i < jb; ++i) {
@@ -1682,14 +1628,6 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
       cudaStreamSynchronize(st);
       fprintf(stderr, "[tq-trace] sytrd phase Mcycles (CTA 0): A %.1f  barrier1 %.1f  B(stream) %.1f  barrier2 %.1f  C %.1f (C1 %.1f C2 %.1f)  [A row loop %.1f]\n",
               (hc[8] + hc[15]) * 1e-6, hc[9] * 1e-6, hc[10] * 1e-6, hc[11] * 1e-6, (hc[12] + hc[13] + hc[14]) * 1e-6, hc[13] * 1e-6, hc[14] * 1e-6, hc[15] * 1e-6);
-    }
-  }
-  if (const char* dbg = getenv("TQ_SYM_DEBUG")) {
-    if (atoi(dbg) == 30) return TQ_OK;      // debug dump of the first column's product sits in w
-    if (atoi(dbg) & 32) {                   // debug: d in w, e and tau in the first two rows of Zout
-      cudaMemcpyAsync(Zout, e, sizeof(double) * n, cudaMemcpyDeviceToDevice, st);
-      cudaMemcpyAsync(Zout + n, tau, sizeof(double) * n, cudaMemcpyDeviceToDevice, st);
-      return TQ_OK;
     }
   }
   {
