@@ -127,7 +127,7 @@ def cpu_sample(seed: int = 0):
                        "extrapolated by T*n^2 (H), n^3 (solver), m*n^2 (loop) to 36 Qwen3-8B layers")}
 
 
-def run_reference(args):
+def run_reference(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -148,7 +148,8 @@ def run_reference(args):
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": vals[0]["sample"]},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    real_stdout.write(json.dumps(out) + "\n")
+    real_stdout.flush()
 
 
 def _config(args, k_list):
@@ -176,7 +177,17 @@ def make_x(torch, rows, n, seed, decay):
     return out
 
 
+def _claim_stdout():
+    """Route everything that writes to fd 1 (NCCL's version banner, library chatter) to stderr and
+    return a file object on the real stdout, so that the bench prints exactly ONE JSON line there."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -193,7 +204,7 @@ def main():
                     help="solve the n <= 8192 Hessians of a layer side by side on one GPU (0: one after another)")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, real_stdout)
 
     import torch
     import torch.distributed as dist
@@ -207,9 +218,9 @@ def main():
     if world == 1 and args.gpus > 1:      # not under torchrun: re-launch ourselves
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        real_stdout.flush()
+        sys.exit(subprocess.call(cmd, stdout=real_stdout))      # the ranks write their JSON line to OUR stdout
     torch.cuda.set_device(local)
-    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
@@ -406,7 +417,8 @@ def main():
                "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64 solver / f32 loop / f16 SYRK inputs", "data": "synthetic", "config": _config(args, ranks_seen),
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()), "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(out))
+        real_stdout.write(json.dumps(out) + "\n")
+        real_stdout.flush()
     if pool is not None:
         pool.close()
     if world > 1:
