@@ -161,7 +161,9 @@ def _config(args, k_list):
             "block_size": 1024, "activations": f"randn @ A^T, column scales logspace(0,{args.decay}), 8 outlier channels x30",
             "retained_rank": k_list, "l2": "inputs per step (12.9 GB) exceed the 126 MB L2; no explicit flush",
             "parallelism": f"layers sharded over {args.gpus} rank(s), no collective",
-            "solves": ("the three n=4096 Hessians of a layer side by side (SM budget 49 each), n=12288 alone"
+            "solves": (("n=12288 first; after its tridiagonal reduction it drops to 48 SMs and the three n=4096 "
+                        "solves run next to its tail (32 SMs each)" if args.overlap_tail else
+                        "the three n=4096 Hessians of a layer side by side (SM budget 49 each), n=12288 alone")
                        if args.concurrent_solves else "one after another")}
 
 
@@ -200,6 +202,10 @@ def main():
     ap.add_argument("--tiny", action="store_true", help="small shapes (functional check only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--overlap-tail", type=int, default=1,
+                    help="start the narrow solves when the wide solve has finished its tridiagonal reduction")
+    ap.add_argument("--overlap-loops", type=int, default=0,
+                    help="run the loops of the narrow groups while the wide solve is in flight")
     ap.add_argument("--concurrent-solves", type=int, default=1,
                     help="solve the n <= 8192 Hessians of a layer side by side on one GPU (0: one after another)")
     args = ap.parse_args()
@@ -237,10 +243,11 @@ def main():
     ranks_seen = []
 
     copy_stream = torch.cuda.Stream(device=dev)
+    prof_acc = {"on": False, "b": 0.0, "ms": 0.0, "samp": 0, "tot": 0}   # wide solves timed on worker threads
     pool = None
     if args.concurrent_solves:
         from gptq_svd_b200.concurrent import SolverPool
-        pool = SolverPool(workers=3, device=dev)
+        pool = SolverPool(workers=4, device=dev)
     staging = {}          # device staging buffers of the e2e leg (allocated once, reused every step)
 
     def layer_step(x_src, w_src, host: bool, sink=None):
@@ -250,11 +257,19 @@ def main():
         and the dequantised fp16 weights go back to pinned host buffers (D2H)."""
         ks = []
         events = {}
+        small = [gi for gi, (n, _) in enumerate(groups) if n <= 8192] if pool is not None else []
+        if len(small) < 2:
+            small = []
+        wides = [gi for gi in range(len(groups)) if gi not in small]
+        tail = bool(args.overlap_tail) and len(small) > 0 and len(wides) == 1
+        order = (wides + small) if tail else (small + wides)
+        budget = max(8, (96 if tail else 148) // max(1, len(small)))
         if host:
             cur = torch.cuda.current_stream(dev)
             copy_stream.wait_stream(cur)          # staging buffers are free once the previous step is done
             with torch.cuda.stream(copy_stream):
-                for gi, (n, outs) in enumerate(groups):
+                for gi in order:                      # copies in the order the groups are consumed
+                    n, outs = groups[gi]
                     for c in range(0, tokens, chunk):
                         key = ("x", gi, c)
                         if key not in staging:
@@ -272,39 +287,13 @@ def main():
         # 1 + 2. Hessians and spectral solves.  The latency-bound n <= 8192 solves run side by side (one host
         #    thread, stream and SM budget each, gptq_svd_b200/concurrent.py) and start as soon as their H is
         #    accumulated; the bandwidth-bound wide one runs alone on the whole GPU afterwards.
-        small = [gi for gi, (n, _) in enumerate(groups) if n <= 8192] if pool is not None else []
-        if len(small) < 2:
-            small = []
-        order = small + [gi for gi in range(len(groups)) if gi not in small]
-        budget = max(8, 148 // max(1, len(small)))
         facs = [None] * len(groups)
         pending = {}
-        for gi in order:
+        looped = set()
+        deferred, wide_handle = [], None
+
+        def run_loops(gi):
             n, outs = groups[gi]
-            acc = G.HessianAccumulator(n, dev)
-            for c in range(0, tokens, chunk):
-                if host:
-                    torch.cuda.current_stream(dev).wait_event(events[("x", gi, c)])
-                    xb = staging[("x", gi, c)]
-                else:
-                    xb = x_src[gi][c:c + chunk]
-                acc.add_batch(xb.view(-1, 2048, n) if (xb.shape[0] % 2048 == 0) else xb)
-            H = acc.get_hessian()
-            del acc
-            if gi in small:
-                def solve(H=H):
-                    H.record_stream(torch.cuda.current_stream(dev))     # read on the worker's stream
-                    return G.process_hessian_alt(H, args.eps, "energy")
-                pending[gi] = pool.submit(solve, budget)
-            else:
-                for gj in list(pending):                 # the wide solve wants the GPU for itself
-                    facs[gj] = pool.result(pending.pop(gj))
-                facs[gi] = G.process_hessian_alt(H, args.eps, "energy")
-            del H
-        for gj in list(pending):
-            facs[gj] = pool.result(pending.pop(gj))
-        # 3. grid + loop of the seven Linears
-        for gi, (n, outs) in enumerate(groups):
             R, R_x, perm = facs[gi]
             ks.append(int(R.shape[0]))
             for li, m in enumerate(outs):
@@ -317,6 +306,87 @@ def main():
                 fw, k = G.gptq_fwrd(W, R, q, perm, block_size=1024, use_triton=True, R_x=R_x)
                 if host:
                     sink[gi][li].copy_(fw, non_blocking=True)
+
+        for gi in order:
+            n, outs = groups[gi]
+            acc = G.HessianAccumulator(n, dev)
+            for c in range(0, tokens, chunk):
+                if host:
+                    torch.cuda.current_stream(dev).wait_event(events[("x", gi, c)])
+                    xb = staging[("x", gi, c)]
+                else:
+                    xb = x_src[gi][c:c + chunk]
+                acc.add_batch(xb.view(-1, 2048, n) if (xb.shape[0] % 2048 == 0) else xb)
+            H = acc.get_hessian()
+            del acc
+            if tail and gi in wides:
+                # the wide solve starts first on a worker with the whole GPU; when its tridiagonal reduction (the
+                # bandwidth-bound part) is done it drops to 48 SMs and the narrow solves start next to its
+                # latency- and DGEMM-bound stages (stage callback of the C ABI)
+                sytrd_done = threading.Semaphore(0)
+
+                def solve_wide(H=H, sem=sytrd_done):
+                    H.record_stream(torch.cuda.current_stream(dev))
+
+                    def on_stage(stage, user, sem=sem):
+                        if stage == _lib.TQ_STAGE_SYTRD_DONE:
+                            lib.tq_set_sm_budget(48)
+                            sem.release()
+                    cb = _lib.STAGE_CALLBACK(on_stage)
+                    lib.tq_set_stage_callback(cb, None)
+                    if prof_acc["on"]:                   # the sampled launch timing is per host thread
+                        lib.tq_profile_begin(4)
+                    try:
+                        return G.process_hessian_alt(H, args.eps, "energy")
+                    finally:
+                        if prof_acc["on"]:
+                            import ctypes as C
+                            b, ms_, sa, to = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_int64(0)
+                            lib.tq_profile_end(C.byref(b), C.byref(ms_), C.byref(sa), C.byref(to))
+                            prof_acc["b"] += b.value
+                            prof_acc["ms"] += ms_.value
+                            prof_acc["samp"] += sa.value
+                            prof_acc["tot"] += to.value
+                        lib.tq_set_stage_callback(_lib.STAGE_CALLBACK(0), None)
+                        sem.release()                    # never leave the main thread waiting
+                wide_handle = pool.submit(solve_wide, 148)
+            elif gi in small:
+                def solve(H=H):
+                    H.record_stream(torch.cuda.current_stream(dev))     # read on the worker's stream
+                    return G.process_hessian_alt(H, args.eps, "energy")
+                if tail:
+                    deferred.append((gi, solve))
+                else:
+                    pending[gi] = pool.submit(solve, budget)
+            elif pending and args.overlap_loops:
+                # the wide solve goes to a worker with the whole GPU as its budget; this thread meanwhile runs
+                # the loops of the narrow groups (ordinary kernels that fit between the solver's launches)
+                for gj in list(pending):
+                    facs[gj] = pool.result(pending.pop(gj))
+                def solve_wide(H=H):
+                    H.record_stream(torch.cuda.current_stream(dev))
+                    return G.process_hessian_alt(H, args.eps, "energy")
+                wide = pool.submit(solve_wide, 148)
+                for gj in small:
+                    run_loops(gj)
+                    looped.add(gj)
+                facs[gi] = pool.result(wide)
+            else:
+                for gj in list(pending):                 # the wide solve wants the GPU for itself
+                    facs[gj] = pool.result(pending.pop(gj))
+                facs[gi] = G.process_hessian_alt(H, args.eps, "energy")
+            del H
+        if tail:
+            sytrd_done.acquire()
+            for gj, fn in deferred:
+                pending[gj] = pool.submit(fn, budget)
+            facs[wides[0]] = pool.result(wide_handle)
+        for gj in list(pending):
+            facs[gj] = pool.result(pending.pop(gj))
+        # 3. grid + loop of the seven Linears
+        for gi in range(len(groups)):
+            if gi not in looped:
+                run_loops(gi)
         del facs
         return ks
 
@@ -333,6 +403,7 @@ def main():
         sampler.start()
     if not os.environ.get("TQ_BENCH_NO_PROF"):
         lib.tq_profile_begin(4)
+        prof_acc["on"] = True
     l0 = lib.tq_launch_count() + (pool.launch_count() if pool else 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -352,6 +423,11 @@ def main():
     import ctypes as C
     pb, pms, psamp, ptot = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_int64(0)
     lib.tq_profile_end(C.byref(pb), C.byref(pms), C.byref(psamp), C.byref(ptot))
+    prof_acc["on"] = False
+    pb.value += prof_acc["b"]
+    pms.value += prof_acc["ms"]
+    psamp.value += prof_acc["samp"]
+    ptot.value += prof_acc["tot"]
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

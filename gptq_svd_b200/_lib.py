@@ -22,11 +22,15 @@ TQ_LOOP_STRICT_FP32 = 0x100
 
 _i64, _i32, _vp, _sz, _dbl = C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_double
 
+STAGE_CALLBACK = C.CFUNCTYPE(None, C.c_int, C.c_void_p)
+TQ_STAGE_SYTRD_DONE = 1
+
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
     "tq_version": [],
     "tq_launch_count": [],
     "tq_set_sm_budget": [_i32],
+    "tq_set_stage_callback": [STAGE_CALLBACK, _vp],
     "tq_profile_begin": [_i32],
     "tq_profile_end": [C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_i64), C.POINTER(_i64)],
     "tq_last_error": [],

@@ -94,6 +94,13 @@ StageTimer::~StageTimer() {
 }
 
 static thread_local int g_sm_budget = 0;
+static thread_local void (*g_stage_cb)(int, void*) = nullptr;
+static thread_local void* g_stage_user = nullptr;
+
+bool stage_callback_set() { return g_stage_cb != nullptr; }
+void notify_stage(int stage) {
+  if (g_stage_cb) g_stage_cb(stage, g_stage_user);
+}
 
 // SMs the calling thread's persistent (co-resident) kernels may occupy: the device's count, or the
 // budget set with tq_set_sm_budget so that several solves can be in flight on one GPU.
@@ -147,6 +154,12 @@ extern "C" int tq_profile_end(double* alg_bytes, double* ms, int64_t* sampled, i
 
 extern "C" int tq_set_sm_budget(int sms) {
   tq::g_sm_budget = sms > 0 ? sms : 0;
+  return TQ_OK;
+}
+
+extern "C" int tq_set_stage_callback(void (*cb)(int, void*), void* user) {
+  tq::g_stage_cb = cb;
+  tq::g_stage_user = user;
   return TQ_OK;
 }
 

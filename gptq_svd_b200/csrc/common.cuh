@@ -76,6 +76,10 @@ static inline size_t ws_bytes_for(size_t count, size_t elem) { return align_up(c
 
 int num_sms();
 
+// optional per-thread stage callback (tq_set_stage_callback)
+bool stage_callback_set();
+void notify_stage(int stage);
+
 // TQ_TRACE=1: print per-stage milliseconds (synchronises the stream at stage boundaries)
 bool trace_enabled();
 struct StageTimer {

@@ -1630,6 +1630,10 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
               (hc[8] + hc[15]) * 1e-6, hc[9] * 1e-6, hc[10] * 1e-6, hc[11] * 1e-6, (hc[12] + hc[13] + hc[14]) * 1e-6, hc[13] * 1e-6, hc[14] * 1e-6, hc[15] * 1e-6);
     }
   }
+  if (stage_callback_set()) {       // the bandwidth-bound part of the solve is over once the stream drains
+    TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+    notify_stage(TQ_STAGE_SYTRD_DONE);
+  }
   {
     Workspace sub = ws;   // D&C scratch is released afterwards
     {

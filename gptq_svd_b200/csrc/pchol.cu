@@ -389,10 +389,12 @@ int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64
     set_error("pchol: n = %lld too large for the shared-memory permutation", (long long)n);
     return TQ_ERR_UNSUPPORTED;
   }
-  static thread_local size_t smem_set = 0;
-  if (smem > smem_set) {
-    TQ_CUDA_CHECK(cudaFuncSetAttribute(pchol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    smem_set = smem;
+  // the attribute is per function, not per thread: always raise it to the same maximum, so that a solve
+  // with a small n on one host thread never lowers it under a solve with a large n on another
+  static thread_local bool smem_set = false;
+  if (!smem_set) {
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(pchol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    smem_set = true;
   }
   int per_sm = 0;
   TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pchol_panel_kernel, kPcThreads, smem));

@@ -76,6 +76,14 @@ const char* tq_last_error(void);
  * reproducible for a given budget and agree across budgets to rounding (R within 2e-12 relative). */
 int tq_set_sm_budget(int sms);
 
+/* Per-thread stage callback: `cb(stage, user)` runs on the calling host thread inside
+ * tq_spectral_solve / tq_eigh when a stage boundary has been reached ON THE DEVICE (the stream is
+ * synchronised first).  TQ_STAGE_SYTRD_DONE: the tridiagonal reduction - the bandwidth-bound part of a
+ * solve - is complete; what follows is latency- and DGEMM-bound, so a scheduler may lower this thread's
+ * SM budget and start other solves next to it.  NULL removes the callback. */
+#define TQ_STAGE_SYTRD_DONE 1
+int tq_set_stage_callback(void (*cb)(int stage, void* user), void* user);
+
 /* --------------------------------------------------------------------------
  * (1) Hessian accumulation - replaces HessianAccumulator.add_batch / get_hessian
  *     (gptq_utils.py:218-228).
