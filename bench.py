@@ -161,8 +161,9 @@ def _config(args, k_list):
             "block_size": 1024, "activations": f"randn @ A^T, column scales logspace(0,{args.decay}), 8 outlier channels x30",
             "retained_rank": k_list, "l2": "inputs per step (12.9 GB) exceed the 126 MB L2; no explicit flush",
             "parallelism": f"layers sharded over {args.gpus} rank(s), no collective",
-            "solves": (("n=12288 first; after its tridiagonal reduction it drops to 48 SMs and the three n=4096 "
-                        "solves run next to its tail (32 SMs each)" if args.overlap_tail else
+            "solves": ((f"n=12288 first; after its tridiagonal reduction it drops to {args.tail_budgets.split(',')[0]} SMs and "
+                        f"the three n=4096 solves run next to its tail ({args.tail_budgets.split(',')[1]} SMs each)"
+                        if args.overlap_tail else
                         "the three n=4096 Hessians of a layer side by side (SM budget 49 each), n=12288 alone")
                        if args.concurrent_solves else "one after another")}
 
@@ -204,6 +205,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--overlap-tail", type=int, default=1,
                     help="start the narrow solves when the wide solve has finished its tridiagonal reduction")
+    ap.add_argument("--tail-budgets", default="100,16",
+                    help="SM budgets in the tail: wide,narrow (measured: 48,32 1.61 s; 64,28 1.59; 100,16 1.58; 124,8 1.62)")
     ap.add_argument("--overlap-loops", type=int, default=0,
                     help="run the loops of the narrow groups while the wide solve is in flight")
     ap.add_argument("--concurrent-solves", type=int, default=1,
@@ -263,7 +266,8 @@ def main():
         wides = [gi for gi in range(len(groups)) if gi not in small]
         tail = bool(args.overlap_tail) and len(small) > 0 and len(wides) == 1
         order = (wides + small) if tail else (small + wides)
-        budget = max(8, (96 if tail else 148) // max(1, len(small)))
+        tail_wide, tail_narrow = (int(v) for v in args.tail_budgets.split(","))
+        budget = tail_narrow if tail else max(8, 148 // max(1, len(small)))
         if host:
             cur = torch.cuda.current_stream(dev)
             copy_stream.wait_stream(cur)          # staging buffers are free once the previous step is done
@@ -330,7 +334,7 @@ def main():
 
                     def on_stage(stage, user, sem=sem):
                         if stage == _lib.TQ_STAGE_SYTRD_DONE:
-                            lib.tq_set_sm_budget(48)
+                            lib.tq_set_sm_budget(tail_wide)
                             sem.release()
                     cb = _lib.STAGE_CALLBACK(on_stage)
                     lib.tq_set_stage_callback(cb, None)

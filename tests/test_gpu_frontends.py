@@ -180,3 +180,32 @@ def test_solver_pool_matches_sequential(G):
     _ = G  # the main thread's budget is untouched
     f = G.spectral_solve(Hs[0], 1e-4, "energy")
     assert torch.equal(f.R, seq[0].R)
+
+
+def test_stage_callback(G):
+    """tq_set_stage_callback: the callback runs once per solve on the calling thread when the tridiagonal
+    reduction has completed on the device; results are unchanged; NULL removes it."""
+    from gptq_svd_b200 import _lib
+    lib = _lib.load()
+    X = O.make_activations(2048, 384, seed=77, dist="llm").astype(np.float64)
+    H = _gpu(X.T @ X / X.shape[0])
+    base = G.spectral_solve(H, 1e-4, "energy")
+    seen = []
+    cb = _lib.STAGE_CALLBACK(lambda stage, user: seen.append(stage))
+    lib.tq_set_stage_callback(cb, None)
+    try:
+        f = G.spectral_solve(H, 1e-4, "energy")
+    finally:
+        lib.tq_set_stage_callback(_lib.STAGE_CALLBACK(0), None)
+    assert seen == [_lib.TQ_STAGE_SYTRD_DONE]
+    assert f.k == base.k and torch.equal(f.R, base.R) and torch.equal(f.perm, base.perm)
+    G.spectral_solve(H, 1e-4, "energy")
+    assert seen == [_lib.TQ_STAGE_SYTRD_DONE]              # removed
+    # an SM budget changes the grid, not the answer (to rounding); 0 restores the whole GPU
+    lib.tq_set_sm_budget(24)
+    try:
+        g = G.spectral_solve(H, 1e-4, "energy")
+    finally:
+        lib.tq_set_sm_budget(0)
+    assert g.k == base.k and torch.equal(g.perm[:g.k], base.perm[:base.k])
+    assert float((g.R - base.R).abs().max() / base.R.abs().max()) <= 1e-9
