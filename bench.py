@@ -16,6 +16,12 @@ All 36 layers of the model have the same shapes, so the headline
   value = "Qwen3-8B end-to-end quantize time (s)" = 36 x mean step time / n_gpus
 (with N GPUs the independent layers are sharded across ranks, no data-path collective:
 weak scaling).  `--steps 36` times a whole model per rank.
+
+Scheduling inside a step (one GPU): the four Hessians of a block are independent once accumulated, so
+the wide (n = 12288) solve starts first with the whole GPU and, when its tridiagonal reduction - the
+bandwidth-bound part - is done, drops to an SM budget while the three narrow solves run next to its
+tail (gptq_svd_b200/concurrent.py; `--overlap-tail 0` / `--concurrent-solves 0` switch this off).
+stdout carries exactly one JSON line; everything else goes to stderr.
 """
 from __future__ import annotations
 

@@ -236,11 +236,12 @@ int tq_sketch_solve(const float* Y, int64_t ldy, int64_t rank, int64_t n, double
  * are not counted). */
 int64_t tq_launch_count(void);
 
-/* Sampled timing of the solver's dominant HBM-bound kernels (sytrd_panel_kernel and
- * qrcp_panel_kernel: one pass over the trailing matrix per reflector in the tridiagonal
- * reduction and in the pivoted QR).  After tq_profile_begin(every), every `every`-th panel
- * launch is bracketed by CUDA events on its own stream; tq_profile_end synchronises them and
- * returns the algorithmic bytes (sum over the panel's columns of rows * columns * 8) and the
+/* Sampled timing of the solver's dominant HBM-bound kernels: the tridiagonal-reduction panel
+ * (sytrd_panel_sym_kernel: the lower triangle of the trailing matrix x one reflector per column; or the
+ * column-dot panel it falls back to) and, on the Householder path, qrcp_panel_kernel.  After
+ * tq_profile_begin(every), every `every`-th panel launch OF THE CALLING THREAD is bracketed by CUDA
+ * events on its own stream; tq_profile_end synchronises them and returns the algorithmic bytes (per
+ * column len * (len / 2 + 2 i) * 8 for the symmetric panel, rows * columns * 8 for the others) and the
  * milliseconds of the sampled launches. */
 int tq_profile_begin(int sample_every);
 int tq_profile_end(double* alg_bytes, double* ms, int64_t* sampled, int64_t* total);
