@@ -14,6 +14,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A persistent (cooperative / cluster) kernel that deadlocks would hang the whole run: every GPU test
+    gets a wall-clock limit when pytest-timeout is installed (the slowest one takes ~6 s on a B200)."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(300, method="thread"))   # a hung CUDA call never returns to Python
+
+
 def golden_cases():
     """Fixtures of the hot path (process_hessian_alt + gptq_fwrd); the chol_* / sketch_* fixtures of the
     other front ends have their own tests (test_oracle_frontends.py, test_gpu_frontends.py)."""
