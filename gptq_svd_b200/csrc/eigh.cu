@@ -39,13 +39,16 @@ constexpr int kOrmNb = 128;  // back-transform block (rank-128 DGEMM updates run
 //       y = A22 v, W^T v, V^T v go to ypart / tmppart; v^T y is accumulated on the fly.
 //       (A variant that reads only the lower triangle - half the DRAM bytes - was measured
 //       slower on B200, 1.58 s vs 1.51 s at n = 12288: it is instruction-bound on the per-column
-//       warp reductions.  A tile-wise symmetric product is the next step, see DESIGN.md.)  | barrier
+//       warp reductions.  The tile-wise symmetric product that does pay is sytrd_panel_sym_kernel below;
+//       this kernel remains for odd n and as the TQ_SYTRD_COLDOT=1 reference.)                  | barrier
 //   C   v scaled in place (own rows), w = tau (y - V W^T v - W V^T v) - tau/2 (w.v) v with
 //       w.v = tau (v^T y - 2 (W^T v).(V^T v)) known without another reduction.
 // Row r is always handled by the same thread (r = global thread id + q * total threads), so
 // values a thread wrote for its own rows need no barrier before it reads them again; the one
 // foreign value the next column update needs, W[c+1, i], is recomputed by every CTA.
-constexpr int kPanelThreads = 256;    // 4 CTAs per SM; measured at n = 12288: 1.99 s (1 x 1024), 1.45 s (2 x 512), 1.33 s (4 x 256), 1.38 s (8 x 128)    // 2 CTAs per SM: measured 1.51 s (n = 12288) vs 1.99 s with 1 x 1024
+// 4 CTAs of 256 threads per SM; measured at n = 12288: 1.99 s (1 x 1024), 1.45 s (2 x 512), 1.33 s (4 x 256),
+// 1.38 s (8 x 128)
+constexpr int kPanelThreads = 256;
 constexpr int kPanelWarps = kPanelThreads / 32;
 constexpr size_t kPanelSmem = size_t(kAsyncDepth) * kPanelThreads * sizeof(double2);
 

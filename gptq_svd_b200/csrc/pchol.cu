@@ -13,8 +13,8 @@
 //
 // Why it is the B200 way.  DGEQP3 is half BLAS-2: every step streams the whole trailing
 // matrix (8 n^3/3 bytes, 4.2 TB at n = 12288 -> 1.3 s at the 4.4 TB/s we reach).  Pivoted
-// Cholesky touches only O(n nb) data per step (the 64-row block history, L2 resident) and does
-// the rest as DGEMM:  ~0.2 s at n = 12288.
+// Cholesky touches only O(n nb) data per step (the 128-row panel history, L2 resident) and does
+// the rest as DGEMM:  0.15 s at n = 12288.
 //
 // Layout: nothing is swapped per step.  The Gram matrix lives in a COMPACT index space that holds
 // the not-yet-pivoted columns (plus the few pivoted since the last compaction): row j of the factor

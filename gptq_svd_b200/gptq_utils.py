@@ -11,6 +11,9 @@ the reference module imported at `src/TruncGPTQ/quantize.py:14`):
     gptq_fwrd(weight_mat, H_inv_sqrt, quantizer, perm, ...)        gptq_utils.py:459-565
     log_quantization_error(W_orig, W_quant, R_x, perm)             gptq_utils.py:275-291
 
+The sibling front ends (process_hessian, Sketcher, process_sketch) are in frontends.py, the caller's
+loop (quantize.main) in pipeline.py, several solves in flight on one GPU in concurrent.py.
+
 New, additive (the reference has no integer output, README.md:133):
     gptq_quantize(...) -> QuantizedLinear(final_W, codes, scale, zero, rank)
     pack_codes(codes, bits)
