@@ -806,6 +806,8 @@ __global__ void pack_vw_kernel(const double* __restrict__ V, int64_t ldv, const 
 int make_tmap_f64(CUtensorMap* tmap, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                   uint32_t box_rows, uint32_t box_cols);
 
+static thread_local bool g_sytrd_notified = false;   // the stage callback already ran inside sytrd_lower
+
 struct SymBuffers {
   double* rowpart;
   double* colpart;
@@ -881,8 +883,25 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
     // W is read through TMA before every column of it has been written: keep stale NaNs out of it
     TQ_CUDA_CHECK(cudaMemsetAsync(W, 0, sizeof(double) * size_t(n) * kTrdNb, st));
   }
+  // With a stage callback set, TQ_STAGE_TAIL_LEN=<rows> reports the end of the bandwidth-bound part EARLY, once
+  // the trailing matrix has shrunk to that many rows.  Off by default: measured with bench.py it is a loss
+  // (1.83 s per layer at 4096 / 6144 rows vs 1.58 s when the callback fires at the end of the reduction) - the
+  // narrow solves' cooperative panels then gang-schedule against the wide solve's remaining panel launches.
+  int64_t early_len = 0;
+  g_sytrd_notified = false;
+  if (stage_callback_set()) {
+    const char* e = getenv("TQ_STAGE_TAIL_LEN");
+    early_len = e ? atoll(e) : 0;
+  }
+  bool notified = false;
   for (int64_t j0 = 0; j0 < n; j0 += kTrdNb) {
     const int jb = int(imin(kTrdNb, n - j0));
+    if (early_len > 0 && !notified && j0 > 0 && n - j0 <= early_len) {
+      TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+      notify_stage(TQ_STAGE_SYTRD_DONE);
+      notified = true;
+      g_sytrd_notified = true;
+    }
     if (use_sym) {
       for (int i = 0; i < jb; ++i) {
         if (sym_max_slots(n - (j0 + i) - 1, int((j0 + i + 1) % align), i > 0, sym_blocks) > kRowSlots) {
@@ -1633,7 +1652,7 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
               (hc[8] + hc[15]) * 1e-6, hc[9] * 1e-6, hc[10] * 1e-6, hc[11] * 1e-6, (hc[12] + hc[13] + hc[14]) * 1e-6, hc[13] * 1e-6, hc[14] * 1e-6, hc[15] * 1e-6);
     }
   }
-  if (stage_callback_set()) {       // the bandwidth-bound part of the solve is over once the stream drains
+  if (stage_callback_set() && !g_sytrd_notified) {   // the bandwidth-bound part is over once the stream drains
     TQ_CUDA_CHECK(cudaStreamSynchronize(st));
     notify_stage(TQ_STAGE_SYTRD_DONE);
   }

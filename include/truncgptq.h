@@ -78,8 +78,9 @@ int tq_set_sm_budget(int sms);
 
 /* Per-thread stage callback: `cb(stage, user)` runs on the calling host thread inside
  * tq_spectral_solve / tq_eigh when a stage boundary has been reached ON THE DEVICE (the stream is
- * synchronised first).  TQ_STAGE_SYTRD_DONE: the tridiagonal reduction - the bandwidth-bound part of a
- * solve - is complete; what follows is latency- and DGEMM-bound, so a scheduler may lower this thread's
+ * synchronised first).  TQ_STAGE_SYTRD_DONE (once per solve): the tridiagonal reduction - the bandwidth-bound
+ * part of a solve - is complete (or, with the environment variable TQ_STAGE_TAIL_LEN=<rows>, its trailing matrix
+ * has shrunk to that many rows); what follows is latency- and DGEMM-bound, so a scheduler may lower this thread's
  * SM budget and start other solves next to it.  NULL removes the callback. */
 #define TQ_STAGE_SYTRD_DONE 1
 int tq_set_stage_callback(void (*cb)(int stage, void* user), void* user);
