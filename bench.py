@@ -294,9 +294,10 @@ def main():
                         staging[key].copy_(w_src[gi][li], non_blocking=True)
                         events[key] = torch.cuda.Event()
                         events[key].record(copy_stream)
-        # 1 + 2. Hessians and spectral solves.  The latency-bound n <= 8192 solves run side by side (one host
-        #    thread, stream and SM budget each, gptq_svd_b200/concurrent.py) and start as soon as their H is
-        #    accumulated; the bandwidth-bound wide one runs alone on the whole GPU afterwards.
+        # 1 + 2. Hessians and spectral solves (one host thread, stream and SM budget per solve,
+        #    gptq_svd_b200/concurrent.py).  Default (`tail`): the bandwidth-bound wide solve starts first with the
+        #    whole GPU; the narrow, latency-bound ones are released next to its tail.  `--overlap-tail 0`: the
+        #    narrow ones first, side by side, then the wide one alone.
         facs = [None] * len(groups)
         pending = {}
         looped = set()
@@ -331,8 +332,8 @@ def main():
             del acc
             if tail and gi in wides:
                 # the wide solve starts first on a worker with the whole GPU; when its tridiagonal reduction (the
-                # bandwidth-bound part) is done it drops to 48 SMs and the narrow solves start next to its
-                # latency- and DGEMM-bound stages (stage callback of the C ABI)
+                # bandwidth-bound part) is done it drops to `tail_wide` SMs and the narrow solves start next to
+                # its latency- and DGEMM-bound stages (stage callback of the C ABI)
                 sytrd_done = threading.Semaphore(0)
 
                 def solve_wide(H=H, sem=sytrd_done):
