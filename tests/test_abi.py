@@ -73,3 +73,29 @@ def test_quantizer_api_mirrors_reference():
     assert sig.parameters["block_size"].default == 128 and sig.parameters["use_triton"].default is True
     sig = inspect.signature(G.process_hessian_alt)
     assert sig.parameters["threshold"].default == 0.0005 and sig.parameters["threshold_method"].default == "mean_trimmed"
+
+
+def test_frontend_entry_points_fail_loudly_and_mirror_reference(lib):
+    """Rows f3 / f4: the new compute entry points refuse to run without a B200, the workspace queries
+    work on the host, and the Python signatures are the reference's (gptq_utils.py:33-36,129-133,176)."""
+    import inspect
+    import gptq_svd_b200 as G
+    e = C.c_int(0)
+    assert lib.tq_cholesky_solve(None, 0, 0, None, 0.01, None, 0, C.byref(e), None, 0, None) == -2
+    assert b"no CPU fallback" in lib.tq_last_error()
+    assert lib.tq_sketch_accum(None, 0, None, 0, None, 0, 0, 0, 0, 0, None, 0, None) == -2
+    k = C.c_int64(0)
+    assert lib.tq_sketch_solve(None, 0, 0, 0, 1e-2, 1, None, None, C.byref(k), None, 0, None) == -2
+    nbytes = C.c_size_t(0)
+    assert lib.tq_cholesky_workspace(1024, C.byref(nbytes)) == 0 and nbytes.value >= 3 * 1024 * 1024 * 8
+    assert lib.tq_sketch_workspace(512, 1024, C.byref(nbytes)) == 0 and nbytes.value >= 6 * 1024 * 1024 * 8
+    assert lib.tq_set_sm_budget(37) == 0 and lib.tq_set_sm_budget(0) == 0
+    assert lib.tq_set_stage_callback(_lib.STAGE_CALLBACK(0), None) == 0
+    sig = inspect.signature(G.process_hessian)
+    assert list(sig.parameters) == ["H", "actorder", "damp_percent"]
+    assert sig.parameters["actorder"].default is False and sig.parameters["damp_percent"].default == 0.01
+    sig = inspect.signature(G.process_sketch)
+    assert list(sig.parameters) == ["sketch", "threshold", "threshold_method"]
+    assert sig.parameters["threshold"].default == 1e-2 and sig.parameters["threshold_method"].default == "mean_trimmed"
+    assert list(inspect.signature(G.Sketcher.__init__).parameters) == ["self", "layer", "rank", "device"]
+    assert hasattr(G.Sketcher, "hook_fn") and hasattr(G.Sketcher, "get_scaled_sketch")
