@@ -61,6 +61,7 @@ def sb2st(B, b):
     for s in range(n - 2):
         c = s                                        # column whose sub-band part is annihilated
         r0 = s + 1
+        k = 0                                        # chase index: reflector (s, k) acts on rows s+1+k b ...
         while r0 < n - 1:
             r1 = min(r0 + b, n)                      # reflector acts on rows [r0, r1)
             if r1 - r0 < 2:
@@ -71,10 +72,11 @@ def sb2st(B, b):
                 lo, hi = max(0, r0 - b), min(n, r1 + b)          # band window the reflector touches
                 B[r0:r1, lo:hi] = H @ B[r0:r1, lo:hi]
                 B[lo:hi, r0:r1] = B[lo:hi, r0:r1] @ H
-            refl.append((r0, v, tau))
+            refl.append((r0, v, tau, s, k))
             # the bulge appears in block (rows [r1, r1+b), columns [r0, r1)); its first column is column r0
             c = r0
             r0 = r1
+            k += 1
     d = np.diag(B).copy()
     e = np.diag(B, -1).copy()
     off = B - np.diag(d) - np.diag(e, -1) - np.diag(e, 1)
@@ -86,9 +88,41 @@ def apply_q2(refl, Z):
     CUDA: reflectors of consecutive sweeps at the same chase position overlap by one row - groups of 64 sweeps
     form a (b + 64) x 64 parallelogram that is applied as one compact-WY block (GEMM-shaped)."""
     Z = Z.copy()
-    for r0, v, tau in reversed(refl):
+    for r0, v, tau, _, _ in reversed(refl):
         if tau != 0.0:
             Z[r0:r0 + len(v), :] -= tau * np.outer(v, v @ Z[r0:r0 + len(v), :])
+    return Z
+
+
+def apply_q2_grouped(refl, Z, b, nb):
+    """The GEMM-shaped version the CUDA kernel needs.  Reflector (s, k) acts on rows [s+1+kb, s+1+(k+1)b); two
+    reflectors overlap iff |(s-s') + (k-k') b| < b, and of two overlapping ones the later generated (larger
+    (s, k) lexicographically) must be applied first.  For blocks of nb <= b consecutive sweeps that order is
+    kept by:  sweep blocks DESCENDING, inside a block chase index k ASCENDING, inside (block, k) sweeps
+    descending - and the nb reflectors of one (block, k) form a (b + nb - 1) x nb staircase V that is applied
+    as ONE compact-WY block  Z[rows] -= V (T (V^T Z[rows]))  (three GEMMs with K = nb)."""
+    assert nb <= b
+    Z = Z.copy()
+    by = {}
+    for r0, v, tau, s, k in refl:
+        by[(s // nb, k)] = by.get((s // nb, k), []) + [(s, r0, v, tau)]
+    blocks = sorted({sb for sb, _ in by}, reverse=True)
+    for sb in blocks:
+        for k in sorted(kk for (s2, kk) in by if s2 == sb):
+            grp = sorted(by[(sb, k)])                 # sweeps ascending: G = H_s0 H_s0+1 ... (apply last one first)
+            rlo = grp[0][1]
+            rhi = max(r0 + len(v) for _, r0, v, _ in grp)
+            V = np.zeros((rhi - rlo, len(grp)))
+            taus = np.zeros(len(grp))
+            for j, (_, r0, v, tau) in enumerate(grp):
+                V[r0 - rlo:r0 - rlo + len(v), j] = v
+                taus[j] = tau
+            T = np.zeros((len(grp), len(grp)))        # forward columnwise larft: H_0 H_1 ... H_{m-1} = I - V T V^T
+            for j in range(len(grp)):
+                T[j, j] = taus[j]
+                if j:
+                    T[:j, j] = -taus[j] * (T[:j, :j] @ (V[:, :j].T @ V[:, j]))
+            Z[rlo:rhi, :] -= V @ (T @ (V.T @ Z[rlo:rhi, :]))
     return Z
 
 
@@ -97,7 +131,10 @@ def eigh_two_stage(A, b):
     d, e, refl, off = sb2st(band, b)
     T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
     w, ZT = np.linalg.eigh(T)                         # CUDA: the existing divide & conquer (stedc)
-    Z = Q1 @ apply_q2(refl, ZT)
+    Z2 = apply_q2(refl, ZT)
+    Z2g = apply_q2_grouped(refl, ZT, b, max(1, b // 2))
+    assert np.abs(Z2 - Z2g).max() <= 1e-12, np.abs(Z2 - Z2g).max()      # the grouped order is the same operator
+    Z = Q1 @ Z2g
     return w, Z, off, len(refl)
 
 
