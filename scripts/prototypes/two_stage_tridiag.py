@@ -53,8 +53,9 @@ def sb2st(B, b):
     """Stage 2: bulge chasing (Schwarz / Bischof-Lang-Sun).  Sweep s annihilates column s below its first
     sub-diagonal; the fill-in (bulge) it creates one block further down is chased off the matrix with one
     more reflector per block.  Works on full storage here; the CUDA kernel holds the (b+1) x n band in L2 and
-    one task (reflector + the <= 2b x 2b window it touches) in shared memory.  Sweep s+1 may start task k as
-    soon as sweep s has finished task k+2 - that is the pipeline a persistent kernel runs."""
+    one task (reflector + the <= 3b x b window it touches) in shared memory.  Sweep s+1 may start task k as
+    soon as sweep s has finished task k+2, i.e. sweeps are released 3 task-times apart (sb2st_wavefront below
+    checks it: a distance of 1 or 2 changes the result, 3 does not) - the pipeline a persistent kernel runs."""
     B = B.copy()
     n = B.shape[0]
     refl = []
@@ -81,6 +82,34 @@ def sb2st(B, b):
     e = np.diag(B, -1).copy()
     off = B - np.diag(d) - np.diag(e, -1) - np.diag(e, 1)
     return d, e, refl, float(np.abs(off).max())
+
+
+def sb2st_wavefront(B, b, lag, rng=None):
+    """The same chase, executed as the persistent CUDA kernel will run it: task (s, k) is released at time
+    lag * s + k; tasks with the same time stamp run concurrently (here: in a shuffled order).  If `lag` is a
+    valid pipeline distance the result equals the sweep-by-sweep order exactly."""
+    B = B.copy()
+    n = B.shape[0]
+    tasks = []
+    for s in range(n - 2):
+        r0, k = s + 1, 0
+        while r0 < n - 1 and min(r0 + b, n) - r0 >= 2:
+            tasks.append((lag * s + k, s, k))
+            r0, k = min(r0 + b, n), k + 1
+    if rng is not None:
+        tasks = [tasks[i] for i in rng.permutation(len(tasks))]
+    tasks.sort(key=lambda t: t[0])                   # stable: equal stamps keep the shuffled order
+    for _, s, k in tasks:
+        r0 = s + 1 + k * b
+        r1 = min(r0 + b, n)
+        c = s if k == 0 else r0 - b
+        v, tau, beta = house(B[r0:r1, c].copy())
+        if tau != 0.0:
+            H = np.eye(r1 - r0) - tau * np.outer(v, v)
+            lo, hi = max(0, r0 - b), min(n, r1 + b)
+            B[r0:r1, lo:hi] = H @ B[r0:r1, lo:hi]
+            B[lo:hi, r0:r1] = B[lo:hi, r0:r1] @ H
+    return np.diag(B).copy(), np.diag(B, -1).copy()
 
 
 def apply_q2(refl, Z):
@@ -149,6 +178,14 @@ if __name__ == "__main__":
         wr = np.linalg.eigvalsh(A)
         res = np.linalg.norm(A @ Z - Z * w[None, :]) / np.linalg.norm(A)
         orth = np.linalg.norm(Z.T @ Z - np.eye(n))
+        d0, e0, _, _ = sb2st(band, b)
+        ok = {}
+        for lag in (1, 2, 3):
+            d1, e1 = sb2st_wavefront(band, b, lag, rng)
+            ok[lag] = bool(np.allclose(d0, d1, rtol=0, atol=1e-12 * np.abs(A).max()) and
+                           np.allclose(np.abs(e0), np.abs(e1), rtol=0, atol=1e-12 * np.abs(A).max()))
+        print(f"   pipeline distance between consecutive sweeps (tasks): {ok}")
+        assert ok[3]
         print(f"n={n} b={b}: bandwidth after stage 1 = {bw}, off-tridiagonal after stage 2 = {off:.1e}, "
               f"{nref} reflectors (n^2/2b = {n * n // (2 * b)}), max|dw|/|w|max = {np.abs(w - wr).max() / wr.max():.1e}, "
               f"residual {res:.1e}, orthogonality {orth:.1e}")
