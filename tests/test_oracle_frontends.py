@@ -110,3 +110,31 @@ def test_solver_pool_fails_loudly_without_gpu():
         pool.result(pool.submit(lambda: 1))
     with pytest.raises(RuntimeError):
         SolverPool(workers=1, device="cpu")
+
+
+def test_pipeline_helpers_match_the_reference_on_a_real_layer():
+    """Only where /root/reference exists (the build container): the group structure and layer lookup of
+    pipeline.py equal the reference's model_utils on a real (random-init, tiny) Qwen3."""
+    import sys
+    ref_src = "/root/reference/src/TruncGPTQ"
+    if not os.path.isfile(os.path.join(ref_src, "model_utils.py")):
+        pytest.skip("reference sources not present")
+    torch = pytest.importorskip("torch")
+    tr = pytest.importorskip("transformers")
+    sys.path.insert(0, ref_src)
+    try:
+        import model_utils as RM
+    finally:
+        sys.path.remove(ref_src)
+    from gptq_svd_b200 import pipeline as P
+    cfg = tr.Qwen3Config(vocab_size=64, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                         num_attention_heads=2, num_key_value_heads=1, head_dim=32, max_position_embeddings=64)
+    model = tr.Qwen3ForCausalLM(cfg)
+    assert P.get_layers(model) is RM.get_layers(model)
+    layer = P.get_layers(model)[0]
+    assert P.get_sequenced_groups(layer) == RM.get_sequenced_groups(layer)
+    ids = [torch.randint(0, 64, (1, 16)) for _ in range(3)]
+    a, ka = P.capture_initial_inputs(model, ids, device="cpu", batch_size=2)
+    b, kb = RM.capture_initial_inputs(model, ids, device="cpu", batch_size=2)
+    assert torch.equal(a, b) and sorted(ka) == sorted(kb)
+    assert RM.get_layers(model)[0] is layer            # the wrapper was removed again
