@@ -93,6 +93,17 @@ StageTimer::~StageTimer() {
   }
 }
 
+static thread_local int g_two_stage = -1;      // -1: follow TQ_EIGH_TWO_STAGE, 0 / 1: tq_set_eigh_two_stage
+bool two_stage_requested() {
+  if (g_two_stage >= 0) return g_two_stage == 1;
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("TQ_EIGH_TWO_STAGE");
+    env = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  return env == 1;
+}
+
 static thread_local int g_sm_budget = 0;
 static thread_local void (*g_stage_cb)(int, void*) = nullptr;
 static thread_local void* g_stage_user = nullptr;
@@ -154,6 +165,11 @@ extern "C" int tq_profile_end(double* alg_bytes, double* ms, int64_t* sampled, i
 
 extern "C" int tq_set_sm_budget(int sms) {
   tq::g_sm_budget = sms > 0 ? sms : 0;
+  return TQ_OK;
+}
+
+extern "C" int tq_set_eigh_two_stage(int on) {
+  tq::g_two_stage = on < 0 ? -1 : (on ? 1 : 0);
   return TQ_OK;
 }
 

@@ -1600,8 +1600,15 @@ int copy_symmetric_lower(cudaStream_t st, const double* H, int64_t ldh, int64_t 
   return TQ_OK;
 }
 
+// two_stage.cu (experimental, off by default)
+bool two_stage_usable(int64_t n);
+size_t two_stage_ws_bytes(int64_t n);
+int two_stage_reduce(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double* d, double* e, Workspace& ws);
+int two_stage_back(cublasHandle_t h, cudaStream_t st, const double* A, int64_t n, double* Z, int64_t ncols,
+                   Workspace scratch);
+
 size_t eigh_ws_bytes(int64_t n) {
-  size_t b = 0;
+  size_t b = two_stage_usable(n) ? two_stage_ws_bytes(n) : 0;
   b += ws_bytes_for(size_t(n) * n, 8) * 4;                 // A, Zg, Zo, U
   b += ws_bytes_for(n, 8) * (14 + 32) + ws_bytes_for(2 * kTrdNb * 32, 8) + ws_bytes_for(n, 4) * 8 + ws_bytes_for(n, sizeof(DcRot));
   b += ws_bytes_for(size_t(n) * kTrdNb, 8) * 5 + ws_bytes_for(size_t(n) * kOrmNb, 8);   // W, XY, Vc
@@ -1641,7 +1648,13 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
     copy_sym_kernel<<<grid, 256, 0, st>>>(H, ldh, n, A);
     TQ_LAUNCH_CHECK();
   }
-  {
+  const bool two_stage = two_stage_usable(n);
+  if (two_stage) {
+    // band reduction + bulge chasing instead of the one-stage reduction (two_stage.cu)
+    StageTimer tm(st, "sytrd (two-stage)");
+    g_sytrd_notified = false;
+    TQ_TRY(two_stage_reduce(h, st, A, n, w, e, ws));
+  } else {
     StageTimer tm(st, "sytrd");
     TQ_TRY(sytrd_lower(h, st, A, n, w, e, tau, W, y, tmp, part, scal, bar, XY, sb));
     if (trace_enabled()) {
@@ -1671,6 +1684,10 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
     if (sub2.overflow) {
       set_error("eigh: workspace too small (ormtr)");
       return TQ_ERR_WORKSPACE;
+    }
+    if (two_stage) {
+      TQ_TRY(two_stage_back(h, st, A, n, Zout, n, ws));
+      return TQ_OK;
     }
     StageTimer tm(st, "ormtr");
     TQ_TRY(ormtr_lower(h, st, A, tau, n, Zout, n, Vc, G, T, w1, w2));

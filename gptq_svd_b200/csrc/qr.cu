@@ -681,9 +681,12 @@ static int qr_block_update(cublasHandle_t h, cudaStream_t st, double* A, int64_t
   return apply_block_reflector(h, Vc, s, s, jb, T, jb, /*trans_t=*/true, A + j0 + c0 * lda, lda, nc, w1, w2);
 }
 
-int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n,
-                  Workspace& ws) {
-  double* tau = ws.take<double>(k);
+// tau_out (optional, min(k, n) entries): keeps the Householder scalars for a caller that applies Q later
+// (stage 1 of the two-stage tridiagonal reduction factors tall panels, k > n, with it).
+int qr_r_colmajor_tau(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n,
+                      Workspace& ws, double* tau_out) {
+  const int64_t kk = imin(k, n);                 // number of reflectors
+  double* tau = tau_out ? tau_out : ws.take<double>(kk);
   double* beta = ws.take<double>(k);
   double* wdot = ws.take<double>(kQrNb * kMaxChunks);
   double* part = ws.take<double>(1024);
@@ -714,8 +717,8 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
     coop_per_sm = per_sm > 2 ? 2 : per_sm;
   }
   const int coop_blocks = num_sms() * coop_per_sm;      // num_sms() honours tq_set_sm_budget
-  for (int64_t j0 = 0; j0 < k; j0 += kQrOb) {
-    const int ob = int(imin(kQrOb, k - j0));
+  for (int64_t j0 = 0; j0 < kk; j0 += kQrOb) {
+    const int ob = int(imin(kQrOb, kk - j0));
     const int64_t oend = j0 + ob;
     int64_t jp = j0;
     while (jp < oend) {
@@ -748,6 +751,11 @@ int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
     TQ_TRY(qr_block_update(h, st, A, lda, k, j0, ob, oend, n - oend, tau, Vc, G, T, w1, w2));
   }
   return TQ_OK;
+}
+
+int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n,
+                  Workspace& ws) {
+  return qr_r_colmajor_tau(h, st, A, lda, k, n, ws, nullptr);
 }
 
 // ------------------------------------------------------------------ pivoted QR (DLAQPS)

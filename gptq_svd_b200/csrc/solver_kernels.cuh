@@ -141,7 +141,11 @@ constexpr size_t kLarftSmem = size_t(kLarftMaxJb) * kLarftMaxJb * 8 + size_t(kLa
 
 static __global__ void __launch_bounds__(kLarftThreads)
 larft_kernel(const double* __restrict__ G, int ldg, const double* __restrict__ tau, int jb, double* __restrict__ T,
-             int ldt) {
+             int ldt, int64_t stride_g = 0, int64_t stride_tau = 0, int64_t stride_t = 0) {
+  // batched use (one CTA per block reflector): CTA x works on G + x stride_g, tau + x stride_tau, T + x stride_t
+  G += int64_t(blockIdx.x) * stride_g;
+  tau += int64_t(blockIdx.x) * stride_tau;
+  T += int64_t(blockIdx.x) * stride_t;
   extern __shared__ double larft_sm[];
   double* M = larft_sm;                 // jb x jb, column-major, ld jb
   double* X = larft_sm + jb * jb;       // <= jb * jb / 4 entries per level

@@ -1,0 +1,275 @@
+// Two-stage tridiagonal reduction for tq_eigh (EXPERIMENTAL, off by default: tq_set_eigh_two_stage(1) or
+// TQ_EIGH_TWO_STAGE=1; n % 64 == 0).  First written at the end of round 1 without GPU time left: it compiles
+// for sm_100a and every index expression below is checked against the numpy model
+// scripts/prototypes/sb2st_band.py (tests/test_two_stage_band_model.py), but it has NOT run on a B200 yet -
+// tests/test_gpu_two_stage.py is its parity test.
+//
+// Why.  The one-stage reduction (eigh.cu) streams the lower triangle of the trailing matrix once per COLUMN:
+// 4 n^3 / 3 bytes, and sytrd_panel_sym_kernel already runs that stream at ~0.93 of the HBM peak (0.82 s at
+// n = 12288, 52 % of a decoder layer).  Only fewer bytes help:
+//   stage 1  sy2sb   A = Q1 B Q1^T, B a band of width b = 64: QR of the block column below the band (cluster /
+//            DSMEM panel kernel of qr.cu) + ONE symmetric rank-2b update per block column (DSYMM + DSYR2K): the
+//            trailing matrix is read once per 64 columns, 4 n^3 / 3 flop of fp64 tensor-core work;
+//   stage 2  sb2st   B = Q2 T Q2^T: bulge chasing on the (2 b) x n band array, which stays in L2 (12.6 MB at
+//            n = 12288).  One persistent kernel; a CTA owns a sweep and walks its tasks, the bulge block travels
+//            from task to task in shared memory, consecutive sweeps run 3 tasks apart under acquire / release
+//            progress counters (pipeline distance proved in scripts/prototypes/two_stage_tridiag.py);
+//   back     Z = Q1 (Q2 Z_T): Q2 in wavefronts of row-disjoint (127 x 64) staircase block reflectors - one
+//            strided-batched DGEMM triple per wavefront, groups of a wavefront sit 3 b rows apart in Z; Q1 like
+//            ormtr with the reflector staircase shifted down by b rows.
+// Expected at n = 12288 (36 TF/s DGEMM): stage 1 ~0.13 s, stage 2 ~0.11 s, Q2 ~0.37 s vs 0.82 s.
+#include <stdlib.h>
+
+#include "solver_kernels.cuh"
+#include "two_stage_kernels.cuh"
+
+namespace tq {
+
+int qr_r_colmajor_tau(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n, Workspace& ws,
+                      double* tau_out);
+bool two_stage_requested();
+
+static inline int64_t chase_tasks(int64_t s, int64_t n) { return s > n - 3 ? 0 : (n - 3 - s) / kBw + 1; }
+
+// ------------------------------------------------------------------------------------------------ buffers
+struct TwoStageBuffers {
+  double* Vs = nullptr;     // n x n
+  double* Bd = nullptr;     // kLdb x n
+  double* tau1 = nullptr;   // n
+  double* tau2 = nullptr;   // n x (n / b + 2)
+  int* prog = nullptr;      // n
+};
+
+size_t two_stage_ws_bytes(int64_t n) {
+  size_t b = ws_bytes_for(size_t(n) * n, 8) + ws_bytes_for(size_t(kLdb) * n, 8) + ws_bytes_for(n, 8);
+  b += ws_bytes_for(size_t(n) * (n / kBw + 2), 8) + ws_bytes_for(n, 4);
+  return b;
+}
+
+static int take_two_stage(Workspace& ws, int64_t n, TwoStageBuffers& tb) {
+  tb.Vs = ws.take<double>(size_t(n) * n);
+  tb.Bd = ws.take<double>(size_t(kLdb) * n);
+  tb.tau1 = ws.take<double>(n);
+  tb.tau2 = ws.take<double>(size_t(n) * (n / kBw + 2));
+  tb.prog = ws.take<int>(n);
+  if (ws.overflow) {
+    set_error("eigh (two-stage): workspace too small - query tq_solver_workspace after tq_set_eigh_two_stage(1)");
+    return TQ_ERR_WORKSPACE;
+  }
+  return TQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stage 1
+// A (n x n column-major, LOWER triangle referenced and updated) -> band of width b in place; the reflectors of
+// block column j stay below R in A[j + b :, j : j + b), their scalars in tau1[j : j + b).
+// scratch: overlays the D&C workspace (>= 3 n^2 doubles).
+static int sy2sb(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double* tau1, Workspace scratch) {
+  constexpr int b = kBw;
+  const int64_t lda = n;
+  const double one = 1.0, zero = 0.0, mone = -1.0, mhalf = -0.5;
+  double* Vc = scratch.take<double>(size_t(n) * b);
+  double* X = scratch.take<double>(size_t(n) * b);
+  double* X2 = scratch.take<double>(size_t(n) * b);
+  double* G = scratch.take<double>(b * b);
+  double* T = scratch.take<double>(b * b);
+  double* M1 = scratch.take<double>(b * b);
+  double* M2 = scratch.take<double>(b * b);
+  if (scratch.overflow) {
+    set_error("sy2sb: workspace too small");
+    return TQ_ERR_WORKSPACE;
+  }
+  TQ_CUDA_CHECK(cudaMemsetAsync(tau1, 0, sizeof(double) * n, st));
+  for (int64_t j = 0; j + b < n; j += b) {
+    const int64_t r0 = j + b, s = n - r0;
+    double* P = A + r0 + j * lda;
+    double* A22 = A + r0 + r0 * lda;
+    Workspace qws = scratch;                         // the panel factorisation's own scratch, released afterwards
+    TQ_TRY(qr_r_colmajor_tau(h, st, P, lda, s, b, qws, tau1 + j));
+    dim3 grid((unsigned)imin(ceil_div(s, 256), 256), (unsigned)b);
+    copy_reflectors_kernel<<<grid, 256, 0, st>>>(P, lda, s, b, Vc, s);
+    TQ_LAUNCH_CHECK();
+    TQ_TRY(build_t_factor(h, st, Vc, s, s, b, tau1 + j, G, T));
+    // X = A22 V (lower triangle of A22 only), X2 = X T
+    TQ_CUBLAS_CHECK(cublasDsymm(h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, int(s), b, &one, A22, int(lda), Vc,
+                                int(s), &zero, X, int(s)));
+    TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, int(s), b, b, &one, X, int(s), T, b, &zero, X2, int(s)));
+    // M2 = T^T (V^T X2);  W = X2 - V M2 / 2  (in X2)
+    TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, b, b, int(s), &one, Vc, int(s), X2, int(s), &zero, M1, b));
+    TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, b, b, b, &one, T, b, M1, b, &zero, M2, b));
+    TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, int(s), b, b, &mhalf, Vc, int(s), M2, b, &one, X2, int(s)));
+    // A22 -= V W^T + W V^T
+    TQ_CUBLAS_CHECK(cublasDsyr2k(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, int(s), b, &mone, Vc, int(s), X2, int(s), &one,
+                                 A22, int(lda)));
+  }
+  return TQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stage 2
+static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuffers& tb, double* d, double* e) {
+  band_extract_kernel<<<unsigned(n), 128, 0, st>>>(A, n, int(n), tb.Bd);
+  TQ_LAUNCH_CHECK();
+  TQ_CUDA_CHECK(cudaMemsetAsync(tb.prog, 0, sizeof(int) * n, st));
+  TQ_CUDA_CHECK(cudaMemsetAsync(tb.tau2, 0, sizeof(double) * size_t(n) * (n / kBw + 2), st));
+  if (n > 2) {
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(sb2st_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(kChaseSmem)));
+    // sweeps run 3 tasks apart, so at most K_0 / 3 + 1 of them are in flight; the launch is cooperative only for
+    // its guarantee that every CTA is resident (a waiting sweep's predecessor must be running)
+    const int64_t want = chase_tasks(0, n) / 3 + 2;
+    const int grid = int(imax(1, imin(num_sms(), want)));
+    ChaseArgs ca{tb.Bd, int(n), tb.Vs, n, tb.tau2, tb.prog};
+    void* kargs[] = {&ca};
+    TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sb2st_chase_kernel, dim3(grid), dim3(kChaseThreads), kargs,
+                                              kChaseSmem, st));
+    ++g_launch_count;
+  }
+  band_diag_kernel<<<unsigned(ceil_div(n, 256)), 256, 0, st>>>(tb.Bd, int(n), d, e);
+  TQ_LAUNCH_CHECK();
+  return TQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Z <- Q2 Z
+// Of two overlapping reflectors the later generated one acts first; for groups that means sweep blocks DESCENDING
+// and, inside a block, chase index ASCENDING.  Group (sb, k) overlaps (sb, k - 1) and (sb + 1, k - 2 .. k), so
+// w = k + 2 (M - sb) is a valid wavefront number, and the groups of one wavefront start 3 b rows apart.
+static int apply_q2_batch(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb, int64_t n, int sb0, int k0,
+                          int count, int hg, double* Z, int64_t ldz, int64_t ncols, double* Vc, double* taub, double* Gb,
+                          double* Tb, double* w1, double* w2) {
+  constexpr int b = kBw;
+  const double one = 1.0, zero = 0.0, mone = -1.0;
+  const int64_t rlo = int64_t(sb0) * b + 1 + int64_t(k0) * b;
+  const long long sv = (long long)kQ2Ld * b, st_t = (long long)b * b, sw = (long long)b * ncols, sz = 3 * b;
+  copy_staircase_kernel<<<dim3(1, b, count), kQ2Ld, 0, st>>>(tb.Vs, n, tb.tau2, int(n), sb0, k0, Vc, taub);
+  TQ_LAUNCH_CHECK();
+  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, b, hg, &one, Vc, kQ2Ld, sv, Vc, kQ2Ld, sv,
+                                            &zero, Gb, b, st_t, count));
+  larft_kernel<<<count, kLarftThreads, size_t(b) * b * 10, st>>>(Gb, b, taub, b, Tb, b, st_t, b, st_t);
+  TQ_LAUNCH_CHECK();
+  double* Zb = Z + rlo;
+  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, int(ncols), hg, &one, Vc, kQ2Ld, sv, Zb,
+                                            int(ldz), sz, &zero, w1, b, sw, count));
+  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, b, int(ncols), b, &one, Tb, b, st_t, w1, b, sw,
+                                            &zero, w2, b, sw, count));
+  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, hg, int(ncols), b, &mone, Vc, kQ2Ld, sv, w2, b,
+                                            sw, &one, Zb, int(ldz), sz, count));
+  return TQ_OK;
+}
+
+static int apply_q2(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb, int64_t n, double* Z, int64_t ldz,
+                    int64_t ncols, Workspace scratch) {
+  constexpr int b = kBw;
+  const int64_t nsweeps = n - 2;
+  if (nsweeps <= 0) return TQ_OK;
+  const int M = int((nsweeps - 1) / b);
+  const int maxb = int(n / (3 * b)) + 2;
+  double* Vc = scratch.take<double>(size_t(maxb) * kQ2Ld * b);
+  double* taub = scratch.take<double>(size_t(maxb) * b);
+  double* Gb = scratch.take<double>(size_t(maxb) * b * b);
+  double* Tb = scratch.take<double>(size_t(maxb) * b * b);
+  double* w1 = scratch.take<double>(size_t(maxb) * b * ncols);
+  double* w2 = scratch.take<double>(size_t(maxb) * b * ncols);
+  if (scratch.overflow) {
+    set_error("apply_q2: workspace too small");
+    return TQ_ERR_WORKSPACE;
+  }
+  const int kmax0 = int(chase_tasks(0, n)) - 1;
+  for (int w = 0; w <= kmax0 + 2 * M; ++w) {
+    int sb_lo = -1, sb_hi = -1;
+    for (int sb = 0; sb <= M; ++sb) {
+      const int k = w - 2 * (M - sb);
+      if (k < 0 || k > int(chase_tasks(int64_t(sb) * b, n)) - 1) continue;
+      if (sb_lo < 0) sb_lo = sb;
+      if (sb_hi >= 0 && sb != sb_hi + 1) {
+        set_error("apply_q2: wavefront %d is not contiguous", w);
+        return TQ_ERR_UNSUPPORTED;
+      }
+      sb_hi = sb;
+    }
+    if (sb_lo < 0) continue;
+    int count = sb_hi - sb_lo + 1;
+    if (count > maxb) {
+      set_error("apply_q2: wavefront %d has %d groups (max %d)", w, count, maxb);
+      return TQ_ERR_UNSUPPORTED;
+    }
+    const int k_lo = w - 2 * (M - sb_lo), k_hi = w - 2 * (M - sb_hi);
+    const int64_t rlo_last = int64_t(sb_hi) * b + 1 + int64_t(k_hi) * b;
+    const int hg_last = int(imin(kQ2H, n - rlo_last));          // only the lowest group can run past row n
+    if (hg_last < kQ2H) {
+      TQ_TRY(apply_q2_batch(h, st, tb, n, sb_hi, k_hi, 1, hg_last, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2));
+      --count;
+    }
+    if (count > 0)
+      TQ_TRY(apply_q2_batch(h, st, tb, n, sb_lo, k_lo, count, kQ2H, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2));
+  }
+  return TQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Z <- Q1 Z
+// Reflector c of stage 1 (c < n - b) has its unit entry in row c + b: the blocks are clean staircases that start b
+// rows below the diagonal; otherwise exactly ormtr_lower (eigh.cu).
+static int apply_q1(cublasHandle_t h, cudaStream_t st, const double* A, const double* tau1, int64_t n, double* Z,
+                    int64_t ldz, int64_t ncols, Workspace scratch) {
+  const int64_t nref = n - kBw;
+  if (nref <= 0) return TQ_OK;
+  double* Vc = scratch.take<double>(size_t(n) * kQ1Nb);
+  double* G = scratch.take<double>(kQ1Nb * kQ1Nb);
+  double* T = scratch.take<double>(kQ1Nb * kQ1Nb);
+  double* w1 = scratch.take<double>(size_t(kQ1Nb) * ncols);
+  double* w2 = scratch.take<double>(size_t(kQ1Nb) * ncols);
+  if (scratch.overflow) {
+    set_error("apply_q1: workspace too small");
+    return TQ_ERR_WORKSPACE;
+  }
+  const int64_t nblk = ceil_div(nref, kQ1Nb);
+  for (int64_t blk = nblk - 1; blk >= 0; --blk) {
+    const int64_t j0 = blk * kQ1Nb;
+    const int jb = int(imin(kQ1Nb, nref - j0));
+    const int64_t s = n - j0 - kBw;
+    dim3 grid((unsigned)imin(ceil_div(s, 256), 256), (unsigned)jb);
+    copy_reflectors_kernel<<<grid, 256, 0, st>>>(A + (j0 + kBw) + j0 * n, n, s, jb, Vc, s);
+    TQ_LAUNCH_CHECK();
+    TQ_TRY(build_t_factor(h, st, Vc, s, s, jb, tau1 + j0, G, T));
+    TQ_TRY(apply_block_reflector(h, Vc, s, s, jb, T, jb, /*trans_t=*/false, Z + (j0 + kBw), ldz, ncols, w1, w2));
+  }
+  return TQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ entry points
+bool two_stage_usable(int64_t n) { return two_stage_requested() && n % kBw == 0 && n >= 4 * kBw && n < (1 << 30); }
+
+struct TwoStageState {
+  TwoStageBuffers tb;
+};
+static thread_local TwoStageState g_ts;
+
+// A -> (d, e); the reflectors of both stages stay in A / in buffers taken from `ws` (by reference: they must
+// outlive the D&C stage); everything after them in `ws` is scratch until this returns.
+int two_stage_reduce(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double* d, double* e, Workspace& ws) {
+  TQ_TRY(take_two_stage(ws, n, g_ts.tb));
+  Workspace scratch = ws;
+  {
+    StageTimer tm(st, "sy2sb");
+    TQ_TRY(sy2sb(h, st, A, n, g_ts.tb.tau1, scratch));
+  }
+  {
+    StageTimer tm(st, "sb2st");
+    TQ_TRY(sb2st(st, A, n, g_ts.tb, d, e));
+  }
+  return TQ_OK;
+}
+
+// Z (n x ncols, column-major, ld n) <- Q1 Q2 Z
+int two_stage_back(cublasHandle_t h, cudaStream_t st, const double* A, int64_t n, double* Z, int64_t ncols,
+                   Workspace scratch) {
+  {
+    StageTimer tm(st, "apply_q2");
+    TQ_TRY(apply_q2(h, st, g_ts.tb, n, Z, n, ncols, scratch));
+  }
+  {
+    StageTimer tm(st, "apply_q1");
+    TQ_TRY(apply_q1(h, st, A, g_ts.tb.tau1, n, Z, n, ncols, scratch));
+  }
+  return TQ_OK;
+}
+
+}  // namespace tq

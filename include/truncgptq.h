@@ -76,6 +76,13 @@ const char* tq_last_error(void);
  * reproducible for a given budget and agree across budgets to rounding (R within 2e-12 relative). */
 int tq_set_sm_budget(int sms);
 
+/* EXPERIMENTAL, per thread: 1 = tq_eigh / tq_spectral_solve reduce to tridiagonal form in TWO stages (band
+ * reduction of width 64 by QR panels and DSYMM / DSYR2K, then bulge chasing on the L2-resident band; two
+ * back-transformations) when n % 64 == 0 and n >= 256; 0 = the one-stage reduction; -1 (default) = follow the
+ * environment variable TQ_EIGH_TWO_STAGE (unset: one-stage).  The workspace queries depend on this setting: query
+ * after changing it.  gptq_svd_b200/csrc/two_stage.cu. */
+int tq_set_eigh_two_stage(int on);
+
 /* Per-thread stage callback: `cb(stage, user)` runs on the calling host thread inside
  * tq_spectral_solve / tq_eigh when a stage boundary has been reached ON THE DEVICE (the stream is
  * synchronised first).  TQ_STAGE_SYTRD_DONE (once per solve): the tridiagonal reduction - the bandwidth-bound

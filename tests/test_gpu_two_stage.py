@@ -1,0 +1,66 @@
+"""GPU parity of the EXPERIMENTAL two-stage tridiagonal reduction (tq_set_eigh_two_stage, csrc/two_stage.cu).
+
+The code was written at the end of round 1 with no GPU time left: its kernels are checked on the CPU
+(tests/test_two_stage_emu.py) but have not run on a B200, so these tests only run when TQ_TEST_TWO_STAGE=1 -
+the default suite must stay green.  First thing to run in round 2:
+    TQ_TEST_TWO_STAGE=1 python -m pytest tests/test_gpu_two_stage.py -x -q
+Bars are those of the one-stage path (tests/test_gpu_solver.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("TQ_TEST_TWO_STAGE") != "1",
+                                 reason="experimental path, not validated on a GPU yet (set TQ_TEST_TWO_STAGE=1)")]
+
+
+@pytest.fixture()
+def two_stage():
+    from gptq_svd_b200 import _lib, stages
+    lib = _lib.load()
+    lib.tq_set_eigh_two_stage(1)
+    yield stages
+    lib.tq_set_eigh_two_stage(-1)
+
+
+def _spd(n, seed, decay=-3.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    X = torch.randn(2 * n, n, device="cuda", dtype=torch.float64, generator=g)
+    X = X * torch.logspace(0, decay, n, device="cuda", dtype=torch.float64)[None, :]
+    return X.T @ X / (2 * n)
+
+
+@pytest.mark.parametrize("n", [256, 320, 1024, 4096])
+def test_two_stage_eigh_is_an_eigendecomposition(two_stage, n):
+    H = _spd(n, n)
+    w, V = two_stage.eigh(H)
+    wr = torch.linalg.eigvalsh(H)
+    scale = float(wr.abs().max())
+    assert bool((w[1:] >= w[:-1]).all())
+    assert float((w - wr).abs().max()) <= 1e-12 * scale * n ** 0.5
+    assert float(torch.linalg.norm(H @ V - V * w[None, :])) <= 1e-12 * float(torch.linalg.norm(H)) * n ** 0.5
+    assert float(torch.linalg.norm(V.T @ V - torch.eye(n, device="cuda", dtype=torch.float64))) <= 1e-12 * n
+
+
+def test_two_stage_matches_one_stage_through_the_solver(two_stage):
+    """Same retained rank, pivots and factors as the default path (the eigenvectors of separated eigenvalues are
+    unique up to sign, and R / R_x do not depend on that sign)."""
+    import gptq_svd_b200 as G
+    from gptq_svd_b200 import _lib
+    n = 1024
+    H = _spd(n, 11, decay=-2.0)
+    f2 = G.spectral_solve(H, 1e-4, "energy")
+    _lib.load().tq_set_eigh_two_stage(0)
+    f1 = G.spectral_solve(H, 1e-4, "energy")
+    assert f1.k == f2.k
+    assert torch.equal(f1.perm[:f1.k], f2.perm[:f2.k])
+    assert float((f1.R[:f1.k] - f2.R[:f2.k]).abs().max()) <= 1e-8 * float(f1.R[:f1.k].abs().max())
+    assert float((f1.R_x[:f1.k] - f2.R_x[:f2.k]).abs().max()) <= 1e-8 * float(f1.R_x[:f1.k].abs().max())
+
+
+def test_two_stage_falls_back_when_n_is_not_a_multiple_of_64(two_stage):
+    H = _spd(300, 3)
+    w, V = two_stage.eigh(H)
+    assert float((w - torch.linalg.eigvalsh(H)).abs().max()) <= 1e-12 * float(w.abs().max()) * 300 ** 0.5

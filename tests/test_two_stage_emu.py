@@ -1,0 +1,158 @@
+"""CPU checks of the experimental two-stage tridiagonal reduction (gptq_svd_b200/csrc/two_stage.cu):
+
+* the numpy model of its data layout (scripts/prototypes/sb2st_band.py) against numpy.linalg.eigh and against the
+  full-storage prototype;
+* the KERNEL SOURCE of two_stage_kernels.cuh compiled for the host (tests/emu/two_stage_emu.cpp: one OS thread per
+  CUDA thread, CTAs running concurrently) against that model - band extraction, the persistent bulge-chase kernel
+  with its acquire / release progress counters, the staircase copies of the Q2 back-transformation;
+* the wavefront schedule of the Q2 back-transformation at the Qwen3-8B sizes.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from scripts.prototypes import sb2st_band as M
+from scripts.prototypes import two_stage_tridiag as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+B = 64
+
+
+def _spd(n, seed):
+    rng = np.random.RandomState(seed)
+    X = rng.standard_normal((n, n)) * np.logspace(0, -2, n)[None, :]
+    return X @ X.T
+
+
+@pytest.mark.parametrize("n,b", [(64, 8), (96, 16), (128, 32)])
+def test_band_model_is_an_eigendecomposition(n, b):
+    A = _spd(n, n)
+    w, Z, d, e = M.eigh_two_stage_model(A, b, ncta=5, rng=np.random.RandomState(3))
+    assert np.abs(w - np.linalg.eigvalsh(A)).max() <= 1e-13 * w.max()
+    assert np.linalg.norm(A @ Z - Z * w) <= 1e-13 * np.linalg.norm(A) * n
+    assert np.linalg.norm(Z.T @ Z - np.eye(n)) <= 1e-12
+
+
+def test_band_model_matches_full_storage_prototype():
+    n, b = 96, 16
+    A = _spd(n, 7)
+    band, _ = P.sy2sb(A, b)
+    d0, e0, refl, off = P.sb2st(band, b)
+    Bd, ldb = M.extract_band(band, b)
+    d1, e1, Vs, tau2, _ = M.sb2st_band(Bd, ldb, n, b, ncta=6, rng=np.random.RandomState(1))
+    sc = np.abs(A).max()
+    assert np.abs(d0 - d1).max() <= 1e-12 * sc and np.abs(e0 - e1).max() <= 1e-12 * sc
+    for r0, v, tau, s, k in refl:                      # same reflectors, stored where the kernel stores them
+        assert np.abs(Vs[r0 + s * n:r0 + len(v) + s * n] - v).max() <= 1e-9
+        assert abs(tau2[s + k * n] - tau) <= 1e-9
+
+
+@pytest.mark.parametrize("n", [4096, 12288])
+def test_q2_wavefronts_at_model_sizes(n):
+    """What apply_q2 (two_stage.cu) relies on: the groups of a wavefront are consecutive sweep blocks, start 3 b
+    rows apart, only the lowest one can be clipped, and a wavefront never exceeds the scratch it sizes."""
+    waves = M.q2_groups(n, B)                          # asserts stride and clipping itself
+    maxb = n // (3 * B) + 2
+    seen = set()
+    for w, grp in waves:
+        assert len(grp) <= maxb
+        sbs = [g[0] for g in grp]
+        assert sbs == list(range(sbs[0], sbs[0] + len(sbs)))
+        for sb, k, rlo, hg, m in grp:
+            assert rlo + hg <= n and 1 <= m <= B
+            seen.add((sb, k))
+    nsweeps = n - 2
+    want = {(s // B, k) for s in range(0, nsweeps, B) for k in range(M.num_tasks(s, n, B))}
+    assert seen == want                                # every group exactly once
+
+
+# --------------------------------------------------------------------------------------------- kernel emulation
+@pytest.fixture(scope="module")
+def emu():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    src = os.path.join(ROOT, "tests", "emu", "two_stage_emu.cpp")
+    out_dir = os.path.join(ROOT, "tests", "emu", "build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "two_stage_emu.so")
+    hdr = os.path.join(ROOT, "gptq_svd_b200", "csrc", "two_stage_kernels.cuh")
+    if not os.path.isfile(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", so, src], check=True)
+    lib = C.CDLL(so)
+    dp = np.ctypeslib.ndpointer(np.float64, flags="C")
+    ip = np.ctypeslib.ndpointer(np.int32, flags="C")
+    lib.emu_constants.argtypes = [ip]
+    lib.emu_band_extract.argtypes = [dp, C.c_int64, C.c_int, dp]
+    lib.emu_band_diag.argtypes = [dp, C.c_int, dp, dp]
+    lib.emu_chase.argtypes = [dp, C.c_int, dp, C.c_int64, dp, ip, C.c_int]
+    lib.emu_copy_staircase.argtypes = [dp, C.c_int64, dp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp]
+    k = np.zeros(8, np.int32)
+    lib.emu_constants(k)
+    assert list(k[:4]) == [B, 2 * B, 2 * B - 1, 2 * B]
+    return lib
+
+
+def _emu_reduce(emu, Astore, n, grid):
+    """band extraction + bulge chase + (d, e) through the emulated kernels; Astore: n x n, lower triangle valid"""
+    Acm = np.ascontiguousarray(Astore.T).reshape(-1)          # column-major
+    Bd = np.full(n * 2 * B, np.nan)
+    emu.emu_band_extract(Acm, n, n, Bd)
+    Bd0 = Bd.copy()
+    Vs = np.zeros(n * n)
+    tau2 = np.zeros(n * (n // B + 2))
+    prog = np.zeros(n, np.int32)
+    emu.emu_chase(Bd, n, Vs, n, tau2, prog, grid)
+    assert np.all(prog[:n - 2] == (1 << 30))
+    d, e = np.zeros(n), np.zeros(n)
+    emu.emu_band_diag(Bd, n, d, e)
+    return Bd0, Bd, Vs, tau2, d, e[:n - 1]
+
+
+@pytest.mark.parametrize("n,grid", [(136, 2), (256, 3)])
+def test_emulated_chase_kernel_matches_model(emu, n, grid):
+    A = _spd(n, 100 + n)
+    band = np.where(np.abs(np.subtract.outer(np.arange(n), np.arange(n))) <= B, A, 0.0)
+    Bd_model, ldb = M.extract_band(band, B)
+    Bd0, Bd, Vs, tau2, d, e = _emu_reduce(emu, np.tril(band), n, grid)
+    assert np.array_equal(Bd0, Bd_model)
+    d1, e1, Vs1, tau21, Bd1 = M.sb2st_band(Bd_model, ldb, n, B, ncta=4, rng=np.random.RandomState(5))
+    sc = np.abs(A).max()
+    assert np.abs(Bd - Bd1).max() <= 1e-10 * sc               # whole band array, bulge room included
+    assert np.abs(d - d1).max() <= 1e-10 * sc and np.abs(e - e1).max() <= 1e-10 * sc
+    assert np.abs(Vs - Vs1).max() <= 1e-8 and np.abs(tau2 - tau21).max() <= 1e-8
+    # and, independently of the model: T has the band matrix's eigenvalues, nothing is left off the tridiagonal
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    assert np.abs(np.linalg.eigvalsh(T) - np.linalg.eigvalsh(band)).max() <= 1e-13 * sc * n
+    full = M.band_to_full(Bd, 2 * B, n)
+    assert np.abs(full - T).max() <= 1e-13 * sc * n
+
+
+def test_emulated_kernels_give_an_eigendecomposition(emu):
+    """stage 1 as the host driver runs it (numpy), stages 2 and the Q2 staircase copies through the emulated kernels"""
+    n = 256
+    A = _spd(n, 9)
+    Ast, tau1 = M.sy2sb_wy(A, B)
+    _, _, Vs, tau2, d, e = _emu_reduce(emu, Ast, n, 3)
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    w, Z = np.linalg.eigh(T)
+    for _, grp in M.q2_groups(n, B):
+        sb0, k0 = grp[0][0], grp[0][1]
+        cnt = len(grp)
+        Vc = np.full(cnt * 2 * B * B, np.nan)
+        taub = np.full(cnt * B, np.nan)
+        emu.emu_copy_staircase(Vs, n, tau2, n, sb0, k0, cnt, Vc, taub)
+        for i, (sb, k, rlo, hg, m) in enumerate(grp):
+            V = Vc[i * 2 * B * B:(i + 1) * 2 * B * B].reshape(B, 2 * B).T      # (2b x b), ld 2b, column-major
+            Vm, taum = M.staircase(Vs, n, tau2, n, B, sb, k)
+            assert np.array_equal(V[:2 * B - 1], Vm) and np.all(V[2 * B - 1] == 0.0)
+            assert np.array_equal(taub[i * B:(i + 1) * B], taum)
+            Vh = V[:hg]
+            Z[rlo:rlo + hg] -= Vh @ (M.larft(V[:2 * B - 1], taum) @ (Vh.T @ Z[rlo:rlo + hg]))
+    Z = M.apply_q1(Ast, tau1, B, Z)
+    assert np.abs(w - np.linalg.eigvalsh(A)).max() <= 1e-13 * w.max() * n
+    assert np.linalg.norm(A @ Z - Z * w) <= 1e-13 * np.linalg.norm(A) * n
+    assert np.linalg.norm(Z.T @ Z - np.eye(n)) <= 1e-11
