@@ -35,6 +35,13 @@ int check_device();  // TQ_OK when the current device is sm_100 (B200)
     if (_s != TQ_OK) return _s; \
   } while (0)
 
+// Kernel launch and dynamic shared memory go through these two macros in the files that tests/emu compiles for
+// the HOST (TQ_HOST_EMU: the emulation defines its own versions before including this header).
+#ifndef TQ_HOST_EMU
+#define TQ_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define TQ_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 extern thread_local int64_t g_launch_count;
 #define TQ_LAUNCH_CHECK()                \
   do {                                   \

@@ -146,7 +146,7 @@ larft_kernel(const double* __restrict__ G, int ldg, const double* __restrict__ t
   G += int64_t(blockIdx.x) * stride_g;
   tau += int64_t(blockIdx.x) * stride_tau;
   T += int64_t(blockIdx.x) * stride_t;
-  extern __shared__ double larft_sm[];
+  TQ_DYN_SMEM(double, larft_sm);
   double* M = larft_sm;                 // jb x jb, column-major, ld jb
   double* X = larft_sm + jb * jb;       // <= jb * jb / 4 entries per level
   const int tid = threadIdx.x;
@@ -238,14 +238,14 @@ static inline int build_t_factor(cublasHandle_t h, cudaStream_t st, const double
                               G, jb));
   static thread_local bool big_smem = false;
   if (!big_smem) {   // jb = 128 needs 160 KB of dynamic shared memory
-    TQ_CUDA_CHECK(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLarftSmem)));
+    TQ_CUDA_CHECK(cudaFuncSetAttribute((const void*)larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLarftSmem)));
     big_smem = true;
   }
   if (jb > kLarftMaxJb) {
     set_error("build_t_factor: jb = %d > %d", jb, kLarftMaxJb);
     return TQ_ERR_INVALID;
   }
-  larft_kernel<<<1, kLarftThreads, size_t(jb) * jb * 10, st>>>(G, jb, tau, jb, T, jb);
+  TQ_LAUNCH(larft_kernel, 1, kLarftThreads, size_t(jb) * jb * 10, st, G, jb, tau, jb, T, jb, int64_t(0), int64_t(0), int64_t(0));
   TQ_LAUNCH_CHECK();
   return TQ_OK;
 }

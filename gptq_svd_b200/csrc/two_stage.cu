@@ -86,7 +86,7 @@ static int sy2sb(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double
     Workspace qws = scratch;                         // the panel factorisation's own scratch, released afterwards
     TQ_TRY(qr_r_colmajor_tau(h, st, P, lda, s, b, qws, tau1 + j));
     dim3 grid((unsigned)imin(ceil_div(s, 256), 256), (unsigned)b);
-    copy_reflectors_kernel<<<grid, 256, 0, st>>>(P, lda, s, b, Vc, s);
+    TQ_LAUNCH(copy_reflectors_kernel, grid, 256, 0, st, P, lda, s, b, Vc, s);
     TQ_LAUNCH_CHECK();
     TQ_TRY(build_t_factor(h, st, Vc, s, s, b, tau1 + j, G, T));
     // X = A22 V (lower triangle of A22 only), X2 = X T
@@ -106,12 +106,12 @@ static int sy2sb(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double
 
 // ------------------------------------------------------------------------------------------------ stage 2
 static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuffers& tb, double* d, double* e) {
-  band_extract_kernel<<<unsigned(n), 128, 0, st>>>(A, n, int(n), tb.Bd);
+  TQ_LAUNCH(band_extract_kernel, unsigned(n), 128, 0, st, A, n, int(n), tb.Bd);
   TQ_LAUNCH_CHECK();
   TQ_CUDA_CHECK(cudaMemsetAsync(tb.prog, 0, sizeof(int) * n, st));
   TQ_CUDA_CHECK(cudaMemsetAsync(tb.tau2, 0, sizeof(double) * size_t(n) * (n / kBw + 2), st));
   if (n > 2) {
-    TQ_CUDA_CHECK(cudaFuncSetAttribute(sb2st_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TQ_CUDA_CHECK(cudaFuncSetAttribute((const void*)sb2st_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        int(kChaseSmem)));
     // sweeps run 3 tasks apart, so at most K_0 / 3 + 1 of them are in flight; the launch is cooperative only for
     // its guarantee that every CTA is resident (a waiting sweep's predecessor must be running)
@@ -123,7 +123,7 @@ static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuff
                                               kChaseSmem, st));
     ++g_launch_count;
   }
-  band_diag_kernel<<<unsigned(ceil_div(n, 256)), 256, 0, st>>>(tb.Bd, int(n), d, e);
+  TQ_LAUNCH(band_diag_kernel, unsigned(ceil_div(n, 256)), 256, 0, st, tb.Bd, int(n), d, e);
   TQ_LAUNCH_CHECK();
   return TQ_OK;
 }
@@ -139,11 +139,11 @@ static int apply_q2_batch(cublasHandle_t h, cudaStream_t st, const TwoStageBuffe
   const double one = 1.0, zero = 0.0, mone = -1.0;
   const int64_t rlo = int64_t(sb0) * b + 1 + int64_t(k0) * b;
   const long long sv = (long long)kQ2Ld * b, st_t = (long long)b * b, sw = (long long)b * ncols, sz = 3 * b;
-  copy_staircase_kernel<<<dim3(1, b, count), kQ2Ld, 0, st>>>(tb.Vs, n, tb.tau2, int(n), sb0, k0, Vc, taub);
+  TQ_LAUNCH(copy_staircase_kernel, dim3(1, b, count), kQ2Ld, 0, st, tb.Vs, n, tb.tau2, int(n), sb0, k0, Vc, taub);
   TQ_LAUNCH_CHECK();
   TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, b, hg, &one, Vc, kQ2Ld, sv, Vc, kQ2Ld, sv,
                                             &zero, Gb, b, st_t, count));
-  larft_kernel<<<count, kLarftThreads, size_t(b) * b * 10, st>>>(Gb, b, taub, b, Tb, b, st_t, b, st_t);
+  TQ_LAUNCH(larft_kernel, count, kLarftThreads, size_t(b) * b * 10, st, Gb, b, taub, b, Tb, b, int64_t(st_t), int64_t(b), int64_t(st_t));
   TQ_LAUNCH_CHECK();
   double* Zb = Z + rlo;
   TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, int(ncols), hg, &one, Vc, kQ2Ld, sv, Zb,
@@ -226,7 +226,7 @@ static int apply_q1(cublasHandle_t h, cudaStream_t st, const double* A, const do
     const int jb = int(imin(kQ1Nb, nref - j0));
     const int64_t s = n - j0 - kBw;
     dim3 grid((unsigned)imin(ceil_div(s, 256), 256), (unsigned)jb);
-    copy_reflectors_kernel<<<grid, 256, 0, st>>>(A + (j0 + kBw) + j0 * n, n, s, jb, Vc, s);
+    TQ_LAUNCH(copy_reflectors_kernel, grid, 256, 0, st, A + (j0 + kBw) + j0 * n, n, s, jb, Vc, s);
     TQ_LAUNCH_CHECK();
     TQ_TRY(build_t_factor(h, st, Vc, s, s, jb, tau1 + j0, G, T));
     TQ_TRY(apply_block_reflector(h, Vc, s, s, jb, T, jb, /*trans_t=*/false, Z + (j0 + kBw), ldz, ncols, w1, w2));

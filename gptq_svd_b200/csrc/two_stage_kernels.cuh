@@ -47,7 +47,9 @@ struct ChaseArgs {
 };
 
 #ifndef TQ_HOST_EMU
+#ifndef TQ_DYN_SMEM
 #define TQ_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
 __device__ __forceinline__ int ld_acquire_s32(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -5,6 +5,9 @@
 * the KERNEL SOURCE of two_stage_kernels.cuh compiled for the host (tests/emu/two_stage_emu.cpp: one OS thread per
   CUDA thread, CTAs running concurrently) against that model - band extraction, the persistent bulge-chase kernel
   with its acquire / release progress counters, the staircase copies of the Q2 back-transformation;
+* the WHOLE two-stage path - host driver of two_stage.cu compiled unchanged with g++, its kernels on the emulation
+  runtime, cuBLAS / CUDA runtime entry points replaced by reference loops (tests/emu/two_stage_host_emu.cpp) -
+  against numpy.linalg.eigh;
 * the wavefront schedule of the Q2 back-transformation at the Qwen3-8B sizes.
 """
 import ctypes as C
@@ -71,18 +74,25 @@ def test_q2_wavefronts_at_model_sizes(n):
 
 
 # --------------------------------------------------------------------------------------------- kernel emulation
-@pytest.fixture(scope="module")
-def emu():
+def _build(name, extra=()):
+    """g++ build of tests/emu/<name>.cpp -> tests/emu/build/<name>.so (rebuilt when a source is newer)"""
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
-    src = os.path.join(ROOT, "tests", "emu", "two_stage_emu.cpp")
+    src = os.path.join(ROOT, "tests", "emu", name + ".cpp")
     out_dir = os.path.join(ROOT, "tests", "emu", "build")
     os.makedirs(out_dir, exist_ok=True)
-    so = os.path.join(out_dir, "two_stage_emu.so")
-    hdr = os.path.join(ROOT, "gptq_svd_b200", "csrc", "two_stage_kernels.cuh")
-    if not os.path.isfile(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", so, src], check=True)
-    lib = C.CDLL(so)
+    so = os.path.join(out_dir, name + ".so")
+    csrc = os.path.join(ROOT, "gptq_svd_b200", "csrc")
+    deps = [src, os.path.join(ROOT, "tests", "emu", "emu_runtime.h")] + [
+        os.path.join(csrc, f) for f in ("two_stage_kernels.cuh", "two_stage.cu", "solver_kernels.cuh", "common.cuh")]
+    if not os.path.isfile(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", *extra, "-o", so, src], check=True)
+    return C.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib = _build("two_stage_emu")
     dp = np.ctypeslib.ndpointer(np.float64, flags="C")
     ip = np.ctypeslib.ndpointer(np.int32, flags="C")
     lib.emu_constants.argtypes = [ip]
@@ -156,3 +166,35 @@ def test_emulated_kernels_give_an_eigendecomposition(emu):
     assert np.abs(w - np.linalg.eigvalsh(A)).max() <= 1e-13 * w.max() * n
     assert np.linalg.norm(A @ Z - Z * w) <= 1e-13 * np.linalg.norm(A) * n
     assert np.linalg.norm(Z.T @ Z - np.eye(n)) <= 1e-11
+
+
+# --------------------------------------------------------------------------------------------- whole path
+@pytest.fixture(scope="module")
+def host_emu():
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.isfile(os.path.join(cuda_inc, "cublas_v2.h")):
+        pytest.skip("CUDA headers not available")
+    lib = _build("two_stage_host_emu", extra=("-I" + cuda_inc,))
+    dp = np.ctypeslib.ndpointer(np.float64, flags="C")
+    lib.emu_two_stage_reduce.argtypes = [dp, C.c_int64, dp, dp, C.c_int]
+    lib.emu_two_stage_back.argtypes = [dp, C.c_int64, dp, C.c_int64]
+    lib.emu_last_error.restype = C.c_char_p
+    return lib
+
+
+@pytest.mark.parametrize("n,sms,ncols", [(256, 3, 256), (320, 2, 200)])
+def test_whole_two_stage_path_on_the_host(host_emu, n, sms, ncols):
+    """two_stage_reduce + two_stage_back exactly as tq_eigh calls them (eigh.cu), D&C replaced by numpy"""
+    A = _spd(n, 31 + n)
+    Acm = np.ascontiguousarray(A.T).reshape(-1).copy()
+    d, e = np.zeros(n), np.zeros(n)
+    assert host_emu.emu_two_stage_reduce(Acm, n, d, e, sms) == 0, host_emu.emu_last_error()
+    T = np.diag(d) + np.diag(e[:n - 1], 1) + np.diag(e[:n - 1], -1)
+    w, ZT = np.linalg.eigh(T)
+    assert np.abs(w - np.linalg.eigvalsh(A)).max() <= 1e-13 * w.max()
+    w, ZT = w[n - ncols:], ZT[:, n - ncols:]                   # back-transform only the leading eigenvectors
+    Zcm = np.ascontiguousarray(ZT.T).reshape(-1).copy()
+    assert host_emu.emu_two_stage_back(Acm, n, Zcm, ncols) == 0, host_emu.emu_last_error()
+    Z = Zcm.reshape(ncols, n).T
+    assert np.linalg.norm(A @ Z - Z * w) <= 1e-13 * np.linalg.norm(A) * n ** 0.5
+    assert np.linalg.norm(Z.T @ Z - np.eye(ncols)) <= 1e-12 * n ** 0.5
