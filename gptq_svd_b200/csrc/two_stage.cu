@@ -79,6 +79,14 @@ static int sy2sb(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double
     return TQ_ERR_WORKSPACE;
   }
   TQ_CUDA_CHECK(cudaMemsetAsync(tau1, 0, sizeof(double) * n, st));
+  // TQ_SY2SB_GEMM=1: X = A22 V as a DGEMM on a trailing matrix kept fully symmetric (one mirror pass per block
+  // column, n^3 / (3 b) * 8 bytes in total) instead of DSYMM on its lower triangle - an A/B switch for the first
+  // GPU measurements (cuBLAS' DSYMM is not always as fast as its DGEMM).  A is fully symmetric on entry.
+  static int use_gemm = -1;
+  if (use_gemm < 0) {
+    const char* env = getenv("TQ_SY2SB_GEMM");
+    use_gemm = (env && env[0] && env[0] != '0') ? 1 : 0;
+  }
   for (int64_t j = 0; j + b < n; j += b) {
     const int64_t r0 = j + b, s = n - r0;
     double* P = A + r0 + j * lda;
@@ -90,8 +98,18 @@ static int sy2sb(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double
     TQ_LAUNCH_CHECK();
     TQ_TRY(build_t_factor(h, st, Vc, s, s, b, tau1 + j, G, T));
     // X = A22 V (lower triangle of A22 only), X2 = X T
-    TQ_CUBLAS_CHECK(cublasDsymm(h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, int(s), b, &one, A22, int(lda), Vc,
-                                int(s), &zero, X, int(s)));
+    if (use_gemm) {
+      if (j > 0) {     // the DSYR2K of the previous block column left only the lower triangle up to date
+        const unsigned nt = unsigned(ceil_div(s, 32));
+        TQ_LAUNCH(mirror_lower_colmajor_kernel, dim3(nt, nt), 256, 32 * 33 * sizeof(double), st, A22, lda, int(s));
+        TQ_LAUNCH_CHECK();
+      }
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, int(s), b, int(s), &one, A22, int(lda), Vc, int(s),
+                                  &zero, X, int(s)));
+    } else {
+      TQ_CUBLAS_CHECK(cublasDsymm(h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, int(s), b, &one, A22, int(lda), Vc,
+                                  int(s), &zero, X, int(s)));
+    }
     TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, int(s), b, b, &one, X, int(s), T, b, &zero, X2, int(s)));
     // M2 = T^T (V^T X2);  W = X2 - V M2 / 2  (in X2)
     TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, b, b, int(s), &one, Vc, int(s), X2, int(s), &zero, M1, b));

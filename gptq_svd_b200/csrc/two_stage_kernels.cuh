@@ -28,6 +28,25 @@ __global__ void band_extract_kernel(const double* __restrict__ A, int64_t lda, i
     Bd[d + int64_t(c) * kLdb] = (d <= kBw && c + d < n) ? A[(c + d) + int64_t(c) * lda] : 0.0;
 }
 
+// A[c + r lda] = A[r + c lda] for r > c (column-major s x s, lower triangle valid): makes the trailing matrix of the
+// band reduction fully symmetric again after a DSYR2K on its lower triangle, for the DGEMM variant of X = A22 V.
+// 256 threads, 32 x 32 tiles through shared memory so that reads and writes are both coalesced.
+__global__ void mirror_lower_colmajor_kernel(double* __restrict__ A, int64_t lda, int s) {
+  TQ_DYN_SMEM(double, mirror_sm);                           // 32 x 33
+  const int bx = blockIdx.x, by = blockIdx.y;               // tile (row block bx, column block by), bx >= by
+  if (bx < by) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < 32; k += 8) {
+    const int r = bx * 32 + tx, c = by * 32 + k;
+    mirror_sm[k * 33 + tx] = (r < s && c < s) ? A[r + int64_t(c) * lda] : 0.0;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int r = bx * 32 + k, c = by * 32 + tx;            // source element (r, c), written to (c, r)
+    if (r < s && c < s && r > c) A[c + int64_t(r) * lda] = mirror_sm[tx * 33 + k];
+  }
+}
+
 __global__ void band_diag_kernel(const double* __restrict__ Bd, int n, double* __restrict__ d, double* __restrict__ e) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < n) {

@@ -112,7 +112,7 @@ static inline void emu_run_serial(dim3 grid, dim3 block, const std::function<voi
 }
 
 // kernels that contain barriers or shuffles are listed by name; everything else runs serially
-#define EMU_NEEDS_THREADS(kernel) (std::string(#kernel) == "larft_kernel")
+#define EMU_NEEDS_THREADS(kernel) (std::string(#kernel) == "larft_kernel" || std::string(#kernel) == "mirror_lower_colmajor_kernel")
 #include <string>
 #define TQ_LAUNCH(kernel, grid, block, smem, stream, ...)                                      \
   do {                                                                                         \

@@ -14,6 +14,7 @@ import ctypes as C
 import os
 import shutil
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -169,8 +170,7 @@ def test_emulated_kernels_give_an_eigendecomposition(emu):
 
 
 # --------------------------------------------------------------------------------------------- whole path
-@pytest.fixture(scope="module")
-def host_emu():
+def _load_host_emu():
     cuda_inc = "/usr/local/cuda/include"
     if not os.path.isfile(os.path.join(cuda_inc, "cublas_v2.h")):
         pytest.skip("CUDA headers not available")
@@ -182,19 +182,37 @@ def host_emu():
     return lib
 
 
-@pytest.mark.parametrize("n,sms,ncols", [(256, 3, 256), (320, 2, 200)])
-def test_whole_two_stage_path_on_the_host(host_emu, n, sms, ncols):
+def _check_whole_path(lib, n, sms, ncols):
     """two_stage_reduce + two_stage_back exactly as tq_eigh calls them (eigh.cu), D&C replaced by numpy"""
     A = _spd(n, 31 + n)
     Acm = np.ascontiguousarray(A.T).reshape(-1).copy()
     d, e = np.zeros(n), np.zeros(n)
-    assert host_emu.emu_two_stage_reduce(Acm, n, d, e, sms) == 0, host_emu.emu_last_error()
+    assert lib.emu_two_stage_reduce(Acm, n, d, e, sms) == 0, lib.emu_last_error()
     T = np.diag(d) + np.diag(e[:n - 1], 1) + np.diag(e[:n - 1], -1)
     w, ZT = np.linalg.eigh(T)
     assert np.abs(w - np.linalg.eigvalsh(A)).max() <= 1e-13 * w.max()
     w, ZT = w[n - ncols:], ZT[:, n - ncols:]                   # back-transform only the leading eigenvectors
     Zcm = np.ascontiguousarray(ZT.T).reshape(-1).copy()
-    assert host_emu.emu_two_stage_back(Acm, n, Zcm, ncols) == 0, host_emu.emu_last_error()
+    assert lib.emu_two_stage_back(Acm, n, Zcm, ncols) == 0, lib.emu_last_error()
     Z = Zcm.reshape(ncols, n).T
     assert np.linalg.norm(A @ Z - Z * w) <= 1e-13 * np.linalg.norm(A) * n ** 0.5
     assert np.linalg.norm(Z.T @ Z - np.eye(ncols)) <= 1e-12 * n ** 0.5
+
+
+@pytest.fixture(scope="module")
+def host_emu():
+    return _load_host_emu()
+
+
+@pytest.mark.parametrize("n,sms,ncols", [(256, 3, 256), (320, 2, 200)])
+def test_whole_two_stage_path_on_the_host(host_emu, n, sms, ncols):
+    _check_whole_path(host_emu, n, sms, ncols)
+
+
+def test_whole_two_stage_path_dgemm_variant():
+    """TQ_SY2SB_GEMM=1 (mirror pass + DGEMM instead of DSYMM) in a fresh process: the switch is read once"""
+    code = ("import os, sys; sys.path[:0] = [%r, %r]; os.environ['TQ_SY2SB_GEMM'] = '1';"
+            "import test_two_stage_emu as t; t._check_whole_path(t._load_host_emu(), 256, 2, 256)"
+            ) % (ROOT, os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
