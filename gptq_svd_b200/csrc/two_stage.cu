@@ -38,11 +38,12 @@ struct TwoStageBuffers {
   double* tau1 = nullptr;   // n
   double* tau2 = nullptr;   // n x (n / b + 2)
   int* prog = nullptr;      // n
+  long long* stats = nullptr;   // 8 cycle counters of the bulge-chase kernel (TQ_TRACE)
 };
 
 size_t two_stage_ws_bytes(int64_t n) {
   size_t b = ws_bytes_for(size_t(n) * n, 8) + ws_bytes_for(size_t(kLdb) * n, 8) + ws_bytes_for(n, 8);
-  b += ws_bytes_for(size_t(n) * (n / kBw + 2), 8) + ws_bytes_for(n, 4);
+  b += ws_bytes_for(size_t(n) * (n / kBw + 2), 8) + ws_bytes_for(n, 4) + ws_bytes_for(8, 8);
   return b;
 }
 
@@ -52,6 +53,7 @@ static int take_two_stage(Workspace& ws, int64_t n, TwoStageBuffers& tb) {
   tb.tau1 = ws.take<double>(n);
   tb.tau2 = ws.take<double>(size_t(n) * (n / kBw + 2));
   tb.prog = ws.take<int>(n);
+  tb.stats = ws.take<long long>(8);
   if (ws.overflow) {
     set_error("eigh (two-stage): workspace too small - query tq_solver_workspace after tq_set_eigh_two_stage(1)");
     return TQ_ERR_WORKSPACE;
@@ -133,13 +135,24 @@ static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuff
                                        int(kChaseSmem)));
     // sweeps run 3 tasks apart, so at most K_0 / 3 + 1 of them are in flight; the launch is cooperative only for
     // its guarantee that every CTA is resident (a waiting sweep's predecessor must be running)
-    const int64_t want = chase_tasks(0, n) / 3 + 2;
+    int64_t want = chase_tasks(0, n) / 3 + 2;
+    if (const char* env = getenv("TQ_CHASE_GRID")) want = imax(1, atoll(env));     // experiments only
     const int grid = int(imax(1, imin(num_sms(), want)));
-    ChaseArgs ca{tb.Bd, int(n), tb.Vs, n, tb.tau2, tb.prog};
+    const bool trace = trace_enabled();
+    if (trace) TQ_CUDA_CHECK(cudaMemsetAsync(tb.stats, 0, 8 * sizeof(long long), st));
+    ChaseArgs ca{tb.Bd, int(n), tb.Vs, n, tb.tau2, tb.prog, trace ? tb.stats : nullptr};
     void* kargs[] = {&ca};
     TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sb2st_chase_kernel, dim3(grid), dim3(kChaseThreads), kargs,
                                               kChaseSmem, st));
     ++g_launch_count;
+    if (trace) {
+      long long hs[8];
+      TQ_CUDA_CHECK(cudaMemcpyAsync(hs, tb.stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+      TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+      const double t = double(hs[4] > 0 ? hs[4] : 1);
+      fprintf(stderr, "[tq-trace] sb2st chase: %d CTAs; CTA 0 ran %lld tasks, cycles per task: wait %.0f  reflector+G %.0f  "
+              "D %.0f  E %.0f\n", grid, hs[4], hs[0] / t, hs[1] / t, hs[2] / t, hs[3] / t);
+    }
   }
   TQ_LAUNCH(band_diag_kernel, unsigned(ceil_div(n, 256)), 256, 0, st, tb.Bd, int(n), d, e);
   TQ_LAUNCH_CHECK();

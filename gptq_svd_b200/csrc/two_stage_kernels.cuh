@@ -63,6 +63,7 @@ struct ChaseArgs {
   int64_t ldv;
   double* tau2;     // tau2[s + k n]
   int* prog;        // prog[s] = tasks of sweep s whose G and D blocks are back in the band array
+  long long* stats; // optional (TQ_TRACE): cycles CTA 0 spent {waiting, in steps 1-2, step 3, step 4}, its task count
 };
 
 #ifndef TQ_HOST_EMU
@@ -122,12 +123,20 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
       const int ln = r1 - r0;                                       // >= 2
       const int ne = (ln == b) ? min(n, r1 + b) - r1 : 0;           // rows of E
       const bool last = (k == K - 1);                               // then ne <= 1, else ne >= 2
+      const bool prof = a.stats != nullptr && blockIdx.x == 0 && tid == 0;
+      long long tc0 = prof ? clock64() : 0, tc1;
       if (s > 0 && tid == 0) {
         while (ld_acquire_s32(a.prog + (s - 1)) < k + 3) {
         }
         __threadfence();
       }
       __syncthreads();
+      if (prof) {
+        tc1 = clock64();
+        a.stats[0] += tc1 - tc0;
+        a.stats[4] += 1;
+        tc0 = tc1;
+      }
       // ---- loads of D (lower triangle) and E, L2 only (other SMs write these lines)
       double* const Dg = a.Bd + int64_t(r0) * kLdb;
       double* const Eg = a.Bd + ln + int64_t(r0) * kLdb;
@@ -181,6 +190,11 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
           }
         }
       }
+      if (prof) {
+        tc1 = clock64();
+        a.stats[1] += tc1 - tc0;
+        tc0 = tc1;
+      }
       // ---- step 3: D <- H D H = D - v w^T - w v^T,  p = tau D v,  w = p - (tau p^T v / 2) v
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
@@ -221,6 +235,11 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
           st_release_s32(a.prog + s, k + 1);
         }
       }
+      if (prof) {
+        tc1 = clock64();
+        a.stats[2] += tc1 - tc0;
+        tc0 = tc1;
+      }
       // ---- step 4: E <- E H = E - (tau E v) v^T
       if (ne > 0) {
         double acc = 0.0;
@@ -246,6 +265,7 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
           st_release_s32(a.prog + s, kProgDone);
         }
       }
+      if (prof) a.stats[3] += clock64() - tc0;
     }
   }
 }

@@ -48,6 +48,7 @@ static inline void __syncthreads() { pthread_barrier_wait(&g_cta->bar); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline double __ldcg(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
 static inline void __stcg(double* p, double v) { *reinterpret_cast<volatile double*>(p) = v; }
+static inline long long clock64() { return 0; }
 static inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
 static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int ld_acquire_s32(const int* p) {

@@ -46,6 +46,7 @@ static inline int ld_acquire_s32(const int* p) {
   return v;
 }
 static inline void st_release_s32(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline long long clock64() { return 0; }
 using std::min;
 
 namespace tq {
@@ -122,7 +123,8 @@ void emu_chase(double* Bd, int n, double* Vs, int64_t ldv, double* tau2, int* pr
     c.shfl.assign(T, 0.0);
     c.smem.assign(tq::kChaseSmemDoubles, NAN);            // uninitialised shared memory must never be consumed
   }
-  tq::ChaseArgs args{Bd, n, Vs, ldv, tau2, prog};
+  long long stats[8] = {0};
+  tq::ChaseArgs args{Bd, n, Vs, ldv, tau2, prog, stats};     // exercises the instrumented path too
   std::vector<std::thread> th;
   th.reserve(size_t(grid) * T);
   for (int bx = 0; bx < grid; ++bx)

@@ -87,7 +87,10 @@ def _build(name, extra=()):
     deps = [src, os.path.join(ROOT, "tests", "emu", "emu_runtime.h")] + [
         os.path.join(csrc, f) for f in ("two_stage_kernels.cuh", "two_stage.cu", "solver_kernels.cuh", "common.cuh")]
     if not os.path.isfile(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", *extra, "-o", so, src], check=True)
+        # -Bsymbolic: the emulation's own cudaMemsetAsync / cublasDgemm_v2 ... must win over a libcudart / libcublas
+        # that another test of the same process has already loaded
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wl,-Bsymbolic", *extra,
+                        "-o", so, src], check=True)
     return C.CDLL(so)
 
 
@@ -144,7 +147,7 @@ def test_emulated_chase_kernel_matches_model(emu, n, grid):
 
 def test_emulated_kernels_give_an_eigendecomposition(emu):
     """stage 1 as the host driver runs it (numpy), stages 2 and the Q2 staircase copies through the emulated kernels"""
-    n = 256
+    n = 192
     A = _spd(n, 9)
     Ast, tau1 = M.sy2sb_wy(A, B)
     _, _, Vs, tau2, d, e = _emu_reduce(emu, Ast, n, 3)
