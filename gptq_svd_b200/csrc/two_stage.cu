@@ -203,6 +203,13 @@ static int apply_q2(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb
     set_error("apply_q2: workspace too small");
     return TQ_ERR_WORKSPACE;
   }
+  // TQ_Q2_UNBATCHED=1: debugging aid for the first GPU runs (bisects between the wavefront schedule and cuBLAS'
+  // handling of strided batches whose output blocks interleave in memory)
+  static int unbatched = -1;
+  if (unbatched < 0) {
+    const char* env = getenv("TQ_Q2_UNBATCHED");
+    unbatched = (env && env[0] && env[0] != '0') ? 1 : 0;
+  }
   const int kmax0 = int(chase_tasks(0, n)) - 1;
   for (int w = 0; w <= kmax0 + 2 * M; ++w) {
     int sb_lo = -1, sb_hi = -1;
@@ -229,8 +236,12 @@ static int apply_q2(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb
       TQ_TRY(apply_q2_batch(h, st, tb, n, sb_hi, k_hi, 1, hg_last, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2));
       --count;
     }
-    if (count > 0)
+    if (count > 0 && unbatched) {      // one block reflector at a time: same arithmetic, no interleaved batches
+      for (int i = 0; i < count; ++i)
+        TQ_TRY(apply_q2_batch(h, st, tb, n, sb_lo + i, k_lo + 2 * i, 1, kQ2H, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2));
+    } else if (count > 0) {
       TQ_TRY(apply_q2_batch(h, st, tb, n, sb_lo, k_lo, count, kQ2H, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2));
+    }
   }
   return TQ_OK;
 }
