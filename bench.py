@@ -167,6 +167,9 @@ def _config(args, k_list):
             "block_size": 1024, "activations": f"randn @ A^T, column scales logspace(0,{args.decay}), 8 outlier channels x30",
             "retained_rank": k_list, "l2": "inputs per step (12.9 GB) exceed the 126 MB L2; no explicit flush",
             "parallelism": f"layers sharded over {args.gpus} rank(s), no collective",
+            "tridiagonal_reduction": ("two-stage (experimental, TQ_EIGH_TWO_STAGE=1: the roofline block below still "
+                                      "describes the one-stage panel kernel and has no samples)"
+                                      if os.environ.get("TQ_EIGH_TWO_STAGE", "0") not in ("", "0") else "one-stage"),
             "solves": ((f"n=12288 first; after its tridiagonal reduction it drops to {args.tail_budgets.split(',')[0]} SMs and "
                         f"the three n=4096 solves run next to its tail ({args.tail_budgets.split(',')[1]} SMs each)"
                         if args.overlap_tail else
