@@ -62,7 +62,7 @@ struct ChaseArgs {
   double* Vs;       // reflector (s, k): Vs[r0 + i + s ldv], r0 = s + 1 + k b  (column s = sweep s, stacked)
   int64_t ldv;
   double* tau2;     // tau2[s + k n]
-  int* prog;        // prog[s] = tasks of sweep s whose G and D blocks are back in the band array
+  int* prog;        // prog[s] = k + 1 once task k of sweep s has written its G block back (earlier tasks: complete)
   long long* stats; // optional (TQ_TRACE): cycles CTA 0 spent {waiting, in steps 1-2, step 3, step 4}, its task count
 };
 
@@ -190,6 +190,17 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
           }
         }
       }
+      // G of this task is final and every earlier task of the sweep is complete: release the next sweep now.  Sweep
+      // s + 1 never touches D or E of a task it has been released for (they are in registers already, and task
+      // (s+1, k) meets task (s, k+2) in ONE entry, the first of G) - checked with half-task interleavings in
+      // scripts/prototypes/sb2st_band.py.
+      if (!last) {
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence();
+          st_release_s32(a.prog + s, k + 1);
+        }
+      }
       if (prof) {
         tc1 = clock64();
         a.stats[1] += tc1 - tc0;
@@ -226,13 +237,6 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
         for (int m = 0; m < 16; ++m) {
           const int lc = tq + 4 * m;
           if (ti >= lc) __stcg(Dg + ti + lc * ldg, dreg[m] - vi * wsh[lc] - wi * vs[lc]);
-        }
-      }
-      if (!last) {        // G and D of this task are final: release the next sweep (E travels in shared memory)
-        __syncthreads();
-        if (tid == 0) {
-          __threadfence();
-          st_release_s32(a.prog + s, k + 1);
         }
       }
       if (prof) {

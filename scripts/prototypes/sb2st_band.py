@@ -7,8 +7,9 @@ layout and index arithmetic as the kernels so that every offset can be checked h
     a dense block with rows R0.. and columns C0.. is the sub-array  base = (R0 - C0) + C0 * ldb,  ld = ldb - 1;
   * task (s, k) of the bulge chase: reflector rows [r0, r1), r0 = s + 1 + k b; blocks  G (bulge, b x b, arrives in
     shared memory from the previous task of the sweep), D (diagonal, lower triangle), E (below, becomes the next G);
-  * progress counters: sweep s + 1 may run task k once  prog[s] >= k + 3  (prog counts tasks whose G and D blocks
-    are written back; E travels in shared memory to the next task);
+  * progress counters: prog[s] = k + 1 is published as soon as task k of sweep s has written its G block back (all
+    earlier tasks are then complete; D_k and E_k are already in registers, E travels in shared memory to the next
+    task); sweep s + 1 may run task k once  prog[s] >= k + 3;
   * reflector store  Vs[r0 + i + s * ldv]  (column s = all reflectors of sweep s, stacked), tau2[s + k * n];
   * Q2 back-transformation in WAVEFRONTS  w = k + 2 (M - sb): groups (sweep block sb of nb = b sweeps, chase index
     k) with equal w sit 3 b rows apart in Z - one strided-batched DGEMM triple per wavefront.
@@ -84,14 +85,21 @@ class Blk:
         self.Bd[self.I[m]] = M[m]
 
 
-def run_task(Bd, ldb, n, b, s, k, carry, Vs, ldv, tau2):
-    """One task exactly as the CTA executes it.  `carry` is the E block of the previous task of this sweep (held in
-    shared memory), None for k = 0.  Returns the new carry (E after the right application) or None."""
+def task_phase_a(Bd, ldb, n, b, s, k, carry, Vs, ldv, tau2):
+    """First half of a task as the CTA executes it: load D and E (registers), form the reflector from the first
+    column of G (the E block of the previous task of this sweep, held in shared memory; column s for k = 0), apply it
+    to the rest of G from the left and write G back.  After this the sweep's progress counter is published: the
+    next sweep only ever needs the G block of a task, never its D or E block (see sb2st_band)."""
     r0 = s + 1 + k * b
     r1 = min(r0 + b, n)
     ln = r1 - r0
     assert ln >= 2
-    # ---- step 1 + 2: reflector from the first column of G, left application to the rest of G, write G back
+    hi = min(n, r1 + b)
+    ne = hi - r1 if ln == b else 0
+    Dv = Blk(Bd, ldb, r0, r0, ln, ln)
+    D = Dv.load(lower_only=True)                              # registers: loaded BEFORE the progress is published
+    Ev = Blk(Bd, ldb, r1, r0, ne, b) if ne > 0 else None
+    E = Ev.load() if ne > 0 else None
     if k == 0:
         base = 1 + s * ldb                                  # column s, rows s+1..: contiguous
         x = Bd[base:base + ln].copy()
@@ -110,42 +118,47 @@ def run_task(Bd, ldb, n, b, s, k, carry, Vs, ldv, tau2):
         Blk(Bd, ldb, r0, r0 - b, ln, b).store(G)
     Vs[r0 + s * ldv:r0 + ln + s * ldv] = v
     tau2[s + k * n] = tau
-    # ---- step 3: diagonal block, two-sided, lower triangle only
-    Dv = Blk(Bd, ldb, r0, r0, ln, ln)
-    D = Dv.load(lower_only=True)
+    return dict(v=v, tau=tau, D=D, Dv=Dv, E=E, Ev=Ev, ne=ne, r1=r1)
+
+
+def task_phase_b(n, st):
+    """Second half: two-sided update of D (lower triangle, written back) and right update of E, which stays in
+    shared memory as the next task's G (or is written back when the sweep ends).  Uses the copies loaded in phase A."""
+    v, tau, D, E = st["v"], st["tau"], st["D"], st["E"]
     if tau != 0.0:
         Dfull = D + np.tril(D, -1).T
         p = tau * (Dfull @ v)
         w = p - 0.5 * tau * (p @ v) * v
         D -= np.tril(np.outer(v, w) + np.outer(w, v))
-    Dv.store(D, lower_only=True)
-    # ---- step 4: block below, right application; stays in shared memory as the next task's G
-    hi = min(n, r1 + b)
-    ne = hi - r1
-    if ne <= 0:
+    st["Dv"].store(D, lower_only=True)
+    if st["ne"] <= 0:
         return None
-    assert ln == b
-    Ev = Blk(Bd, ldb, r1, r0, ne, b)
-    E = Ev.load()
     if tau != 0.0:
         u = E @ v
         E -= tau * np.outer(u, v)
-    if ne >= 2 and r1 <= n - 2:
+    if st["ne"] >= 2 and st["r1"] <= n - 2:
         return E                                             # next task exists: carried in shared memory
-    Ev.store(E)
+    st["Ev"].store(E)
     return None
 
 
-def sb2st_band(Bd, ldb, n, b, ncta=5, rng=None):
-    """The persistent kernel: CTA g owns sweeps g, g + ncta, ...; a CTA may run task (s, k) when
-    prog[s-1] >= k + 3 or sweep s-1 is finished.  CTAs are stepped in random order, one task at a time."""
+def run_task(Bd, ldb, n, b, s, k, carry, Vs, ldv, tau2):
+    return task_phase_b(n, task_phase_a(Bd, ldb, n, b, s, k, carry, Vs, ldv, tau2))
+
+
+def sb2st_band(Bd, ldb, n, b, ncta=5, rng=None, lag=3):
+    """The persistent kernel: CTA g owns sweeps g, g + ncta, ...  prog[s] = k + 1 is published when task k of
+    sweep s has written its G block back (phase A) - tasks < k are then complete, D_k / E_k are still in
+    registers - and a CTA may start task (s, k) when prog[s-1] >= k + lag or sweep s-1 is finished.  lag = 3 is the
+    smallest valid distance: (s+1, k) touches the first entry of G_{k+2} of sweep s and nothing of D_{k+2} / E_{k+2}.
+    CTAs are stepped in random order, HALF a task at a time, so that other sweeps do run between the two halves."""
     Bd = Bd.copy()
     ldv = n
     Vs = np.zeros(n * n)
     tau2 = np.zeros(n * (n // b + 2))
     BIG = 1 << 30
     prog = np.zeros(max(n, 1), dtype=np.int64)
-    state = [{"s": g, "k": 0, "carry": None} for g in range(ncta)]
+    state = [{"s": g, "k": 0, "carry": None, "half": None} for g in range(ncta)]
     nsweeps = max(0, n - 2)
     rng = rng or np.random.RandomState(0)
     live = True
@@ -159,16 +172,21 @@ def sb2st_band(Bd, ldb, n, b, ncta=5, rng=None):
             live = True
             K = num_tasks(s, n, b)
             k = stt["k"]
-            if s > 0 and prog[s - 1] < k + 3:
-                continue                                     # spin
-            stt["carry"] = run_task(Bd, ldb, n, b, s, k, stt["carry"], Vs, ldv, tau2)
+            if stt["half"] is None:
+                if s > 0 and prog[s - 1] < k + lag:
+                    continue                                 # spin
+                stt["half"] = task_phase_a(Bd, ldb, n, b, s, k, stt["carry"], Vs, ldv, tau2)
+                if k + 1 < K:
+                    prog[s] = k + 1                          # early publish: G_k is final
+                continue
+            stt["carry"] = task_phase_b(n, stt["half"])
+            stt["half"] = None
             k += 1
             if k == K:
                 assert stt["carry"] is None
                 prog[s] = BIG
                 stt["s"], stt["k"] = s + ncta, 0
             else:
-                prog[s] = k
                 stt["k"] = k
     d = np.array([Bd[c * ldb] for c in range(n)])
     e = np.array([Bd[1 + c * ldb] for c in range(n - 1)])

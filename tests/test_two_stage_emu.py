@@ -55,6 +55,26 @@ def test_band_model_matches_full_storage_prototype():
         assert abs(tau2[s + k * n] - tau) <= 1e-9
 
 
+def test_progress_protocol_distance_three_is_valid_and_minimal():
+    """The chase kernel publishes prog[s] = k + 1 as soon as task k has written its G block (its D / E blocks are
+    still in registers) and releases task (s + 1, k) at prog[s] >= k + 3.  With CTAs stepped half a task at a time
+    in random order the result must not depend on the schedule - and a distance of 2 must break it (the test
+    would otherwise prove nothing)."""
+    n, b = 96, 8
+    A = _spd(n, 21)
+    band, _ = P.sy2sb(A, b)
+    d0, e0, _, _ = P.sb2st(band, b)
+    Bd, ldb = M.extract_band(band, b)
+    sc = np.abs(A).max()
+    broken = 0
+    for trial in range(5):
+        d, e, *_ = M.sb2st_band(Bd, ldb, n, b, ncta=3 + trial, rng=np.random.RandomState(trial), lag=3)
+        assert np.abs(d - d0).max() <= 1e-12 * sc and np.abs(np.abs(e) - np.abs(e0)).max() <= 1e-12 * sc
+        d, e, *_ = M.sb2st_band(Bd, ldb, n, b, ncta=3 + trial, rng=np.random.RandomState(trial), lag=2)
+        broken += not (np.abs(d - d0).max() <= 1e-9 * sc and np.abs(np.abs(e) - np.abs(e0)).max() <= 1e-9 * sc)
+    assert broken > 0
+
+
 @pytest.mark.parametrize("n", [4096, 12288])
 def test_q2_wavefronts_at_model_sizes(n):
     """What apply_q2 (two_stage.cu) relies on: the groups of a wavefront are consecutive sweep blocks, start 3 b
