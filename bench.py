@@ -451,10 +451,22 @@ def main():
 
     # ---- e2e: same step through the public API with HOST buffers (pinned), copies inside the timed region
     e2e = None
+    Xh = Wh = Oh = None
+    pin_err = ""
     try:
-        Xh = [x.cpu().pin_memory() for x in Xs]
-        Wh = [[w.cpu().pin_memory() for w in ws] for ws in Ws]
-        Oh = [[torch.empty_like(w).pin_memory() for w in ws] for ws in Wh]
+        def to_pinned(t):         # straight into pinned memory: no pageable copy of the 12.9 GB of activations
+            return torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+        Xh = [to_pinned(x) for x in Xs]
+        Wh = [[to_pinned(w) for w in ws] for ws in Ws]
+        Oh = [[torch.empty(w.shape, dtype=w.dtype, pin_memory=True) for w in ws] for ws in Wh]
+    except Exception as ex:       # pinned allocation can fail on a small host
+        pin_err = str(ex)[:200]
+    pinned_ok = torch.tensor([0 if pin_err else 1], device=dev, dtype=torch.int32)
+    if world > 1:                 # every rank takes the same branch: the timed region below contains barriers
+        dist.all_reduce(pinned_ok, op=dist.ReduceOp.MIN)
+    try:
+        if int(pinned_ok.item()) == 0:
+            raise RuntimeError(pin_err or "pinned host allocation failed on another rank")
         layer_step(Xh, Wh, True, Oh)
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -471,9 +483,9 @@ def main():
         e2e = {"value": LAYERS * float(ems.item()) / args.e2e_steps / 1e3 / world, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                "note": "pinned host X / W -> device inside the timed region (copies of later groups overlap the solves of earlier ones on a side stream), dequantised fp16 weights read back"}
-        del Xh, Wh, Oh
-    except Exception as ex:       # pinned allocation can fail on a small host
+    except Exception as ex:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
+    del Xh, Wh, Oh
 
     if rank == 0:
         peak, which = _peaks()
