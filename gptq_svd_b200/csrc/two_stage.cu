@@ -186,30 +186,19 @@ static int apply_q2_batch(cublasHandle_t h, cudaStream_t st, const TwoStageBuffe
   return TQ_OK;
 }
 
-static int apply_q2(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb, int64_t n, double* Z, int64_t ldz,
-                    int64_t ncols, Workspace scratch) {
+static inline int q2_max_batch(int64_t n) { return int(n / (3 * kBw)) + 2; }
+
+// The schedule: calls f(sb0, k0, count, hg) for every batch of `count` row-disjoint groups (sb0 + i, k0 + 2 i) of
+// height hg, in an order that respects the dependencies above.  Only the lowest group of a wavefront can run past
+// row n; it becomes a batch of its own (hg < kQ2H).  tests/test_two_stage_emu.py compares this enumeration with the
+// numpy model at the Qwen3-8B sizes.
+template <class F>
+static int q2_for_each_batch(int64_t n, F&& f) {
   constexpr int b = kBw;
   const int64_t nsweeps = n - 2;
   if (nsweeps <= 0) return TQ_OK;
   const int M = int((nsweeps - 1) / b);
-  const int maxb = int(n / (3 * b)) + 2;
-  double* Vc = scratch.take<double>(size_t(maxb) * kQ2Ld * b);
-  double* taub = scratch.take<double>(size_t(maxb) * b);
-  double* Gb = scratch.take<double>(size_t(maxb) * b * b);
-  double* Tb = scratch.take<double>(size_t(maxb) * b * b);
-  double* w1 = scratch.take<double>(size_t(maxb) * b * ncols);
-  double* w2 = scratch.take<double>(size_t(maxb) * b * ncols);
-  if (scratch.overflow) {
-    set_error("apply_q2: workspace too small");
-    return TQ_ERR_WORKSPACE;
-  }
-  // TQ_Q2_UNBATCHED=1: debugging aid for the first GPU runs (bisects between the wavefront schedule and cuBLAS'
-  // handling of strided batches whose output blocks interleave in memory)
-  static int unbatched = -1;
-  if (unbatched < 0) {
-    const char* env = getenv("TQ_Q2_UNBATCHED");
-    unbatched = (env && env[0] && env[0] != '0') ? 1 : 0;
-  }
+  const int maxb = q2_max_batch(n);
   const int kmax0 = int(chase_tasks(0, n)) - 1;
   for (int w = 0; w <= kmax0 + 2 * M; ++w) {
     int sb_lo = -1, sb_hi = -1;
@@ -231,19 +220,46 @@ static int apply_q2(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb
     }
     const int k_lo = w - 2 * (M - sb_lo), k_hi = w - 2 * (M - sb_hi);
     const int64_t rlo_last = int64_t(sb_hi) * b + 1 + int64_t(k_hi) * b;
-    const int hg_last = int(imin(kQ2H, n - rlo_last));          // only the lowest group can run past row n
+    const int hg_last = int(imin(kQ2H, n - rlo_last));
     if (hg_last < kQ2H) {
-      TQ_TRY(apply_q2_batch(h, st, tb, n, sb_hi, k_hi, 1, hg_last, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2));
+      TQ_TRY(f(sb_hi, k_hi, 1, hg_last));
       --count;
     }
-    if (count > 0 && unbatched) {      // one block reflector at a time: same arithmetic, no interleaved batches
-      for (int i = 0; i < count; ++i)
-        TQ_TRY(apply_q2_batch(h, st, tb, n, sb_lo + i, k_lo + 2 * i, 1, kQ2H, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2));
-    } else if (count > 0) {
-      TQ_TRY(apply_q2_batch(h, st, tb, n, sb_lo, k_lo, count, kQ2H, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2));
-    }
+    if (count > 0) TQ_TRY(f(sb_lo, k_lo, count, kQ2H));
   }
   return TQ_OK;
+}
+
+static int apply_q2(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb, int64_t n, double* Z, int64_t ldz,
+                    int64_t ncols, Workspace scratch) {
+  constexpr int b = kBw;
+  if (n <= 2) return TQ_OK;
+  const int maxb = q2_max_batch(n);
+  double* Vc = scratch.take<double>(size_t(maxb) * kQ2Ld * b);
+  double* taub = scratch.take<double>(size_t(maxb) * b);
+  double* Gb = scratch.take<double>(size_t(maxb) * b * b);
+  double* Tb = scratch.take<double>(size_t(maxb) * b * b);
+  double* w1 = scratch.take<double>(size_t(maxb) * b * ncols);
+  double* w2 = scratch.take<double>(size_t(maxb) * b * ncols);
+  if (scratch.overflow) {
+    set_error("apply_q2: workspace too small");
+    return TQ_ERR_WORKSPACE;
+  }
+  // TQ_Q2_UNBATCHED=1: debugging aid for the first GPU runs (bisects between the wavefront schedule and cuBLAS'
+  // handling of strided batches whose output blocks interleave in memory)
+  static int unbatched = -1;
+  if (unbatched < 0) {
+    const char* env = getenv("TQ_Q2_UNBATCHED");
+    unbatched = (env && env[0] && env[0] != '0') ? 1 : 0;
+  }
+  return q2_for_each_batch(n, [&](int sb0, int k0, int count, int hg) -> int {
+    if (unbatched) {      // one block reflector at a time: same arithmetic, no interleaved batches
+      for (int i = 0; i < count; ++i)
+        TQ_TRY(apply_q2_batch(h, st, tb, n, sb0 + i, k0 + 2 * i, 1, hg, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2));
+      return TQ_OK;
+    }
+    return apply_q2_batch(h, st, tb, n, sb0, k0, count, hg, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2);
+  });
 }
 
 // ------------------------------------------------------------------------------------------------ Z <- Q1 Z

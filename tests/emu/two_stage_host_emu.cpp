@@ -149,6 +149,20 @@ static size_t g_ws_off = 0;
 
 const char* emu_last_error(void) { return tq::g_err_buf; }
 
+// the batches apply_q2 issues for an n x n problem, as (sb0, k0, count, hg) quadruples; returns their number
+// (or a negative status).  No arithmetic: this is the schedule alone, cheap at any n.
+int emu_q2_schedule(int64_t n, int* out, int cap) {
+  int cnt = 0;
+  const int st = tq::q2_for_each_batch(n, [&](int sb0, int k0, int count, int hg) -> int {
+    if (cnt < cap) {
+      out[4 * cnt + 0] = sb0, out[4 * cnt + 1] = k0, out[4 * cnt + 2] = count, out[4 * cnt + 3] = hg;
+    }
+    ++cnt;
+    return TQ_OK;
+  });
+  return st == TQ_OK ? cnt : st;
+}
+
 // A: n x n column-major (both triangles valid on entry; only the lower one is used).  On exit A holds the band and
 // the stage-1 reflectors, (d, e) the tridiagonal matrix.  `sms` = CTAs the bulge chase may use.
 int emu_two_stage_reduce(double* A, int64_t n, double* d, double* e, int sms) {

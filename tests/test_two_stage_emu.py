@@ -75,7 +75,7 @@ def test_progress_protocol_distance_three_is_valid_and_minimal():
     assert broken > 0
 
 
-@pytest.mark.parametrize("n", [4096, 12288])
+@pytest.mark.parametrize("n", list(range(256, 1600, 64)) + [4096, 8192, 12288, 14336, 28672])
 def test_q2_wavefronts_at_model_sizes(n):
     """What apply_q2 (two_stage.cu) relies on: the groups of a wavefront are consecutive sweep blocks, start 3 b
     rows apart, only the lowest one can be clipped, and a wavefront never exceeds the scratch it sizes."""
@@ -202,6 +202,7 @@ def _load_host_emu():
     lib.emu_two_stage_reduce.argtypes = [dp, C.c_int64, dp, dp, C.c_int]
     lib.emu_two_stage_back.argtypes = [dp, C.c_int64, dp, C.c_int64]
     lib.emu_last_error.restype = C.c_char_p
+    lib.emu_q2_schedule.argtypes = [C.c_int64, np.ctypeslib.ndpointer(np.int32, flags="C"), C.c_int]
     return lib
 
 
@@ -241,3 +242,28 @@ def test_whole_two_stage_path_dgemm_variant():
             ) % (ROOT, os.path.join(ROOT, "tests"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [256, 448, 1024, 4096, 12288, 28672])
+def test_host_q2_schedule_equals_model(host_emu, n):
+    """The wavefront enumeration of apply_q2 (C++, two_stage.cu) issues exactly the model's groups, in an order
+    that keeps every dependency: (sb, k) after (sb, k-1) and after (sb+1, k-2 .. k)."""
+    cap = 1 << 16
+    out = np.zeros(4 * cap, np.int32)
+    cnt = host_emu.emu_q2_schedule(n, out, cap)
+    assert 0 < cnt <= cap, host_emu.emu_last_error()
+    batches = out[:4 * cnt].reshape(cnt, 4)
+    order = {}
+    for bi, (sb0, k0, count, hg) in enumerate(batches):
+        assert 1 <= count <= n // (3 * B) + 2
+        for i in range(count):
+            sb, k = int(sb0 + i), int(k0 + 2 * i)
+            rlo = sb * B + 1 + k * B
+            assert (sb, k) not in order and hg == min(2 * B - 1, n - rlo)
+            order[(sb, k)] = bi
+    want = {(g[0], g[1]) for _, grp in M.q2_groups(n, B) for g in grp}
+    assert set(order) == want
+    for (sb, k), pos in order.items():
+        for dep in ((sb, k - 1), (sb + 1, k - 2), (sb + 1, k - 1), (sb + 1, k)):
+            if dep in order:
+                assert order[dep] < pos, ((sb, k), dep)
