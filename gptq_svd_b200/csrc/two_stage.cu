@@ -154,6 +154,7 @@ static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuff
               "D %.0f  E %.0f\n", grid, hs[4], hs[0] / t, hs[1] / t, hs[2] / t, hs[3] / t);
     }
   }
+  TQ_CUDA_CHECK(cudaMemsetAsync(e, 0, sizeof(double) * n, st));      // e[n-1] = 0 like sytrd_lower leaves it
   TQ_LAUNCH(band_diag_kernel, unsigned(ceil_div(n, 256)), 256, 0, st, tb.Bd, int(n), d, e);
   TQ_LAUNCH_CHECK();
   return TQ_OK;
