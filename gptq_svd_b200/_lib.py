@@ -31,6 +31,7 @@ SIGNATURES = {
     "tq_launch_count": [],
     "tq_set_sm_budget": [_i32],
     "tq_set_eigh_two_stage": [_i32],
+    "tq_two_stage_debug": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp],
     "tq_set_stage_callback": [STAGE_CALLBACK, _vp],
     "tq_profile_begin": [_i32],
     "tq_profile_end": [C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_i64), C.POINTER(_i64)],

@@ -125,9 +125,12 @@ static int sy2sb(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double
 }
 
 // ------------------------------------------------------------------------------------------------ stage 2
-static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuffers& tb, double* d, double* e) {
+static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuffers& tb, double* d, double* e,
+                 double* band_out = nullptr) {
   TQ_LAUNCH(band_extract_kernel, unsigned(n), 128, 0, st, A, n, int(n), tb.Bd);
   TQ_LAUNCH_CHECK();
+  if (band_out)     // debugging: the band matrix as stage 1 left it
+    TQ_CUDA_CHECK(cudaMemcpyAsync(band_out, tb.Bd, sizeof(double) * size_t(kLdb) * n, cudaMemcpyDeviceToDevice, st));
   TQ_CUDA_CHECK(cudaMemsetAsync(tb.prog, 0, sizeof(int) * n, st));
   TQ_CUDA_CHECK(cudaMemsetAsync(tb.tau2, 0, sizeof(double) * size_t(n) * (n / kBw + 2), st));
   if (n > 2) {
@@ -331,4 +334,30 @@ int two_stage_back(cublasHandle_t h, cudaStream_t st, const double* A, int64_t n
   return TQ_OK;
 }
 
+int copy_symmetric_lower(cudaStream_t st, const double* H, int64_t ldh, int64_t n, double* A);
+
 }  // namespace tq
+
+using namespace tq;
+
+extern "C" int tq_two_stage_debug(const double* H, int64_t ldh, int64_t n, double* band_out, double* d, double* e,
+                                  void* ws, size_t ws_bytes, void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(H && d && e && ldh >= n, "tq_two_stage_debug: bad arguments");
+  TQ_REQUIRE(n % kBw == 0 && n >= 4 * kBw && n < (1 << 30), "tq_two_stage_debug: n must be a multiple of %d, >= %d", kBw,
+             4 * kBw);
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace wsp(ws, ws_bytes);
+  double* A = wsp.take<double>(size_t(n) * n);
+  TwoStageBuffers tb;
+  TQ_TRY(take_two_stage(wsp, n, tb));
+  if (wsp.overflow) {
+    set_error("tq_two_stage_debug: workspace too small");
+    return TQ_ERR_WORKSPACE;
+  }
+  cublasHandle_t h;
+  TQ_TRY(get_cublas(&h, st));
+  TQ_TRY(copy_symmetric_lower(st, H, ldh, n, A));
+  TQ_TRY(sy2sb(h, st, A, n, tb.tau1, wsp));
+  return sb2st(st, A, n, tb, d, e, band_out);
+}

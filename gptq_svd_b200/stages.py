@@ -75,3 +75,25 @@ def qr_r(A: torch.Tensor):
         R = torch.empty((k, n), dtype=torch.float64, device=A.device)
         check(lib.tq_qr_r(_ptr(Ad), Ad.stride(0), k, n, _ptr(R), n, _ptr(ws), ws.numel(), _stream(Ad)), "tq_qr_r")
     return R
+
+
+def two_stage_debug(H: torch.Tensor):
+    """Experimental two-stage tridiagonal reduction, stage by stage (tq_two_stage_debug): returns
+    (band, d, e) - band[c, i - c] = B[i, c] of the band matrix after stage 1 (bandwidth 64), (d, e) the tridiagonal
+    matrix after the bulge chase.  H, B and T share their eigenvalues."""
+    _require_cuda(H, "two_stage_debug")
+    lib = _lib.load()
+    n = H.shape[0]
+    Hd = H.to(torch.float64).contiguous()
+    with torch.cuda.device(H.device):
+        lib.tq_set_eigh_two_stage(1)
+        try:
+            ws = _ws(n, H.device)
+        finally:
+            lib.tq_set_eigh_two_stage(-1)
+        band = torch.empty((n, 128), dtype=torch.float64, device=H.device)
+        d = torch.empty(n, dtype=torch.float64, device=H.device)
+        e = torch.empty(n, dtype=torch.float64, device=H.device)
+        check(lib.tq_two_stage_debug(_ptr(Hd), Hd.stride(0), n, _ptr(band), _ptr(d), _ptr(e), _ptr(ws), ws.numel(),
+                                     _stream(Hd)), "tq_two_stage_debug")
+    return band, d, e[: n - 1]

@@ -83,6 +83,14 @@ int tq_set_sm_budget(int sms);
  * after changing it.  gptq_svd_b200/csrc/two_stage.cu. */
 int tq_set_eigh_two_stage(int on);
 
+/* Debugging aid for that path: runs the two reductions of an n x n symmetric H (n % 64 == 0, n >= 256) and returns
+ * band_out (optional): the band matrix after stage 1 as a column-major 128 x n array, entry (i - c) + 128 c holds
+ * B[i, c] for 0 <= i - c <= 64; d, e (n each): the tridiagonal matrix after stage 2.  H, band and T must share
+ * their eigenvalues - which tells a failing stage from a sound one.  Workspace: tq_solver_workspace(n) bytes
+ * queried with the two-stage path switched on. */
+int tq_two_stage_debug(const double* H, int64_t ldh, int64_t n, double* band_out, double* d, double* e, void* ws,
+                       size_t ws_bytes, void* stream);
+
 /* Per-thread stage callback: `cb(stage, user)` runs on the calling host thread inside
  * tq_spectral_solve / tq_eigh when a stage boundary has been reached ON THE DEVICE (the stream is
  * synchronised first).  TQ_STAGE_SYTRD_DONE (once per solve): the tridiagonal reduction - the bandwidth-bound

@@ -30,6 +30,18 @@ bool two_stage_requested() { return true; }
 StageTimer::StageTimer(cudaStream_t s, const char* n) : st(s), name(n), t0(0) {}
 StageTimer::~StageTimer() {}
 
+int check_device() { return TQ_OK; }
+int get_cublas(cublasHandle_t* out, cudaStream_t) {
+  *out = nullptr;
+  return TQ_OK;
+}
+// eigh.cu: A (column-major, both triangles) = the symmetric matrix defined by the lower triangle of the row-major H
+int copy_symmetric_lower(cudaStream_t, const double* H, int64_t ldh, int64_t n, double* A) {
+  for (int64_t c = 0; c < n; ++c)
+    for (int64_t r = 0; r < n; ++r) A[r + c * n] = (r >= c) ? H[r * ldh + c] : H[c * ldh + r];
+  return TQ_OK;
+}
+
 // stands in for qr_r_colmajor_tau (qr.cu): unblocked Householder QR, R on / above the diagonal, reflector tails
 // below it (unit diagonal implied), tau_out[j]
 int qr_r_colmajor_tau(cublasHandle_t, cudaStream_t, double* A, int64_t lda, int64_t k, int64_t n, Workspace&,
@@ -174,6 +186,13 @@ int emu_two_stage_reduce(double* A, int64_t n, double* d, double* e, int sms) {
   const int st = tq::two_stage_reduce(nullptr, nullptr, A, n, d, e, ws);
   g_ws_off = ws.off;
   return st;
+}
+
+// the C ABI's debug entry point itself (H row-major), on host memory
+int emu_two_stage_debug(const double* H, int64_t n, double* band_out, double* d, double* e, int sms) {
+  tq::g_emu_sms = sms;
+  std::vector<char> ws(tq::two_stage_ws_bytes(n) + size_t(n) * n * 8 * 4 + (1 << 20), 0);
+  return tq_two_stage_debug(H, n, n, band_out, d, e, ws.data(), ws.size(), nullptr);
 }
 
 // Z (n x ncols column-major, ld n) <- Q1 Q2 Z with the reflectors of the last emu_two_stage_reduce

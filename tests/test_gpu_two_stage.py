@@ -32,6 +32,25 @@ def _spd(n, seed, decay=-3.0):
     return X.T @ X / (2 * n)
 
 
+@pytest.mark.parametrize("n", [256, 1024, 4096])
+def test_each_stage_keeps_the_spectrum(two_stage, n):
+    """Run this one first when something is off: it tells the band reduction from the bulge chase."""
+    H = _spd(n, 5 + n)
+    band, d, e = two_stage.two_stage_debug(H)
+    wr = torch.linalg.eigvalsh(H)
+    scale = float(wr.abs().max())
+    i = torch.arange(n, device="cuda")
+    Bf = torch.zeros(n, n, device="cuda", dtype=torch.float64)
+    for off in range(0, 65):                       # band[c, off] = B[c + off, c]
+        m = n - off
+        Bf[i[:m] + off, i[:m]] = band[:m, off]
+    Bf = torch.tril(Bf) + torch.tril(Bf, -1).T
+    assert float(band[:, 65:].abs().max()) == 0.0, "bulge room is not empty after stage 1"
+    assert float((torch.linalg.eigvalsh(Bf) - wr).abs().max()) <= 1e-12 * scale * n ** 0.5, "stage 1 (sy2sb)"
+    T = torch.diag(d) + torch.diag(e, 1) + torch.diag(e, -1)
+    assert float((torch.linalg.eigvalsh(T) - wr).abs().max()) <= 1e-12 * scale * n ** 0.5, "stage 2 (sb2st)"
+
+
 @pytest.mark.parametrize("n", [256, 320, 1024, 4096])
 def test_two_stage_eigh_is_an_eigendecomposition(two_stage, n):
     H = _spd(n, n)

@@ -203,6 +203,7 @@ def _load_host_emu():
     lib.emu_two_stage_back.argtypes = [dp, C.c_int64, dp, C.c_int64]
     lib.emu_last_error.restype = C.c_char_p
     lib.emu_q2_schedule.argtypes = [C.c_int64, np.ctypeslib.ndpointer(np.int32, flags="C"), C.c_int]
+    lib.emu_two_stage_debug.argtypes = [dp, C.c_int64, dp, dp, dp, C.c_int]
     return lib
 
 
@@ -267,3 +268,20 @@ def test_host_q2_schedule_equals_model(host_emu, n):
         for dep in ((sb, k - 1), (sb + 1, k - 2), (sb + 1, k - 1), (sb + 1, k)):
             if dep in order:
                 assert order[dep] < pos, ((sb, k), dep)
+
+
+def test_debug_entry_point_returns_band_and_tridiagonal(host_emu):
+    """tq_two_stage_debug (the C ABI's stage-by-stage view, used by tests/test_gpu_two_stage.py): H, the band matrix
+    after stage 1 and the tridiagonal matrix after stage 2 share their eigenvalues."""
+    n = 256
+    A = _spd(n, 77)
+    band = np.full(n * 2 * B, np.nan)
+    d, e = np.zeros(n), np.zeros(n)
+    assert host_emu.emu_two_stage_debug(np.ascontiguousarray(A).reshape(-1), n, band, d, e, 3) == 0, \
+        host_emu.emu_last_error()
+    Bf = M.band_to_full(band, 2 * B, n)
+    assert np.abs(np.tril(Bf, -(B + 1))).max() == 0.0
+    wr = np.linalg.eigvalsh(A)
+    assert np.abs(np.linalg.eigvalsh(Bf) - wr).max() <= 1e-13 * wr.max()
+    T = np.diag(d) + np.diag(e[:n - 1], 1) + np.diag(e[:n - 1], -1)
+    assert np.abs(np.linalg.eigvalsh(T) - wr).max() <= 1e-13 * wr.max()
