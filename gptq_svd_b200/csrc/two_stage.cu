@@ -1,8 +1,9 @@
 // Two-stage tridiagonal reduction for tq_eigh (EXPERIMENTAL, off by default: tq_set_eigh_two_stage(1) or
-// TQ_EIGH_TWO_STAGE=1; n % 64 == 0).  First written at the end of round 1 without GPU time left: it compiles
-// for sm_100a and every index expression below is checked against the numpy model
-// scripts/prototypes/sb2st_band.py (tests/test_two_stage_band_model.py), but it has NOT run on a B200 yet -
-// tests/test_gpu_two_stage.py is its parity test.
+// TQ_EIGH_TWO_STAGE=1; n % 64 == 0, n >= 256).  Written at the end of round 1 with no GPU time left: it compiles for
+// sm_100a and has been executed on the CPU - the kernels of two_stage_kernels.cuh and this file's host driver are
+// compiled unchanged by tests/emu/ (one OS thread per CUDA thread, reference BLAS in place of cuBLAS) and checked
+// against the numpy model scripts/prototypes/sb2st_band.py and numpy.linalg.eigh (tests/test_two_stage_emu.py) -
+// but it has NOT run on a B200 yet; tests/test_gpu_two_stage.py (TQ_TEST_TWO_STAGE=1) is its parity test.
 //
 // Why.  The one-stage reduction (eigh.cu) streams the lower triangle of the trailing matrix once per COLUMN:
 // 4 n^3 / 3 bytes, and sytrd_panel_sym_kernel already runs that stream at ~0.93 of the HBM peak (0.82 s at
@@ -12,12 +13,13 @@
 //            trailing matrix is read once per 64 columns, 4 n^3 / 3 flop of fp64 tensor-core work;
 //   stage 2  sb2st   B = Q2 T Q2^T: bulge chasing on the (2 b) x n band array, which stays in L2 (12.6 MB at
 //            n = 12288).  One persistent kernel; a CTA owns a sweep and walks its tasks, the bulge block travels
-//            from task to task in shared memory, consecutive sweeps run 3 tasks apart under acquire / release
-//            progress counters (pipeline distance proved in scripts/prototypes/two_stage_tridiag.py);
+//            from task to task in shared memory, consecutive sweeps run ~2.4 tasks apart under acquire / release
+//            progress counters (the protocol is checked with half-task interleavings in the numpy model);
 //   back     Z = Q1 (Q2 Z_T): Q2 in wavefronts of row-disjoint (127 x 64) staircase block reflectors - one
 //            strided-batched DGEMM triple per wavefront, groups of a wavefront sit 3 b rows apart in Z; Q1 like
 //            ormtr with the reflector staircase shifted down by b rows.
-// Expected at n = 12288 (36 TF/s DGEMM): stage 1 ~0.13 s, stage 2 ~0.11 s, Q2 ~0.37 s vs 0.82 s.
+// Cost model at n = 12288: stage 1 ~0.13 s of BLAS-3 + ~0.1 s of panel latency, stage 2 ~0.1 s,
+// Q2 ~0.37 s, against 0.82 s - to be measured (scripts/two_stage_probe.py) before it becomes a default anywhere.
 #include <stdlib.h>
 
 #include "solver_kernels.cuh"
