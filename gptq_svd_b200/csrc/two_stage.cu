@@ -3,7 +3,9 @@
 // sm_100a and has been executed on the CPU - the kernels of two_stage_kernels.cuh and this file's host driver are
 // compiled unchanged by tests/emu/ (one OS thread per CUDA thread, reference BLAS in place of cuBLAS) and checked
 // against the numpy model scripts/prototypes/sb2st_band.py and numpy.linalg.eigh (tests/test_two_stage_emu.py) -
-// but it has NOT run on a B200 yet; tests/test_gpu_two_stage.py (TQ_TEST_TWO_STAGE=1) is its parity test.
+// and then ran correctly on a B200 the first time (profiles/r01_two_stage_probe.log): at n = 12288 the reduction
+// takes 196 (sy2sb) + 205 (sb2st) ms against 822 ms one-stage, the extra back-transformation 429 ms, tq_eigh 1051 ms
+// against 1048 ms - level, hence still off.  tests/test_gpu_two_stage.py (TQ_TEST_TWO_STAGE=1) is its parity test.
 //
 // Why.  The one-stage reduction (eigh.cu) streams the lower triangle of the trailing matrix once per COLUMN:
 // 4 n^3 / 3 bytes, and sytrd_panel_sym_kernel already runs that stream at ~0.93 of the HBM peak (0.82 s at
@@ -18,8 +20,8 @@
 //   back     Z = Q1 (Q2 Z_T): Q2 in wavefronts of row-disjoint (127 x 64) staircase block reflectors - one
 //            strided-batched DGEMM triple per wavefront, groups of a wavefront sit 3 b rows apart in Z; Q1 like
 //            ormtr with the reflector staircase shifted down by b rows.
-// Cost model at n = 12288: stage 1 ~0.13 s of BLAS-3 + ~0.1 s of panel latency, stage 2 ~0.1 s,
-// Q2 ~0.37 s, against 0.82 s - to be measured (scripts/two_stage_probe.py) before it becomes a default anywhere.
+// The bulge chase is bound by its dependency chain (its CTAs wait half the time; per task 6.4k cycles for the
+// reflector / G block / progress fence, 3.0k for D, 1.3k for E): DESIGN.md 3.10 lists what to change.
 #include <stdlib.h>
 
 #include "solver_kernels.cuh"
