@@ -138,8 +138,16 @@ static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuff
   TQ_CUDA_CHECK(cudaMemsetAsync(tb.prog, 0, sizeof(int) * n, st));
   TQ_CUDA_CHECK(cudaMemsetAsync(tb.tau2, 0, sizeof(double) * size_t(n) * (n / kBw + 2), st));
   if (n > 2) {
-    TQ_CUDA_CHECK(cudaFuncSetAttribute((const void*)sb2st_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(kChaseSmem)));
+    // TQ_CHASE_HELPER=1: the variant whose ninth warp owns the progress counter (two_stage_kernels.cuh); the
+    // default is the variant that has run on the B200
+    static int helper = -1;
+    if (helper < 0) {
+      const char* env = getenv("TQ_CHASE_HELPER");
+      helper = (env && env[0] && env[0] != '0') ? 1 : 0;
+    }
+    const void* kfn = helper ? (const void*)sb2st_chase_kernel_t<true> : (const void*)sb2st_chase_kernel_t<false>;
+    const int kthreads = kChaseThreads + (helper ? 32 : 0);
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kChaseSmem)));
     // sweeps run 3 tasks apart, so at most K_0 / 3 + 1 of them are in flight; the launch is cooperative only for
     // its guarantee that every CTA is resident (a waiting sweep's predecessor must be running)
     int64_t want = chase_tasks(0, n) / 3 + 2;
@@ -149,16 +157,15 @@ static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuff
     if (trace) TQ_CUDA_CHECK(cudaMemsetAsync(tb.stats, 0, 8 * sizeof(long long), st));
     ChaseArgs ca{tb.Bd, int(n), tb.Vs, n, tb.tau2, tb.prog, trace ? tb.stats : nullptr};
     void* kargs[] = {&ca};
-    TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sb2st_chase_kernel, dim3(grid), dim3(kChaseThreads), kargs,
-                                              kChaseSmem, st));
+    TQ_CUDA_CHECK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kthreads), kargs, kChaseSmem, st));
     ++g_launch_count;
     if (trace) {
       long long hs[8];
       TQ_CUDA_CHECK(cudaMemcpyAsync(hs, tb.stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
       TQ_CUDA_CHECK(cudaStreamSynchronize(st));
       const double t = double(hs[4] > 0 ? hs[4] : 1);
-      fprintf(stderr, "[tq-trace] sb2st chase: %d CTAs; CTA 0 ran %lld tasks, cycles per task: wait %.0f  reflector+G %.0f  "
-              "D %.0f  E %.0f\n", grid, hs[4], hs[0] / t, hs[1] / t, hs[2] / t, hs[3] / t);
+      fprintf(stderr, "[tq-trace] sb2st chase%s: %d CTAs; CTA 0 ran %lld tasks, cycles per task: wait %.0f  reflector+G %.0f  "
+              "D %.0f  E %.0f\n", helper ? " (helper warp)" : "", grid, hs[4], hs[0] / t, hs[1] / t, hs[2] / t, hs[3] / t);
     }
   }
   TQ_CUDA_CHECK(cudaMemsetAsync(e, 0, sizeof(double) * n, st));      // e[n-1] = 0 like sytrd_lower leaves it

@@ -12,7 +12,7 @@ constexpr int kLdb = 2 * kBw;           // rows of the band array: 0 <= i - c < 
 constexpr int kLds = kBw + 1;           // shared-memory leading dimension (rows and columns conflict-free)
 constexpr int kChaseThreads = 256;
 constexpr int kProgDone = 1 << 30;
-constexpr int kChaseSmemDoubles = 2 * kBw * kLds + 2 * kBw + 4 * kBw + kChaseThreads / 32 + 1;
+constexpr int kChaseSmemDoubles = 2 * kBw * kLds + 2 * kBw + 4 * kBw + kChaseThreads / 32 + 2;
 constexpr size_t kChaseSmem = size_t(kChaseSmemDoubles) * sizeof(double);
 constexpr int kQ2H = 2 * kBw - 1;       // rows of a staircase block reflector
 constexpr int kQ2Ld = 2 * kBw;          // its leading dimension
@@ -78,6 +78,21 @@ __device__ __forceinline__ int ld_acquire_s32(const int* p) {
 __device__ __forceinline__ void st_release_s32(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// CTA-scope release / acquire on a shared-memory word (the ticket between the compute warps and the helper warp)
+__device__ __forceinline__ void st_release_cta_smem(int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(p))), "r"(v)
+               : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta_smem(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];"
+               : "=r"(v)
+               : "r"(static_cast<unsigned>(__cvta_generic_to_shared(p)))
+               : "memory");
+  return v;
+}
+// barrier over the kChaseThreads compute threads only (named barrier 1; the helper warp never joins it)
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kChaseThreads) : "memory"); }
 #endif
 
 __device__ __forceinline__ void house_scalars(double alpha, double sumsq, int len, double& tau, double& beta,
@@ -87,7 +102,7 @@ __device__ __forceinline__ void house_scalars(double alpha, double sumsq, int le
     beta = alpha;
     scl = 0.0;
   } else {
-    beta = -copysign(hypot(alpha, sqrt(sumsq)), alpha);
+    beta = -copysign(sqrt(fma(alpha, alpha, sumsq)), alpha);   // entries of a Hessian: no overflow guard needed
     tau = (beta - alpha) / beta;
     scl = 1.0 / (alpha - beta);
   }
@@ -102,7 +117,21 @@ __device__ __forceinline__ void house_scalars(double alpha, double sumsq, int le
 //   E  rows [r1, r1 + b) x columns [r0, r1): E H, kept in shared memory as the G of task k + 1.
 // Thread (ti, tq) = (tid % 64, tid / 64) owns row ti, columns tq + 4 m (m < 16) of D and E in registers; the loads
 // are issued before the reflector is formed so that their L2 latency overlaps steps 1 and 2.
-__global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs a) {
+//
+// kHelper = true (TQ_CHASE_HELPER=1, not validated on a GPU yet): a ninth warp owns the progress counter.  Measured
+// on the B200 the reflector / G step is the longest of a task (6.4k of 10.7k cycles) and counts three times in the
+// dependency chain between sweeps; a good part of it is thread 0's gpu-scope fence + release store, for which all
+// other threads then wait at the next barrier.  With the helper the compute warps only bump a ticket in shared
+// memory (CTA-scope release) and go on; the helper acquires the ticket, fences and publishes.
+#define TQ_CHASE_SYNC()   \
+  do {                    \
+    if (kHelper)          \
+      compute_sync();     \
+    else                  \
+      __syncthreads();    \
+  } while (0)
+template <bool kHelper>
+__global__ void __launch_bounds__(kChaseThreads + (kHelper ? 32 : 0), 1) sb2st_chase_kernel_t(ChaseArgs a) {
   TQ_DYN_SMEM(double, chase_sm);
   double* const G = chase_sm;                   // kBw x kLds
   double* const D = G + kBw * kLds;             // kBw x kLds
@@ -111,10 +140,32 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
   double(*const red)[kBw] = reinterpret_cast<double(*)[kBw]>(wsh + kBw);   // [4][kBw] partial sums
   double* const wred = wsh + kBw + 4 * kBw;     // one slot per warp
   double& alpha_s = wred[kChaseThreads / 32];
+  int* const ticket = reinterpret_cast<int*>(wred + kChaseThreads / 32 + 1);   // publish events handed to the helper
   constexpr int b = kBw, ldg = kLdb - 1;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int ti = tid & (b - 1), tq = tid >> 6;
   const int n = a.n;
+  int seq = 0;                                  // publish events of this CTA so far (thread 0)
+  if (kHelper) {
+    if (tid == 0) *ticket = 0;
+    __syncthreads();                            // the only barrier all kChaseThreads + 32 threads share
+    if (tid >= kChaseThreads) {
+      if (tid != kChaseThreads) return;
+      // helper: one publish event per task, in task order
+      int ev = 0;
+      for (int s = blockIdx.x; s < n - 2; s += gridDim.x) {
+        const int K = (n - 3 - s) / b + 1;
+        for (int k = 0; k < K; ++k) {
+          ++ev;
+          while (ld_acquire_cta_smem(ticket) < ev) {
+          }
+          __threadfence();
+          st_release_s32(a.prog + s, k == K - 1 ? kProgDone : k + 1);
+        }
+      }
+      return;
+    }
+  }
   for (int s = blockIdx.x; s < n - 2; s += gridDim.x) {
     const int K = (n - 3 - s) / b + 1;
     for (int k = 0; k < K; ++k) {
@@ -130,7 +181,7 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
         }
         __threadfence();
       }
-      __syncthreads();
+      TQ_CHASE_SYNC();
       if (prof) {
         tc1 = clock64();
         a.stats[0] += tc1 - tc0;
@@ -154,7 +205,7 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
       sq = warp_sum(sq);
       if (lane == 0) wred[wid] = sq;
       if (tid == 0) alpha_s = x;
-      __syncthreads();
+      TQ_CHASE_SYNC();
       double tau, beta, scl;
       house_scalars(alpha_s, wred[0] + wred[1], ln, tau, beta, scl);
       if (tid < b) {
@@ -163,7 +214,7 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
         if (tid < ln) a.Vs[r0 + tid + int64_t(s) * a.ldv] = v;
       }
       if (tid == 0) a.tau2[s + int64_t(k) * n] = tau;
-      __syncthreads();
+      TQ_CHASE_SYNC();
       // ---- step 2: G <- H G (columns 1..b-1), column 0 <- beta e_0; back to the band array
       if (k == 0) {
         if (tid < ln) __stcg(a.Bd + 1 + int64_t(s) * kLdb + tid, tid == 0 ? beta : 0.0);
@@ -172,7 +223,7 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
 #pragma unroll
         for (int ii = 0; ii < 16; ++ii) acc = fma(vs[tq * 16 + ii], G[tq * 16 + ii + ti * kLds], acc);
         red[tq][ti] = acc;
-        __syncthreads();
+        TQ_CHASE_SYNC();
         const double wj = tau * ((red[0][ti] + red[1][ti]) + (red[2][ti] + red[3][ti]));
 #pragma unroll
         for (int ii = 0; ii < 16; ++ii) {
@@ -180,7 +231,7 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
           const double g = G[i + ti * kLds];
           G[i + ti * kLds] = (ti == 0) ? (i == 0 ? beta : 0.0) : fma(-vs[i], wj, g);
         }
-        __syncthreads();
+        TQ_CHASE_SYNC();
         double* const Gg = a.Bd + b + int64_t(r0 - b) * kLdb;
         if (ti < ln) {
 #pragma unroll
@@ -195,10 +246,14 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
       // (s+1, k) meets task (s, k+2) in ONE entry, the first of G) - checked with half-task interleavings in
       // scripts/prototypes/sb2st_band.py.
       if (!last) {
-        __syncthreads();
+        TQ_CHASE_SYNC();
         if (tid == 0) {
-          __threadfence();
-          st_release_s32(a.prog + s, k + 1);
+          if (kHelper) {
+            st_release_cta_smem(ticket, ++seq);
+          } else {
+            __threadfence();
+            st_release_s32(a.prog + s, k + 1);
+          }
         }
       }
       if (prof) {
@@ -215,22 +270,22 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
           if (ti > lc) D[lc + ti * kLds] = dreg[m];
         }
       }
-      __syncthreads();
+      TQ_CHASE_SYNC();
       {
         double acc = 0.0;                                            // row ti, columns of quarter tq
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) acc = fma(D[ti + (tq * 16 + jj) * kLds], vs[tq * 16 + jj], acc);
         red[tq][ti] = acc;
       }
-      __syncthreads();
+      TQ_CHASE_SYNC();
       double p = 0.0;
       if (tid < b) p = tau * ((red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]));
       double pv = (tid < b) ? p * vs[tid] : 0.0;
       pv = warp_sum(pv);
       if (lane == 0) wred[wid] = pv;
-      __syncthreads();
+      TQ_CHASE_SYNC();
       if (tid < b) wsh[tid] = fma(-0.5 * tau * (wred[0] + wred[1]), vs[tid], p);
-      __syncthreads();
+      TQ_CHASE_SYNC();
       if (ti < ln) {
         const double vi = vs[ti], wi = wsh[ti];
 #pragma unroll
@@ -250,7 +305,7 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
 #pragma unroll
         for (int m = 0; m < 16; ++m) acc = fma(ereg[m], vs[tq + 4 * m], acc);
         red[tq][ti] = acc;
-        __syncthreads();
+        TQ_CHASE_SYNC();
         const double u = tau * ((red[0][ti] + red[1][ti]) + (red[2][ti] + red[3][ti]));
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
@@ -263,16 +318,21 @@ __global__ void __launch_bounds__(kChaseThreads, 1) sb2st_chase_kernel(ChaseArgs
         }
       }
       if (last) {
-        __syncthreads();
+        TQ_CHASE_SYNC();
         if (tid == 0) {
-          __threadfence();
-          st_release_s32(a.prog + s, kProgDone);
+          if (kHelper) {
+            st_release_cta_smem(ticket, ++seq);
+          } else {
+            __threadfence();
+            st_release_s32(a.prog + s, kProgDone);
+          }
         }
       }
       if (prof) a.stats[3] += clock64() - tc0;
     }
   }
 }
+#undef TQ_CHASE_SYNC
 
 // ------------------------------------------------------------------------------------------------ Q2 groups
 // Group (sb, k) = reflectors (s, k), s in [sb b, (sb + 1) b): a staircase of b columns, column j non-zero in rows

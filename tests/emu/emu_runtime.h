@@ -22,6 +22,7 @@ static thread_local dim3 threadIdx, blockIdx, gridDim, blockDim;
 
 struct EmuCta {
   pthread_barrier_t bar;
+  pthread_barrier_t cbar;                      // compute_sync(): the first 256 threads only
   std::vector<pthread_barrier_t> wbar;
   std::vector<double> shfl;
   std::vector<double> smem;
@@ -29,6 +30,7 @@ struct EmuCta {
   void init(int threads, size_t smem_bytes) {
     nthreads = threads;
     pthread_barrier_init(&bar, nullptr, threads);
+    pthread_barrier_init(&cbar, nullptr, std::min(threads, 256));
     const int nw = (threads + 31) / 32;
     wbar.resize(nw);
     for (int w = 0; w < nw; ++w) pthread_barrier_init(&wbar[w], nullptr, std::min(32, threads - 32 * w));
@@ -37,6 +39,7 @@ struct EmuCta {
   }
   void destroy() {
     pthread_barrier_destroy(&bar);
+    pthread_barrier_destroy(&cbar);
     for (auto& b : wbar) pthread_barrier_destroy(&b);
   }
 };
@@ -57,6 +60,14 @@ static inline int ld_acquire_s32(const int* p) {
   return v;
 }
 static inline void st_release_s32(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline void st_release_cta_smem(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline int ld_acquire_cta_smem(const int* p) {
+  const int v = __atomic_load_n(p, __ATOMIC_ACQUIRE);
+  sched_yield();
+  return v;
+}
+// named barrier over the first `compute_threads` threads of the CTA (the chase kernel's helper warp stays out)
+static inline void compute_sync() { pthread_barrier_wait(&g_cta->cbar); }
 using std::max;
 using std::min;
 

@@ -89,9 +89,13 @@ cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
 cudaError_t cudaLaunchCooperativeKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t) {
-  if (func != (const void*)tq::sb2st_chase_kernel) return cudaErrorInvalidDeviceFunction;
   tq::ChaseArgs a = *static_cast<tq::ChaseArgs*>(args[0]);
-  emu_run(grid, block, smem, /*concurrent=*/true, [&] { tq::sb2st_chase_kernel(a); });
+  if (func == (const void*)tq::sb2st_chase_kernel_t<false>)
+    emu_run(grid, block, smem, /*concurrent=*/true, [&] { tq::sb2st_chase_kernel_t<false>(a); });
+  else if (func == (const void*)tq::sb2st_chase_kernel_t<true>)
+    emu_run(grid, block, smem, /*concurrent=*/true, [&] { tq::sb2st_chase_kernel_t<true>(a); });
+  else
+    return cudaErrorInvalidDeviceFunction;
   return cudaSuccess;
 }
 

@@ -116,13 +116,16 @@ def _build(name, extra=()):
 
 @pytest.fixture(scope="module")
 def emu():
-    lib = _build("two_stage_emu")
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.isfile(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not available")
+    lib = _build("two_stage_emu", extra=("-I" + cuda_inc,))
     dp = np.ctypeslib.ndpointer(np.float64, flags="C")
     ip = np.ctypeslib.ndpointer(np.int32, flags="C")
     lib.emu_constants.argtypes = [ip]
     lib.emu_band_extract.argtypes = [dp, C.c_int64, C.c_int, dp]
     lib.emu_band_diag.argtypes = [dp, C.c_int, dp, dp]
-    lib.emu_chase.argtypes = [dp, C.c_int, dp, C.c_int64, dp, ip, C.c_int]
+    lib.emu_chase.argtypes = [dp, C.c_int, dp, C.c_int64, dp, ip, C.c_int, C.c_int]
     lib.emu_copy_staircase.argtypes = [dp, C.c_int64, dp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp]
     k = np.zeros(8, np.int32)
     lib.emu_constants(k)
@@ -130,7 +133,7 @@ def emu():
     return lib
 
 
-def _emu_reduce(emu, Astore, n, grid):
+def _emu_reduce(emu, Astore, n, grid, helper=0):
     """band extraction + bulge chase + (d, e) through the emulated kernels; Astore: n x n, lower triangle valid"""
     Acm = np.ascontiguousarray(Astore.T).reshape(-1)          # column-major
     Bd = np.full(n * 2 * B, np.nan)
@@ -139,19 +142,20 @@ def _emu_reduce(emu, Astore, n, grid):
     Vs = np.zeros(n * n)
     tau2 = np.zeros(n * (n // B + 2))
     prog = np.zeros(n, np.int32)
-    emu.emu_chase(Bd, n, Vs, n, tau2, prog, grid)
+    emu.emu_chase(Bd, n, Vs, n, tau2, prog, grid, helper)
     assert np.all(prog[:n - 2] == (1 << 30))
     d, e = np.zeros(n), np.zeros(n)
     emu.emu_band_diag(Bd, n, d, e)
     return Bd0, Bd, Vs, tau2, d, e[:n - 1]
 
 
-@pytest.mark.parametrize("n,grid", [(136, 2), (256, 3)])
-def test_emulated_chase_kernel_matches_model(emu, n, grid):
+@pytest.mark.parametrize("n,grid,helper", [(136, 2, 0), (256, 3, 0), (136, 3, 1), (256, 2, 1)])
+def test_emulated_chase_kernel_matches_model(emu, n, grid, helper):
+    """helper = 1: the variant whose ninth warp owns the progress counters (TQ_CHASE_HELPER=1)"""
     A = _spd(n, 100 + n)
     band = np.where(np.abs(np.subtract.outer(np.arange(n), np.arange(n))) <= B, A, 0.0)
     Bd_model, ldb = M.extract_band(band, B)
-    Bd0, Bd, Vs, tau2, d, e = _emu_reduce(emu, np.tril(band), n, grid)
+    Bd0, Bd, Vs, tau2, d, e = _emu_reduce(emu, np.tril(band), n, grid, helper)
     assert np.array_equal(Bd0, Bd_model)
     d1, e1, Vs1, tau21, Bd1 = M.sb2st_band(Bd_model, ldb, n, B, ncta=4, rng=np.random.RandomState(5))
     sc = np.abs(A).max()
@@ -236,11 +240,13 @@ def test_whole_two_stage_path_on_the_host(host_emu, n, sms, ncols):
     _check_whole_path(host_emu, n, sms, ncols)
 
 
-def test_whole_two_stage_path_dgemm_variant():
-    """TQ_SY2SB_GEMM=1 (mirror pass + DGEMM instead of DSYMM) in a fresh process: the switch is read once"""
-    code = ("import os, sys; sys.path[:0] = [%r, %r]; os.environ['TQ_SY2SB_GEMM'] = '1';"
+@pytest.mark.parametrize("switch", ["TQ_SY2SB_GEMM", "TQ_CHASE_HELPER"])
+def test_whole_two_stage_path_with_a_switch(switch):
+    """TQ_SY2SB_GEMM=1 (mirror pass + DGEMM instead of DSYMM) / TQ_CHASE_HELPER=1 (helper-warp variant of the bulge
+    chase) in a fresh process: the library reads its switches once"""
+    code = ("import os, sys; sys.path[:0] = [%r, %r]; os.environ[%r] = '1';"
             "import test_two_stage_emu as t; t._check_whole_path(t._load_host_emu(), 256, 2, 256)"
-            ) % (ROOT, os.path.join(ROOT, "tests"))
+            ) % (ROOT, os.path.join(ROOT, "tests"), switch)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
