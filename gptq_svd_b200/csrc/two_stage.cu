@@ -183,20 +183,21 @@ static int apply_q2_batch(cublasHandle_t h, cudaStream_t st, const TwoStageBuffe
                           double* Tb, double* w1, double* w2) {
   constexpr int b = kBw;
   const double one = 1.0, zero = 0.0, mone = -1.0;
-  const int64_t rlo = int64_t(sb0) * b + 1 + int64_t(k0) * b;
+  const int64_t row0 = (int64_t(sb0) + k0) * b;       // one row above the staircase: see copy_staircase_kernel
+  const int hw = hg + 1;                              // rows of the window (128 unless the group is clipped)
   const long long sv = (long long)kQ2Ld * b, st_t = (long long)b * b, sw = (long long)b * ncols, sz = 3 * b;
   TQ_LAUNCH(copy_staircase_kernel, dim3(1, b, count), kQ2Ld, 0, st, tb.Vs, n, tb.tau2, int(n), sb0, k0, Vc, taub);
   TQ_LAUNCH_CHECK();
-  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, b, hg, &one, Vc, kQ2Ld, sv, Vc, kQ2Ld, sv,
+  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, b, hw, &one, Vc, kQ2Ld, sv, Vc, kQ2Ld, sv,
                                             &zero, Gb, b, st_t, count));
   TQ_LAUNCH(larft_kernel, count, kLarftThreads, size_t(b) * b * 10, st, Gb, b, taub, b, Tb, b, int64_t(st_t), int64_t(b), int64_t(st_t));
   TQ_LAUNCH_CHECK();
-  double* Zb = Z + rlo;
-  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, int(ncols), hg, &one, Vc, kQ2Ld, sv, Zb,
+  double* Zb = Z + row0;
+  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, int(ncols), hw, &one, Vc, kQ2Ld, sv, Zb,
                                             int(ldz), sz, &zero, w1, b, sw, count));
   TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, b, int(ncols), b, &one, Tb, b, st_t, w1, b, sw,
                                             &zero, w2, b, sw, count));
-  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, hg, int(ncols), b, &mone, Vc, kQ2Ld, sv, w2, b,
+  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, hw, int(ncols), b, &mone, Vc, kQ2Ld, sv, w2, b,
                                             sw, &one, Zb, int(ldz), sz, count));
   return TQ_OK;
 }

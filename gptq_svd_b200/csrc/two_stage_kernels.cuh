@@ -337,10 +337,12 @@ __global__ void __launch_bounds__(kChaseThreads + (kHelper ? 32 : 0), 1) sb2st_c
 // ------------------------------------------------------------------------------------------------ Q2 groups
 // Group (sb, k) = reflectors (s, k), s in [sb b, (sb + 1) b): a staircase of b columns, column j non-zero in rows
 // [j, j + b) counted from rlo = sb b + 1 + k b.  Clean copy (zeros outside the stairs, zero column and tau = 0 for
-// a task that does not exist) of `count` groups (sb0 + i, k0 + 2 i).
+// a task that does not exist) of `count` groups (sb0 + i, k0 + 2 i).  The copy is SHIFTED DOWN BY ONE ROW: row 0 of
+// the 128 x 64 block is zero and the block acts on the rows of Z from rlo - 1 = (sb + k) b, a multiple of 64 - so
+// the batched DGEMMs see 512-byte aligned operands and K = M = 128 instead of an odd start row and 127.
 __global__ void copy_staircase_kernel(const double* __restrict__ Vs, int64_t ldv, const double* __restrict__ tau2,
                                       int n, int sb0, int k0, double* __restrict__ Vc, double* __restrict__ taub) {
-  const int bi = blockIdx.z, j = blockIdx.y, r = threadIdx.x;       // blockDim.x == kQ2Ld
+  const int bi = blockIdx.z, j = blockIdx.y, r = int(threadIdx.x) - 1;   // blockDim.x == kQ2Ld; r = staircase row
   const int sb = sb0 + bi, k = k0 + 2 * bi;
   const int s = sb * kBw + j;
   const int r0 = s + 1 + k * kBw;
@@ -348,8 +350,8 @@ __global__ void copy_staircase_kernel(const double* __restrict__ Vs, int64_t ldv
   const bool exists = (s <= n - 3) && (r0 <= n - 2);
   const int ln = exists ? min(kBw, n - r0) : 0;
   const double v = (r >= j && r < j + ln) ? Vs[rlo + r + int64_t(s) * ldv] : 0.0;
-  Vc[int64_t(bi) * kQ2Ld * kBw + r + j * kQ2Ld] = v;
-  if (r == 0) taub[bi * kBw + j] = exists ? tau2[s + int64_t(k) * n] : 0.0;
+  Vc[int64_t(bi) * kQ2Ld * kBw + (r + 1) + j * kQ2Ld] = v;
+  if (threadIdx.x == 0) taub[bi * kBw + j] = exists ? tau2[s + int64_t(k) * n] : 0.0;
 }
 
 }  // namespace tq
