@@ -180,7 +180,7 @@ static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuff
 // w = k + 2 (M - sb) is a valid wavefront number, and the groups of one wavefront start 3 b rows apart.
 static int apply_q2_batch(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb, int64_t n, int sb0, int k0,
                           int count, int hg, double* Z, int64_t ldz, int64_t ncols, double* Vc, double* taub, double* Gb,
-                          double* Tb, double* w1, double* w2) {
+                          double* Tb, double* VT, double* w1) {
   constexpr int b = kBw;
   const double one = 1.0, zero = 0.0, mone = -1.0;
   const int64_t row0 = (int64_t(sb0) + k0) * b;       // one row above the staircase: see copy_staircase_kernel
@@ -192,12 +192,14 @@ static int apply_q2_batch(cublasHandle_t h, cudaStream_t st, const TwoStageBuffe
                                             &zero, Gb, b, st_t, count));
   TQ_LAUNCH(larft_kernel, count, kLarftThreads, size_t(b) * b * 10, st, Gb, b, taub, b, Tb, b, int64_t(st_t), int64_t(b), int64_t(st_t));
   TQ_LAUNCH_CHECK();
+  // (I - V T V^T) Z = Z - (V T)(V^T Z): T is folded into V once per group (128 x 64 x 64) instead of being applied to
+  // the 64 x ncols product - one batched GEMM over Z fewer (20 % of the flops of this stage)
+  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, hw, b, b, &one, Vc, kQ2Ld, sv, Tb, b, st_t, &zero,
+                                            VT, kQ2Ld, sv, count));
   double* Zb = Z + row0;
   TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, int(ncols), hw, &one, Vc, kQ2Ld, sv, Zb,
                                             int(ldz), sz, &zero, w1, b, sw, count));
-  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, b, int(ncols), b, &one, Tb, b, st_t, w1, b, sw,
-                                            &zero, w2, b, sw, count));
-  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, hw, int(ncols), b, &mone, Vc, kQ2Ld, sv, w2, b,
+  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, hw, int(ncols), b, &mone, VT, kQ2Ld, sv, w1, b,
                                             sw, &one, Zb, int(ldz), sz, count));
   return TQ_OK;
 }
@@ -255,8 +257,8 @@ static int apply_q2(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb
   double* taub = scratch.take<double>(size_t(maxb) * b);
   double* Gb = scratch.take<double>(size_t(maxb) * b * b);
   double* Tb = scratch.take<double>(size_t(maxb) * b * b);
+  double* VT = scratch.take<double>(size_t(maxb) * kQ2Ld * b);
   double* w1 = scratch.take<double>(size_t(maxb) * b * ncols);
-  double* w2 = scratch.take<double>(size_t(maxb) * b * ncols);
   if (scratch.overflow) {
     set_error("apply_q2: workspace too small");
     return TQ_ERR_WORKSPACE;
@@ -271,10 +273,10 @@ static int apply_q2(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb
   return q2_for_each_batch(n, [&](int sb0, int k0, int count, int hg) -> int {
     if (unbatched) {      // one block reflector at a time: same arithmetic, no interleaved batches
       for (int i = 0; i < count; ++i)
-        TQ_TRY(apply_q2_batch(h, st, tb, n, sb0 + i, k0 + 2 * i, 1, hg, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2));
+        TQ_TRY(apply_q2_batch(h, st, tb, n, sb0 + i, k0 + 2 * i, 1, hg, Z, ldz, ncols, Vc, taub, Gb, Tb, VT, w1));
       return TQ_OK;
     }
-    return apply_q2_batch(h, st, tb, n, sb0, k0, count, hg, Z, ldz, ncols, Vc, taub, Gb, Tb, w1, w2);
+    return apply_q2_batch(h, st, tb, n, sb0, k0, count, hg, Z, ldz, ncols, Vc, taub, Gb, Tb, VT, w1);
   });
 }
 
