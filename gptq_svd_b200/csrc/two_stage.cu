@@ -145,7 +145,13 @@ static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuff
       const char* env = getenv("TQ_CHASE_HELPER");
       helper = (env && env[0] && env[0] != '0') ? 1 : 0;
     }
-    const void* kfn = helper ? (const void*)sb2st_chase_kernel_t<true> : (const void*)sb2st_chase_kernel_t<false>;
+    static int late = -1;        // TQ_CHASE_LATE=1: second wait in front of the D / E loads (two_stage_kernels.cuh)
+    if (late < 0) {
+      const char* env = getenv("TQ_CHASE_LATE");
+      late = (env && env[0] && env[0] != '0') ? 1 : 0;
+    }
+    const void* kfn = helper ? (late ? (const void*)sb2st_chase_kernel_t<true, true> : (const void*)sb2st_chase_kernel_t<true, false>)
+                             : (late ? (const void*)sb2st_chase_kernel_t<false, true> : (const void*)sb2st_chase_kernel_t<false, false>);
     const int kthreads = kChaseThreads + (helper ? 32 : 0);
     TQ_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kChaseSmem)));
     // sweeps run 3 tasks apart, so at most K_0 / 3 + 1 of them are in flight; the launch is cooperative only for
@@ -165,7 +171,7 @@ static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuff
       TQ_CUDA_CHECK(cudaStreamSynchronize(st));
       const double t = double(hs[4] > 0 ? hs[4] : 1);
       fprintf(stderr, "[tq-trace] sb2st chase%s: %d CTAs; CTA 0 ran %lld tasks, cycles per task: wait %.0f  reflector+G %.0f  "
-              "D %.0f  E %.0f\n", helper ? " (helper warp)" : "", grid, hs[4], hs[0] / t, hs[1] / t, hs[2] / t, hs[3] / t);
+              "D %.0f  E %.0f\n", helper ? (late ? " (helper warp, late loads)" : " (helper warp)") : (late ? " (late loads)" : ""), grid, hs[4], hs[0] / t, hs[1] / t, hs[2] / t, hs[3] / t);
     }
   }
   TQ_CUDA_CHECK(cudaMemsetAsync(e, 0, sizeof(double) * n, st));      // e[n-1] = 0 like sytrd_lower leaves it

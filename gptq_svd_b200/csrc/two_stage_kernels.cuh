@@ -130,7 +130,14 @@ __device__ __forceinline__ void house_scalars(double alpha, double sumsq, int le
     else                  \
       __syncthreads();    \
   } while (0)
-template <bool kHelper>
+//
+// kLate = true (TQ_CHASE_LATE=1, not validated on a GPU yet): the reflector step of a task k >= 1 only works on the
+// block carried in shared memory, so it does not wait for the previous sweep at all (task 0 needs prog >= 2 for
+// column s); the wait for prog >= k + 3 moves in front of the D / E loads, which then follow the reflector step
+// instead of overlapping it.  A task gets longer by one L2 round trip, but the dependency chain between sweeps
+// shrinks from 3a + 2d + 2e to 2 (a + L + d + e) - and the chase is bound by that chain (its CTAs wait half the
+// time).  Both waits are valid and minimal under half-task interleavings in scripts/prototypes/sb2st_band.py.
+template <bool kHelper, bool kLate>
 __global__ void __launch_bounds__(kChaseThreads + (kHelper ? 32 : 0), 1) sb2st_chase_kernel_t(ChaseArgs a) {
   TQ_DYN_SMEM(double, chase_sm);
   double* const G = chase_sm;                   // kBw x kLds
@@ -176,8 +183,9 @@ __global__ void __launch_bounds__(kChaseThreads + (kHelper ? 32 : 0), 1) sb2st_c
       const bool last = (k == K - 1);                               // then ne <= 1, else ne >= 2
       const bool prof = a.stats != nullptr && blockIdx.x == 0 && tid == 0;
       long long tc0 = prof ? clock64() : 0, tc1;
-      if (s > 0 && tid == 0) {
-        while (ld_acquire_s32(a.prog + (s - 1)) < k + 3) {
+      if (s > 0 && tid == 0 && (!kLate || k == 0)) {
+        const int need = kLate ? 2 : k + 3;
+        while (ld_acquire_s32(a.prog + (s - 1)) < need) {
         }
         __threadfence();
       }
@@ -192,11 +200,13 @@ __global__ void __launch_bounds__(kChaseThreads + (kHelper ? 32 : 0), 1) sb2st_c
       double* const Dg = a.Bd + int64_t(r0) * kLdb;
       double* const Eg = a.Bd + ln + int64_t(r0) * kLdb;
       double dreg[16], ereg[16];
+      if (!kLate) {
 #pragma unroll
-      for (int m = 0; m < 16; ++m) {
-        const int lc = tq + 4 * m;
-        dreg[m] = (ti >= lc && ti < ln) ? __ldcg(Dg + ti + lc * ldg) : 0.0;
-        ereg[m] = (ti < ne) ? __ldcg(Eg + ti + lc * ldg) : 0.0;
+        for (int m = 0; m < 16; ++m) {
+          const int lc = tq + 4 * m;
+          dreg[m] = (ti >= lc && ti < ln) ? __ldcg(Dg + ti + lc * ldg) : 0.0;
+          ereg[m] = (ti < ne) ? __ldcg(Eg + ti + lc * ldg) : 0.0;
+        }
       }
       // ---- step 1: reflector from the first column of G
       double x = 0.0;
@@ -260,6 +270,25 @@ __global__ void __launch_bounds__(kChaseThreads + (kHelper ? 32 : 0), 1) sb2st_c
         tc1 = clock64();
         a.stats[1] += tc1 - tc0;
         tc0 = tc1;
+      }
+      if (kLate) {        // second wait: D and E of this task are final once the previous sweep has published k + 3
+        if (s > 0 && tid == 0) {
+          while (ld_acquire_s32(a.prog + (s - 1)) < k + 3) {
+          }
+          __threadfence();
+        }
+        TQ_CHASE_SYNC();
+        if (prof) {
+          tc1 = clock64();
+          a.stats[0] += tc1 - tc0;
+          tc0 = tc1;
+        }
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const int lc = tq + 4 * m;
+          dreg[m] = (ti >= lc && ti < ln) ? __ldcg(Dg + ti + lc * ldg) : 0.0;
+          ereg[m] = (ti < ne) ? __ldcg(Eg + ti + lc * ldg) : 0.0;
+        }
       }
       // ---- step 3: D <- H D H = D - v w^T - w v^T,  p = tau D v,  w = p - (tau p^T v / 2) v
 #pragma unroll

@@ -85,7 +85,7 @@ class Blk:
         self.Bd[self.I[m]] = M[m]
 
 
-def task_phase_a(Bd, ldb, n, b, s, k, carry, Vs, ldv, tau2):
+def task_phase_a(Bd, ldb, n, b, s, k, carry, Vs, ldv, tau2, late_loads=False):
     """First half of a task as the CTA executes it: load D and E (registers), form the reflector from the first
     column of G (the E block of the previous task of this sweep, held in shared memory; column s for k = 0), apply it
     to the rest of G from the left and write G back.  After this the sweep's progress counter is published: the
@@ -97,9 +97,11 @@ def task_phase_a(Bd, ldb, n, b, s, k, carry, Vs, ldv, tau2):
     hi = min(n, r1 + b)
     ne = hi - r1 if ln == b else 0
     Dv = Blk(Bd, ldb, r0, r0, ln, ln)
-    D = Dv.load(lower_only=True)                              # registers: loaded BEFORE the progress is published
     Ev = Blk(Bd, ldb, r1, r0, ne, b) if ne > 0 else None
-    E = Ev.load() if ne > 0 else None
+    D = E = None
+    if not late_loads:                                        # variant 1: D and E loaded before the reflector step
+        D = Dv.load(lower_only=True)
+        E = Ev.load() if ne > 0 else None
     if k == 0:
         base = 1 + s * ldb                                  # column s, rows s+1..: contiguous
         x = Bd[base:base + ln].copy()
@@ -125,6 +127,9 @@ def task_phase_b(n, st):
     """Second half: two-sided update of D (lower triangle, written back) and right update of E, which stays in
     shared memory as the next task's G (or is written back when the sweep ends).  Uses the copies loaded in phase A."""
     v, tau, D, E = st["v"], st["tau"], st["D"], st["E"]
+    if D is None:                                             # variant 2: loaded only now, after the second wait
+        D = st["Dv"].load(lower_only=True)
+        E = st["Ev"].load() if st["ne"] > 0 else None
     if tau != 0.0:
         Dfull = D + np.tril(D, -1).T
         p = tau * (Dfull @ v)
@@ -146,7 +151,7 @@ def run_task(Bd, ldb, n, b, s, k, carry, Vs, ldv, tau2):
     return task_phase_b(n, task_phase_a(Bd, ldb, n, b, s, k, carry, Vs, ldv, tau2))
 
 
-def sb2st_band(Bd, ldb, n, b, ncta=5, rng=None, lag=3):
+def sb2st_band(Bd, ldb, n, b, ncta=5, rng=None, lag=3, late_loads=False, lag_a=2):
     """The persistent kernel: CTA g owns sweeps g, g + ncta, ...  prog[s] = k + 1 is published when task k of
     sweep s has written its G block back (phase A) - tasks < k are then complete, D_k / E_k are still in
     registers - and a CTA may start task (s, k) when prog[s-1] >= k + lag or sweep s-1 is finished.  lag = 3 is the
@@ -173,12 +178,19 @@ def sb2st_band(Bd, ldb, n, b, ncta=5, rng=None, lag=3):
             K = num_tasks(s, n, b)
             k = stt["k"]
             if stt["half"] is None:
-                if s > 0 and prog[s - 1] < k + lag:
+                if late_loads:
+                    # variant 2: the reflector step of a task k >= 1 works on the block carried in shared memory and
+                    # waits for nothing; task 0 reads column s from the band array and needs prog[s-1] >= lag_a
+                    if s > 0 and k == 0 and prog[s - 1] < lag_a:
+                        continue
+                elif s > 0 and prog[s - 1] < k + lag:
                     continue                                 # spin
-                stt["half"] = task_phase_a(Bd, ldb, n, b, s, k, stt["carry"], Vs, ldv, tau2)
+                stt["half"] = task_phase_a(Bd, ldb, n, b, s, k, stt["carry"], Vs, ldv, tau2, late_loads)
                 if k + 1 < K:
                     prog[s] = k + 1                          # early publish: G_k is final
                 continue
+            if late_loads and s > 0 and prog[s - 1] < k + lag:
+                continue                                     # variant 2: second wait, in front of the D / E loads
             stt["carry"] = task_phase_b(n, stt["half"])
             stt["half"] = None
             k += 1

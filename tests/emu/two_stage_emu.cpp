@@ -42,14 +42,18 @@ void emu_copy_staircase(const double* Vs, int64_t ldv, const double* tau2, int n
                  [&] { tq::copy_staircase_kernel(Vs, ldv, tau2, n, sb0, k0, Vc, taub); });
 }
 
-// the persistent bulge-chase kernel on `grid` concurrently running CTAs; helper != 0: the variant whose ninth warp
-// publishes the progress counters.  The cycle counters are switched on to exercise the instrumented path too.
-void emu_chase(double* Bd, int n, double* Vs, int64_t ldv, double* tau2, int* prog, int grid, int helper) {
+// the persistent bulge-chase kernel on `grid` concurrently running CTAs; variant bit 0: the ninth warp publishes the
+// progress counters, bit 1: second wait in front of the D / E loads.  The cycle counters are switched on to
+// exercise the instrumented path too.
+void emu_chase(double* Bd, int n, double* Vs, int64_t ldv, double* tau2, int* prog, int grid, int variant) {
   long long stats[8] = {0};
   tq::ChaseArgs args{Bd, n, Vs, ldv, tau2, prog, stats};
-  if (helper)
-    emu_run(dim3(grid), dim3(tq::kChaseThreads + 32), tq::kChaseSmem, true, [&] { tq::sb2st_chase_kernel_t<true>(args); });
-  else
-    emu_run(dim3(grid), dim3(tq::kChaseThreads), tq::kChaseSmem, true, [&] { tq::sb2st_chase_kernel_t<false>(args); });
+  const dim3 g(grid), t256(tq::kChaseThreads), t288(tq::kChaseThreads + 32);
+  switch (variant & 3) {
+    case 0: emu_run(g, t256, tq::kChaseSmem, true, [&] { tq::sb2st_chase_kernel_t<false, false>(args); }); break;
+    case 1: emu_run(g, t288, tq::kChaseSmem, true, [&] { tq::sb2st_chase_kernel_t<true, false>(args); }); break;
+    case 2: emu_run(g, t256, tq::kChaseSmem, true, [&] { tq::sb2st_chase_kernel_t<false, true>(args); }); break;
+    default: emu_run(g, t288, tq::kChaseSmem, true, [&] { tq::sb2st_chase_kernel_t<true, true>(args); }); break;
+  }
 }
 }

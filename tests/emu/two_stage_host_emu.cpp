@@ -90,10 +90,14 @@ const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
 cudaError_t cudaLaunchCooperativeKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t) {
   tq::ChaseArgs a = *static_cast<tq::ChaseArgs*>(args[0]);
-  if (func == (const void*)tq::sb2st_chase_kernel_t<false>)
-    emu_run(grid, block, smem, /*concurrent=*/true, [&] { tq::sb2st_chase_kernel_t<false>(a); });
-  else if (func == (const void*)tq::sb2st_chase_kernel_t<true>)
-    emu_run(grid, block, smem, /*concurrent=*/true, [&] { tq::sb2st_chase_kernel_t<true>(a); });
+  if (func == (const void*)tq::sb2st_chase_kernel_t<false, false>)
+    emu_run(grid, block, smem, /*concurrent=*/true, [&] { tq::sb2st_chase_kernel_t<false, false>(a); });
+  else if (func == (const void*)tq::sb2st_chase_kernel_t<true, false>)
+    emu_run(grid, block, smem, /*concurrent=*/true, [&] { tq::sb2st_chase_kernel_t<true, false>(a); });
+  else if (func == (const void*)tq::sb2st_chase_kernel_t<false, true>)
+    emu_run(grid, block, smem, /*concurrent=*/true, [&] { tq::sb2st_chase_kernel_t<false, true>(a); });
+  else if (func == (const void*)tq::sb2st_chase_kernel_t<true, true>)
+    emu_run(grid, block, smem, /*concurrent=*/true, [&] { tq::sb2st_chase_kernel_t<true, true>(a); });
   else
     return cudaErrorInvalidDeviceFunction;
   return cudaSuccess;

@@ -75,6 +75,26 @@ def test_progress_protocol_distance_three_is_valid_and_minimal():
     assert broken > 0
 
 
+def test_late_load_protocol_is_valid_and_minimal():
+    """TQ_CHASE_LATE: no wait in front of the reflector step of a task k >= 1, prog >= 2 in front of task 0,
+    prog >= k + 3 in front of the D / E loads - valid under half-task interleavings, and neither wait can be weaker"""
+    n, b = 96, 8
+    A = _spd(n, 22)
+    band, _ = P.sy2sb(A, b)
+    d0, e0, _, _ = P.sb2st(band, b)
+    Bd, ldb = M.extract_band(band, b)
+    sc = np.abs(A).max()
+
+    def same(lag, lag_a, trial):
+        d, e, *_ = M.sb2st_band(Bd, ldb, n, b, ncta=3 + trial, rng=np.random.RandomState(trial), lag=lag,
+                                late_loads=True, lag_a=lag_a)
+        return np.abs(d - d0).max() <= 1e-10 * sc and np.abs(np.abs(e) - np.abs(e0)).max() <= 1e-10 * sc
+
+    assert all(same(3, 2, t) for t in range(6))
+    assert not all(same(3, 1, t) for t in range(6))
+    assert not all(same(2, 2, t) for t in range(6))
+
+
 @pytest.mark.parametrize("n", list(range(256, 1600, 64)) + [4096, 8192, 12288, 14336, 28672])
 def test_q2_wavefronts_at_model_sizes(n):
     """What apply_q2 (two_stage.cu) relies on: the groups of a wavefront are consecutive sweep blocks, start 3 b
@@ -149,9 +169,10 @@ def _emu_reduce(emu, Astore, n, grid, helper=0):
     return Bd0, Bd, Vs, tau2, d, e[:n - 1]
 
 
-@pytest.mark.parametrize("n,grid,helper", [(136, 2, 0), (256, 3, 0), (136, 3, 1)])
+@pytest.mark.parametrize("n,grid,helper", [(136, 2, 0), (256, 3, 0), (136, 3, 1), (136, 3, 2), (200, 4, 3)])
 def test_emulated_chase_kernel_matches_model(emu, n, grid, helper):
-    """helper = 1: the variant whose ninth warp owns the progress counters (TQ_CHASE_HELPER=1)"""
+    """helper bit 0: the ninth warp owns the progress counters (TQ_CHASE_HELPER=1); bit 1: second wait in front of the
+    D / E loads (TQ_CHASE_LATE=1)"""
     A = _spd(n, 100 + n)
     band = np.where(np.abs(np.subtract.outer(np.arange(n), np.arange(n))) <= B, A, 0.0)
     Bd_model, ldb = M.extract_band(band, B)
@@ -241,10 +262,10 @@ def test_whole_two_stage_path_on_the_host(host_emu, n, sms, ncols):
     _check_whole_path(host_emu, n, sms, ncols)
 
 
-@pytest.mark.parametrize("switch", ["TQ_SY2SB_GEMM", "TQ_CHASE_HELPER"])
+@pytest.mark.parametrize("switch", ["TQ_SY2SB_GEMM", "TQ_CHASE_HELPER", "TQ_CHASE_LATE"])
 def test_whole_two_stage_path_with_a_switch(switch):
-    """TQ_SY2SB_GEMM=1 (mirror pass + DGEMM instead of DSYMM) / TQ_CHASE_HELPER=1 (helper-warp variant of the bulge
-    chase) in a fresh process: the library reads its switches once"""
+    """TQ_SY2SB_GEMM=1 (mirror pass + DGEMM instead of DSYMM) / TQ_CHASE_HELPER=1, TQ_CHASE_LATE=1 (variants of the
+    bulge-chase kernel) in a fresh process: the library reads its switches once"""
     code = ("import os, sys; sys.path[:0] = [%r, %r]; os.environ[%r] = '1';"
             "import test_two_stage_emu as t; t._check_whole_path(t._load_host_emu(), 256, 2, 256)"
             ) % (ROOT, os.path.join(ROOT, "tests"), switch)
