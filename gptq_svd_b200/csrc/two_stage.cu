@@ -317,7 +317,16 @@ static int apply_q1(cublasHandle_t h, cudaStream_t st, const double* A, const do
 }
 
 // ------------------------------------------------------------------------------------------------ entry points
-bool two_stage_usable(int64_t n) { return two_stage_requested() && n % kBw == 0 && n >= 4 * kBw && n < (1 << 30); }
+// TQ_EIGH_TWO_STAGE_MIN_N=<n>: smallest order the two-stage path is used for when it is switched on (measured: level
+// with the one-stage path at n = 12288, behind it at n = 4096 - a model run wants it for the wide Hessian only)
+bool two_stage_usable(int64_t n) {
+  static int64_t min_n = -1;
+  if (min_n < 0) {
+    const char* env = getenv("TQ_EIGH_TWO_STAGE_MIN_N");
+    min_n = env ? imax(0, atoll(env)) : 0;
+  }
+  return two_stage_requested() && n % kBw == 0 && n >= 4 * kBw && n >= min_n && n < (1 << 30);
+}
 
 struct TwoStageState {
   TwoStageBuffers tb;

@@ -79,7 +79,7 @@ int tq_set_sm_budget(int sms);
 /* EXPERIMENTAL, per thread: 1 = tq_eigh / tq_spectral_solve reduce to tridiagonal form in TWO stages (band
  * reduction of width 64 by QR panels and DSYMM / DSYR2K, then bulge chasing on the L2-resident band; two
  * back-transformations) when n % 64 == 0 and n >= 256; 0 = the one-stage reduction; -1 (default) = follow the
- * environment variable TQ_EIGH_TWO_STAGE (unset: one-stage).  The workspace queries depend on this setting: query
+ * environment variable TQ_EIGH_TWO_STAGE (unset: one-stage); TQ_EIGH_TWO_STAGE_MIN_N=<n> restricts it to orders >= n.  The workspace queries depend on this setting: query
  * after changing it.  gptq_svd_b200/csrc/two_stage.cu. */
 int tq_set_eigh_two_stage(int on);
 
