@@ -69,6 +69,30 @@ static int take_two_stage(Workspace& ws, int64_t n, TwoStageBuffers& tb) {
 // A (n x n column-major, LOWER triangle referenced and updated) -> band of width b in place; the reflectors of
 // block column j stay below R in A[j + b :, j : j + b), their scalars in tau1[j : j + b).
 // scratch: overlays the D&C workspace (>= 3 n^2 doubles).
+// Side stream of the look-ahead (one per host thread, created on first use): its own cuBLAS handle, two events.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cublasHandle_t h = nullptr;
+  cudaEvent_t ev_cols = nullptr, ev_qr = nullptr;
+  int dev = -1;
+};
+static int get_side_stream(SideStream** out) {
+  static thread_local SideStream ss;
+  int dev = 0;
+  TQ_CUDA_CHECK(cudaGetDevice(&dev));
+  if (ss.s == nullptr || ss.dev != dev) {
+    TQ_CUDA_CHECK(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
+    TQ_CUDA_CHECK(cudaEventCreateWithFlags(&ss.ev_cols, cudaEventDisableTiming));
+    TQ_CUDA_CHECK(cudaEventCreateWithFlags(&ss.ev_qr, cudaEventDisableTiming));
+    TQ_CUBLAS_CHECK(cublasCreate(&ss.h));
+    TQ_CUBLAS_CHECK(cublasSetMathMode(ss.h, CUBLAS_PEDANTIC_MATH));
+    TQ_CUBLAS_CHECK(cublasSetStream(ss.h, ss.s));
+    ss.dev = dev;
+  }
+  *out = &ss;
+  return TQ_OK;
+}
+
 static int sy2sb(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double* tau1, Workspace scratch) {
   constexpr int b = kBw;
   const int64_t lda = n;
@@ -93,12 +117,29 @@ static int sy2sb(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double
     const char* env = getenv("TQ_SY2SB_GEMM");
     use_gemm = (env && env[0] && env[0] != '0') ? 1 : 0;
   }
+  // TQ_SY2SB_LOOKAHEAD=1 (not validated on a GPU yet).  Measured: ~75 of the 196 ms of this stage at n = 12288 are
+  // the latency of the panel factorisations (a 16-CTA cluster kernel, 64 columns x 3.5 - 5 us).  With the look-ahead
+  // the block column of the NEXT panel receives this panel's update first (two s x 64 x 64 DGEMMs), its QR then runs
+  // on a side stream while the main stream applies the rank-128 update to the rest of the trailing matrix
+  // (DSYR2K on rows / columns >= b): the two touch disjoint columns of A.
+  static int lookahead = -1;
+  if (lookahead < 0) {
+    const char* env = getenv("TQ_SY2SB_LOOKAHEAD");
+    lookahead = (env && env[0] && env[0] != '0') ? 1 : 0;
+  }
+  SideStream* side = nullptr;
+  if (lookahead) TQ_TRY(get_side_stream(&side));
+  bool panel_ready = false;          // the current panel has been factored already (by the previous iteration)
   for (int64_t j = 0; j + b < n; j += b) {
     const int64_t r0 = j + b, s = n - r0;
     double* P = A + r0 + j * lda;
     double* A22 = A + r0 + r0 * lda;
-    Workspace qws = scratch;                         // the panel factorisation's own scratch, released afterwards
-    TQ_TRY(qr_r_colmajor_tau(h, st, P, lda, s, b, qws, tau1 + j));
+    if (panel_ready) {
+      TQ_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev_qr, 0));      // its QR ran on the side stream
+    } else {
+      Workspace qws = scratch;                       // the panel factorisation's own scratch, released afterwards
+      TQ_TRY(qr_r_colmajor_tau(h, st, P, lda, s, b, qws, tau1 + j));
+    }
     dim3 grid((unsigned)imin(ceil_div(s, 256), 256), (unsigned)b);
     TQ_LAUNCH(copy_reflectors_kernel, grid, 256, 0, st, P, lda, s, b, Vc, s);
     TQ_LAUNCH_CHECK();
@@ -121,10 +162,31 @@ static int sy2sb(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double
     TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, b, b, int(s), &one, Vc, int(s), X2, int(s), &zero, M1, b));
     TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, b, b, b, &one, T, b, M1, b, &zero, M2, b));
     TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, int(s), b, b, &mhalf, Vc, int(s), M2, b, &one, X2, int(s)));
-    // A22 -= V W^T + W V^T
-    TQ_CUBLAS_CHECK(cublasDsyr2k(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, int(s), b, &mone, Vc, int(s), X2, int(s), &one,
-                                 A22, int(lda)));
+    panel_ready = false;
+    if (lookahead && s > b) {
+      // block column [0, b) of A22 (the next diagonal block and the next panel below it) first:
+      //   A22[:, 0:b] -= V W[0:b, :]^T + W V[0:b, :]^T
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(s), b, b, &mone, Vc, int(s), X2, int(s), &one, A22,
+                                  int(lda)));
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(s), b, b, &mone, X2, int(s), Vc, int(s), &one, A22,
+                                  int(lda)));
+      // the next panel (rows >= b of that block column) is final: factor it on the side stream ...
+      TQ_CUDA_CHECK(cudaEventRecord(side->ev_cols, st));
+      TQ_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->ev_cols, 0));
+      Workspace qws = scratch;
+      TQ_TRY(qr_r_colmajor_tau(side->h, side->s, A22 + b, lda, s - b, b, qws, tau1 + j + b));
+      TQ_CUDA_CHECK(cudaEventRecord(side->ev_qr, side->s));
+      panel_ready = true;
+      // ... while the main stream updates the rest: rows and columns >= b
+      TQ_CUBLAS_CHECK(cublasDsyr2k(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, int(s - b), b, &mone, Vc + b, int(s), X2 + b,
+                                   int(s), &one, A22 + b + b * lda, int(lda)));
+    } else {
+      // A22 -= V W^T + W V^T
+      TQ_CUBLAS_CHECK(cublasDsyr2k(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, int(s), b, &mone, Vc, int(s), X2, int(s), &one,
+                                   A22, int(lda)));
+    }
   }
+  if (panel_ready) TQ_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev_qr, 0));
   return TQ_OK;
 }
 

@@ -8,10 +8,11 @@ cd "$(dirname "$0")/.."
 sizes="${*:-4096 12288}"
 echo "== gated parity tests (default variant)"
 TQ_TEST_TWO_STAGE=1 timeout 300 python -m pytest tests/test_gpu_two_stage.py -x -q 2>&1 | tail -5
-for v in "" "TQ_CHASE_HELPER=1" "TQ_CHASE_LATE=1" "TQ_CHASE_HELPER=1 TQ_CHASE_LATE=1" "TQ_SY2SB_GEMM=1"; do
+for v in "" "TQ_CHASE_HELPER=1" "TQ_CHASE_LATE=1" "TQ_CHASE_HELPER=1 TQ_CHASE_LATE=1" "TQ_SY2SB_GEMM=1" \
+         "TQ_SY2SB_LOOKAHEAD=1" "TQ_SY2SB_LOOKAHEAD=1 TQ_CHASE_HELPER=1 TQ_CHASE_LATE=1"; do
   echo "== variant: ${v:-default}"
   # shellcheck disable=SC2086
   env $v TQ_TRACE=1 timeout 120 python scripts/two_stage_probe.py $sizes 2>&1 | grep -E "sy2sb|sb2st|apply_q|^\{" | tail -24
 done
-echo "== parity tests once more with the fastest-looking chase variant (edit as needed)"
-TQ_CHASE_HELPER=1 TQ_CHASE_LATE=1 TQ_TEST_TWO_STAGE=1 timeout 300 python -m pytest tests/test_gpu_two_stage.py -x -q 2>&1 | tail -5
+echo "== parity tests once more with every new variant switched on"
+TQ_SY2SB_LOOKAHEAD=1 TQ_CHASE_HELPER=1 TQ_CHASE_LATE=1 TQ_TEST_TWO_STAGE=1 timeout 300 python -m pytest tests/test_gpu_two_stage.py -x -q 2>&1 | tail -5

@@ -86,6 +86,28 @@ cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind
   return cudaSuccess;
 }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+// streams and events: every operation of the emulation runs at once and in program order, so a side stream is only
+// a tag here - the look-ahead's ARITHMETIC is checked, its two event dependencies are argued in two_stage.cu
+cudaError_t cudaGetDevice(int* dev) {
+  *dev = 0;
+  return cudaSuccess;
+}
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned int) {
+  *s = reinterpret_cast<cudaStream_t>(0x1);
+  return cudaSuccess;
+}
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned int) {
+  *e = reinterpret_cast<cudaEvent_t>(0x1);
+  return cudaSuccess;
+}
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int) { return cudaSuccess; }
+cublasStatus_t cublasCreate_v2(cublasHandle_t* h) {
+  *h = nullptr;
+  return CUBLAS_STATUS_SUCCESS;
+}
+cublasStatus_t cublasSetMathMode(cublasHandle_t, cublasMath_t) { return CUBLAS_STATUS_SUCCESS; }
+cublasStatus_t cublasSetStream_v2(cublasHandle_t, cudaStream_t) { return CUBLAS_STATUS_SUCCESS; }
 const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
 cudaError_t cudaLaunchCooperativeKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t) {

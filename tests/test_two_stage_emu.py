@@ -262,10 +262,11 @@ def test_whole_two_stage_path_on_the_host(host_emu, n, sms, ncols):
     _check_whole_path(host_emu, n, sms, ncols)
 
 
-@pytest.mark.parametrize("switch", ["TQ_SY2SB_GEMM", "TQ_CHASE_HELPER", "TQ_CHASE_LATE"])
+@pytest.mark.parametrize("switch", ["TQ_SY2SB_GEMM", "TQ_SY2SB_LOOKAHEAD", "TQ_CHASE_HELPER", "TQ_CHASE_LATE"])
 def test_whole_two_stage_path_with_a_switch(switch):
-    """TQ_SY2SB_GEMM=1 (mirror pass + DGEMM instead of DSYMM) / TQ_CHASE_HELPER=1, TQ_CHASE_LATE=1 (variants of the
-    bulge-chase kernel) in a fresh process: the library reads its switches once"""
+    """TQ_SY2SB_GEMM=1 (mirror pass + DGEMM instead of DSYMM), TQ_SY2SB_LOOKAHEAD=1 (next panel factored next to the
+    trailing update; the emulation checks its arithmetic, not its stream dependencies), TQ_CHASE_HELPER=1,
+    TQ_CHASE_LATE=1 (variants of the bulge-chase kernel) in a fresh process: the library reads its switches once"""
     code = ("import os, sys; sys.path[:0] = [%r, %r]; os.environ[%r] = '1';"
             "import test_two_stage_emu as t; t._check_whole_path(t._load_host_emu(), 256, 2, 256)"
             ) % (ROOT, os.path.join(ROOT, "tests"), switch)
