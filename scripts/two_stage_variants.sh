@@ -16,3 +16,6 @@ for v in "" "TQ_CHASE_HELPER=1" "TQ_CHASE_LATE=1" "TQ_CHASE_HELPER=1 TQ_CHASE_LA
 done
 echo "== parity tests once more with every new variant switched on"
 TQ_SY2SB_LOOKAHEAD=1 TQ_CHASE_HELPER=1 TQ_CHASE_LATE=1 TQ_TEST_TWO_STAGE=1 timeout 300 python -m pytest tests/test_gpu_two_stage.py -x -q 2>&1 | tail -5
+echo "== whole solver (tq_spectral_solve) at n = 12288: one-stage, then two-stage with every new variant"
+timeout 120 python scripts/solver_sweep.py 12288 2>&1 | tail -1
+TQ_EIGH_TWO_STAGE=1 TQ_SY2SB_LOOKAHEAD=1 TQ_CHASE_HELPER=1 TQ_CHASE_LATE=1 timeout 120 python scripts/solver_sweep.py 12288 2>&1 | tail -1
