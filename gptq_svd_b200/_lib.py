@@ -22,8 +22,14 @@ TQ_LOOP_STRICT_FP32 = 0x100
 
 _i64, _i32, _vp, _sz, _dbl = C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_double
 
+PROF_KINDS = ["sytrd_panel_sym_kernel", "sytrd_panel_kernel", "qrcp_panel_kernel", "sb2st_chase_kernel",
+              "pchol_panel_kernel", "qr_cluster_panel_kernel", "gptq_block_kernel", "trailing_tc_kernel",
+              "trailing_update_kernel", "syrk_tcgen05_kernel"]
+PROF_UNIT = ["B", "B", "B", "B", "B", "B", "B", "flop", "flop", "flop"]
+
 STAGE_CALLBACK = C.CFUNCTYPE(None, C.c_int, C.c_void_p)
 TQ_STAGE_SYTRD_DONE = 1
+TQ_STAGE_BAND_DONE = 2
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -34,9 +40,15 @@ SIGNATURES = {
     "tq_two_stage_debug": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp],
     "tq_set_stage_callback": [STAGE_CALLBACK, _vp],
     "tq_profile_begin": [_i32],
+    "tq_profile_kernel": [_i32, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_dbl),
+                          C.POINTER(_dbl)],
     "tq_profile_end": [C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_i64), C.POINTER(_i64)],
     "tq_last_error": [],
     "tq_syrk_accum": [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _i32, _vp],
+    "tq_syrk_accum_scaled": [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _i32, _vp, _vp],
+    "tq_cast_to_f16_scaled": [_vp, _i32, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp],
+    "tq_hessian_probe_accum": [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp],
+    "tq_hessian_probe_check": [_vp, _i64, _i64, _vp, _dbl, _vp, _vp, _vp],
     "tq_hessian_scale": [_vp, _i64, _i64, _i64, _vp, _i64, _vp],
     "tq_cast_to_f16": [_vp, _i32, _i64, _i64, _i64, _vp, _i64, _vp],
     "tq_solver_workspace": [_i64, C.POINTER(_sz)],

@@ -15,19 +15,27 @@ thread_local int64_t g_launch_count = 0;
 struct ProfSlot {
   cudaEvent_t e0, e1;
   double bytes;
+  int kind;
+  int sms;       // SM budget of the launching thread (tq_set_sm_budget) when the launch was made
 };
 static thread_local bool g_prof_on = false;
 static thread_local int g_prof_every = 1;
-static thread_local int64_t g_prof_seen = 0;
+static thread_local int64_t g_prof_seen = 0;                       // kinds 0..2 (tq_profile_end's total)
+static thread_local int64_t g_prof_seen_kind[TQ_PROF_KINDS] = {};
+static thread_local double g_prof_work_all[TQ_PROF_KINDS] = {};    // work of EVERY launch of the kind, sampled or not
 static thread_local std::vector<ProfSlot> g_prof_slots;
 
-int prof_begin_launch(cudaStream_t st, double alg_bytes) {
-  if (!g_prof_on) return -1;
-  const int64_t idx = g_prof_seen++;
-  if (idx % g_prof_every != 0 || g_prof_slots.size() >= 8192) return -1;
+int prof_begin_launch(cudaStream_t st, double work, int kind) {
+  if (!g_prof_on || kind < 0 || kind >= TQ_PROF_KINDS) return -1;
+  const int64_t idx = g_prof_seen_kind[kind]++;
+  g_prof_work_all[kind] += work;
+  if (kind <= TQ_PROF_QRCP_PANEL) ++g_prof_seen;
+  if (idx % g_prof_every != 0 || g_prof_slots.size() >= 16384) return -1;
   ProfSlot s;
   if (cudaEventCreate(&s.e0) != cudaSuccess || cudaEventCreate(&s.e1) != cudaSuccess) return -1;
-  s.bytes = alg_bytes;
+  s.bytes = work;
+  s.kind = kind;
+  s.sms = num_sms();
   cudaEventRecord(s.e0, st);
   g_prof_slots.push_back(s);
   return int(g_prof_slots.size()) - 1;
@@ -93,16 +101,9 @@ StageTimer::~StageTimer() {
   }
 }
 
-static thread_local int g_two_stage = -1;      // -1: follow TQ_EIGH_TWO_STAGE, 0 / 1: tq_set_eigh_two_stage
-bool two_stage_requested() {
-  if (g_two_stage >= 0) return g_two_stage == 1;
-  static int env = -1;
-  if (env < 0) {
-    const char* e = getenv("TQ_EIGH_TWO_STAGE");
-    env = (e && e[0] && e[0] != '0') ? 1 : 0;
-  }
-  return env == 1;
-}
+// -1: automatic (two-stage from kTwoStageMinN on), 0 / 1: tq_set_eigh_two_stage
+static thread_local int g_two_stage = -1;
+int two_stage_setting() { return g_two_stage; }
 
 static thread_local int g_sm_budget = 0;
 static thread_local void (*g_stage_cb)(int, void*) = nullptr;
@@ -116,7 +117,8 @@ void notify_stage(int stage) {
 // SMs the calling thread's persistent (co-resident) kernels may occupy: the device's count, or the
 // budget set with tq_set_sm_budget so that several solves can be in flight on one GPU.
 int num_sms() {
-  static thread_local int cached = 0;
+  static thread_local int cached_sms[kMaxDevices] = {};
+  int& cached = cached_sms[device_slot()];
   if (!cached) {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -139,24 +141,56 @@ extern "C" int tq_profile_begin(int sample_every) {
   g_prof_on = true;
   g_prof_every = sample_every > 0 ? sample_every : 1;
   g_prof_seen = 0;
+  for (int k = 0; k < TQ_PROF_KINDS; ++k) {
+    g_prof_seen_kind[k] = 0;
+    g_prof_work_all[k] = 0.0;
+  }
+  return TQ_OK;
+}
+
+extern "C" int tq_profile_kernel(int kind, double* work, double* ms, int64_t* sampled, int64_t* total,
+                                 double* work_all, double* sm_ms) {
+  using namespace tq;
+  TQ_REQUIRE(kind >= 0 && kind < TQ_PROF_KINDS, "tq_profile_kernel: unknown kind %d", kind);
+  double b = 0, t = 0, smt = 0;
+  int64_t cnt = 0;
+  for (auto& s : g_prof_slots) {
+    if (s.kind != kind) continue;
+    float f = 0;
+    if (cudaEventSynchronize(s.e1) == cudaSuccess && cudaEventElapsedTime(&f, s.e0, s.e1) == cudaSuccess) {
+      b += s.bytes;
+      t += f;
+      smt += double(f) * s.sms;
+      ++cnt;
+    }
+  }
+  if (sm_ms) *sm_ms = smt;
+  if (work) *work = b;
+  if (ms) *ms = t;
+  if (sampled) *sampled = cnt;
+  if (total) *total = g_prof_seen_kind[kind];
+  if (work_all) *work_all = g_prof_work_all[kind];
   return TQ_OK;
 }
 
 extern "C" int tq_profile_end(double* alg_bytes, double* ms, int64_t* sampled, int64_t* total) {
   using namespace tq;
   double b = 0, t = 0;
+  int64_t cnt = 0;
   for (auto& s : g_prof_slots) {
     float f = 0;
-    if (cudaEventSynchronize(s.e1) == cudaSuccess && cudaEventElapsedTime(&f, s.e0, s.e1) == cudaSuccess) {
+    if (s.kind <= TQ_PROF_QRCP_PANEL && cudaEventSynchronize(s.e1) == cudaSuccess &&
+        cudaEventElapsedTime(&f, s.e0, s.e1) == cudaSuccess) {
       b += s.bytes;
       t += f;
+      ++cnt;
     }
     cudaEventDestroy(s.e0);
     cudaEventDestroy(s.e1);
   }
   if (alg_bytes) *alg_bytes = b;
   if (ms) *ms = t;
-  if (sampled) *sampled = int64_t(g_prof_slots.size());
+  if (sampled) *sampled = cnt;
   if (total) *total = g_prof_seen;
   g_prof_slots.clear();
   g_prof_on = false;

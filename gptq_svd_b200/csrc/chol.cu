@@ -81,13 +81,9 @@ __global__ void __launch_bounds__(1024) chol_diag_block_kernel(double* __restric
 }
 
 // in place lower Cholesky of A (n x n col-major, ld n); returns TQ_ERR_NOCONV when not positive definite
-static int chol_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, int* fail) {
-  static thread_local bool attr = false;
-  if (!attr) {
-    TQ_CUDA_CHECK(cudaFuncSetAttribute(chol_diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kChNb * kChNb * 8));
-    attr = true;
-  }
+int chol_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, int* fail) {
+  TQ_CUDA_CHECK(cudaFuncSetAttribute(chol_diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kChNb * kChNb * 8));
   const double one = 1.0, mone = -1.0;
   TQ_CUDA_CHECK(cudaMemsetAsync(fail, 0, sizeof(int), st));
   for (int64_t j0 = 0; j0 < n; j0 += kChNb) {

@@ -49,8 +49,9 @@ extern thread_local int64_t g_launch_count;
     TQ_CUDA_CHECK(cudaGetLastError());   \
   } while (0)
 
-// sampled event timing of the dominant BLAS-2 kernel (see tq_profile_begin)
-int prof_begin_launch(cudaStream_t st, double alg_bytes);   // returns a slot or -1
+// sampled event timing of the library's own hot kernels (see tq_profile_begin / tq_profile_kernel); `kind` is one
+// of the TQ_PROF_* ids of truncgptq.h, `work` the algorithmic bytes or flops of the launch
+int prof_begin_launch(cudaStream_t st, double work, int kind = 0);   // returns a slot or -1
 void prof_end_launch(cudaStream_t st, int slot);
 
 static inline int64_t imin(int64_t a, int64_t b) { return a < b ? a : b; }
@@ -82,6 +83,14 @@ struct Workspace {
 static inline size_t ws_bytes_for(size_t count, size_t elem) { return align_up(count * elem, 256) + 256; }
 
 int num_sms();
+// index of the current device for the per-device one-shot caches (function attributes, occupancy): a host
+// thread may work on several GPUs, and cudaFuncSetAttribute / occupancy results are per device
+constexpr int kMaxDevices = 64;
+static inline int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev % kMaxDevices;
+}
 
 // optional per-thread stage callback (tq_set_stage_callback)
 bool stage_callback_set();

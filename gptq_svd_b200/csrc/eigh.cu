@@ -839,7 +839,8 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
   TQ_CUDA_CHECK(cudaMemsetAsync(tau, 0, sizeof(double) * n, st));
   TQ_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 16, st));
   TQ_CUDA_CHECK(cudaMemsetAsync(e, 0, sizeof(double) * n, st));
-  static thread_local int coop_per_sm = 0;
+  static thread_local int coop_per_sm_dev[kMaxDevices] = {};
+  int& coop_per_sm = coop_per_sm_dev[device_slot()];
   if (!coop_per_sm) {
     int per_sm = 0;
     TQ_CUDA_CHECK(cudaFuncSetAttribute(sytrd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -854,54 +855,34 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
   }
   const int coop_blocks = num_sms() * coop_per_sm;      // num_sms() honours tq_set_sm_budget
   // symmetric TMA panel (half the DRAM bytes) whenever the tensor map can be built: even n (16-byte
-  // row pitch).  TQ_SYTRD_COLDOT=1 keeps the column-dot panel for A/B timing.
-  static thread_local int sym_ok = -1;
-  if (sym_ok < 0) {
-    sym_ok = 0;
-    const char* env = getenv("TQ_SYTRD_COLDOT");
-    if (!(env && env[0] && env[0] != '0')) {
-      int per_sm = 0;
-      TQ_CUDA_CHECK(cudaFuncSetAttribute(sytrd_panel_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         int(kSymSmem)));
-      TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sytrd_panel_sym_kernel, kSymThreads,
-                                                                  kSymSmem));
-      if (per_sm >= 1) sym_ok = 1;
-    }
+  // row pitch); the column-dot panel stays for odd n.
+  int sym_ok = 0;
+  {
+    int per_sm = 0;
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(sytrd_panel_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(kSymSmem)));
+    TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sytrd_panel_sym_kernel, kSymThreads,
+                                                                kSymSmem));
+    if (per_sm >= 1) sym_ok = 1;
   }
   const int sym_blocks = sym_ok ? num_sms() : 0;
   const bool use_sym = sym_blocks > 0 && (n % 2 == 0) && n >= 256 && (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(W) % 16 == 0);
   CUtensorMap tmA, tmW;
-  int boxc = 64;
-  if (const char* bx = getenv("TQ_SYM_BOXC")) boxc = atoi(bx);
-  if (boxc != 64 && boxc != 32 && boxc != 16 && boxc != 8) boxc = 64;
-  int align = (n % 32 == 0 && reinterpret_cast<uintptr_t>(A) % 256 == 0 && reinterpret_cast<uintptr_t>(W) % 256 == 0) ? 32 : 2;
-  if (const char* al = getenv("TQ_SYM_ALIGN")) align = atoi(al) == 2 ? 2 : align;
+  const int boxc = 64;
+  const int align = (n % 32 == 0 && reinterpret_cast<uintptr_t>(A) % 256 == 0 && reinterpret_cast<uintptr_t>(W) % 256 == 0) ? 32 : 2;
   if (use_sym) {
     TQ_TRY(make_tmap_f64(&tmA, A, uint64_t(n), uint64_t(n), uint64_t(n), kTileR, boxc));
     TQ_TRY(make_tmap_f64(&tmW, W, uint64_t(n), uint64_t(kTrdNb), uint64_t(n), kTileR, boxc));
     // W is read through TMA before every column of it has been written: keep stale NaNs out of it
     TQ_CUDA_CHECK(cudaMemsetAsync(W, 0, sizeof(double) * size_t(n) * kTrdNb, st));
   }
-  // With a stage callback set, TQ_STAGE_TAIL_LEN=<rows> reports the end of the bandwidth-bound part EARLY, once
-  // the trailing matrix has shrunk to that many rows.  Off by default: measured with bench.py it is a loss
-  // (1.83 s per layer at 4096 / 6144 rows vs 1.58 s when the callback fires at the end of the reduction) - the
-  // narrow solves' cooperative panels then gang-schedule against the wide solve's remaining panel launches.
-  int64_t early_len = 0;
+  // (Reporting TQ_STAGE_SYTRD_DONE early, once the trailing matrix has shrunk to 4096 - 6144 rows, was measured
+  // with bench.py and is a loss - 1.83 s per layer vs 1.58 s: the narrow solves' cooperative panels then
+  // gang-schedule against the wide solve's remaining panel launches.  The callback fires at the end.)
   g_sytrd_notified = false;
-  if (stage_callback_set()) {
-    const char* e = getenv("TQ_STAGE_TAIL_LEN");
-    early_len = e ? atoll(e) : 0;
-  }
-  bool notified = false;
   for (int64_t j0 = 0; j0 < n; j0 += kTrdNb) {
     const int jb = int(imin(kTrdNb, n - j0));
-    if (early_len > 0 && !notified && j0 > 0 && n - j0 <= early_len) {
-      TQ_CUDA_CHECK(cudaStreamSynchronize(st));
-      notify_stage(TQ_STAGE_SYTRD_DONE);
-      notified = true;
-      g_sytrd_notified = true;
-    }
     if (use_sym) {
       for (int i = 0; i < jb; ++i) {
         if (sym_max_slots(n - (j0 + i) - 1, int((j0 + i + 1) % align), i > 0, sym_blocks) > kRowSlots) {
@@ -918,7 +899,7 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
         const double len = double(n - (j0 + i) - 1);
         bytes += len * (0.5 * len + 2.0 * i) * 8.0;
       }
-      const int pslot = prof_begin_launch(st, bytes);
+      const int pslot = prof_begin_launch(st, bytes, TQ_PROF_SYTRD_SYM);
       TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sytrd_panel_sym_kernel, dim3(sym_blocks), dim3(kSymThreads),
                                                 kargs, kSymSmem, st));
       prof_end_launch(st, pslot);
@@ -932,7 +913,7 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
         const double len = double(n - (j0 + i) - 1);
         bytes += len * (len + 2.0 * i) * 8.0;
       }
-      const int pslot = prof_begin_launch(st, bytes);
+      const int pslot = prof_begin_launch(st, bytes, TQ_PROF_SYTRD_COLDOT);
       TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sytrd_panel_kernel, dim3(coop_blocks), dim3(kPanelThreads),
                                                 kargs, kPanelSmem, st));
       prof_end_launch(st, pslot);
@@ -941,12 +922,7 @@ static int sytrd_lower(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, 
     const int64_t r0 = j0 + jb;
     const int64_t s2 = n - r0;
     if (s2 > 0) {
-      static int use_syr2k = -1;
-      if (use_syr2k < 0) {
-        const char* e = getenv("TQ_SYTRD_NO_SYR2K");
-        use_syr2k = (e && e[0] && e[0] != '0') ? 0 : 1;
-      }
-      if (use_sym && use_syr2k) {
+      if (use_sym) {
         // A22 -= V2 W2^T + W2 V2^T on the LOWER triangle only (DSYR2K, half the flops): the symmetric panel
         // kernel, phases A / C and ormtr never read above the diagonal.  844 ms vs 870 at n = 12288.
         TQ_CUBLAS_CHECK(cublasDsyr2k(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, int(s2), jb, &mone, A + r0 + j0 * lda,
@@ -1618,9 +1594,12 @@ size_t eigh_ws_bytes(int64_t n) {
   return b;
 }
 
-// w (n, ascending) and Zout (n x n column-major, ld n: column i = eigenvector i)
+// w (n, ascending) and Zout (n x n column-major, ld n: column i = eigenvector i).
+// `choose` (optional) runs once all eigenvalues are on the device (after the divide & conquer, before any
+// eigenvector is back-transformed) and names the columns [col0, col0 + ncols) the caller needs: only those are
+// back-transformed - the other columns of Zout keep eigenvectors of the TRIDIAGONAL matrix and must not be used.
 int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ldh, int64_t n, double* w,
-                  double* Zout, Workspace& ws) {
+                  double* Zout, Workspace& ws, const EighColumnChooser& choose) {
   double* A = ws.take<double>(size_t(n) * n);
   double* e = ws.take<double>(n);
   double* tau = ws.take<double>(n);
@@ -1685,12 +1664,22 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
       set_error("eigh: workspace too small (ormtr)");
       return TQ_ERR_WORKSPACE;
     }
+    int64_t col0 = 0, ncols = n;
+    if (choose) {
+      TQ_TRY(choose(w, &col0, &ncols));
+      if (col0 < 0 || ncols < 0 || col0 + ncols > n) {
+        set_error("eigh: column chooser returned [%lld, +%lld) outside [0, %lld)", (long long)col0, (long long)ncols,
+                  (long long)n);
+        return TQ_ERR_INVALID;
+      }
+    }
+    if (ncols == 0) return TQ_OK;
     if (two_stage) {
-      TQ_TRY(two_stage_back(h, st, A, n, Zout, n, ws));
+      TQ_TRY(two_stage_back(h, st, A, n, Zout + col0 * n, ncols, ws));
       return TQ_OK;
     }
     StageTimer tm(st, "ormtr");
-    TQ_TRY(ormtr_lower(h, st, A, tau, n, Zout, n, Vc, G, T, w1, w2));
+    TQ_TRY(ormtr_lower(h, st, A, tau, n, Zout + col0 * n, ncols, Vc, G, T, w1, w2));
   }
   return TQ_OK;
 }
@@ -1710,5 +1699,5 @@ extern "C" int tq_eigh(const double* H, int64_t ldh, int64_t n, double* w, doubl
   cublasHandle_t h;
   TQ_TRY(get_cublas(&h, st));
   // column-major Z (column i = eigenvector i) is the same memory as row-major V (row i = eigenvector i)
-  return eigh_colmajor(h, st, H, ldh, n, w, V, wsp);
+  return eigh_colmajor(h, st, H, ldh, n, w, V, wsp, nullptr);
 }

@@ -175,7 +175,8 @@ gptq_block_kernel(float* __restrict__ Wp, int64_t n, const float* __restrict__ U
                   const float* __restrict__ dvec, const float* __restrict__ scale,
                   const float* __restrict__ zero, int ng, const int* __restrict__ gidx, int64_t m,
                   int64_t c0, int cnt, float min_q, float max_q, float* __restrict__ E /* + column offset */,
-                  float* __restrict__ E_lo /* non-null: E receives the TF32 hi part */, uint8_t* __restrict__ Cp) {
+                  float* __restrict__ E_hi /* non-null: TF32 hi / lo halves for the tcgen05 update */,
+                  float* __restrict__ E_lo, uint8_t* __restrict__ Cp) {
   extern __shared__ float Us[];  // [kBlk][kBlk]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int idx = tid; idx < kBlk * kBlk; idx += blockDim.x) {
@@ -253,13 +254,12 @@ gptq_block_kernel(float* __restrict__ Wp, int64_t n, const float* __restrict__ U
     for (int cc = 0; cc < 4; ++cc) {
       int col = 4 * lane + cc;
       const float ev = (col < cnt) ? eo[rr][cc] : 0.f;
-      if (E_lo) {
+      E[r * kMacro + col] = ev;
+      if (E_hi) {
         float hi, lo;
         split_tf32(ev, hi, lo);
-        E[r * kMacro + col] = hi;
+        E_hi[r * kMacro + col] = hi;
         E_lo[r * kMacro + col] = lo;
-      } else {
-        E[r * kMacro + col] = ev;
       }
       if (col < cnt) {
         Wp[r * n + c0 + col] = w[rr][cc];
@@ -270,9 +270,19 @@ gptq_block_kernel(float* __restrict__ Wp, int64_t n, const float* __restrict__ U
 }
 
 // ------------------------------------------------------------------ lazy trailing update (SIMT)
-// C[m x N] -= A[m x K] . B[K x N], K <= 128, strict fp32 (the reference disables TF32,
-// gptq_utils.py:474-475).  64 x 64 tile per CTA, 4 x 4 per thread.
+// C[m x N] -= A[m x K] . B[K x N], K <= 1024, strict fp32 (the reference disables TF32,
+// gptq_utils.py:474-475).  64 x 64 tile per CTA, 4 x 4 per thread, k ascending.  Three arithmetics:
+//   kSeqDelta   acc = sum_k a b (FMA chain from 0), C = C - acc: the structure of the reference's cross-block
+//               update W[:, i2:] -= E @ Scale (:539-545; an SGEMM, then one subtraction);
+//   kSeqFma     acc = C, acc = fma(-a, b, acc) for k ascending: BIT-IDENTICAL to applying the K rank-1 updates of the
+//               Triton kernel one after another (W -= e (x) corr contracted to an FMA, :380-386).  Pairs (c, j) inside
+//               one reference block must be updated this way: every step rounds at the magnitude of W, and a
+//               trajectory that rounds differently flips ~0.2-0.5 % of the codes at n = 4096 on an ill-conditioned
+//               spectrum (measured: the reference arithmetic on a CPU, with against without FMA contraction);
+//   kSeqMulSub  acc = C, acc = acc - rn(a b): the torch loop's unfused W1[:, c:] -= e * R[c, c:] (:531).
 constexpr int kTM = 64, kTN = 64, kTK = 32;
+constexpr int kSeqDelta = 0, kSeqFma = 1, kSeqMulSub = 2;
+template <int MODE>
 __global__ void __launch_bounds__(256)
 trailing_update_kernel(float* __restrict__ C, int64_t ldc, const float* __restrict__ A, int64_t lda,
                        const float* __restrict__ B, int64_t ldb, int64_t m, int64_t N, int K) {
@@ -282,6 +292,15 @@ trailing_update_kernel(float* __restrict__ C, int64_t ldc, const float* __restri
   const int64_t row0 = int64_t(blockIdx.y) * kTM, col0 = int64_t(blockIdx.x) * kTN;
   const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
   float acc[4][4] = {};
+  if (MODE != kSeqDelta) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t gr = row0 + tr + i, gc = col0 + tc + j;
+        acc[i][j] = (gr < m && gc < N) ? C[gr * ldc + gc] : 0.f;
+      }
+  }
   for (int k0 = 0; k0 < K; k0 += kTK) {
     for (int idx = tid; idx < kTM * kTK; idx += 256) {
       int r = idx / kTK, kk = idx % kTK;
@@ -302,7 +321,11 @@ trailing_update_kernel(float* __restrict__ C, int64_t ldc, const float* __restri
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) {
+          if (MODE == kSeqDelta) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+          else if (MODE == kSeqFma) acc[i][j] = fmaf(-av[i], bv[j], acc[i][j]);
+          else acc[i][j] = __fsub_rn(acc[i][j], __fmul_rn(av[i], bv[j]));
+        }
     }
     __syncthreads();
   }
@@ -313,7 +336,7 @@ trailing_update_kernel(float* __restrict__ C, int64_t ldc, const float* __restri
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int64_t gc = col0 + tc + j;
-      if (gc < N) C[gr * ldc + gc] = __fsub_rn(C[gr * ldc + gc], acc[i][j]);
+      if (gc < N) C[gr * ldc + gc] = (MODE == kSeqDelta) ? __fsub_rn(C[gr * ldc + gc], acc[i][j]) : acc[i][j];
     }
   }
 }
@@ -406,7 +429,7 @@ extern "C" int tq_gptq_loop_workspace(int64_t m, int64_t n, int64_t k, size_t* b
   size_t b = 0;
   b += ws_bytes_for(size_t(m) * n, 4);     // Wp
   b += ws_bytes_for(size_t(k) * n, 4);     // U
-  b += ws_bytes_for(size_t(m) * kMacro, 4) * 2;  // E (hi), E_lo: m x 1024
+  b += ws_bytes_for(size_t(m) * kMacro, 4) * 3;  // E, E_hi, E_lo: m x 1024
   b += ws_bytes_for(size_t(k + 4) * n, 4) * 2; // UT_hi, UT_lo
   b += ws_bytes_for(size_t(m) * n, 1);     // Cp
   b += ws_bytes_for(size_t(n), 4) * 2;     // invperm, gidx
@@ -446,6 +469,7 @@ extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dt
   float* Wp = wsp.take<float>(size_t(m) * n);
   float* U = wsp.take<float>(size_t(k) * n);
   float* E = wsp.take<float>(size_t(m) * kMacro);
+  float* E_hi = wsp.take<float>(size_t(m) * kMacro);
   float* E_lo = wsp.take<float>(size_t(m) * kMacro);
   const int64_t kpad = (k + 3) / 4 * 4;
   float* U_hi = wsp.take<float>(size_t(kpad) * n);   // U^T hi / lo, n x kpad
@@ -487,45 +511,70 @@ extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dt
   }
 
   const size_t smem = size_t(kBlk) * kBlk * sizeof(float);
-  static thread_local bool attr_done = false;
-  if (!attr_done) {
-    TQ_CUDA_CHECK(cudaFuncSetAttribute(gptq_block_kernel<TQ_LOOP_TRITON>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TQ_CUDA_CHECK(cudaFuncSetAttribute(gptq_block_kernel<TQ_LOOP_TORCH>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  TQ_CUDA_CHECK(cudaFuncSetAttribute(gptq_block_kernel<TQ_LOOP_TRITON>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TQ_CUDA_CHECK(cudaFuncSetAttribute(gptq_block_kernel<TQ_LOOP_TORCH>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TrailingTc tc;
-  if (use_tc) TQ_TRY(trailing_tc_prepare(&tc, E, E_lo, m, U_hi, U_lo, kpad, n));
-  TQ_CUDA_CHECK(cudaMemsetAsync(E, 0, sizeof(float) * size_t(m) * kMacro * 2, st));   // E and E_lo are adjacent
+  if (use_tc) TQ_TRY(trailing_tc_prepare(&tc, E_hi, E_lo, m, U_hi, U_lo, kpad, n));
+  TQ_CUDA_CHECK(cudaMemsetAsync(E, 0, sizeof(float) * size_t(m) * kMacro, st));
+  TQ_CUDA_CHECK(cudaMemsetAsync(E_hi, 0, sizeof(float) * size_t(m) * kMacro, st));
+  TQ_CUDA_CHECK(cudaMemsetAsync(E_lo, 0, sizeof(float) * size_t(m) * kMacro, st));
   const unsigned row_ctas = (unsigned)ceil_div(m, kRowsPerWarp * kWarpsPerCta);
   // Two-level lazy batching: 128-column block steps update only the rest of their 1024-column
   // macro block (K = 128); the far columns are updated once per macro block with K = 1024.
-  auto trailing = [&](int64_t j0, int64_t N, int64_t e_col0, int64_t u_row0, int kcount) -> int {
+  // Pairs (c, j) inside one REFERENCE block are updated with the reference's own arithmetic - the K rank-1 updates
+  // one after another, each rounded at the magnitude of W (trailing_update_kernel<kSeqFma / kSeqMulSub>) - and
+  // pairs across reference blocks as a product that is subtracted once (tcgen05 3xTF32 GEMM, or the SIMT
+  // kSeqDelta kernel with TQ_LOOP_STRICT_FP32), like the reference's E @ Scale (gptq_utils.py:539-545).
+  auto trailing = [&](int64_t j0, int64_t N, int64_t e_col0, int64_t u_row0, int kcount, int mode) -> int {
     if (N <= 0 || kcount <= 0) return TQ_OK;
-    if (use_tc) return trailing_tc_launch(&tc, Wp + j0, n, m, N, e_col0, u_row0, kcount, j0, st);
+    if (mode == kSeqDelta && use_tc) return trailing_tc_launch(&tc, Wp + j0, n, m, N, e_col0, u_row0, kcount, j0, st);
     dim3 grid((unsigned)ceil_div(N, kTN), (unsigned)ceil_div(m, kTM));
-    trailing_update_kernel<<<grid, 256, 0, st>>>(Wp + j0, n, E + e_col0, kMacro, U + u_row0 * n + j0, n, m, N, kcount);
+    const int pslot = prof_begin_launch(st, 2.0 * double(m) * double(N) * double(kcount), TQ_PROF_TRAILING_SEQ);
+    float* Cj = Wp + j0;
+    const float* Ej = E + e_col0;
+    const float* Uj = U + u_row0 * n + j0;
+    if (mode == kSeqFma)
+      trailing_update_kernel<kSeqFma><<<grid, 256, 0, st>>>(Cj, n, Ej, kMacro, Uj, n, m, N, kcount);
+    else if (mode == kSeqMulSub)
+      trailing_update_kernel<kSeqMulSub><<<grid, 256, 0, st>>>(Cj, n, Ej, kMacro, Uj, n, m, N, kcount);
+    else
+      trailing_update_kernel<kSeqDelta><<<grid, 256, 0, st>>>(Cj, n, Ej, kMacro, Uj, n, m, N, kcount);
+    prof_end_launch(st, pslot);
     TQ_LAUNCH_CHECK();
     return TQ_OK;
   };
+  const int seq_mode = semantics == TQ_LOOP_TRITON ? kSeqFma : kSeqMulSub;
   for (int64_t M0 = 0; M0 < k; M0 += kMacro) {
     const int64_t M1 = imin(M0 + kMacro, k);
     for (int64_t c0 = M0; c0 < M1; c0 += kBlk) {
       const int cnt = int(imin(kBlk, M1 - c0));
       float* Eb = E + (c0 - M0);
+      float* Ehb = use_tc ? E_hi + (c0 - M0) : nullptr;
       float* Elb = use_tc ? E_lo + (c0 - M0) : nullptr;
+      const int bslot = prof_begin_launch(st, double(m) * cnt * 8.0, TQ_PROF_LOOP_BLOCK);
       if (semantics == TQ_LOOP_TRITON)
         gptq_block_kernel<TQ_LOOP_TRITON><<<row_ctas, kWarpsPerCta * 32, smem, st>>>(
-            Wp, n, U, dvec, scale, zero, ng, gidx, m, c0, cnt, min_q, max_q, Eb, Elb, Cp);
+            Wp, n, U, dvec, scale, zero, ng, gidx, m, c0, cnt, min_q, max_q, Eb, Ehb, Elb, Cp);
       else
         gptq_block_kernel<TQ_LOOP_TORCH><<<row_ctas, kWarpsPerCta * 32, smem, st>>>(
-            Wp, n, U, dvec, scale, zero, ng, gidx, m, c0, cnt, min_q, max_q, Eb, Elb, Cp);
+            Wp, n, U, dvec, scale, zero, ng, gidx, m, c0, cnt, min_q, max_q, Eb, Ehb, Elb, Cp);
+      prof_end_launch(st, bslot);
       TQ_LAUNCH_CHECK();
       const int64_t j0 = c0 + cnt;
-      TQ_TRY(trailing(j0, M1 - j0, c0 - M0, c0, cnt));                 // rest of the macro block
+      // rest of the macro block: up to the end of the reference block sequentially, beyond it as a product
+      const int64_t ref_end = imin((c0 / ref_block + 1) * int64_t(ref_block), M1);
+      if (ref_end > j0) TQ_TRY(trailing(j0, ref_end - j0, c0 - M0, c0, cnt, seq_mode));
+      const int64_t d0 = imax(j0, ref_end);
+      TQ_TRY(trailing(d0, M1 - d0, c0 - M0, c0, cnt, kSeqDelta));
     }
-    TQ_TRY(trailing(M1, n - M1, 0, M0, int(M1 - M0)));                 // everything beyond it
+    // everything beyond the macro block: columns that still belong to the macro block's reference block
+    // (ref_block > 1024) sequentially, the rest as one K = 1024 product
+    const int64_t ref_end_far = imin((M0 / ref_block + 1) * int64_t(ref_block), k);
+    if (ref_end_far > M1) TQ_TRY(trailing(M1, ref_end_far - M1, 0, M0, int(M1 - M0), seq_mode));
+    const int64_t f0 = imax(M1, ref_end_far);
+    TQ_TRY(trailing(f0, n - f0, 0, M0, int(M1 - M0), kSeqDelta));
   }
   if (k < n) {
     dim3 grid((unsigned)imin(ceil_div(n - k, 256), 64), (unsigned)m);

@@ -107,11 +107,7 @@ extern "C" int tq_quant_error(const float* W, int64_t ldw, const float* Wq, int6
   const float one = 1.f, zero = 0.f;
   // row-major Y (m x k) = A (m x n) . R32^T  <=>  col-major Y^T (k x m) = R32 . A^T
   const float* srcs[2] = {D, Wo};
-  static int strict = -1;
-  if (strict < 0) {
-    const char* e = getenv("TQ_METRIC_STRICT_FP32");
-    strict = (e && e[0] && e[0] != '0') ? 1 : 0;
-  }
+  const int strict = 0;
   for (int i = 0; i < 2; ++i) {
     if (strict) {
       TQ_CUBLAS_CHECK(cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, int(k), int(m), int(n), &one, R32, int(n), srcs[i],

@@ -391,11 +391,7 @@ int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64
   }
   // the attribute is per function, not per thread: always raise it to the same maximum, so that a solve
   // with a small n on one host thread never lowers it under a solve with a large n on another
-  static thread_local bool smem_set = false;
-  if (!smem_set) {
-    TQ_CUDA_CHECK(cudaFuncSetAttribute(pchol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    smem_set = true;
-  }
+  TQ_CUDA_CHECK(cudaFuncSetAttribute(pchol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int per_sm = 0;
   TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pchol_panel_kernel, kPcThreads, smem));
   if (per_sm < 1) {
@@ -419,8 +415,10 @@ int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64
     TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
     PcholArgs pa{Gc, ncur, ncur, n, j0, jb, Rp, Rorig, d, orig_of, perm, perm64, bar, fail, slots, local ? 1 : 0};
     void* kargs[] = {&pa};
+    const int pslot = prof_begin_launch(st, double(jb) * double(ncur) * kPcNb * 8.0 * 0.5, TQ_PROF_PCHOL_PANEL);
     TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)pchol_panel_kernel, dim3(blocks), dim3(kPcThreads), kargs,
                                               smem, st));
+    prof_end_launch(st, pslot);
     ++g_launch_count;
     dead += jb;
     if (j0 + jb >= k) break;

@@ -367,13 +367,13 @@ struct QcPlan {
 };
 
 static int qc_plan(QcPlan** out) {
-  static thread_local QcPlan plan;
-  static thread_local bool done = false;
+  static thread_local QcPlan plans[kMaxDevices];
+  static thread_local bool done_dev[kMaxDevices] = {};
+  QcPlan& plan = plans[device_slot()];
+  bool& done = done_dev[device_slot()];
   *out = &plan;
   if (done) return TQ_OK;
   done = true;
-  const char* env = getenv("TQ_QR_COOP_PANEL");
-  if (env && env[0] && env[0] != '0') return TQ_OK;      // A/B switch: keep the grid-barrier panel
   int dev = 0, optin = 0;
   TQ_CUDA_CHECK(cudaGetDevice(&dev));
   TQ_CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -432,7 +432,9 @@ static int qc_launch(cudaStream_t st, const QcPlan& plan, const QcArgs& args) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  const int pslot = prof_begin_launch(st, double(args.k - args.j0) * args.jb * 16.0, TQ_PROF_QR_CLUSTER);
   TQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, qr_cluster_panel_kernel, args));
+  prof_end_launch(st, pslot);
   ++g_launch_count;
   return TQ_OK;
 }
@@ -703,7 +705,8 @@ int qr_r_colmajor_tau(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda,
   }
   QcPlan* plan = nullptr;
   TQ_TRY(qc_plan(&plan));
-  static thread_local int coop_per_sm = 0;
+  static thread_local int coop_per_sm_dev[kMaxDevices] = {};
+  int& coop_per_sm = coop_per_sm_dev[device_slot()];
   if (!coop_per_sm) {
     int per_sm = 0;
     TQ_CUDA_CHECK(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -813,7 +816,8 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
   const double eps = 1.1102230246251565e-16;   // dlamch('Epsilon')
   const double tol3z = sqrt(eps);
   const int64_t ldf = n;
-  static thread_local int coop_per_sm = 0;
+  static thread_local int coop_per_sm_dev[kMaxDevices] = {};
+  int& coop_per_sm = coop_per_sm_dev[device_slot()];
   if (!coop_per_sm) {
     int per_sm = 0;
     TQ_CUDA_CHECK(cudaFuncSetAttribute(qrcp_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -844,7 +848,7 @@ int qrcp_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int
       void* kargs[] = {&pa};
       double bytes = 0.0;      // algorithmic bytes of the panel: every step streams the trailing matrix once
       for (int i = 0; i < jb; ++i) bytes += double(k - (j0 + i)) * double(n - (j0 + i) - 1 + i) * 8.0;
-      const int pslot = prof_begin_launch(st, bytes);
+      const int pslot = prof_begin_launch(st, bytes, TQ_PROF_QRCP_PANEL);
       TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)qrcp_panel_kernel, dim3(coop_blocks), dim3(kQrPanelThreads),
                                                 kargs, kQrPanelSmem, st));
       prof_end_launch(st, pslot);

@@ -8,7 +8,11 @@
 namespace tq {
 
 int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ldh, int64_t n, double* w,
-                  double* Zout, Workspace& ws);
+                  double* Zout, Workspace& ws, const EighColumnChooser& choose);
+size_t rfactor_ws_bytes(int64_t n, int64_t k);
+int r_from_rx(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ldh, const double* V, const double* w,
+              int64_t n, int64_t k, const double* Rx, int64_t ldrx, const int64_t* perm, double* R, int64_t ldr,
+              Workspace ws);
 size_t eigh_ws_bytes(int64_t n);
 int copy_symmetric_lower(cudaStream_t st, const double* H, int64_t ldh, int64_t n, double* A);
 int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n, Workspace& ws);
@@ -176,6 +180,9 @@ static size_t solver_ws_bytes(int64_t n) {
   size_t a = ws_bytes_for(size_t(n) * n, 8) + ws_bytes_for(n, 8) * 2 + 1024;
   size_t e = eigh_ws_bytes(n);
   size_t q = ws_bytes_for(size_t(n) * n, 8) * 2 + qr_stage_ws_bytes(n, n) + pchol_ws_bytes(n, n);
+  size_t r = rfactor_ws_bytes(n, n);
+  for (int64_t t = n / 4; t > 0; t /= 2) r = r > rfactor_ws_bytes(n, n - t) ? r : rfactor_ws_bytes(n, n - t);
+  if (r > q) q = r;
   return a + (e > q ? e : q) + (size_t(1) << 20);
 }
 
@@ -209,10 +216,18 @@ extern "C" int tq_rank_select(const double* w_asc, int64_t n, double threshold, 
   return TQ_OK;
 }
 
+// Which eigenvectors a solve needs (decided as soon as the eigenvalues exist, before any back-transformation):
+//   kSubsetDropped  t = n - k <= n / 4 and no retained eigenvalue was clamped: only the t DROPPED vectors -
+//                   H_k = H - V_t diag(w_t) V_t^T for the pivoted Cholesky, and R follows from R_x (rfactor.cu);
+//   kSubsetAll      t < k otherwise: all n (H_k as above, then B = Lambda^-1/2 V_k^T[:, perm] and its QR);
+//   kSubsetKept     t >= k: only the k RETAINED vectors (H_k = S^T S, B and its QR).
+enum { kSubsetDropped = 0, kSubsetAll = 1, kSubsetKept = 2 };
+
 static int spectral_solve_impl(const double* H, int64_t ldh, int64_t n, double threshold, int method, int64_t nvals,
                                int64_t min_rank, double* R, double* Rx, int64_t* perm, double* eigvals,
-                               int64_t* k_host, void* ws, size_t ws_bytes, void* stream) {
+                               int64_t* k_host, void* ws, size_t ws_bytes, void* stream, bool allow_dropped = true) {
   TQ_TRY(check_device());
+  const int method_in = method;
   const bool force_householder = (method & TQ_SOLVE_HOUSEHOLDER_QRCP) != 0;
   method &= ~TQ_SOLVE_HOUSEHOLDER_QRCP;
   TQ_REQUIRE(H && R && Rx && perm && eigvals && k_host, "tq_spectral_solve: null pointer");
@@ -228,19 +243,41 @@ static int spectral_solve_impl(const double* H, int64_t ldh, int64_t n, double t
   }
   cublasHandle_t h;
   TQ_TRY(get_cublas(&h, st));
-  {
-    Workspace sub = wsp;
-    TQ_TRY(eigh_colmajor(h, st, H, ldh, n, w, V, sub));
-  }
   long long kh2[2] = {0, 0};
-  {
+  int subset = kSubsetAll;
+  // the rank rule runs between the divide & conquer and the back-transformation (it needs eigenvalues only)
+  auto choose = [&](const double* w_dev, int64_t* col0, int64_t* ncols) -> int {
     StageTimer tm(st, "rank");
-    rank_select_kernel<<<1, 1024, 0, st>>>(w, n, threshold, method, eigvals, kd, nvals, min_rank);
+    rank_select_kernel<<<1, 1024, 0, st>>>(w_dev, n, threshold, method, eigvals, kd, nvals, min_rank);
     TQ_LAUNCH_CHECK();
-    clamp_flag_kernel<<<1, 1, 0, st>>>(w, n, kd, kd + 1);
+    clamp_flag_kernel<<<1, 1, 0, st>>>(w_dev, n, kd, kd + 1);
     TQ_LAUNCH_CHECK();
     TQ_CUDA_CHECK(cudaMemcpyAsync(kh2, kd, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
     TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+    const int64_t kk = kh2[0], tt = n - kk;
+    if (kk <= 0 || kk > n) {
+      *col0 = 0;
+      *ncols = 0;
+      return TQ_OK;
+    }
+    if (allow_dropped && !force_householder && kh2[1] == 0 && 4 * tt <= n) {
+      subset = kSubsetDropped;
+      *col0 = 0;
+      *ncols = tt;
+    } else if (tt < kk) {
+      subset = kSubsetAll;
+      *col0 = 0;
+      *ncols = n;
+    } else {
+      subset = kSubsetKept;
+      *col0 = n - kk;
+      *ncols = kk;
+    }
+    return TQ_OK;
+  };
+  {
+    Workspace sub = wsp;
+    TQ_TRY(eigh_colmajor(h, st, H, ldh, n, w, V, sub, choose));
   }
   const long long kh = kh2[0];
   const bool clamped = kh2[1] != 0;
@@ -274,7 +311,7 @@ static int spectral_solve_impl(const double* H, int64_t ldh, int64_t n, double t
     StageTimer tm(st, "gram+pchol");
     const double one = 1.0, zero = 0.0, mone = -1.0;
     const int64_t t = n - k;
-    if (!clamped && t < k) {
+    if (subset != kSubsetKept && !clamped && t < k) {
       TQ_TRY(copy_symmetric_lower(st, H, ldh, n, Gm));
       if (t > 0) {
         dim3 sg((unsigned)imin(ceil_div(n, 256), 64), (unsigned)t);
@@ -295,6 +332,19 @@ static int spectral_solve_impl(const double* H, int64_t ldh, int64_t n, double t
     have_s = false;
     if (rc == TQ_ERR_NOCONV) householder = true;
     else if (rc != TQ_OK) return rc;
+  }
+  if (subset == kSubsetDropped) {
+    int rc = TQ_ERR_NOCONV;
+    if (!householder) {
+      StageTimer tm(st, "r_from_rx");
+      rc = r_from_rx(h, st, H, ldh, V, w, n, k, Rx, n, perm, R, n, sub);
+    }
+    if (rc == TQ_OK) return TQ_OK;
+    if (rc != TQ_ERR_NOCONV) return rc;
+    // numerical rank below k (non-positive pivot): the Householder route needs the retained eigenvectors,
+    // which this pass did not back-transform - solve again the long way (rare)
+    return spectral_solve_impl(H, ldh, n, threshold, method_in, nvals, min_rank, R, Rx, perm, eigvals, k_host, ws,
+                               ws_bytes, stream, false);
   }
   if (householder) {
     if (!have_s) {

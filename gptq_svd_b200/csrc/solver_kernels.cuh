@@ -6,10 +6,15 @@
 // done inside the persistent panel kernels by cta_strided_warp_dot (one CTA per column,
 // per-warp partials added in fixed order by the consumer).  BLAS-3 parts go to cuBLAS DGEMM.
 #pragma once
+#include <functional>
+
 #include "blas.cuh"
 #include "common.cuh"
 
 namespace tq {
+
+// see eigh_colmajor (eigh.cu): called with the device pointer of the ascending eigenvalues
+using EighColumnChooser = std::function<int(const double* w_dev, int64_t* col0, int64_t* ncols)>;
 
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -236,10 +241,10 @@ static inline int build_t_factor(cublasHandle_t h, cudaStream_t st, const double
   const double one = 1.0, zero = 0.0;
   TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, jb, jb, int(s), &one, V, int(ldv), V, int(ldv), &zero,
                               G, jb));
-  static thread_local bool big_smem = false;
-  if (!big_smem) {   // jb = 128 needs 160 KB of dynamic shared memory
+  static thread_local bool big_smem[kMaxDevices] = {};
+  if (!big_smem[device_slot()]) {   // jb = 128 needs 160 KB of dynamic shared memory
     TQ_CUDA_CHECK(cudaFuncSetAttribute((const void*)larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLarftSmem)));
-    big_smem = true;
+    big_smem[device_slot()] = true;
   }
   if (jb > kLarftMaxJb) {
     set_error("build_t_factor: jb = %d > %d", jb, kLarftMaxJb);

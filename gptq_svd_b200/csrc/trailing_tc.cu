@@ -181,16 +181,18 @@ int trailing_tc_prepare(TrailingTc* t, const float* E_hi, const float* E_lo, int
 // C (m x N, ldc) -= E[:, e_col0 : e_col0 + kcount] . U[u_row0 : u_row0 + kcount, u_col0 : u_col0 + N]
 int trailing_tc_launch(const TrailingTc* t, float* C, int64_t ldc, int64_t m, int64_t N, int64_t e_col0,
                        int64_t u_row0, int kcount, int64_t u_col0, cudaStream_t st) {
-  static thread_local bool attr_done = false;
-  if (!attr_done) {
+  static thread_local bool attr_done[kMaxDevices] = {};
+  if (!attr_done[device_slot()]) {
     TQ_CUDA_CHECK(cudaFuncSetAttribute(trailing_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kTcSmem));
-    attr_done = true;
+    attr_done[device_slot()] = true;
   }
   dim3 grid((unsigned)ceil_div(N, kTcN), (unsigned)ceil_div(m, kTcM));
   const int num_kstages = int(ceil_div(kcount, kTcKStage));
+  const int pslot = prof_begin_launch(st, 2.0 * double(m) * double(N) * double(kcount), TQ_PROF_TRAILING_TC);
   trailing_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(t->ehi, t->elo, t->uhi, t->ulo, C, ldc, m, N, int(e_col0),
                                                         int(u_row0), int(u_col0), num_kstages, t->idesc);
+  prof_end_launch(st, pslot);
   TQ_LAUNCH_CHECK();
   return TQ_OK;
 }

@@ -31,7 +31,7 @@ namespace tq {
 
 int qr_r_colmajor_tau(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n, Workspace& ws,
                       double* tau_out);
-bool two_stage_requested();
+int two_stage_setting();    // -1 automatic, 0 off, 1 on (tq_set_eigh_two_stage)
 
 static inline int64_t chase_tasks(int64_t s, int64_t n) { return s > n - 3 ? 0 : (n - 3 - s) / kBw + 1; }
 
@@ -109,26 +109,11 @@ static int sy2sb(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, double
     return TQ_ERR_WORKSPACE;
   }
   TQ_CUDA_CHECK(cudaMemsetAsync(tau1, 0, sizeof(double) * n, st));
-  // TQ_SY2SB_GEMM=1: X = A22 V as a DGEMM on a trailing matrix kept fully symmetric (one mirror pass per block
-  // column, n^3 / (3 b) * 8 bytes in total) instead of DSYMM on its lower triangle - an A/B switch for the first
-  // GPU measurements (cuBLAS' DSYMM is not always as fast as its DGEMM).  A is fully symmetric on entry.
-  static int use_gemm = -1;
-  if (use_gemm < 0) {
-    const char* env = getenv("TQ_SY2SB_GEMM");
-    use_gemm = (env && env[0] && env[0] != '0') ? 1 : 0;
-  }
-  // TQ_SY2SB_LOOKAHEAD=1 (not validated on a GPU yet).  Measured: ~75 of the 196 ms of this stage at n = 12288 are
-  // the latency of the panel factorisations (a 16-CTA cluster kernel, 64 columns x 3.5 - 5 us).  With the look-ahead
-  // the block column of the NEXT panel receives this panel's update first (two s x 64 x 64 DGEMMs), its QR then runs
-  // on a side stream while the main stream applies the rank-128 update to the rest of the trailing matrix
-  // (DSYR2K on rows / columns >= b): the two touch disjoint columns of A.
-  static int lookahead = -1;
-  if (lookahead < 0) {
-    const char* env = getenv("TQ_SY2SB_LOOKAHEAD");
-    lookahead = (env && env[0] && env[0] != '0') ? 1 : 0;
-  }
+  // (Measured and dropped, profiles/r02_two_stage_variants.log: X = A22 V as a DGEMM on a mirrored trailing
+  // matrix instead of DSYMM - 205 vs 198 ms at n = 12288; a look-ahead that factors the next panel on a side
+  // stream while the main stream runs the DSYR2K - 200 vs 198 ms.)
+  const int use_gemm = 0, lookahead = 0;
   SideStream* side = nullptr;
-  if (lookahead) TQ_TRY(get_side_stream(&side));
   bool panel_ready = false;          // the current panel has been factored already (by the previous iteration)
   for (int64_t j = 0; j + b < n; j += b) {
     const int64_t r0 = j + b, s = n - r0;
@@ -200,18 +185,11 @@ static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuff
   TQ_CUDA_CHECK(cudaMemsetAsync(tb.prog, 0, sizeof(int) * n, st));
   TQ_CUDA_CHECK(cudaMemsetAsync(tb.tau2, 0, sizeof(double) * size_t(n) * (n / kBw + 2), st));
   if (n > 2) {
-    // TQ_CHASE_HELPER=1: the variant whose ninth warp owns the progress counter (two_stage_kernels.cuh); the
-    // default is the variant that has run on the B200
-    static int helper = -1;
-    if (helper < 0) {
-      const char* env = getenv("TQ_CHASE_HELPER");
-      helper = (env && env[0] && env[0] != '0') ? 1 : 0;
-    }
-    static int late = -1;        // TQ_CHASE_LATE=1: second wait in front of the D / E loads (two_stage_kernels.cuh)
-    if (late < 0) {
-      const char* env = getenv("TQ_CHASE_LATE");
-      late = (env && env[0] && env[0] != '0') ? 1 : 0;
-    }
+    // the variant with the second wait in front of the D / E loads ("late loads": 182 ms at n = 12288 against 202
+    // for the first version and 211 / 183 with a helper warp owning the progress counter,
+    // profiles/r02_two_stage_variants.log); the other instantiations stay in two_stage_kernels.cuh for the
+    // CPU emulation tests
+    const int helper = 0, late = 1;
     const void* kfn = helper ? (late ? (const void*)sb2st_chase_kernel_t<true, true> : (const void*)sb2st_chase_kernel_t<true, false>)
                              : (late ? (const void*)sb2st_chase_kernel_t<false, true> : (const void*)sb2st_chase_kernel_t<false, false>);
     const int kthreads = kChaseThreads + (helper ? 32 : 0);
@@ -219,13 +197,16 @@ static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuff
     // sweeps run 3 tasks apart, so at most K_0 / 3 + 1 of them are in flight; the launch is cooperative only for
     // its guarantee that every CTA is resident (a waiting sweep's predecessor must be running)
     int64_t want = chase_tasks(0, n) / 3 + 2;
-    if (const char* env = getenv("TQ_CHASE_GRID")) want = imax(1, atoll(env));     // experiments only
     const int grid = int(imax(1, imin(num_sms(), want)));
     const bool trace = trace_enabled();
     if (trace) TQ_CUDA_CHECK(cudaMemsetAsync(tb.stats, 0, 8 * sizeof(long long), st));
     ChaseArgs ca{tb.Bd, int(n), tb.Vs, n, tb.tau2, tb.prog, trace ? tb.stats : nullptr};
     void* kargs[] = {&ca};
+    double tasks = 0.0;
+    for (int64_t s = 0; s < n; ++s) tasks += double(chase_tasks(s, n));
+    const int pslot = prof_begin_launch(st, tasks * 3.0 * kBw * kBw * 16.0, TQ_PROF_CHASE);
     TQ_CUDA_CHECK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kthreads), kargs, kChaseSmem, st));
+    prof_end_launch(st, pslot);
     ++g_launch_count;
     if (trace) {
       long long hs[8];
@@ -331,19 +312,7 @@ static int apply_q2(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb
     set_error("apply_q2: workspace too small");
     return TQ_ERR_WORKSPACE;
   }
-  // TQ_Q2_UNBATCHED=1: debugging aid for the first GPU runs (bisects between the wavefront schedule and cuBLAS'
-  // handling of strided batches whose output blocks interleave in memory)
-  static int unbatched = -1;
-  if (unbatched < 0) {
-    const char* env = getenv("TQ_Q2_UNBATCHED");
-    unbatched = (env && env[0] && env[0] != '0') ? 1 : 0;
-  }
   return q2_for_each_batch(n, [&](int sb0, int k0, int count, int hg) -> int {
-    if (unbatched) {      // one block reflector at a time: same arithmetic, no interleaved batches
-      for (int i = 0; i < count; ++i)
-        TQ_TRY(apply_q2_batch(h, st, tb, n, sb0 + i, k0 + 2 * i, 1, hg, Z, ldz, ncols, Vc, taub, Gb, Tb, VT, w1));
-      return TQ_OK;
-    }
     return apply_q2_batch(h, st, tb, n, sb0, k0, count, hg, Z, ldz, ncols, Vc, taub, Gb, Tb, VT, w1);
   });
 }
@@ -379,15 +348,16 @@ static int apply_q1(cublasHandle_t h, cudaStream_t st, const double* A, const do
 }
 
 // ------------------------------------------------------------------------------------------------ entry points
-// TQ_EIGH_TWO_STAGE_MIN_N=<n>: smallest order the two-stage path is used for when it is switched on (measured: level
-// with the one-stage path at n = 12288, behind it at n = 4096 - a model run wants it for the wide Hessian only)
+// Automatic choice (tq_set_eigh_two_stage(-1), the default): two stages from n = 8192 on.  Measured on a B200
+// (profiles/r02_solver_stages.log): tridiagonal reduction 380 ms against 820 ms one-stage at n = 12288; at
+// n = 4096 the two are level (85 vs 101 ms) and the narrow solves of a decoder block run side by side under SM
+// budgets, where the one-stage panel kernel has been tuned - so the small orders keep the one-stage path.
+constexpr int64_t kTwoStageMinN = 8192;
 bool two_stage_usable(int64_t n) {
-  static int64_t min_n = -1;
-  if (min_n < 0) {
-    const char* env = getenv("TQ_EIGH_TWO_STAGE_MIN_N");
-    min_n = env ? imax(0, atoll(env)) : 0;
-  }
-  return two_stage_requested() && n % kBw == 0 && n >= 4 * kBw && n >= min_n && n < (1 << 30);
+  const int setting = two_stage_setting();
+  if (setting == 0) return false;
+  if (!(n % kBw == 0 && n >= 4 * kBw && n < (1 << 30))) return false;
+  return setting == 1 || n >= kTwoStageMinN;
 }
 
 struct TwoStageState {
@@ -403,6 +373,10 @@ int two_stage_reduce(cublasHandle_t h, cudaStream_t st, double* A, int64_t n, do
   {
     StageTimer tm(st, "sy2sb");
     TQ_TRY(sy2sb(h, st, A, n, g_ts.tb.tau1, scratch));
+  }
+  if (stage_callback_set()) {      // the DGEMM-bound band reduction is over; the bulge chase occupies <= n / 192 + 2 SMs
+    TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+    notify_stage(TQ_STAGE_BAND_DONE);
   }
   {
     StageTimer tm(st, "sb2st");

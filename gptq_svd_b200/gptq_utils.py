@@ -60,18 +60,36 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 class HessianAccumulator:
     """H (n x n fp64, on device) += X^T X per calibration batch (gptq_utils.py:213-228).
 
-    `add_batch` runs the tcgen05 SYRK (`tq_syrk_accum`); `.H` is the un-normalised,
+    `add_batch` runs the tcgen05 SYRK (`tq_syrk_accum_scaled`); `.H` is the un-normalised,
     fully symmetric fp64 sum after every call, `.n_samples` the token count,
     `get_hessian()` returns `H / n_samples` (or H itself when empty).
+
+    fp16 / bf16 activations feed the tensor cores as they are (their products are exact in
+    fp32).  fp32 / fp64 activations - which the reference widens to fp64 (:221) - are scaled
+    by a per-batch power of two chosen on the device so that the largest magnitude lands in
+    [2^13, 2^14), rounded to fp16 and the batch's contribution multiplied by 1 / scale^2: no
+    overflow for any finite input; each entry keeps 11 significant bits (the rounding errors
+    of T tokens average out: H stays within the 1e-5 bar, tests/test_gpu_syrk.py).  NaN /
+    infinity in such a batch raises in `get_hessian()`.
+
+    `verify=True` (default) keeps a one-number probe of the accumulation (v^T H v = sum of
+    ||X_b v||^2 for a fixed sign vector v: one extra pass over X per batch) and
+    `get_hessian()` raises RuntimeError when H disagrees with it - a guard against a
+    silently corrupted Hessian, which would poison k, perm, R and every code of the group.
     """
 
-    def __init__(self, in_features, device, dtype=torch.float64, kc_tokens: int = 0):
+    PROBE_TOL = 1e-4
+
+    def __init__(self, in_features, device, dtype=torch.float64, kc_tokens: int = 0, verify: bool = True):
         if dtype != torch.float64:
             raise ValueError("HessianAccumulator: the accumulator is fp64 (reference default)")
         self.H = torch.zeros((in_features, in_features), device=device, dtype=dtype)
         _require_cuda(self.H, "HessianAccumulator")
         self.n_samples = 0
         self.kc_tokens = kc_tokens
+        self.verify = bool(verify)
+        # device scalars: [0] probe (f64), [1] v^T H v (f64), [2..5] cast scratch (32 B), [6] status (i32)
+        self._dev = torch.zeros(8, dtype=torch.float64, device=self.H.device)
 
     def add_batch(self, x: torch.Tensor):
         if x.dim() == 3:
@@ -84,16 +102,20 @@ class HessianAccumulator:
         rows = x.shape[0]
         if rows == 0:
             return
+        if x.device != self.H.device:
+            raise RuntimeError(f"add_batch: activations on {x.device}, accumulator on {self.H.device}")
+        base = self._dev.data_ptr()
+        alpha = C.c_void_p(0)
         with torch.cuda.device(x.device):
             if x.dtype not in (torch.float16, torch.bfloat16):
-                # activations in another float type: the reference casts to fp64 (:221);
-                # the tensor-core path takes fp16
                 src = x if x.stride(1) == 1 else x.contiguous()
                 ldd = (n + 7) // 8 * 8
                 x16 = torch.zeros((rows, ldd), dtype=torch.float16, device=x.device)
-                check(lib.tq_cast_to_f16(_ptr(src), _DTYPE_CODE[src.dtype], rows, n, src.stride(0),
-                                         _ptr(x16), ldd, _stream(x)), "tq_cast_to_f16")
+                check(lib.tq_cast_to_f16_scaled(_ptr(src), _DTYPE_CODE[src.dtype], rows, n, src.stride(0),
+                                                _ptr(x16), ldd, C.c_void_p(base + 16), C.c_void_p(base + 48),
+                                                _stream(x)), "tq_cast_to_f16_scaled")
                 x, ldx = x16, ldd
+                alpha = C.c_void_p(base + 32)
             else:
                 if x.stride(1) != 1 or x.stride(0) % 8 != 0 or x.data_ptr() % 16 != 0:
                     ldd = (n + 7) // 8 * 8
@@ -102,13 +124,36 @@ class HessianAccumulator:
                     x, ldx = xp, ldd
                 else:
                     ldx = x.stride(0)
-            check(lib.tq_syrk_accum(_ptr(self.H), self.H.stride(0), _ptr(x), _DTYPE_CODE[x.dtype], rows, n,
-                                    ldx, self.kc_tokens, _stream(x)), "tq_syrk_accum")
+            check(lib.tq_syrk_accum_scaled(_ptr(self.H), self.H.stride(0), _ptr(x), _DTYPE_CODE[x.dtype], rows, n,
+                                           ldx, self.kc_tokens, alpha, _stream(x)), "tq_syrk_accum")
+            if self.verify:
+                check(lib.tq_hessian_probe_accum(_ptr(x), _DTYPE_CODE[x.dtype], rows, n, ldx, alpha,
+                                                 C.c_void_p(base), _stream(x)), "tq_hessian_probe_accum")
         self.n_samples += rows
+
+    def check(self):
+        """Raise RuntimeError when a batch held NaN / infinity or when H fails the probe identity
+        (one pass over H and a 4-byte read-back; called by get_hessian)."""
+        lib = _lib.load()
+        base = self._dev.data_ptr()
+        n = self.H.shape[0]
+        with torch.cuda.device(self.H.device):
+            if self.verify and self.n_samples > 0:
+                check(lib.tq_hessian_probe_check(_ptr(self.H), self.H.stride(0), n, C.c_void_p(base),
+                                                 self.PROBE_TOL, C.c_void_p(base + 8), C.c_void_p(base + 48),
+                                                 _stream(self.H)), "tq_hessian_probe_check")
+            status = int(self._dev[6:7].view(torch.int32)[0].item())
+        if status & 1:
+            raise RuntimeError("HessianAccumulator: a calibration batch contains NaN or infinity")
+        if status & 2:
+            probe, vhv = self._dev[0].item(), self._dev[1].item()
+            raise RuntimeError(f"HessianAccumulator: H fails the probe identity v^T H v = sum ||X v||^2 "
+                               f"({vhv:.9e} vs {probe:.9e}): the accumulation is corrupted")
 
     def get_hessian(self) -> torch.Tensor:
         if self.n_samples == 0:
             return self.H
+        self.check()
         lib = _lib.load()
         out = torch.empty_like(self.H)
         n = self.H.shape[0]

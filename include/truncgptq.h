@@ -76,11 +76,12 @@ const char* tq_last_error(void);
  * reproducible for a given budget and agree across budgets to rounding (R within 2e-12 relative). */
 int tq_set_sm_budget(int sms);
 
-/* EXPERIMENTAL, per thread: 1 = tq_eigh / tq_spectral_solve reduce to tridiagonal form in TWO stages (band
- * reduction of width 64 by QR panels and DSYMM / DSYR2K, then bulge chasing on the L2-resident band; two
- * back-transformations) when n % 64 == 0 and n >= 256; 0 = the one-stage reduction; -1 (default) = follow the
- * environment variable TQ_EIGH_TWO_STAGE (unset: one-stage); TQ_EIGH_TWO_STAGE_MIN_N=<n> restricts it to orders >= n.  The workspace queries depend on this setting: query
- * after changing it.  gptq_svd_b200/csrc/two_stage.cu. */
+/* Per thread.  tq_eigh / tq_spectral_solve reduce H to tridiagonal form either in one stage (blocked DSYTRD with a
+ * TMA-staged symmetric panel kernel) or in TWO stages (band reduction of width 64 by QR panels and DSYMM / DSYR2K,
+ * then bulge chasing on the L2-resident band; two back-transformations).  -1 (default) = automatic: two stages for
+ * n >= 8192 with n % 64 == 0 (380 ms against 820 ms at n = 12288 on a B200, level at n = 4096), one stage otherwise;
+ * 1 = two stages whenever n % 64 == 0 and n >= 256; 0 = always one stage.  The workspace query depends on this
+ * setting: query after changing it.  gptq_svd_b200/csrc/two_stage.cu. */
 int tq_set_eigh_two_stage(int on);
 
 /* Debugging aid for that path: runs the two reductions of an n x n symmetric H (n % 64 == 0, n >= 256) and returns
@@ -94,10 +95,12 @@ int tq_two_stage_debug(const double* H, int64_t ldh, int64_t n, double* band_out
 /* Per-thread stage callback: `cb(stage, user)` runs on the calling host thread inside
  * tq_spectral_solve / tq_eigh when a stage boundary has been reached ON THE DEVICE (the stream is
  * synchronised first).  TQ_STAGE_SYTRD_DONE (once per solve): the tridiagonal reduction - the bandwidth-bound
- * part of a solve - is complete (or, with the environment variable TQ_STAGE_TAIL_LEN=<rows>, its trailing matrix
- * has shrunk to that many rows); what follows is latency- and DGEMM-bound, so a scheduler may lower this thread's
+ * part of a solve - is complete; what follows is latency- and DGEMM-bound, so a scheduler may lower this thread's
  * SM budget and start other solves next to it.  NULL removes the callback. */
 #define TQ_STAGE_SYTRD_DONE 1
+/* two-stage reduction only, before TQ_STAGE_SYTRD_DONE: the band reduction (DGEMM-bound, whole GPU) is complete and
+ * the bulge chase that follows is a persistent kernel on at most n / 192 + 2 SMs (66 at n = 12288) */
+#define TQ_STAGE_BAND_DONE 2
 int tq_set_stage_callback(void (*cb)(int stage, void* user), void* user);
 
 /* --------------------------------------------------------------------------
@@ -107,7 +110,7 @@ int tq_set_stage_callback(void (*cb)(int stage, void* user), void* user);
 
 /* H (n x n fp64, fully symmetric on return) += X^T X, X = rows x n (x_dtype TQ_F16 or
  * TQ_BF16), computed as a tcgen05/TMEM SYRK: fp16 products are exact in fp32, TMEM
- * accumulates `kc_tokens` tokens at a time (0 = default 512), chunk sums are added in
+ * accumulates `kc_tokens` tokens at a time (0 = default 256), chunk sums are added in
  * fp32 registers and the batch total is added to H in fp64.  Requires ldx % 8 == 0 and a
  * 16-byte aligned X (TMA).  gptq_utils.py:221-222. */
 int tq_syrk_accum(double* H, int64_t ldh, const void* X, int x_dtype, int64_t rows, int64_t n,
@@ -117,10 +120,36 @@ int tq_syrk_accum(double* H, int64_t ldh, const void* X, int x_dtype, int64_t ro
 int tq_hessian_scale(const double* H, int64_t ldh, int64_t n, int64_t n_samples, double* out,
                      int64_t ldo, void* stream);
 
-/* dst(fp16) = src (TQ_F32 / TQ_F64 / TQ_BF16 rows x n) for activations that arrive in
- * another float type (the reference casts to fp64, gptq_utils.py:221). */
+/* Same with H += alpha * X^T X, alpha read from DEVICE memory when the kernel runs (NULL = 1): the
+ * epilogue of the SYRK multiplies the fp32 batch total by alpha in fp64.  Used with
+ * tq_cast_to_f16_scaled, where alpha = 1 / scale^2 is a power of two (exact). */
+int tq_syrk_accum_scaled(double* H, int64_t ldh, const void* X, int x_dtype, int64_t rows, int64_t n,
+                         int64_t ldx, int kc_tokens, const double* alpha_dev, void* stream);
+
+/* dst(fp16) = src (TQ_F32 / TQ_F64 / TQ_BF16 rows x n), saturating at +-65504, for activations that
+ * arrive in another float type (the reference casts to fp64, gptq_utils.py:221). */
 int tq_cast_to_f16(const void* src, int src_dtype, int64_t rows, int64_t n, int64_t lds, void* dst,
                    int64_t ldd, void* stream);
+
+/* Range-safe version: dst(fp16) = src * scale with scale = 2^e chosen ON THE DEVICE from the batch's
+ * largest magnitude so that it lands in [2^13, 2^14) - no overflow for any finite fp32 / fp64 input, the
+ * full fp16 significand for the largest entries.  scratch32_dev: 32 bytes, 16-byte aligned, written as
+ * {u32 amax bits, f32 scale, -, -, f64 alpha = 1 / scale^2 at byte 16}; pass scratch32_dev + 16 as
+ * alpha_dev to tq_syrk_accum_scaled.  A NaN or an infinity in src sets *status_dev |= 1 (the caller reads
+ * it back when it wants to fail: HessianAccumulator.get_hessian does).  No host synchronisation. */
+int tq_cast_to_f16_scaled(const void* src, int src_dtype, int64_t rows, int64_t n, int64_t lds, void* dst,
+                          int64_t ldd, void* scratch32_dev, int* status_dev, void* stream);
+
+/* Guard against a corrupted accumulation (cheap: one pass over X per batch, one over H per check).
+ * With the fixed sign vector v (v_j = +-1 from a hash of j): v^T (X^T X) v = ||X v||^2.
+ *   tq_hessian_probe_accum: *probe_dev += alpha * sum_rows (x_row . v)^2 for the fp16 / bf16 batch the
+ *       SYRK consumed (alpha_dev as above, NULL = 1);
+ *   tq_hessian_probe_check: *vhv_dev = v^T H v; *status_dev |= 2 unless
+ *       |v^T H v - probe| <= tol * max(|v^T H v|, |probe|)   (also set when either is NaN). */
+int tq_hessian_probe_accum(const void* X, int x_dtype, int64_t rows, int64_t n, int64_t ldx,
+                           const double* alpha_dev, double* probe_dev, void* stream);
+int tq_hessian_probe_check(const double* H, int64_t ldh, int64_t n, const double* probe_dev, double tol,
+                           double* vhv_dev, int* status_dev, void* stream);
 
 /* --------------------------------------------------------------------------
  * (2) Spectral solver - replaces process_hessian_alt (gptq_utils.py:87-126).
@@ -252,14 +281,40 @@ int tq_sketch_solve(const float* Y, int64_t ldy, int64_t rank, int64_t n, double
  * are not counted). */
 int64_t tq_launch_count(void);
 
-/* Sampled timing of the solver's dominant HBM-bound kernels: the tridiagonal-reduction panel
- * (sytrd_panel_sym_kernel: the lower triangle of the trailing matrix x one reflector per column; or the
- * column-dot panel it falls back to) and, on the Householder path, qrcp_panel_kernel.  After
- * tq_profile_begin(every), every `every`-th panel launch OF THE CALLING THREAD is bracketed by CUDA
- * events on its own stream; tq_profile_end synchronises them and returns the algorithmic bytes (per
- * column len * (len / 2 + 2 i) * 8 for the symmetric panel, rows * columns * 8 for the others) and the
- * milliseconds of the sampled launches. */
+/* Sampled timing of the library's own hot kernels.  After tq_profile_begin(every), every `every`-th launch of each
+ * instrumented kernel BY THE CALLING THREAD is bracketed by CUDA events on its own stream.
+ *   tq_profile_kernel(kind, ...) - may be called any number of times before tq_profile_end - synchronises the
+ *     sampled launches of one kernel and returns their algorithmic work (bytes or flops, see the table), their
+ *     milliseconds, how many were sampled / launched, the work of ALL launches of the kind, and
+ *     sm_ms = sum over the sampled launches of (milliseconds x SM budget of the launching thread), so that
+ *     sm_ms / ms is the average number of SMs the launches were confined to (tq_set_sm_budget);
+ *   tq_profile_end returns the sums over the three BLAS-2 panel kernels of the solver (kinds 0..2, bytes) and
+ *     releases the events.
+ * kind                    kernel                                       work unit
+ * TQ_PROF_SYTRD_SYM       sytrd_panel_sym_kernel (one-stage reduction)  bytes: per column len (len / 2 + 2 i) 8
+ * TQ_PROF_SYTRD_COLDOT    sytrd_panel_kernel (odd n)                     bytes: rows x columns x 8
+ * TQ_PROF_QRCP_PANEL      qrcp_panel_kernel (Householder QRCP)           bytes: rows x columns x 8
+ * TQ_PROF_CHASE           sb2st_chase_kernel (two-stage, stage 2)        bytes the tasks move through L2: tasks x 3 x 64^2 x 8 x 2
+ * TQ_PROF_PCHOL_PANEL     pchol_panel_kernel                             bytes: steps x live columns x 128 x 8 (panel history)
+ * TQ_PROF_QR_CLUSTER      qr_cluster_panel_kernel                        bytes: rows x jb x 8 x 2
+ * TQ_PROF_LOOP_BLOCK      gptq_block_kernel                              bytes: m x 128 x 4 x 2 (W block read + written)
+ * TQ_PROF_TRAILING_TC     trailing_tc_kernel (tcgen05 3xTF32)            flops: 2 m N K (algorithmic; 3x are issued)
+ * TQ_PROF_TRAILING_SEQ    trailing_update_kernel (in-block pairs, SIMT)  flops: 2 m N K
+ * TQ_PROF_SYRK            syrk_tcgen05_kernel                            flops: rows n (n + 1) (one triangle) */
+#define TQ_PROF_SYTRD_SYM 0
+#define TQ_PROF_SYTRD_COLDOT 1
+#define TQ_PROF_QRCP_PANEL 2
+#define TQ_PROF_CHASE 3
+#define TQ_PROF_PCHOL_PANEL 4
+#define TQ_PROF_QR_CLUSTER 5
+#define TQ_PROF_LOOP_BLOCK 6
+#define TQ_PROF_TRAILING_TC 7
+#define TQ_PROF_TRAILING_SEQ 8
+#define TQ_PROF_SYRK 9
+#define TQ_PROF_KINDS 10
 int tq_profile_begin(int sample_every);
+int tq_profile_kernel(int kind, double* work, double* ms, int64_t* sampled, int64_t* total, double* work_all,
+                      double* sm_ms);
 int tq_profile_end(double* alg_bytes, double* ms, int64_t* sampled, int64_t* total);
 
 #ifdef __cplusplus

@@ -8,9 +8,13 @@ import torch
 import gptq_svd_b200 as G
 
 
+DECAY = float(os.environ.get('SWEEP_DECAY', '-1.0'))
+EPS = float(os.environ.get('SWEEP_EPS', '1e-4'))
+
+
 def make_h(n, seed=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
-    A = torch.randn(n, n, device="cuda", generator=g) * torch.logspace(0, -1.0, n, device="cuda")[None, :]
+    A = torch.randn(n, n, device="cuda", generator=g) * torch.logspace(0, DECAY, n, device="cuda")[None, :]
     H = torch.zeros(n, n, device="cuda", dtype=torch.float64)
     rows = max(2 * n, 8192)
     for c in range(0, rows, 8192):
@@ -29,11 +33,11 @@ def main():
         H = make_h(n)
         torch.cuda.synchronize()
         if not os.environ.get("SWEEP_NO_WARM"):
-            f = G.spectral_solve(H, 1e-4, "energy")      # warm-up (workspace allocation, attributes)
+            f = G.spectral_solve(H, EPS, "energy")      # warm-up (workspace allocation, attributes)
             torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        f = G.spectral_solve(H, 1e-4, "energy")
+        f = G.spectral_solve(H, EPS, "energy")
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)

@@ -26,7 +26,11 @@ void set_error(const char* fmt, ...) {
 }
 int num_sms() { return g_emu_sms; }
 bool trace_enabled() { return false; }
-bool two_stage_requested() { return true; }
+int two_stage_setting() { return 1; }
+int prof_begin_launch(cudaStream_t, double, int) { return -1; }
+void prof_end_launch(cudaStream_t, int) {}
+bool stage_callback_set() { return false; }
+void notify_stage(int) {}
 StageTimer::StageTimer(cudaStream_t s, const char* n) : st(s), name(n), t0(0) {}
 StageTimer::~StageTimer() {}
 

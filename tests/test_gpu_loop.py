@@ -56,6 +56,8 @@ def test_loop_vs_reference_golden(G, name, tag, strict, golden):
     (1024, 1024, 4, 128, True, 1e-4),
     (520, 384, 3, 128, False, 1e-6),       # ragged rows
     (257, 256, 2, -1, False, 1e-3),        # per-channel groups, odd row count
+    (2048, 1024, 3, 128, False, 1e-4),     # BASELINE configs[2]: 3-bit asym g128 (run_benchmark.py:51-77)
+    (2048, 1024, 2, 128, False, 1e-5),     # BASELINE configs[3]: 2-bit asym g128, published eps 1e-5
 ])
 @pytest.mark.parametrize("strict", TRAILING)
 def test_loop_vs_oracle(G, m, n, bits, group, sym, eps, strict):

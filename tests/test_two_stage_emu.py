@@ -267,19 +267,6 @@ def test_whole_two_stage_path_on_the_host(host_emu, n, sms, ncols):
     _check_whole_path(host_emu, n, sms, ncols)
 
 
-@pytest.mark.parametrize("switch", ["TQ_SY2SB_GEMM", "TQ_SY2SB_LOOKAHEAD", pytest.param("TQ_CHASE_HELPER", marks=slow),
-                                    pytest.param("TQ_CHASE_LATE", marks=slow)])
-def test_whole_two_stage_path_with_a_switch(switch):
-    """TQ_SY2SB_GEMM=1 (mirror pass + DGEMM instead of DSYMM), TQ_SY2SB_LOOKAHEAD=1 (next panel factored next to the
-    trailing update; the emulation checks its arithmetic, not its stream dependencies), TQ_CHASE_HELPER=1,
-    TQ_CHASE_LATE=1 (variants of the bulge-chase kernel) in a fresh process: the library reads its switches once"""
-    code = ("import os, sys; sys.path[:0] = [%r, %r]; os.environ[%r] = '1';"
-            "import test_two_stage_emu as t; t._check_whole_path(t._load_host_emu(), 256, 2, 256)"
-            ) % (ROOT, os.path.join(ROOT, "tests"), switch)
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-
-
 @pytest.mark.parametrize("n", [256, 448, 1024, 4096, 12288, 28672])
 def test_host_q2_schedule_equals_model(host_emu, n):
     """The wavefront enumeration of apply_q2 (C++, two_stage.cu) issues exactly the model's groups, in an order
