@@ -269,6 +269,361 @@ gptq_block_kernel(float* __restrict__ Wp, int64_t n, const float* __restrict__ U
   }
 }
 
+// ------------------------------------------------------------------ fused macro-block kernel
+// One launch per 1024-column macro block = what the reference's Triton kernel does per block (gptq_utils.py:298-386:
+// a tile of rows walks all columns of the block, every column quantised and its error propagated to the later
+// columns of the block with one rank-1 FMA update per column), restructured for the SM.  A CTA owns 32 rows and
+// walks the macro block in sub-blocks of 64 columns with two kinds of warps:
+//   * the QUANTISER warp (warp 0, LANE = ROW; the other warps of its scheduler, 4 / 8 / 12, stay idle while it
+//     works: next to four busy worker warps it received a fifth of the issue slots and took 480 - 650 cycles per
+//     column, measured with the kernel's cycle counters) keeps its row's 64 values in registers, quantises column c and
+//     applies w[j] = fma(-e, U[c, j], w[j]) to the later columns of the sub-block; U[c, :] is a shared-memory
+//     broadcast.  No lane computes a redundant quantisation (the 2-rows-per-warp kernel above executes ~150
+//     instructions per column and warp, 16 warps per 32 rows: issue-bound at 1070 cycles per column,
+//     profiles/r02_ncu_gptq_block.txt);
+//   * 12 WORKER warps (the warps of the other three schedulers) apply the previous sub-block's 64 rank-1 updates to the later columns of the macro block, in
+//     column order, each one FMA - bit-identical to the Triton kernel's sequence.  Part A: the 64 columns the
+//     quantiser needs next (all workers, a few hundred cycles); part B: everything beyond them, WHILE the
+//     quantiser works on the next sub-block.  A worker warp owns 8 rows x a third of the columns (<= 80
+//     accumulators per lane, one shared-memory value of U feeds 8 FMAs); U rows stream through shared memory in
+//     double-buffered chunks of 8; the errors are stored k-major so that 8 rows are two 16-byte broadcasts.
+// W stays in global memory (the 16 - 50 MB slab of a macro block is L2-resident); E / codes / dequantised values
+// leave through shared memory with coalesced stores.  Requires ref_block % 1024 == 0 (every pair inside the macro
+// block is then inside one reference block) and n % 4 == 0; other shapes take the kernels above.
+constexpr int kFBlk = 64;
+constexpr int kFRows = 32;
+constexpr int kFWorkers = 12;                            // worker warps: the warps with id % 4 != 0
+constexpr int kFThreads = 16 * 32;                       // warp 0 = quantiser, warps 4 / 8 / 12 only load and store
+constexpr int kFChunk = 8;
+constexpr int kFStages = 3;                              // U-chunk ring of part B
+constexpr int kFMaxLen = kMacro - 2 * kFBlk;             // part B: at most 896 columns
+constexpr int kFLd = kFBlk + 1;                          // lane = row: stride 65 is conflict-free
+constexpr int kFNi = (kFMaxLen / 3 + 31) / 32;           // 10 column groups of 32 per lane and third
+struct FusedSmem {
+  // double-buffered per sub-block (the next sub-block's copies arrive with cp.async during this one's work)
+  float Us[2][kFBlk][kFBlk];              // U[c0 + c, c0 + j]: the sub-block's own triangle
+  float Ua[2][kFBlk][kFBlk];              // U[c0 - 64 + k, c0 + j]: previous sub-block's rows against this one's columns
+  float Sb[2][kFRows][kFLd];
+  float Zb[2][kFRows][kFLd];
+  float Wb[kFRows][kFLd];
+  float Et[2][kFBlk][kFRows];             // errors, k-major, double-buffered
+  float Dv[2][kFBlk];
+  uint8_t Cb[kFBlk][kFRows];              // codes, column-major: a warp store is 32 consecutive bytes
+  float Uc[kFStages][kFChunk][kFMaxLen + 64];      // + 64: a third rounded up to 32 columns may reach past 896 (values unused)
+};
+
+__device__ __forceinline__ void cp_async_f4(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_f1(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 384;" ::: "memory"); }
+
+// part B for one worker warp: NI column groups of 32 per lane.  3-stage ring of U chunks, ONE barrier per chunk:
+// chunk ck + 2 is issued after the barrier of chunk ck, i.e. when every worker has finished chunk ck - 1, whose
+// buffer it overwrites.
+template <int SEM, int NI>
+__device__ __forceinline__ void fused_part_b(FusedSmem& sm, float* __restrict__ Wp, int64_t n, const float* __restrict__ U,
+                                             int64_t m, int64_t r0, int64_t krow0 /*first U row*/, int kcnt,
+                                             int64_t j0 /*first column*/, int len, int quarter, int ebuf, int wtid) {
+  const int lane = wtid & 31, widx = wtid >> 5;                   // worker index 0 .. 11
+  const int rg = widx / 3, cq = widx % 3;
+  const int jbase = cq * quarter + lane;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(U) & 15) == 0) && (n % 4 == 0) && (j0 % 4 == 0);
+  const int nchunks = (kcnt + kFChunk - 1) / kFChunk;
+  auto load_chunk = [&](int ck) {
+    if (ck < nchunks) {
+      const int buf = ck % kFStages;
+      const int ngran = (len + 3) / 4;
+      for (int idx = wtid; idx < kFChunk * ngran; idx += kFWorkers * 32) {
+        const int kk = idx / ngran, g = idx % ngran;
+        const int krow = ck * kFChunk + kk;
+        float* dst = &sm.Uc[buf][kk][4 * g];
+        if (krow < kcnt) {
+          const float* src = U + (krow0 + krow) * n + j0 + 4 * g;
+          if (vec_ok && 4 * g + 4 <= len) {
+            cp_async_f4(dst, src);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (4 * g + e < len) cp_async_f1(dst + e, src + e);
+          }
+        }
+      }
+    }
+    cp_async_commit_group();            // one group per call, empty or not: the wait counts below stay exact
+  };
+  load_chunk(0);
+  load_chunk(1);
+  float acc[8][NI];
+  float* const wbase = Wp + (r0 + rg * 8) * n + j0 + jbase;      // row a of the group: wbase + a n
+  const int64_t rleft = m - (r0 + rg * 8);
+  const int nrows = rleft < 8 ? int(rleft) : 8;                     // rows of this group inside the matrix (may be <= 0)
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const bool okc = jbase + 32 * i < len;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) acc[a][i] = (okc && a < nrows) ? __ldcg(wbase + a * n + 32 * i) : 0.f;
+  }
+  for (int ck = 0; ck < nchunks; ++ck) {
+    const int buf = ck % kFStages;
+    cp_async_wait_group<1>();             // chunk ck has landed (chunk ck + 1 may still be in flight)
+    worker_barrier();
+    load_chunk(ck + 2);
+    const int kmax = min(kFChunk, kcnt - ck * kFChunk);
+#pragma unroll 2
+    for (int kk = 0; kk < kmax; ++kk) {
+      const float4 ea = *reinterpret_cast<const float4*>(&sm.Et[ebuf][ck * kFChunk + kk][rg * 8]);
+      const float4 eb = *reinterpret_cast<const float4*>(&sm.Et[ebuf][ck * kFChunk + kk][rg * 8 + 4]);
+      const float e[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+      const float* ucol = &sm.Uc[buf][kk][jbase];                // jbase + 32 i < 3 * 320 = 960: inside the padded row
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const float u = ucol[32 * i];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          if (SEM == TQ_LOOP_TRITON) acc[a][i] = fmaf(-e[a], u, acc[a][i]);
+          else acc[a][i] = __fsub_rn(acc[a][i], __fmul_rn(e[a], u));
+        }
+      }
+    }
+  }
+  cp_async_wait_group<0>();
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const bool okc = jbase + 32 * i < len;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+      if (okc && a < nrows) wbase[a * n + 32 * i] = acc[a][i];
+  }
+}
+
+// The quantiser warp's work on one sub-block (LANE = ROW), a function of its own so that the register allocator
+// sees only this loop: inlined into the kernel it spilled the row's values around every column.  s / z arrive one
+// column ahead of their use; the value the NEXT column's quantisation depends on, w[c + 1], is updated first, the
+// other updates fill the shadow of its latency.
+template <int SEM>
+__device__ __noinline__ void fused_quantise(FusedSmem& sm, int eb, int lane, int cnt, float min_q, float max_q) {
+      float w[kFBlk];
+#pragma unroll
+      for (int j = 0; j < kFBlk; ++j) w[j] = sm.Wb[lane][j];
+      float s_cur = sm.Sb[eb][lane][0], z_cur = sm.Zb[eb][lane][0];
+#pragma unroll
+      for (int c = 0; c < kFBlk; ++c) {
+        // next column's grid parameters and the one U value on the critical path: issued before this column's chain
+        const float s_nxt = (c + 1 < kFBlk) ? sm.Sb[eb][lane][c + 1 < kFBlk ? c + 1 : c] : 1.f;
+        const float z_nxt = (c + 1 < kFBlk) ? sm.Zb[eb][lane][c + 1 < kFBlk ? c + 1 : c] : 0.f;
+        if (c < cnt) {
+          const float unext = (c + 1 < kFBlk) ? sm.Us[eb][c][c + 1 < kFBlk ? c + 1 : c] : 0.f;
+          float qq, qv;
+          quantize<SEM == TQ_LOOP_TRITON>(w[c], s_cur, z_cur, min_q, max_q, qq, qv);
+          float ev = __fsub_rn(w[c], qv);
+          if (SEM == TQ_LOOP_TORCH) ev = __fdiv_rn(ev, sm.Dv[eb][c]);
+          if (c + 1 < kFBlk) {
+            if (SEM == TQ_LOOP_TRITON) w[c + 1] = fmaf(-ev, unext, w[c + 1]);
+            else w[c + 1] = __fsub_rn(w[c + 1], __fmul_rn(ev, unext));
+          }
+          sm.Wb[lane][c] = qv;
+          sm.Et[eb][c][lane] = ev;
+          sm.Cb[c][lane] = uint8_t(int(qq - min_q) & 0xff);
+#pragma unroll
+          for (int j = c + 2; j < kFBlk; ++j) {
+            const float u = sm.Us[eb][c][j];                   // broadcast
+            if (SEM == TQ_LOOP_TRITON) w[j] = fmaf(-ev, u, w[j]);
+            else w[j] = __fsub_rn(w[j], __fmul_rn(ev, u));
+          }
+        } else {
+          sm.Et[eb][c][lane] = 0.f;
+        }
+        s_cur = s_nxt;
+        z_cur = z_nxt;
+      }
+}
+
+template <int SEM>
+__global__ void __launch_bounds__(kFThreads, 1)
+gptq_macro_kernel(float* __restrict__ Wp, int64_t n, const float* __restrict__ U, const float* __restrict__ dvec,
+                  const float* __restrict__ scale, const float* __restrict__ zero, int ng,
+                  const int* __restrict__ gidx, int64_t m, int64_t M0, int cntM, float min_q, float max_q,
+                  float* __restrict__ E, float* __restrict__ E_hi, float* __restrict__ E_lo,
+                  uint8_t* __restrict__ Cp, long long* __restrict__ stats /* TQ_TRACE: cycle counters of CTA 0 */) {
+  extern __shared__ __align__(16) uint8_t fused_raw[];
+  FusedSmem& sm = *reinterpret_cast<FusedSmem*>(fused_raw);      // no integer round trip: keeps the accesses LDS / STS
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool quantiser = warp == 0;
+  const bool worker = (warp & 3) != 0;
+  const int wtid = ((warp >> 2) * 3 + (warp & 3) - 1) * 32 + lane;     // dense worker thread id 0 .. 383
+  const int64_t r0 = int64_t(blockIdx.x) * kFRows;
+  const bool timed = stats != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 1 || quantiser);
+  long long tmark = timed ? clock64() : 0;
+  auto lap = [&](int slot) {
+    if (timed) {
+      const long long t = clock64();
+      atomicAdd(reinterpret_cast<unsigned long long*>(stats + slot), (unsigned long long)(t - tmark));
+      tmark = t;
+    }
+  };
+  const bool u_vec = ((reinterpret_cast<uintptr_t>(U) & 15) == 0) && (n % 4 == 0) && (M0 % 4 == 0);
+
+  // U triangle, U rows of the previous sub-block, scales / zeros (through the permutation) and diagonal of sub-block
+  // `bi` into buffer bi & 1: asynchronous copies, none of them depends on W
+  auto prefetch = [&](int bi) {
+    const int b0 = bi * kFBlk;
+    if (b0 < cntM) {
+      const int cnt = min(kFBlk, cntM - b0);
+      const int64_t c0 = M0 + b0;
+      const int pb = bi & 1;
+      for (int idx = tid; idx < kFBlk * (kFBlk / 4); idx += kFThreads) {
+        const int c = idx / (kFBlk / 4), j4 = (idx % (kFBlk / 4)) * 4;
+        float* du = &sm.Us[pb][c][j4];
+        float* da = &sm.Ua[pb][c][j4];
+        if (u_vec && c < cnt && j4 + 4 <= cnt) {
+          cp_async_f4(du, U + (c0 + c) * n + c0 + j4);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (c < cnt && j4 + e < cnt) cp_async_f1(du + e, U + (c0 + c) * n + c0 + j4 + e);
+            else du[e] = 0.f;
+          }
+        }
+        if (b0 > 0) {
+          if (u_vec && j4 + 4 <= cnt) {
+            cp_async_f4(da, U + (c0 - kFBlk + c) * n + c0 + j4);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (j4 + e < cnt) cp_async_f1(da + e, U + (c0 - kFBlk + c) * n + c0 + j4 + e);
+              else da[e] = 0.f;
+            }
+          }
+        }
+      }
+      for (int idx = tid; idx < kFRows * kFBlk; idx += kFThreads) {
+        const int r = idx / kFBlk, j = idx % kFBlk;
+        if ((r0 + r < m) && (j < cnt)) {
+          const int g = gidx[c0 + j];
+          cp_async_f1(&sm.Sb[pb][r][j], scale + (r0 + r) * ng + g);
+          cp_async_f1(&sm.Zb[pb][r][j], zero + (r0 + r) * ng + g);
+        } else {
+          sm.Sb[pb][r][j] = 1.f;
+          sm.Zb[pb][r][j] = 0.f;
+        }
+      }
+      if (tid < kFBlk) sm.Dv[pb][tid] = (SEM == TQ_LOOP_TORCH && tid < cnt) ? dvec[c0 + tid] : 1.f;
+    }
+    cp_async_commit_group();
+  };
+  prefetch(0);
+
+  for (int b0 = 0, bi = 0; b0 < cntM; b0 += kFBlk, ++bi) {
+    const int cnt = min(kFBlk, cntM - b0);
+    const int64_t c0 = M0 + b0;
+    const int eb = bi & 1;                 // this sub-block's buffers; the previous one's are eb ^ 1
+    // ---- W sub-block (after the previous iteration's part B has written it)
+    for (int idx = tid; idx < kFRows * kFBlk; idx += kFThreads) {
+      const int r = idx / kFBlk, j = idx % kFBlk;
+      sm.Wb[r][j] = ((r0 + r < m) && (j < cnt)) ? __ldcg(&Wp[(r0 + r) * n + c0 + j]) : 0.f;
+    }
+    cp_async_wait_group<0>();              // this sub-block's prefetch (issued one iteration ago)
+    __syncthreads();
+    prefetch(bi + 1);                      // lands while the quantiser and part B work
+    lap(quantiser ? 7 : 0);                                        // 0: load phase
+
+    // ---- part A (workers): the previous sub-block's 64 updates on THIS sub-block's columns, in shared memory
+    if (b0 > 0) {
+      const int j = tid & 63, r4 = tid >> 6;                    // 8 groups of 4 rows x 64 columns
+      float a0 = sm.Wb[r4 * 4 + 0][j], a1 = sm.Wb[r4 * 4 + 1][j], a2 = sm.Wb[r4 * 4 + 2][j], a3 = sm.Wb[r4 * 4 + 3][j];
+#pragma unroll
+      for (int k8 = 0; k8 < kFBlk; k8 += 8) {
+        float4 e[8];
+        float u[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {                            // all loads of 8 steps first, then the dependent FMAs
+          e[q] = *reinterpret_cast<const float4*>(&sm.Et[eb ^ 1][k8 + q][r4 * 4]);
+          u[q] = sm.Ua[eb][k8 + q][j];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (SEM == TQ_LOOP_TRITON) {
+            a0 = fmaf(-e[q].x, u[q], a0);
+            a1 = fmaf(-e[q].y, u[q], a1);
+            a2 = fmaf(-e[q].z, u[q], a2);
+            a3 = fmaf(-e[q].w, u[q], a3);
+          } else {
+            a0 = __fsub_rn(a0, __fmul_rn(e[q].x, u[q]));
+            a1 = __fsub_rn(a1, __fmul_rn(e[q].y, u[q]));
+            a2 = __fsub_rn(a2, __fmul_rn(e[q].z, u[q]));
+            a3 = __fsub_rn(a3, __fmul_rn(e[q].w, u[q]));
+          }
+        }
+      }
+      sm.Wb[r4 * 4 + 0][j] = a0;
+      sm.Wb[r4 * 4 + 1][j] = a1;
+      sm.Wb[r4 * 4 + 2][j] = a2;
+      sm.Wb[r4 * 4 + 3][j] = a3;
+    }
+    __syncthreads();
+    lap(quantiser ? 7 : 1);                                        // 1: part A
+
+    if (quantiser) {
+      fused_quantise<SEM>(sm, eb, lane, cnt, min_q, max_q);
+    } else if (worker && b0 > 0) {
+      // ---- part B (workers): the previous sub-block's updates on the columns beyond this sub-block
+      const int len = cntM - (b0 + kFBlk);
+      if (len > 0) {
+        const int quarter = ((len + 2) / 3 + 31) / 32 * 32;       // columns per worker third
+        const int64_t j0 = M0 + b0 + kFBlk;
+        const int64_t krow0 = c0 - kFBlk;
+#define TQ_PART_B(NI) fused_part_b<SEM, NI>(sm, Wp, n, U, m, r0, krow0, kFBlk, j0, len, quarter, eb ^ 1, wtid)
+        switch (quarter / 32) {
+          case 1: TQ_PART_B(1); break;
+          case 2: TQ_PART_B(2); break;
+          case 3: TQ_PART_B(3); break;
+          case 4: TQ_PART_B(4); break;
+          case 5: TQ_PART_B(5); break;
+          case 6: TQ_PART_B(6); break;
+          case 7: TQ_PART_B(7); break;
+          case 8: TQ_PART_B(8); break;
+          case 9: TQ_PART_B(9); break;
+          default: TQ_PART_B(kFNi); break;
+        }
+#undef TQ_PART_B
+      }
+    }
+    lap(quantiser ? 2 : 3);                                        // 2: quantiser, 3: part B (own work, before the barrier)
+    __syncthreads();
+    lap(quantiser ? 7 : 4);                                        // 4: workers waiting for the quantiser
+
+    // ---- store: dequantised values, codes, errors (coalesced along the columns)
+    for (int idx = tid; idx < kFRows * kFBlk; idx += kFThreads) {
+      const int r = idx / kFBlk, j = idx % kFBlk;
+      if (r0 + r >= m) continue;
+      const float ev = sm.Et[eb][j][r];
+      const int64_t eo = (r0 + r) * kMacro + b0 + j;
+      E[eo] = ev;
+      if (E_hi) {
+        float hi, lo;
+        split_tf32(ev, hi, lo);
+        E_hi[eo] = hi;
+        E_lo[eo] = lo;
+      }
+      if (j < cnt) {
+        Wp[(r0 + r) * n + c0 + j] = sm.Wb[r][j];
+        if (Cp) Cp[(r0 + r) * n + c0 + j] = sm.Cb[j][r];
+      }
+    }
+    __syncthreads();       // Wb is reloaded next; part B's global writes precede the next loads
+    lap(quantiser ? 7 : 5);                                        // 5: store phase
+  }
+  cp_async_wait_group<0>();
+}
+
 // ------------------------------------------------------------------ lazy trailing update (SIMT)
 // C[m x N] -= A[m x K] . B[K x N], K <= 1024, strict fp32 (the reference disables TF32,
 // gptq_utils.py:474-475).  64 x 64 tile per CTA, 4 x 4 per thread, k ascending.  Three arithmetics:
@@ -435,6 +790,7 @@ extern "C" int tq_gptq_loop_workspace(int64_t m, int64_t n, int64_t k, size_t* b
   b += ws_bytes_for(size_t(n), 4) * 2;     // invperm, gidx
   b += ws_bytes_for(size_t(k) + 1, 4);     // dvec
   b += ws_bytes_for(1, 4);                 // bad flag
+  b += ws_bytes_for(8, 8);                 // cycle counters of the fused kernel (TQ_TRACE)
   *bytes = b;
   return TQ_OK;
 }
@@ -479,6 +835,7 @@ extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dt
   int* gidx = wsp.take<int>(n);
   float* dvec = wsp.take<float>(k + 1);
   int* bad = wsp.take<int>(1);
+  long long* fstats = wsp.take<long long>(8);
   if (wsp.overflow) {
     set_error("tq_gptq_loop: workspace too small (%zu < %zu)", ws_bytes, wsp.off);
     return TQ_ERR_WORKSPACE;
@@ -546,8 +903,34 @@ extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dt
     return TQ_OK;
   };
   const int seq_mode = semantics == TQ_LOOP_TRITON ? kSeqFma : kSeqMulSub;
+  // fused macro-block kernel whenever every pair inside a macro block lies inside one reference block
+  const bool fused = (ref_block % kMacro == 0) && (n % 4 == 0);
+  const size_t fsmem = sizeof(FusedSmem) + 16;
+  const bool ftrace = fused && trace_enabled();
+  if (ftrace) TQ_CUDA_CHECK(cudaMemsetAsync(fstats, 0, 8 * sizeof(long long), st));
+  if (fused) {
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(gptq_macro_kernel<TQ_LOOP_TRITON>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)fsmem));
+    TQ_CUDA_CHECK(cudaFuncSetAttribute(gptq_macro_kernel<TQ_LOOP_TORCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)fsmem));
+  }
   for (int64_t M0 = 0; M0 < k; M0 += kMacro) {
     const int64_t M1 = imin(M0 + kMacro, k);
+    if (fused) {
+      const unsigned fgrid = (unsigned)ceil_div(m, kFRows);
+      const int cntM = int(M1 - M0);
+      const int bslot = prof_begin_launch(st, double(m) * cntM * 8.0, TQ_PROF_LOOP_BLOCK);
+      if (semantics == TQ_LOOP_TRITON)
+        gptq_macro_kernel<TQ_LOOP_TRITON><<<fgrid, kFThreads, fsmem, st>>>(
+            Wp, n, U, dvec, scale, zero, ng, gidx, m, M0, cntM, min_q, max_q, E, use_tc ? E_hi : nullptr,
+            use_tc ? E_lo : nullptr, Cp, ftrace ? fstats : nullptr);
+      else
+        gptq_macro_kernel<TQ_LOOP_TORCH><<<fgrid, kFThreads, fsmem, st>>>(
+            Wp, n, U, dvec, scale, zero, ng, gidx, m, M0, cntM, min_q, max_q, E, use_tc ? E_hi : nullptr,
+            use_tc ? E_lo : nullptr, Cp, ftrace ? fstats : nullptr);
+      prof_end_launch(st, bslot);
+      TQ_LAUNCH_CHECK();
+    } else {
     for (int64_t c0 = M0; c0 < M1; c0 += kBlk) {
       const int cnt = int(imin(kBlk, M1 - c0));
       float* Eb = E + (c0 - M0);
@@ -569,12 +952,21 @@ extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dt
       const int64_t d0 = imax(j0, ref_end);
       TQ_TRY(trailing(d0, M1 - d0, c0 - M0, c0, cnt, kSeqDelta));
     }
+    }
     // everything beyond the macro block: columns that still belong to the macro block's reference block
     // (ref_block > 1024) sequentially, the rest as one K = 1024 product
     const int64_t ref_end_far = imin((M0 / ref_block + 1) * int64_t(ref_block), k);
     if (ref_end_far > M1) TQ_TRY(trailing(M1, ref_end_far - M1, 0, M0, int(M1 - M0), seq_mode));
     const int64_t f0 = imax(M1, ref_end_far);
     TQ_TRY(trailing(f0, n - f0, 0, M0, int(M1 - M0), kSeqDelta));
+  }
+  if (ftrace) {
+    long long hs[8];
+    TQ_CUDA_CHECK(cudaMemcpyAsync(hs, fstats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+    fprintf(stderr, "[tq-trace] gptq_macro_kernel CTA 0, kcycles over %lld macro blocks: load %.0f  part A %.0f  quantiser %.0f  "
+            "part B %.0f  workers waiting %.0f  store %.0f\n", (long long)ceil_div(k, kMacro), hs[0] * 1e-3, hs[1] * 1e-3,
+            hs[2] * 1e-3, hs[3] * 1e-3, hs[4] * 1e-3, hs[5] * 1e-3);
   }
   if (k < n) {
     dim3 grid((unsigned)imin(ceil_div(n - k, 256), 64), (unsigned)m);
