@@ -24,8 +24,8 @@ _i64, _i32, _vp, _sz, _dbl = C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_dou
 
 PROF_KINDS = ["sytrd_panel_sym_kernel", "sytrd_panel_kernel", "qrcp_panel_kernel", "sb2st_chase_kernel",
               "pchol_panel_kernel", "qr_cluster_panel_kernel", "gptq_block_kernel", "trailing_tc_kernel",
-              "trailing_update_kernel", "syrk_tcgen05_kernel"]
-PROF_UNIT = ["B", "B", "B", "B", "B", "B", "B", "flop", "flop", "flop"]
+              "trailing_update_kernel", "syrk_tcgen05_kernel", "metric_tc_kernel"]
+PROF_UNIT = ["B", "B", "B", "B", "B", "B", "B", "flop", "flop", "flop", "flop"]
 
 STAGE_CALLBACK = C.CFUNCTYPE(None, C.c_int, C.c_void_p)
 TQ_STAGE_SYTRD_DONE = 1
@@ -62,9 +62,11 @@ SIGNATURES = {
     "tq_gptq_loop": [_vp, _i64, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32,
                      _i32, _vp, _i64, _vp, _i64, _vp, _sz, _vp],
     "tq_pack_codes": [_vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp],
+    "tq_pack_gptq": [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _i64, _vp],
     "tq_quant_error_workspace": [_i64, _i64, _i64, C.POINTER(_sz)],
     "tq_cholesky_workspace": [_i64, C.POINTER(_sz)],
     "tq_cholesky_solve": [_vp, _i64, _i64, _vp, _dbl, _vp, _i64, C.POINTER(_i32), _vp, _sz, _vp],
+    "tq_sketch_accum_workspace": [_i64, _i64, _i64, C.POINTER(_sz)],
     "tq_sketch_accum": [_vp, _i64, _vp, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _sz, _vp],
     "tq_sketch_workspace": [_i64, _i64, C.POINTER(_sz)],
     "tq_sketch_solve": [_vp, _i64, _i64, _i64, _dbl, _i32, _vp, _vp, C.POINTER(_i64), _vp, _sz, _vp],

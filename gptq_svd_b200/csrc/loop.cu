@@ -754,9 +754,50 @@ __global__ void pack_codes_kernel(const uint8_t* __restrict__ codes, int64_t ldc
   }
 }
 
+// GPTQ / AutoGPTQ checkpoint layout: words [ceil(n bits / 32), m] int32, word w of OUTPUT row j holds bits
+// [32 w, 32 w + 32) of that row's LSB-first bitstream over the INPUT dimension (for 2 / 4 / 8 bits: 32 / bits
+// consecutive input columns per word; for 3 bits AutoGPTQ's 32-values-in-3-words scheme, which is the same
+// bitstream).  `add` is added to every code first (modulo 2^bits) - qzeros store zero - 1 in the v1 format.
+__global__ void pack_gptq_kernel(const uint8_t* __restrict__ codes, int64_t ldc, int64_t m, int64_t n, int bits,
+                                 int add, uint32_t* __restrict__ out, int64_t ldo, int64_t nwords) {
+  const int64_t w = blockIdx.y;
+  const uint32_t mask = (1u << bits) - 1u;
+  for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < m; j += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t bit0 = w * 32;
+    int64_t i = bit0 / bits;
+    int off = int(bit0 - i * bits);
+    uint64_t acc = 0;
+    int have = 0;
+    if (off) {
+      acc = uint64_t((uint32_t(codes[j * ldc + i]) + uint32_t(add)) & mask) >> off;
+      have = bits - off;
+      ++i;
+    }
+    while (have < 32 && i < n) {
+      acc |= uint64_t((uint32_t(codes[j * ldc + i]) + uint32_t(add)) & mask) << have;
+      have += bits;
+      ++i;
+    }
+    out[w * ldo + j] = uint32_t(acc & 0xffffffffu);
+  }
+}
+
 }  // namespace tq
 
 using namespace tq;
+
+extern "C" int tq_pack_gptq(const uint8_t* codes, int64_t ldc, int64_t m, int64_t n, int bits, int add,
+                            uint32_t* out, int64_t ldo, void* stream) {
+  TQ_TRY(check_device());
+  TQ_REQUIRE(codes && out && m > 0 && n > 0 && ldc >= n && ldo >= m, "tq_pack_gptq: bad arguments");
+  TQ_REQUIRE(bits >= 2 && bits <= 8, "tq_pack_gptq: bits=%d outside [2,8]", bits);
+  const int64_t nwords = (n * bits + 31) / 32;
+  TQ_REQUIRE(nwords <= 65535, "tq_pack_gptq: too many words per row");
+  dim3 grid((unsigned)imin(ceil_div(m, 128), 1024), (unsigned)nwords);
+  pack_gptq_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(codes, ldc, m, n, bits, add, out, ldo, nwords);
+  TQ_LAUNCH_CHECK();
+  return TQ_OK;
+}
 
 extern "C" int tq_find_params(const float* W, int64_t ldw, int64_t m, int64_t n, int bits, int group,
                               int sym, float* scale, float* zero, void* stream) {

@@ -3,6 +3,8 @@
 //   built from warp-level scans) -> S = Lambda^1/2 V_k^T -> pivot order + R_x (pivoted Cholesky of
 //   S^T S, pchol.cu; or the Householder column-pivoted QR of S, qr.cu) ->
 //   B = Lambda^-1/2 V_k^T[:, perm] -> unpivoted QR -> sign-normalised R_x, R (row-major).
+#include <cuda.h>
+
 #include "solver_kernels.cuh"
 
 namespace tq {
@@ -408,42 +410,84 @@ __global__ void any_to_f32_kernel(const void* __restrict__ src, int dtype, int64
 }
 }  // namespace tq
 
-/* Y (rank x n fp32) += Rb (rank x rows fp32) @ float32(X) (rows x n): Sketcher.hook_fn, gptq_utils.py:185-203.
- * Plain fp32 SGEMM (TF32 off, like torch's default for addmm_).  ws: rows * n floats when X is not fp32. */
+namespace tq {
+struct TrailingTc {
+  CUtensorMap ehi, elo, uhi, ulo;
+  uint32_t idesc;
+};
+int trailing_tc_prepare_ex(TrailingTc* t, const float* A_hi, const float* A_lo, int64_t m, int64_t lda, int64_t kdim,
+                           const float* BT_hi, const float* BT_lo, int64_t kpad, int64_t n);
+int trailing_tc_launch_ex(const TrailingTc* t, float* C, int64_t ldc, int64_t m, int64_t N, int64_t e_col0,
+                          int64_t u_row0, int64_t kcount, int64_t u_col0, float sign, cudaStream_t st);
+__global__ void split_transpose_u_kernel(const float* __restrict__ U, int64_t k, int64_t n, int64_t kpad,
+                                         float* __restrict__ UT_hi, float* __restrict__ UT_lo);
+
+// hi / lo TF32 planes (rows x ldp, zero padded) of a row-major fp32 matrix
+__global__ void split_planes_kernel(const float* __restrict__ A, int64_t lda, int64_t rows, int64_t cols, int64_t ldp,
+                                    float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t r = blockIdx.y;
+  for (int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; c < ldp; c += int64_t(gridDim.x) * blockDim.x) {
+    float h = 0.f, l = 0.f;
+    if (c < cols) {
+      const float x = A[r * lda + c];
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+      h = __uint_as_float(hb);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fsub_rn(x, h)));
+      l = __uint_as_float(lb);
+    }
+    hi[r * ldp + c] = h;
+    lo[r * ldp + c] = l;
+  }
+}
+}  // namespace tq
+
+extern "C" int tq_sketch_accum_workspace(int64_t rank, int64_t rows, int64_t n, size_t* bytes) {
+  TQ_REQUIRE(bytes && rank > 0 && rows > 0 && n > 0, "tq_sketch_accum_workspace: bad arguments");
+  const size_t rp = size_t((rows + 3) / 4 * 4);
+  *bytes = ws_bytes_for(size_t(rows) * n, 4) + 2 * ws_bytes_for(size_t(n) * rp, 4) + 2 * ws_bytes_for(size_t(rank) * rp, 4) +
+           4096;
+  return TQ_OK;
+}
+
+/* Y (rank x n fp32) += Rb (rank x rows fp32) @ float32(X) (rows x n): Sketcher.hook_fn, gptq_utils.py:185-203 (an fp32
+ * matmul with TF32 off in the reference).  Runs on the tensor cores with fp32-grade arithmetic: both operands split
+ * into TF32 hi + lo planes, three tcgen05 MMAs per k-step, 128 k per TMEM accumulation, chunks added in fp32
+ * registers, ONE rounding when the batch's product is added to Y - the kernel of the GPTQ trailing update
+ * (trailing_tc.cu) with sign +1.  X is cast to fp32 and transposed first (the tensor core wants both operands
+ * k-contiguous).  ws: tq_sketch_accum_workspace(rank, rows, n) bytes. */
 extern "C" int tq_sketch_accum(float* Y, int64_t ldy, const float* Rb, int64_t ldr, const void* X, int x_dtype,
                                int64_t ldx, int64_t rank, int64_t rows, int64_t n, void* ws, size_t ws_bytes,
                                void* stream) {
   TQ_TRY(check_device());
   TQ_REQUIRE(Y && Rb && X && rank > 0 && rows > 0 && n > 0 && ldy >= n && ldr >= rows && ldx >= n,
              "tq_sketch_accum: bad arguments");
+  TQ_REQUIRE(rows < (int64_t(1) << 31) && n < (int64_t(1) << 31), "tq_sketch_accum: shape too large");
   cudaStream_t st = (cudaStream_t)stream;
-  cublasHandle_t h;
-  TQ_TRY(get_cublas(&h, st));
-  const float* Xf = reinterpret_cast<const float*>(X);
-  int64_t ldxf = ldx;
-  if (x_dtype != TQ_F32) {
-    Workspace wsp(ws, ws_bytes);
-    float* tmp = wsp.take<float>(size_t(rows) * n);
-    if (wsp.overflow) {
-      set_error("tq_sketch_accum: workspace too small (need rows * n floats)");
-      return TQ_ERR_WORKSPACE;
-    }
-    any_to_f32_kernel<<<(unsigned)imin(ceil_div(rows * n, 256), 65535), 256, 0, st>>>(X, x_dtype, ldx, rows, n, tmp);
+  const int64_t rp = (rows + 3) / 4 * 4;
+  Workspace wsp(ws, ws_bytes);
+  float* Xf = wsp.take<float>(size_t(rows) * n);
+  float* XT_hi = wsp.take<float>(size_t(n) * rp);
+  float* XT_lo = wsp.take<float>(size_t(n) * rp);
+  float* R_hi = wsp.take<float>(size_t(rank) * rp);
+  float* R_lo = wsp.take<float>(size_t(rank) * rp);
+  if (wsp.overflow) {
+    set_error("tq_sketch_accum: workspace too small (see tq_sketch_accum_workspace)");
+    return TQ_ERR_WORKSPACE;
+  }
+  any_to_f32_kernel<<<(unsigned)imin(ceil_div(rows * n, 256), 65535), 256, 0, st>>>(X, x_dtype, ldx, rows, n, Xf);
+  TQ_LAUNCH_CHECK();
+  {
+    dim3 tg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(rp, 32));
+    split_transpose_u_kernel<<<tg, dim3(32, 8), 0, st>>>(Xf, rows, n, rp, XT_hi, XT_lo);
     TQ_LAUNCH_CHECK();
-    Xf = tmp;
-    ldxf = n;
+    dim3 sg((unsigned)imin(ceil_div(rp, 256), 64), (unsigned)rank);
+    split_planes_kernel<<<sg, 256, 0, st>>>(Rb, ldr, rank, rows, rp, R_hi, R_lo);
+    TQ_LAUNCH_CHECK();
   }
-  const float one = 1.0f;
-  // row-major Y += Rb X  ==  column-major Y^T (n x rank) += X^T (n x rows) Rb^T (rows x rank)
-  TQ_CUBLAS_CHECK(cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH));
-  cublasStatus_t cs = cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, int(n), int(rank), int(rows), &one, Xf, int(ldxf), Rb,
-                                  int(ldr), &one, Y, int(ldy));
-  cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
-  if (cs != CUBLAS_STATUS_SUCCESS) {
-    set_error("tq_sketch_accum: cublasSgemm failed with status %d", int(cs));
-    return TQ_ERR_CUDA;
-  }
-  return TQ_OK;
+  TrailingTc tc;
+  TQ_TRY(trailing_tc_prepare_ex(&tc, R_hi, R_lo, rank, rp, rp, XT_hi, XT_lo, rp, n));
+  return trailing_tc_launch_ex(&tc, Y, ldy, rank, n, 0, 0, rows, 0, 1.0f, st);
 }
 
 extern "C" int tq_sketch_workspace(int64_t rank, int64_t n, size_t* bytes) {

@@ -55,7 +55,7 @@ trailing_tc_kernel(const __grid_constant__ CUtensorMap map_ehi, const __grid_con
                    const __grid_constant__ CUtensorMap map_uhi, const __grid_constant__ CUtensorMap map_ulo,
                    float* __restrict__ C, int64_t ldc, int64_t m, int64_t N, int e_col0 /*first E column*/,
                    int k_row0 /*first U row*/, int u_col0 /*first U column of this update*/, int num_kstages,
-                   uint32_t idesc) {
+                   uint32_t idesc, float sign /* C += sign * (E . U): -1 for the GPTQ update, +1 for the sketch */) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + size_t(kTcStages) * kTcStageBytes);
@@ -122,16 +122,16 @@ trailing_tc_kernel(const __grid_constant__ CUtensorMap map_ehi, const __grid_con
 #pragma unroll
         for (int c = 0; c < 128; c += 4) {
           float4 v = *reinterpret_cast<float4*>(crow + c);
-          v.x = __fsub_rn(v.x, acc[c]);
-          v.y = __fsub_rn(v.y, acc[c + 1]);
-          v.z = __fsub_rn(v.z, acc[c + 2]);
-          v.w = __fsub_rn(v.w, acc[c + 3]);
+          v.x = __fadd_rn(v.x, sign * acc[c]);          // sign = -1: exactly v - acc
+          v.y = __fadd_rn(v.y, sign * acc[c + 1]);
+          v.z = __fadd_rn(v.z, sign * acc[c + 2]);
+          v.w = __fadd_rn(v.w, sign * acc[c + 3]);
           *reinterpret_cast<float4*>(crow + c) = v;
         }
       } else {
 #pragma unroll
         for (int c = 0; c < 128; ++c)
-          if (col0 + c < N) crow[c] = __fsub_rn(crow[c], acc[c]);
+          if (col0 + c < N) crow[c] = __fadd_rn(crow[c], sign * acc[c]);
       }
     }
   } else {
@@ -207,20 +207,27 @@ struct TrailingTc {
   uint32_t idesc;
 };
 
-// UT_hi / UT_lo: n x kpad (U transposed, k contiguous, kpad = k rounded up to 4, zero padded)
-int trailing_tc_prepare(TrailingTc* t, const float* E_hi, const float* E_lo, int64_t m, const float* UT_hi,
-                        const float* UT_lo, int64_t kpad, int64_t n) {
-  TQ_TRY(make_tmap_2d(&t->ehi, E_hi, TQ_F32, 1024, uint64_t(m), 1024 * 4, kTcKStage, kTcM));
-  TQ_TRY(make_tmap_2d(&t->elo, E_lo, TQ_F32, 1024, uint64_t(m), 1024 * 4, kTcKStage, kTcM));
-  TQ_TRY(make_tmap_2d(&t->uhi, UT_hi, TQ_F32, uint64_t(kpad), uint64_t(n), uint64_t(kpad) * 4, kTcKStage, kTcN));
-  TQ_TRY(make_tmap_2d(&t->ulo, UT_lo, TQ_F32, uint64_t(kpad), uint64_t(n), uint64_t(kpad) * 4, kTcKStage, kTcN));
+// A_hi / A_lo: m x lda planes of the left operand (k contiguous, `kdim` valid columns);
+// BT_hi / BT_lo: n x kpad planes of the right operand TRANSPOSED (k contiguous, kpad = k rounded up to 4, zero padded)
+int trailing_tc_prepare_ex(TrailingTc* t, const float* A_hi, const float* A_lo, int64_t m, int64_t lda, int64_t kdim,
+                           const float* BT_hi, const float* BT_lo, int64_t kpad, int64_t n) {
+  TQ_TRY(make_tmap_2d(&t->ehi, A_hi, TQ_F32, uint64_t(kdim), uint64_t(m), uint64_t(lda) * 4, kTcKStage, kTcM));
+  TQ_TRY(make_tmap_2d(&t->elo, A_lo, TQ_F32, uint64_t(kdim), uint64_t(m), uint64_t(lda) * 4, kTcKStage, kTcM));
+  TQ_TRY(make_tmap_2d(&t->uhi, BT_hi, TQ_F32, uint64_t(kpad), uint64_t(n), uint64_t(kpad) * 4, kTcKStage, kTcN));
+  TQ_TRY(make_tmap_2d(&t->ulo, BT_lo, TQ_F32, uint64_t(kpad), uint64_t(n), uint64_t(kpad) * 4, kTcKStage, kTcN));
   t->idesc = ptx::make_idesc(/*TF32*/ 2u, /*A K-major*/ 0u, /*B K-major*/ 0u, kTcM, kTcN);
   return TQ_OK;
 }
 
-// C (m x N, ldc) -= E[:, e_col0 : e_col0 + kcount] . U[u_row0 : u_row0 + kcount, u_col0 : u_col0 + N]
-int trailing_tc_launch(const TrailingTc* t, float* C, int64_t ldc, int64_t m, int64_t N, int64_t e_col0,
-                       int64_t u_row0, int kcount, int64_t u_col0, cudaStream_t st) {
+// UT_hi / UT_lo: n x kpad (U transposed, k contiguous, kpad = k rounded up to 4, zero padded); E planes m x 1024
+int trailing_tc_prepare(TrailingTc* t, const float* E_hi, const float* E_lo, int64_t m, const float* UT_hi,
+                        const float* UT_lo, int64_t kpad, int64_t n) {
+  return trailing_tc_prepare_ex(t, E_hi, E_lo, m, 1024, 1024, UT_hi, UT_lo, kpad, n);
+}
+
+// C (m x N, ldc) += sign * E[:, e_col0 : e_col0 + kcount] . U[u_row0 : u_row0 + kcount, u_col0 : u_col0 + N]
+int trailing_tc_launch_ex(const TrailingTc* t, float* C, int64_t ldc, int64_t m, int64_t N, int64_t e_col0,
+                          int64_t u_row0, int64_t kcount, int64_t u_col0, float sign, cudaStream_t st) {
   static thread_local bool attr_done[kMaxDevices] = {};
   if (!attr_done[device_slot()]) {
     TQ_CUDA_CHECK(cudaFuncSetAttribute(trailing_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -231,10 +238,15 @@ int trailing_tc_launch(const TrailingTc* t, float* C, int64_t ldc, int64_t m, in
   const int num_kstages = int(ceil_div(kcount, kTcKStage));
   const int pslot = prof_begin_launch(st, 2.0 * double(m) * double(N) * double(kcount), TQ_PROF_TRAILING_TC);
   trailing_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(t->ehi, t->elo, t->uhi, t->ulo, C, ldc, m, N, int(e_col0),
-                                                        int(u_row0), int(u_col0), num_kstages, t->idesc);
+                                                        int(u_row0), int(u_col0), num_kstages, t->idesc, sign);
   prof_end_launch(st, pslot);
   TQ_LAUNCH_CHECK();
   return TQ_OK;
+}
+
+int trailing_tc_launch(const TrailingTc* t, float* C, int64_t ldc, int64_t m, int64_t N, int64_t e_col0,
+                       int64_t u_row0, int kcount, int64_t u_col0, cudaStream_t st) {
+  return trailing_tc_launch_ex(t, C, ldc, m, N, e_col0, u_row0, kcount, u_col0, -1.0f, st);
 }
 
 }  // namespace tq

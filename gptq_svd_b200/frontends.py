@@ -91,12 +91,13 @@ class Sketcher:
             R_batch = torch.randn((self.rank, batch_count), device=self.device, dtype=torch.float32)
         lib = _lib.load()
         with torch.cuda.device(self.Y.device):
-            ws = None
-            if x.dtype != torch.float32:
-                ws = _workspace(batch_count * self.in_features * 4 + 512, self.Y.device)
+            nbytes = C.c_size_t(0)
+            check(lib.tq_sketch_accum_workspace(self.rank, batch_count, self.in_features, C.byref(nbytes)),
+                  "tq_sketch_accum_workspace")
+            ws = _workspace(nbytes.value, self.Y.device)
             check(lib.tq_sketch_accum(_ptr(self.Y), self.Y.stride(0), _ptr(R_batch), R_batch.stride(0), _ptr(x),
                                       _DTYPE_CODE[x.dtype], x.stride(0), self.rank, batch_count, self.in_features,
-                                      _ptr(ws), ws.numel() if ws is not None else 0, _stream(self.Y)),
+                                      _ptr(ws), ws.numel(), _stream(self.Y)),
                   "tq_sketch_accum")
 
     def hook_fn(self, module: nn.Module, input_args, output):

@@ -378,3 +378,38 @@ def pack_codes(codes: torch.Tensor, bits: int) -> torch.Tensor:
         check(lib.tq_pack_codes(_ptr(codes), codes.stride(0), m, n, bits, _ptr(out), nwords, _stream(codes)),
               "tq_pack_codes")
     return out
+
+
+def export_gptq(q: QuantizedLinear, group_size: int, scales_dtype: torch.dtype = torch.float16, v1_zero_offset: bool = True):
+    """Checkpoint tensors of one Linear in the GPTQ / AutoGPTQ layout that vLLM's `gptq` loader reads (the
+    packed-weight output the reference lists as a roadmap item, README.md:133):
+
+        qweight  int32 [in_features * bits / 32, out_features]   codes packed along the INPUT dimension
+        qzeros   int32 [n_groups, out_features * bits / 32]       zero points packed along the OUTPUT dimension
+        scales   fp16  [n_groups, out_features]
+        g_idx    int32 [in_features] = i // group_size            sequential groups (static groups: README.md:43)
+
+    Stored values are unsigned: code' = code - min_q, zero' = zero - min_q (symmetric grids: min_q = -(2^(b-1) - 1),
+    zero = 0), so W[j, i] = scales[g, j] * (code'[i, j] - zero'[g, j]).  `v1_zero_offset=True` stores zero' - 1
+    (modulo 2^bits) as the v1 format does; readers add the 1 back.  2 / 4 / 8 bits put 32 / bits values into a
+    word, 3 bits 32 values into 3 words (AutoGPTQ's scheme = the LSB-first bitstream)."""
+    _require_cuda(q.codes, "export_gptq")
+    lib = _lib.load()
+    m, n = q.codes.shape
+    bits = q.bits
+    g = group_size if group_size > 0 else n
+    if n % g != 0 or (n * bits) % 32 != 0 or (m * bits) % 32 != 0:
+        raise ValueError(f"export_gptq: in_features {n} / out_features {m} do not pack into whole 32-bit words at {bits} bits")
+    ng = n // g
+    dev = q.codes.device
+    codes = q.codes.contiguous()
+    qweight = torch.empty((n * bits // 32, m), dtype=torch.int32, device=dev)
+    zeros_u8 = (q.zero.to(torch.float32) - float(q.min_q)).round().to(torch.uint8).t().contiguous()      # [ng, m]
+    qz_t = torch.empty((m * bits // 32, ng), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.tq_pack_gptq(_ptr(codes), n, m, n, bits, 0, _ptr(qweight), m, _stream(codes)), "tq_pack_gptq")
+        check(lib.tq_pack_gptq(_ptr(zeros_u8), m, ng, m, bits, -1 if v1_zero_offset else 0, _ptr(qz_t),
+                               ng, _stream(codes)), "tq_pack_gptq")
+    return {"qweight": qweight, "qzeros": qz_t.t().contiguous(), "scales": q.scale.t().contiguous().to(scales_dtype),
+            "g_idx": (torch.arange(n, device=dev, dtype=torch.int32) // g), "bits": bits, "group_size": g,
+            "sym": q.min_q < 0, "zero_offset": 1 if v1_zero_offset else 0}

@@ -226,6 +226,17 @@ int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dtype, int64_
 int tq_pack_codes(const uint8_t* codes, int64_t ldc, int64_t m, int64_t n, int bits,
                   uint32_t* packed, int64_t ldp, void* stream);
 
+/* GPTQ / AutoGPTQ / vLLM checkpoint layout (the packed-weight output the reference lists as a roadmap item,
+ * README.md:133; sequential groups, no act-order g_idx, README.md:43).  `codes`: rows x cols uint8, value < 2^bits.
+ * out: [ceil(cols * bits / 32), rows] uint32 with leading dimension ldo: word w of row j holds bits [32 w, 32 w + 32)
+ * of that row's LSB-first bitstream - for 2 / 4 / 8 bits 32 / bits consecutive columns per word, for 3 bits
+ * AutoGPTQ's 32-values-in-3-words scheme (the same bitstream).  `add` is added to every code modulo 2^bits.
+ *   qweight = tq_pack_gptq(codes [out_features x in_features], add = 0)        -> [in * bits / 32, out]
+ *   qzeros  = tq_pack_gptq(zeros^T [n_groups x out_features], add = -1) ^T     (v1 stores zero - 1; see
+ *             gptq_svd_b200/gptq_utils.py: export_gptq) */
+int tq_pack_gptq(const uint8_t* codes, int64_t ldc, int64_t rows, int64_t cols, int bits, int add, uint32_t* out,
+                 int64_t ldo, void* stream);
+
 int tq_quant_error_workspace(int64_t m, int64_t n, int64_t k, size_t* bytes);
 
 /* out2[0] = ||(W - Wq)[:,perm] Rx^T||_F^2, out2[1] = ||W[:,perm] Rx^T||_F^2 in fp32
@@ -255,10 +266,13 @@ int tq_cholesky_solve(const double* H, int64_t ldh, int64_t n, const int64_t* pe
                       double* Hinv_chol, int64_t ldo, int* damp_exp_host, void* ws, size_t ws_bytes,
                       void* stream);
 
+int tq_sketch_accum_workspace(int64_t rank, int64_t rows, int64_t n, size_t* bytes);
+
 /* Sketch accumulation - replaces the GEMM of Sketcher.hook_fn (gptq_utils.py:185-203):
  * Y (rank x n fp32) += Rb (rank x rows fp32, the caller's Gaussian block) @ float32(X) with X
- * rows x n (TQ_F16 / TQ_BF16 / TQ_F32 / TQ_F64).  Strict fp32 SGEMM (no TF32).
- * ws: rows * n floats when X is not fp32 (may be NULL otherwise). */
+ * rows x n (TQ_F16 / TQ_BF16 / TQ_F32 / TQ_F64).  fp32-grade arithmetic on the tensor cores (3xTF32 with
+ * 128-deep TMEM accumulations added in fp32 registers; the reference runs an fp32 matmul with TF32 off).
+ * ws: tq_sketch_accum_workspace(rank, rows, n) bytes. */
 int tq_sketch_accum(float* Y, int64_t ldy, const float* Rb, int64_t ldr, const void* X, int x_dtype,
                     int64_t ldx, int64_t rank, int64_t rows, int64_t n, void* ws, size_t ws_bytes,
                     void* stream);
@@ -300,7 +314,8 @@ int64_t tq_launch_count(void);
  * TQ_PROF_LOOP_BLOCK      gptq_block_kernel                              bytes: m x 128 x 4 x 2 (W block read + written)
  * TQ_PROF_TRAILING_TC     trailing_tc_kernel (tcgen05 3xTF32)            flops: 2 m N K (algorithmic; 3x are issued)
  * TQ_PROF_TRAILING_SEQ    trailing_update_kernel (in-block pairs, SIMT)  flops: 2 m N K
- * TQ_PROF_SYRK            syrk_tcgen05_kernel                            flops: rows n (n + 1) (one triangle) */
+ * TQ_PROF_SYRK            syrk_tcgen05_kernel                            flops: rows n (n + 1) (one triangle)
+ * TQ_PROF_METRIC          metric_tc_kernel (error metric, tcgen05 TF32)  flops: 2 (2 m) k n */
 #define TQ_PROF_SYTRD_SYM 0
 #define TQ_PROF_SYTRD_COLDOT 1
 #define TQ_PROF_QRCP_PANEL 2
@@ -311,7 +326,8 @@ int64_t tq_launch_count(void);
 #define TQ_PROF_TRAILING_TC 7
 #define TQ_PROF_TRAILING_SEQ 8
 #define TQ_PROF_SYRK 9
-#define TQ_PROF_KINDS 10
+#define TQ_PROF_METRIC 10
+#define TQ_PROF_KINDS 11
 int tq_profile_begin(int sample_every);
 int tq_profile_kernel(int kind, double* work, double* ms, int64_t* sampled, int64_t* total, double* work_all,
                       double* sm_ms);
