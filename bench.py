@@ -261,7 +261,8 @@ def _config(args, k_list):
             "block_size": 1024, "activations": f"randn @ A^T, column scales logspace(0,{args.decay}), 8 outlier channels x30",
             "retained_rank": k_list, "l2": "inputs per step (12.9 GB) exceed the 126 MB L2; no explicit flush",
             "parallelism": f"layers sharded over {world} rank(s), no collective",
-            "tridiagonal_reduction": "two-stage (band + bulge chase) for n >= 8192, one-stage below",
+            "tridiagonal_reduction": {-1: "two-stage (band + bulge chase) for n >= 8192, one-stage below",
+                                      0: "one-stage", 1: "two-stage (band + bulge chase)"}[args.two_stage],
             "solves": ((f"n=12288 first; after its band reduction it drops to {args.tail_budgets.split(',')[0]} SMs and "
                         f"the three n=4096 solves run next to its bulge chase and tail ({args.tail_budgets.split(',')[1]} SMs each)"
                         if args.overlap_tail else
@@ -369,6 +370,8 @@ def main():
     ap.add_argument("--overlap-tail", type=int, default=1,
                     help="start the narrow solves when the wide solve has finished its band reduction")
     ap.add_argument("--tail-budgets", default="100,16", help="SM budgets in the tail: wide,narrow")
+    ap.add_argument("--two-stage", type=int, default=-1,
+                    help="tridiagonal reduction: -1 automatic (two-stage for n >= 8192), 0 one-stage, 1 two-stage everywhere")
     ap.add_argument("--concurrent-solves", type=int, default=1,
                     help="solve the n <= 8192 Hessians of a layer side by side on one GPU (0: one after another)")
     args = ap.parse_args()
@@ -433,6 +436,7 @@ def main():
     def solve(H):
         """process_hessian_alt on the calling (worker) thread, with that thread's kernel sampling."""
         H.record_stream(torch.cuda.current_stream(dev))
+        lib.tq_set_eigh_two_stage(args.two_stage)          # per host thread
         if prof["on"]:
             lib.tq_profile_begin(4)
         try:
