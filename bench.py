@@ -364,7 +364,7 @@ def main():
     ap.add_argument("--tiny", action="store_true", help="small shapes (functional check only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip solver_ms / kernels / block_parallel")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=3, help="0 skips the end-to-end leg (parameter sweeps)")
     ap.add_argument("--reference-sample", default="full", choices=["full", "bounded"],
                     help="--impl reference: every distinct shape once (minutes) or the 20 s sample of the ours arm")
     ap.add_argument("--overlap-tail", type=int, default=1,
@@ -606,13 +606,16 @@ def main():
     e2e = None
     Xh = Wh = Oh = None
     pin_err = ""
-    try:
+    if args.e2e_steps <= 0:
+        pin_err = "skipped (--e2e-steps 0)"
+    else:
+      try:
         def to_pinned(t):         # straight into pinned memory: no pageable copy of the 12.9 GB of activations
             return torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
         Xh = [to_pinned(x) for x in Xs]
         Wh = [[to_pinned(w) for w in ws] for ws in Ws]
         Oh = [[torch.empty(w.shape, dtype=w.dtype, pin_memory=True) for w in ws] for ws in Wh]
-    except Exception as ex:       # pinned allocation can fail on a small host
+      except Exception as ex:       # pinned allocation can fail on a small host
         pin_err = str(ex)[:200]
     pinned_ok = torch.tensor([0 if pin_err else 1], device=dev, dtype=torch.int32)
     if world > 1:                 # every rank takes the same branch: the timed region below contains barriers

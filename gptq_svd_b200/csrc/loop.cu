@@ -132,6 +132,8 @@ __global__ void split_transpose_u_kernel(const float* __restrict__ U, int64_t k,
   }
 }
 
+// invperm must be filled with -1 first: an entry out of range or seen twice sets *bad (the reference raises an
+// IndexError / silently duplicates columns; here the call fails with TQ_ERR_INVALID before anything is gathered)
 __global__ void perm_meta_kernel(const int64_t* __restrict__ perm, int64_t n, int g,
                                  int* __restrict__ invperm, int* __restrict__ gidx,
                                  int* __restrict__ bad) {
@@ -140,18 +142,19 @@ __global__ void perm_meta_kernel(const int64_t* __restrict__ perm, int64_t n, in
   int64_t p = perm[j];
   if (p < 0 || p >= n) {
     atomicExch(bad, 1);
+    gidx[j] = 0;
     return;
   }
-  invperm[p] = int(j);
+  if (atomicCAS(&invperm[p], -1, int(j)) != -1) atomicExch(bad, 1);
   gidx[j] = int(p / g);
 }
 
 __global__ void gather_cols_kernel(const float* __restrict__ W, int64_t ldw, int64_t m, int64_t n,
                                    const int64_t* __restrict__ perm, float* __restrict__ Wp) {
-  int64_t r = blockIdx.y;
-  for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
-       j += int64_t(gridDim.x) * blockDim.x)
-    Wp[r * n + j] = W[r * ldw + perm[j]];
+  for (int64_t r = blockIdx.y; r < m; r += gridDim.y)          // gridDim.y <= 65535: rows loop (lm_head-sized m)
+    for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
+         j += int64_t(gridDim.x) * blockDim.x)
+      Wp[r * n + j] = W[r * ldw + perm[j]];
 }
 
 // ------------------------------------------------------------------ quantise one value
@@ -702,15 +705,15 @@ __global__ void tail_rtn_kernel(float* __restrict__ Wp, int64_t n, int64_t m, in
                                 const float* __restrict__ scale, const float* __restrict__ zero,
                                 int ng, const int* __restrict__ gidx, float min_q, float max_q,
                                 uint8_t* __restrict__ Cp) {
-  int64_t r = blockIdx.y;
-  for (int64_t j = k + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
-       j += int64_t(gridDim.x) * blockDim.x) {
-    int g = gidx[j];
-    float q, qv;
-    quantize<false>(Wp[r * n + j], scale[r * ng + g], zero[r * ng + g], min_q, max_q, q, qv);
-    Wp[r * n + j] = qv;
-    if (Cp) Cp[r * n + j] = uint8_t(int(q - min_q));
-  }
+  for (int64_t r = blockIdx.y; r < m; r += gridDim.y)
+    for (int64_t j = k + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
+         j += int64_t(gridDim.x) * blockDim.x) {
+      int g = gidx[j];
+      float q, qv;
+      quantize<false>(Wp[r * n + j], scale[r * ng + g], zero[r * ng + g], min_q, max_q, q, qv);
+      Wp[r * n + j] = qv;
+      if (Cp) Cp[r * n + j] = uint8_t(int(q - min_q));
+    }
 }
 
 // Restore the original column order (gptq_utils.py:556-557) with coalesced writes.
@@ -718,13 +721,13 @@ __global__ void unpermute_kernel(const float* __restrict__ Wp, const uint8_t* __
                                  int64_t m, int64_t n, const int* __restrict__ invperm,
                                  float* __restrict__ Wq, int64_t ldq, uint8_t* __restrict__ codes,
                                  int64_t ldc) {
-  int64_t r = blockIdx.y;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += int64_t(gridDim.x) * blockDim.x) {
-    int j = invperm[i];
-    Wq[r * ldq + i] = Wp[r * n + j];
-    if (codes) codes[r * ldc + i] = Cp[r * n + j];
-  }
+  for (int64_t r = blockIdx.y; r < m; r += gridDim.y)
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += int64_t(gridDim.x) * blockDim.x) {
+      int j = invperm[i];
+      Wq[r * ldq + i] = Wp[r * n + j];
+      if (codes) codes[r * ldc + i] = Cp[r * n + j];
+    }
 }
 
 // ------------------------------------------------------------------ packing
@@ -732,7 +735,7 @@ __global__ void unpermute_kernel(const float* __restrict__ Wp, const uint8_t* __
 __global__ void pack_codes_kernel(const uint8_t* __restrict__ codes, int64_t ldc, int64_t m,
                                   int64_t n, int bits, uint32_t* __restrict__ packed, int64_t ldp,
                                   int64_t nwords) {
-  int64_t r = blockIdx.y;
+  for (int64_t r = blockIdx.y; r < m; r += gridDim.y)
   for (int64_t w = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; w < nwords;
        w += int64_t(gridDim.x) * blockDim.x) {
     int64_t bit0 = w * 32;
@@ -887,10 +890,17 @@ extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dt
   const float min_q = sym ? -max_q : 0.f;
 
   TQ_CUDA_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+  TQ_CUDA_CHECK(cudaMemsetAsync(invperm, 0xff, sizeof(int) * n, st));        // -1
   perm_meta_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(perm, n, int(g), invperm, gidx, bad);
   TQ_LAUNCH_CHECK();
   {
-    dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)m);
+    int hbad = 0;      // the one host synchronisation of this call: a 4-byte read-back before anything is gathered
+    TQ_CUDA_CHECK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+    TQ_REQUIRE(hbad == 0, "tq_gptq_loop: perm is not a permutation of 0 .. %lld", (long long)(n - 1));
+  }
+  {
+    dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)imin(m, 65535));
     gather_cols_kernel<<<grid, 256, 0, st>>>(W, ldw, m, n, perm, Wp);
     TQ_LAUNCH_CHECK();
   }
@@ -1010,12 +1020,12 @@ extern "C" int tq_gptq_loop(const float* W, int64_t ldw, const void* R, int r_dt
             hs[2] * 1e-3, hs[3] * 1e-3, hs[4] * 1e-3, hs[5] * 1e-3);
   }
   if (k < n) {
-    dim3 grid((unsigned)imin(ceil_div(n - k, 256), 64), (unsigned)m);
+    dim3 grid((unsigned)imin(ceil_div(n - k, 256), 64), (unsigned)imin(m, 65535));
     tail_rtn_kernel<<<grid, 256, 0, st>>>(Wp, n, m, k, scale, zero, ng, gidx, min_q, max_q, Cp);
     TQ_LAUNCH_CHECK();
   }
   {
-    dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)m);
+    dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)imin(m, 65535));
     unpermute_kernel<<<grid, 256, 0, st>>>(Wp, Cp, m, n, invperm, Wq_out, ldq, codes_out, ldc);
     TQ_LAUNCH_CHECK();
   }
@@ -1029,7 +1039,7 @@ extern "C" int tq_pack_codes(const uint8_t* codes, int64_t ldc, int64_t m, int64
   TQ_REQUIRE(bits >= 1 && bits <= 8, "tq_pack_codes: bits=%d outside [1,8]", bits);
   int64_t nwords = (n * bits + 31) / 32;
   TQ_REQUIRE(ldp >= nwords, "tq_pack_codes: ldp %lld < %lld words", (long long)ldp, (long long)nwords);
-  dim3 grid((unsigned)imin(ceil_div(nwords, 128), 64), (unsigned)m);
+  dim3 grid((unsigned)imin(ceil_div(nwords, 128), 64), (unsigned)imin(m, 65535));
   pack_codes_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(codes, ldc, m, n, bits, packed, ldp, nwords);
   TQ_LAUNCH_CHECK();
   return TQ_OK;

@@ -196,13 +196,13 @@ metric_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 __global__ void gather_diff_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ Wq,
                                    int64_t ldq, const int64_t* __restrict__ perm, int64_t m, int64_t n,
                                    float* __restrict__ Wo, float* __restrict__ D) {
-  int64_t r = blockIdx.y;
-  for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += int64_t(gridDim.x) * blockDim.x) {
-    int64_t p = perm[j];
-    float w = W[r * ldw + p];
-    Wo[r * n + j] = w;
-    D[r * n + j] = __fsub_rn(w, Wq[r * ldq + p]);
-  }
+  for (int64_t r = blockIdx.y; r < m; r += gridDim.y)
+    for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += int64_t(gridDim.x) * blockDim.x) {
+      int64_t p = perm[j];
+      float w = W[r * ldw + p];
+      Wo[r * n + j] = w;
+      D[r * n + j] = __fsub_rn(w, Wq[r * ldq + p]);
+    }
 }
 
 __global__ void sumsq_kernel(const float* __restrict__ x, int64_t count, double* __restrict__ out) {
@@ -256,7 +256,7 @@ extern "C" int tq_quant_error(const float* W, int64_t ldw, const float* Wq, int6
     TQ_LAUNCH_CHECK();
   }
   {
-    dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)m);
+    dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)imin(m, 65535));
     gather_diff_kernel<<<grid, 256, 0, st>>>(W, ldw, Wq, ldq, perm, m, n, Wo, D);
     TQ_LAUNCH_CHECK();
   }

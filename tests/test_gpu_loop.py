@@ -114,6 +114,31 @@ def test_edge_cases(G):
     # CPU tensors are refused loudly (no CPU fallback)
     with pytest.raises(RuntimeError):
         G.Quantizer(4, 128, False).find_params(torch.from_numpy(W))
+    # a perm that is not a permutation (duplicate / out of range) fails before anything is gathered
+    bad = perm.copy()
+    bad[3] = bad[4]
+    with pytest.raises(RuntimeError, match="not a permutation"):
+        G.gptq_fwrd(to_gpu(W), torch.zeros((0, n), dtype=torch.float64, device="cuda"), q, to_gpu(bad))
+    bad = perm.copy()
+    bad[0] = n
+    with pytest.raises(RuntimeError, match="not a permutation"):
+        G.gptq_fwrd(to_gpu(W), torch.zeros((0, n), dtype=torch.float64, device="cuda"), q, to_gpu(bad))
+
+
+def test_more_rows_than_a_grid_dimension(G):
+    """m > 65535 (lm_head-sized Linears): the row loops of gather / tail / un-permute and the fused kernel's grid."""
+    from gpu_common import to_gpu
+    m, n = 66000, 256
+    rng = np.random.RandomState(1)
+    W = (rng.standard_normal((m, n)) * 0.02).astype(np.float16).astype(np.float32)
+    X = O.make_activations(2048, n, seed=9, dist="llm").astype(np.float64)
+    f = O.process_hessian_alt(X.T @ X / X.shape[0], 1e-3, "energy")
+    res = G.gptq_quantize(to_gpu(W), to_gpu(f.R), G.Quantizer(4, 128, False), to_gpu(f.perm), block_size=1024)
+    rows = np.r_[0:64, 65500:65600, m - 64:m]
+    oq = O.Quantizer(4, 128, False)
+    _, _, codes_o = O.gptq_fwrd(W[rows], f.R, oq, f.perm, block_size=1024, use_triton=True, fma=True, return_codes=True)
+    codes = res.codes[torch.from_numpy(rows).cuda()].cpu().numpy().astype(np.int32) + res.min_q
+    assert np.mean(codes == codes_o) >= 0.999
 
 
 def test_full_size_properties(G):
