@@ -295,8 +295,15 @@ def _pin_to_gpu_numa(torch, local):
     """Run this process (and so first-touch its pinned staging buffers) on the NUMA node of its GPU: with all
     ranks on node 0 the host -> device staging of 8 ranks x 13.3 GB per step was the e2e limiter in round 1."""
     try:
-        prop = torch.cuda.get_device_properties(local)
-        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        try:
+            prop = torch.cuda.get_device_properties(local)
+            bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = vis.split(",")[local] if vis else str(local)
+            q = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", idx],
+                               capture_output=True, text=True, timeout=20).stdout.strip().lower()
+            bdf = q[-12:] if len(q) >= 12 else q              # "00000000:1b:00.0" -> "0000:1b:00.0"
         with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
             node = int(f.read().strip())
         if node < 0:

@@ -183,7 +183,7 @@ static size_t solver_ws_bytes(int64_t n) {
   size_t e = eigh_ws_bytes(n);
   size_t q = ws_bytes_for(size_t(n) * n, 8) * 2 + qr_stage_ws_bytes(n, n) + pchol_ws_bytes(n, n);
   size_t r = rfactor_ws_bytes(n, n);
-  for (int64_t t = n / 4; t > 0; t /= 2) r = r > rfactor_ws_bytes(n, n - t) ? r : rfactor_ws_bytes(n, n - t);
+  for (int64_t t = n / 2; t > 0; t /= 2) r = r > rfactor_ws_bytes(n, n - t) ? r : rfactor_ws_bytes(n, n - t);
   if (r > q) q = r;
   return a + (e > q ? e : q) + (size_t(1) << 20);
 }
@@ -219,9 +219,10 @@ extern "C" int tq_rank_select(const double* w_asc, int64_t n, double threshold, 
 }
 
 // Which eigenvectors a solve needs (decided as soon as the eigenvalues exist, before any back-transformation):
-//   kSubsetDropped  t = n - k <= n / 4 and no retained eigenvalue was clamped: only the t DROPPED vectors -
+//   kSubsetDropped  t = n - k < k and no retained eigenvalue was clamped: only the t DROPPED vectors -
 //                   H_k = H - V_t diag(w_t) V_t^T for the pivoted Cholesky, and R follows from R_x (rfactor.cu);
-//   kSubsetAll      t < k otherwise: all n (H_k as above, then B = Lambda^-1/2 V_k^T[:, perm] and its QR);
+//   kSubsetAll      t < k with a clamped eigenvalue (H_k must be built from the clamped spectrum): all n vectors,
+//                   then B = Lambda^-1/2 V_k^T[:, perm] and its QR;
 //   kSubsetKept     t >= k: only the k RETAINED vectors (H_k = S^T S, B and its QR).
 enum { kSubsetDropped = 0, kSubsetAll = 1, kSubsetKept = 2 };
 
@@ -262,7 +263,7 @@ static int spectral_solve_impl(const double* H, int64_t ldh, int64_t n, double t
       *ncols = 0;
       return TQ_OK;
     }
-    if (allow_dropped && !force_householder && kh2[1] == 0 && 4 * tt <= n) {
+    if (allow_dropped && !force_householder && kh2[1] == 0 && tt < kk) {
       subset = kSubsetDropped;
       *col0 = 0;
       *ncols = tt;

@@ -57,6 +57,26 @@ def _worker(rank, world, port, tmp):
                                   perm=torch.arange(n), eigvals=torch.ones(n, dtype=torch.float64), k=3)
         g = D.broadcast_factors(f, n, 1, torch.device("cpu"))
         assert g.k == 3 and g.R.shape == (3, n) and float(g.R[2, 5]) == 2 * n + 5 and int(g.perm[7]) == 7
+        # point-to-point hand-offs in the global exchange order (what quantize_block_parallel does with factors)
+        groups = [(n, [8, 8]), (n, [8]), (2 * n, [8])]
+        plan = D.BlockPlan(solve_owner=[0, 1, 0], loop_owner=[[1, 0], [0], [1]])
+        order = D.exchange_order(groups, plan)
+        assert order == [(0, 0, 1), (1, 1, 0), (2, 0, 1)]            # narrow groups first, every (src, dst) once
+        mine = {gi: D.SpectralFactors(R=torch.full((2, nn), float(gi)), R_x=torch.full((2, nn), 10.0 + gi),
+                                      perm=torch.arange(nn), eigvals=torch.ones(nn, dtype=torch.float64), k=2)
+                for gi, (nn, _) in enumerate(groups) if plan.solve_owner[gi] == rank}
+        mine = {gi: D.SpectralFactors(R=f.R.double(), R_x=f.R_x.double(), perm=f.perm, eigvals=f.eigvals, k=f.k)
+                for gi, f in mine.items()}
+        got = {}
+        for gi, src, dst in order:
+            if rank == src:
+                D.send_factors(mine[gi], dst)
+            elif rank == dst:
+                got[gi] = D.recv_factors(groups[gi][0], src, torch.device("cpu"))
+        want = {0: [1, 2], 1: [0]}[1 - rank] if False else ([1] if rank == 0 else [0, 2])
+        assert sorted(got) == want
+        for gi, f in got.items():
+            assert f.k == 2 and float(f.R[1, 3]) == float(gi) and float(f.R_x[0, 0]) == 10.0 + gi
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
