@@ -452,6 +452,33 @@ def main():
             if prof["on"]:
                 prof_collect()
 
+    e2e_state = {"step": 0, "total": 0, "pending": None, "done": [None, None]}
+
+    def enqueue_copies(x_src, w_src, order, slot):
+        """All host -> device copies of one layer into staging set `slot`, on the copy stream, in the order the groups
+        are consumed; an event per tensor.  The set is free once the step that used it last has finished."""
+        events = {}
+        if e2e_state["done"][slot] is not None:
+            copy_stream.wait_event(e2e_state["done"][slot])
+        with torch.cuda.stream(copy_stream):
+            for gi in order:
+                n, outs = groups[gi]
+                for c in range(0, tokens, chunk):
+                    key = (slot, "x", gi, c)
+                    if key not in staging:
+                        staging[key] = torch.empty((min(chunk, tokens - c), n), dtype=torch.float16, device=dev)
+                    staging[key].copy_(x_src[gi][c:c + chunk], non_blocking=True)
+                    events[("x", gi, c)] = torch.cuda.Event()
+                    events[("x", gi, c)].record(copy_stream)
+                for li, m in enumerate(outs):
+                    key = (slot, "w", gi, li)
+                    if key not in staging:
+                        staging[key] = torch.empty((m, n), dtype=torch.float16, device=dev)
+                    staging[key].copy_(w_src[gi][li], non_blocking=True)
+                    events[("w", gi, li)] = torch.cuda.Event()
+                    events[("w", gi, li)].record(copy_stream)
+        return events
+
     def layer_step(x_src, w_src, host: bool, sink=None):
         """One decoder layer through the public API.  host=True: inputs come from pinned host
         buffers - every H2D copy of the step is enqueued on a side stream up front and the compute
@@ -468,25 +495,15 @@ def main():
         tail_wide, tail_narrow = (int(v) for v in args.tail_budgets.split(","))
         budget = tail_narrow if tail else max(8, 148 // max(1, len(small)))
         if host:
-            cur = torch.cuda.current_stream(dev)
-            copy_stream.wait_stream(cur)          # staging buffers are free once the previous step is done
-            with torch.cuda.stream(copy_stream):
-                for gi in order:                      # copies in the order the groups are consumed
-                    n, outs = groups[gi]
-                    for c in range(0, tokens, chunk):
-                        key = ("x", gi, c)
-                        if key not in staging:
-                            staging[key] = torch.empty((min(chunk, tokens - c), n), dtype=torch.float16, device=dev)
-                        staging[key].copy_(x_src[gi][c:c + chunk], non_blocking=True)
-                        events[key] = torch.cuda.Event()
-                        events[key].record(copy_stream)
-                    for li, m in enumerate(outs):
-                        key = ("w", gi, li)
-                        if key not in staging:
-                            staging[key] = torch.empty((m, n), dtype=torch.float16, device=dev)
-                        staging[key].copy_(w_src[gi][li], non_blocking=True)
-                        events[key] = torch.cuda.Event()
-                        events[key].record(copy_stream)
+            # double-buffered staging: this step's copies were enqueued one step ago (or just now for the first
+            # step); the NEXT step's copies are enqueued here, behind them on the copy stream, so that the PCIe
+            # transfer of layer i + 1 runs under the solves of layer i
+            slot = e2e_state["step"] % 2
+            if e2e_state["pending"] is None:
+                e2e_state["pending"] = enqueue_copies(x_src, w_src, order, slot)
+            events = e2e_state["pending"]
+            e2e_state["pending"] = (enqueue_copies(x_src, w_src, order, slot ^ 1)
+                                    if e2e_state["step"] + 1 < e2e_state["total"] else None)
         facs = [None] * len(groups)
         pending = {}
         looped = set()
@@ -501,7 +518,7 @@ def main():
             for li, m in enumerate(outs):
                 if host:
                     torch.cuda.current_stream(dev).wait_event(events[("w", gi, li)])
-                    W = staging[("w", gi, li)]
+                    W = staging[(slot, "w", gi, li)]
                 else:
                     W = w_src[gi][li]
                 q = G.Quantizer(args.bits, 128, bool(args.sym))
@@ -515,7 +532,7 @@ def main():
             for c in range(0, tokens, chunk):
                 if host:
                     torch.cuda.current_stream(dev).wait_event(events[("x", gi, c)])
-                    xb = staging[("x", gi, c)]
+                    xb = staging[(slot, "x", gi, c)]
                 else:
                     xb = x_src[gi][c:c + chunk]
                 acc.add_batch(xb.view(-1, 2048, n) if (xb.shape[0] % 2048 == 0) else xb)
@@ -568,6 +585,11 @@ def main():
             if gi not in looped:
                 run_loops(gi)
         del facs
+        if host:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            e2e_state["done"][slot] = ev
+            e2e_state["step"] += 1
         return ks
 
     def barrier():
@@ -630,8 +652,10 @@ def main():
     try:
         if int(pinned_ok.item()) == 0:
             raise RuntimeError(pin_err or "pinned host allocation failed on another rank")
-        layer_step(Xh, Wh, True, Oh)
+        e2e_state.update(step=0, total=1, pending=None)
+        layer_step(Xh, Wh, True, Oh)                   # warm-up (staging allocation)
         barrier()
+        e2e_state.update(step=0, total=args.e2e_steps, pending=None)
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(args.e2e_steps):
@@ -646,9 +670,9 @@ def main():
         e2e = {"value": layers_per_rank * float(ems.item()) / args.e2e_steps / 1e3, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                "numa_node_rank0": numa_node,
-               "note": "pinned host X / W -> device inside the timed region (copies of later groups overlap the solves of "
-                       "earlier ones on a side stream), dequantised fp16 weights read back; every rank runs on the NUMA "
-                       "node of its GPU"}
+               "note": "pinned host X / W -> device inside the timed region on a side stream, double-buffered: the copies of "
+                       "layer i + 1 run under the solves of layer i (the first layer's are exposed); dequantised fp16 "
+                       "weights read back; every rank runs on the NUMA node of its GPU"}
     except Exception as ex:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
     del Xh, Wh, Oh

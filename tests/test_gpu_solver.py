@@ -190,7 +190,10 @@ def test_pivoted_cholesky_matches_householder_qrcp(G, n, eps, dist):
     assert torch.equal(a.perm, b.perm)
     sx = float(b.R_x.abs().max())
     assert float((a.R_x - b.R_x).abs().max()) <= 1e-10 * sx
-    assert torch.equal(a.R, b.R) or float((a.R - b.R).abs().max()) <= 1e-12 * float(b.R.abs().max())
+    # R: the default path derives it from R_x (rfactor.cu), the Householder path from a QR of Lambda^-1/2 V_k^T[:, perm]:
+    # two fp64 routes to the same unique factor, equal to first order in cond(H_k) (the bar of the golden tests)
+    cond = float(a.eigvals[0] / a.eigvals[a.k - 1])
+    assert float((a.R - b.R).abs().max()) <= (2e-14 * cond + 1e-12) * float(b.R.abs().max())
 
 
 def test_rank_deficient_falls_back(G):
