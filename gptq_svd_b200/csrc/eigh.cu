@@ -20,7 +20,8 @@
 namespace tq {
 
 constexpr int kTrdNb = 64;   // sytrd panel width
-constexpr int kLeaf = 32;    // D&C leaf size (one warp)
+constexpr int kLeaf = 128;   // D&C leaf size (one CTA of 128 threads; 32 in round 1: the merges of 48 - 192 rows it
+                             // removes were pure launch / round-trip latency, ~100 us each, 384 of them at n = 12288)
 constexpr int kOrmNb = 128;  // back-transform block (rank-128 DGEMM updates run at 30 TF/s, rank-64 at 20: profiles/r01_dgemm_probe.log)
 
 
@@ -953,33 +954,39 @@ __global__ void dc_tear_serial_kernel(double* d, const double* e, const int* cut
   }
 }
 
-// QL implicit (EISPACK tql2 / "tqli") on leaves of size <= 32: one warp per leaf.
-// Lane 0 runs the scalar recurrence and records the plane rotations of one sweep; every
-// lane then applies them to its own row of the leaf's eigenvector block.
-__global__ void __launch_bounds__(32)
+// QL implicit (EISPACK tql2 / "tqli") on leaves of size <= kLeaf: one CTA of kLeaf threads per leaf.
+// Thread 0 runs the scalar recurrence and records the plane rotations of one sweep; every
+// thread then applies them to its own row of the leaf's eigenvector block (shared memory).
+constexpr size_t kLeafSmem = size_t(kLeaf) * (kLeaf + 1) * sizeof(double);
+__global__ void __launch_bounds__(kLeaf)
 dc_leaf_kernel(double* __restrict__ d, const double* __restrict__ e, double* __restrict__ Z, int64_t ldz,
                const int* __restrict__ leaf_off, const int* __restrict__ leaf_len, int* __restrict__ fail) {
-  __shared__ double sd[kLeaf], se[kLeaf], rc[kLeaf], rs[kLeaf], zz[kLeaf][kLeaf + 1];
+  extern __shared__ double zz_raw[];                         // zz[row][col], row stride kLeaf + 1
+  __shared__ double sd[kLeaf], se[kLeaf], rc[kLeaf], rs[kLeaf];
   __shared__ int ctl[4];   // 0: first rotation index (high), 1: last rotation index (low), 2: done flag
   __shared__ int order[kLeaf];
   const int lane = threadIdx.x;
+  double* zrow = zz_raw + size_t(lane) * (kLeaf + 1);
   const int off = leaf_off[blockIdx.x], len = leaf_len[blockIdx.x];
   if (lane < len) {
     sd[lane] = d[off + lane];
     se[lane] = (lane < len - 1) ? e[off + lane] : 0.0;
+    for (int c = 0; c < len; ++c) zrow[c] = (lane == c) ? 1.0 : 0.0;
   }
-  for (int c = 0; c < len; ++c)
-    if (lane < len) zz[lane][c] = (lane == c) ? 1.0 : 0.0;
-  __syncwarp();
+  __syncthreads();
   const double eps = 1.1102230246251565e-16;
+  double tst1 = 0.0;         // thread 0: EISPACK tql2's running max of |d| + |e| - the scale of the leaf seen so far
   for (int l = 0; l < len; ++l) {
     int iter = 0;
+    if (lane == 0) tst1 = fmax(tst1, fabs(sd[l]) + fabs(se[l]));
     while (true) {
       if (lane == 0) {
         int m = l;
         for (; m < len - 1; ++m) {
+          // negligible against its neighbours (keeps the relative accuracy of a graded leaf) or against the leaf's
+          // scale (tql2's test: a cluster of zero eigenvalues - a rank-deficient H - never passes the first one)
           double dd = fabs(sd[m]) + fabs(sd[m + 1]);
-          if (fabs(se[m]) <= eps * dd) break;
+          if (fabs(se[m]) <= eps * dd || fabs(se[m]) <= eps * tst1) break;
         }
         if (m == l) {
           ctl[2] = 1;
@@ -1023,20 +1030,21 @@ dc_leaf_kernel(double* __restrict__ d, const double* __restrict__ e, double* __r
           }
         }
       }
-      __syncwarp();
-      if (ctl[2]) break;
-      if (lane < len) {
-        for (int i = ctl[0]; i >= ctl[1]; --i) {
-          double f = zz[lane][i + 1];
-          zz[lane][i + 1] = rs[i] * zz[lane][i] + rc[i] * f;
-          zz[lane][i] = rc[i] * zz[lane][i] - rs[i] * f;
+      __syncthreads();
+      const bool done = ctl[2] != 0;
+      const int ihi = ctl[0], ilo = ctl[1];
+      if (!done && lane < len) {
+        for (int i = ihi; i >= ilo; --i) {
+          double f = zrow[i + 1];
+          zrow[i + 1] = rs[i] * zrow[i] + rc[i] * f;
+          zrow[i] = rc[i] * zrow[i] - rs[i] * f;
         }
       }
-      __syncwarp();
+      __syncthreads();        // thread 0 overwrites ctl / rc / rs in the next sweep
+      if (done) break;
     }
-    __syncwarp();
   }
-  // ascending order (selection sort on lane 0)
+  // ascending order (selection sort on thread 0)
   if (lane == 0) {
     for (int i = 0; i < len; ++i) order[i] = i;
     for (int i = 0; i < len - 1; ++i) {
@@ -1048,10 +1056,10 @@ dc_leaf_kernel(double* __restrict__ d, const double* __restrict__ e, double* __r
       order[kmin] = t;
     }
   }
-  __syncwarp();
+  __syncthreads();
   if (lane < len) {
     d[off + lane] = sd[order[lane]];
-    for (int c = 0; c < len; ++c) Z[(off + lane) + int64_t(off + c) * ldz] = zz[lane][order[c]];
+    for (int c = 0; c < len; ++c) Z[(off + lane) + int64_t(off + c) * ldz] = zrow[order[c]];
   }
 }
 
@@ -1523,7 +1531,8 @@ static int stedc(cublasHandle_t h, cudaStream_t st, double* d, const double* e, 
     dc_tear_serial_kernel<<<1, 1, 0, st>>>(d, e, d_cuts, int(cuts.size()));
     TQ_LAUNCH_CHECK();
   }
-  dc_leaf_kernel<<<(unsigned)leaves.size(), 32, 0, st>>>(d, e, Z, n, d_leaf_off, d_leaf_len, d_fail);
+  TQ_CUDA_CHECK(cudaFuncSetAttribute(dc_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLeafSmem)));
+  dc_leaf_kernel<<<(unsigned)leaves.size(), kLeaf, kLeafSmem, st>>>(d, e, Z, n, d_leaf_off, d_leaf_len, d_fail);
   TQ_LAUNCH_CHECK();
   TQ_CUDA_CHECK(cudaStreamSynchronize(st));
   for (size_t q = 0; q < merges.size(); ++q) {

@@ -12,7 +12,7 @@
 //     R   = [T11, T11 Z]
 // Proof: with G = R_x R_x^T = R11 (I + Z Z^T) R11^T, (P^T H_k P)^+ = R_x^T G^-2 R_x, so R = C R_x with C upper
 // triangular and C^T C = G^-2; then T11 = C R11 satisfies (T11^T T11)^-1 = (I + Z Z^T) A11 (I + Z Z^T).
-// A11 is taken from the DATA (H minus the t dropped eigenpairs, gathered through perm), not from R11^T R11, so the
+// A11 is taken from the DATA (the solver's copy of H_k, gathered through perm), not from R11^T R11, so the
 // only ill-conditioned steps are one Cholesky and one triangular inverse: the error against the reference route is
 // ~3e-16 cond(H_k) (bar: 2e-14 cond(H_k); numpy prototype at n = 768 / 1024, eps 1e-2 .. 0).
 // Work: 2/3 k^3 + ~7 k^2 t, all DGEMM / DSYRK / DTRSM-shaped, against 2 n^2 k + 2 n k^2 - 2/3 k^3 before.
@@ -52,26 +52,13 @@ __global__ void rf_flip_transpose_kernel(const double* __restrict__ Zt, int64_t 
   }
 }
 
-// M (k x k, ld k) = H[p', p'] with p'[r] = perm[k - 1 - r]   (H row-major and symmetric: read along rows)
+// M (k x k, ld k) = Hk[p', p'] with p'[r] = perm[k - 1 - r]   (Hk symmetric, leading dimension ldh: read along one line)
 __global__ void rf_gather_h_kernel(const double* __restrict__ H, int64_t ldh, const int64_t* __restrict__ perm,
                                    int64_t k, double* __restrict__ M) {
   const int64_t c = blockIdx.y;
   const int64_t pc = perm[k - 1 - c];
   for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < k; r += int64_t(gridDim.x) * blockDim.x)
     M[r + c * k] = H[pc * ldh + perm[k - 1 - r]];
-}
-
-// Vp (k x t, ld k): Vp[r, i] = V[perm[k - 1 - r] + i n];  VpL = Vp diag(w)
-__global__ void rf_gather_v_kernel(const double* __restrict__ V, int64_t n, const double* __restrict__ w,
-                                   const int64_t* __restrict__ perm, int64_t k, double* __restrict__ Vp,
-                                   double* __restrict__ VpL) {
-  const int64_t i = blockIdx.y;
-  const double wi = w[i];
-  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < k; r += int64_t(gridDim.x) * blockDim.x) {
-    const double v = V[perm[k - 1 - r] + i * n];
-    Vp[r + i * k] = v;
-    VpL[r + i * k] = v * wi;
-  }
 }
 
 // In-place inverse of one lower-triangular diagonal block (jb <= 128) per CTA: thread c owns column c of the
@@ -173,22 +160,19 @@ __global__ void rf_emit_t11_kernel(const double* __restrict__ Linv, int64_t k, d
 
 size_t rfactor_ws_bytes(int64_t n, int64_t k) {
   const int64_t t = n - k;
-  return ws_bytes_for(size_t(k) * k, 8) + ws_bytes_for(size_t(k) * imax(t, 1), 8) * 5 + ws_bytes_for(size_t(t) * t + 1, 8) +
+  return ws_bytes_for(size_t(k) * k, 8) + ws_bytes_for(size_t(k) * imax(t, 1), 8) * 3 + ws_bytes_for(size_t(t) * t + 1, 8) +
          ws_bytes_for(size_t(k / kRfLeaf + 2), sizeof(RfLeaf)) + ws_bytes_for(4, 4) + 4096;
 }
 
-// H: the solver's input (row-major, symmetric).  V: eigenvectors, column-major ld n, columns [0, t) = the t DROPPED
-// eigenpairs (ascending eigenvalues w[0..t)).  Rx: row-major k x n (ld ldrx) from the pivoted Cholesky of H_k,
-// perm its pivots.  R: row-major k x n (ld ldr), written completely.
-int r_from_rx(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ldh, const double* V, const double* w,
-              int64_t n, int64_t k, const double* Rx, int64_t ldrx, const int64_t* perm, double* R, int64_t ldr,
-              Workspace ws) {
+// Hk: the truncated Hessian H_k = H - V_t diag(w_t) V_t^T (symmetric, leading dimension ldh) - the solver keeps the
+// copy it made for the pivoted Cholesky; it may alias R (it is gathered before R is written).  Rx: row-major k x n
+// (ld ldrx) from the pivoted Cholesky of H_k, perm its pivots.  R: row-major k x n (ld ldr), written completely.
+int r_from_rx(cublasHandle_t h, cudaStream_t st, const double* Hk, int64_t ldh, int64_t n, int64_t k, const double* Rx,
+              int64_t ldrx, const int64_t* perm, double* R, int64_t ldr, Workspace ws) {
   const int64_t t = n - k;
   double* M = ws.take<double>(size_t(k) * k);
   double* Zt = ws.take<double>(size_t(imax(t, 1)) * k);
   double* Zf = ws.take<double>(size_t(imax(t, 1)) * k);
-  double* Vp = ws.take<double>(size_t(imax(t, 1)) * k);
-  double* VpL = ws.take<double>(size_t(imax(t, 1)) * k);
   double* Q = ws.take<double>(size_t(imax(t, 1)) * k);
   double* S = ws.take<double>(size_t(t) * t + 1);
   RfLeaf* d_leaves = ws.take<RfLeaf>(size_t(k / kRfLeaf + 2));
@@ -197,23 +181,15 @@ int r_from_rx(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ldh, c
     set_error("r_from_rx: workspace too small");
     return TQ_ERR_WORKSPACE;
   }
-  const double one = 1.0, zero = 0.0, half = 0.5, mhalf = -0.5;
+  const double one = 1.0, zero = 0.0, half = 0.5;
   TQ_REQUIRE(ldrx == n && ldr == n, "r_from_rx: R and R_x must have leading dimension n");
   const double* L = Rx;                   // column-major n x k view of the row-major R_x: L = R_x^T
   double* Rt = R;                         // column-major n x k view of R
   dim3 gk((unsigned)imin(ceil_div(k, 256), 64), (unsigned)k);
   {
     StageTimer tm(st, "rfac: A11");
-    rf_gather_h_kernel<<<gk, 256, 0, st>>>(H, ldh, perm, k, M);
+    rf_gather_h_kernel<<<gk, 256, 0, st>>>(Hk, ldh, perm, k, M);       // A11' = H_k[p', p']
     TQ_LAUNCH_CHECK();
-    if (t > 0) {
-      dim3 gt((unsigned)imin(ceil_div(k, 256), 64), (unsigned)t);
-      rf_gather_v_kernel<<<gt, 256, 0, st>>>(V, n, w, perm, k, Vp, VpL);
-      TQ_LAUNCH_CHECK();
-      // A11' = H[p', p'] - Vp diag(w) Vp^T (lower triangle): -1/2 (VpL Vp^T + Vp VpL^T)
-      TQ_CUBLAS_CHECK(cublasDsyr2k(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, int(k), int(t), &mhalf, VpL, int(k), Vp,
-                                   int(k), &one, M, int(k)));
-    }
   }
   if (t > 0) {
     StageTimer tm(st, "rfac: M");

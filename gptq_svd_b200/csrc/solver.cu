@@ -12,9 +12,8 @@ namespace tq {
 int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ldh, int64_t n, double* w,
                   double* Zout, Workspace& ws, const EighColumnChooser& choose);
 size_t rfactor_ws_bytes(int64_t n, int64_t k);
-int r_from_rx(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ldh, const double* V, const double* w,
-              int64_t n, int64_t k, const double* Rx, int64_t ldrx, const int64_t* perm, double* R, int64_t ldr,
-              Workspace ws);
+int r_from_rx(cublasHandle_t h, cudaStream_t st, const double* Hk, int64_t ldh, int64_t n, int64_t k, const double* Rx,
+              int64_t ldrx, const int64_t* perm, double* R, int64_t ldr, Workspace ws);
 size_t eigh_ws_bytes(int64_t n);
 int copy_symmetric_lower(cudaStream_t st, const double* H, int64_t ldh, int64_t n, double* A);
 int qr_r_colmajor(cublasHandle_t h, cudaStream_t st, double* A, int64_t lda, int64_t k, int64_t n, Workspace& ws);
@@ -330,6 +329,9 @@ static int spectral_solve_impl(const double* H, int64_t ldh, int64_t n, double t
       TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, int(n), int(n), int(k), &one, SB, int(k), SB, int(k),
                                   &zero, Gm, int(n)));
     }
+    // the R-from-R_x stage needs (P^T H_k P)[:k, :k] again: keep a copy in the R buffer, which is written last
+    if (subset == kSubsetDropped)
+      TQ_CUDA_CHECK(cudaMemcpyAsync(R, Gm, sizeof(double) * size_t(n) * n, cudaMemcpyDeviceToDevice, st));
     // SB (k x n) is free until S / B are built: the compacted Gram matrix ping-pongs into it
     const int rc = pchol_pivoted(h, st, Gm, n, k, Rx, n, perm, SB, size_t(k) * n, s2);
     have_s = false;
@@ -340,7 +342,7 @@ static int spectral_solve_impl(const double* H, int64_t ldh, int64_t n, double t
     int rc = TQ_ERR_NOCONV;
     if (!householder) {
       StageTimer tm(st, "r_from_rx");
-      rc = r_from_rx(h, st, H, ldh, V, w, n, k, Rx, n, perm, R, n, sub);
+      rc = r_from_rx(h, st, R, n, n, k, Rx, n, perm, R, n, sub);
     }
     if (rc == TQ_OK) return TQ_OK;
     if (rc != TQ_ERR_NOCONV) return rc;
