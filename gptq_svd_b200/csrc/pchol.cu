@@ -27,7 +27,7 @@
 //   P1  four threads per compact column a (not yet pivoted):
 //         r = (G[a, cj] - sum_{t in panel} Rp[t, cj] Rp[t, a]) / sqrt(d[cj])
 //         d[a] = max(d[a] - r^2, 0)                                               | barrier
-// after the panel  G -= Rp^T Rp  as ONE rank-128 DGEMM (30 TF/s; rank-64 updates run at 20), and
+// after the panel  G -= Rp^T Rp  as ONE rank-128 DSYRK on the lower triangle (rank-64 updates run at 2/3 the rate), and
 // every 512 pivots the matrix is COMPACTED (gather of the live rows / columns into the other
 // buffer) so the DGEMM only touches live x live entries: 2/3 (n^3 - (n-k)^3) flop in total instead
 // of 2 n^2 k.  If a pivot is not positive (numerical rank below k) the kernel raises a flag and the
@@ -45,7 +45,7 @@ constexpr int kPcTpc = 4;              // threads per column in P1
 constexpr int kPcCompactEvery = 512;   // pivots between compactions
 
 struct PcholArgs {
-  const double* G;   // ncur x ncur symmetric (both triangles valid), leading dimension ldg
+  const double* G;   // ncur x ncur symmetric, LOWER triangle valid (the trailing update is a DSYRK), leading dimension ldg
   int64_t ldg;
   int64_t ncur;      // compact columns
   int64_t n;         // original size (leading dimension of Rp / Rorig, length of perm)
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
       const bool live = inr && c != cj && dc != -INFINITY;
       double s0 = 0.0, s1 = 0.0;
       if (live) {
-        if (q4 == 0) s0 = Gc[c];
+        if (q4 == 0) s0 = (c >= cj) ? Gc[c] : a.G[cj + c * ldg];     // only the LOWER triangle of G is kept up to date
         const double* Rh = a.Rp + c;
         int t = q4;
         for (; t + 7 * kPcTpc < i; t += 8 * kPcTpc) {     // 8 independent loads in flight (panel history, L2)
@@ -314,7 +314,8 @@ __global__ void pchol_compact_gather_kernel(const double* __restrict__ Gold, int
   const int64_t b = blockIdx.y;
   const double* src = Gold + int64_t(keep[b]) * ldo;
   double* dst = Gnew + b * nnew;
-  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < nnew; r += int64_t(gridDim.x) * blockDim.x)
+  // keep[] is increasing, so the lower triangle maps onto the lower triangle: only r >= b is read and written
+  for (int64_t r = b + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < nnew; r += int64_t(gridDim.x) * blockDim.x)
     dst[r] = src[keep[r]];
 }
 
@@ -443,9 +444,10 @@ int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64
       ncur = nlive;
       dead = 0;
     }
-    // G -= Rp^T Rp: Rp (jb x n row-major, ld n) is the column-major ncur x jb matrix Rp^T
-    TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, int(ncur), int(ncur), jb, &mone, Rp, int(n), Rp, int(n),
-                                &one, Gc, int(ncur)));
+    // G -= Rp^T Rp on the lower triangle (DSYRK: half the flops of the DGEMM of round 1; the panel kernel reads
+    // G[max, min]): Rp (jb x n row-major, ld n) is the column-major ncur x jb matrix Rp^T
+    TQ_CUBLAS_CHECK(cublasDsyrk(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, int(ncur), jb, &mone, Rp, int(n), &one, Gc,
+                                int(ncur)));
   }
   int hfail = 0;
   TQ_CUDA_CHECK(cudaMemcpyAsync(&hfail, fail, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -58,7 +58,7 @@ __global__ void rf_gather_h_kernel(const double* __restrict__ H, int64_t ldh, co
   const int64_t c = blockIdx.y;
   const int64_t pc = perm[k - 1 - c];
   for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < k; r += int64_t(gridDim.x) * blockDim.x)
-    M[r + c * k] = H[pc * ldh + perm[k - 1 - r]];
+    M[r + c * k] = H[pc * ldh + perm[k - 1 - r]];      // Hk is fully symmetric (both triangles written by the solver)
 }
 
 // In-place inverse of one lower-triangular diagonal block (jb <= 128) per CTA: thread c owns column c of the
