@@ -377,6 +377,10 @@ def main():
     ap.add_argument("--overlap-tail", type=int, default=1,
                     help="start the narrow solves when the wide solve has finished its band reduction")
     ap.add_argument("--tail-budgets", default="100,16", help="SM budgets in the tail: wide,narrow")
+    ap.add_argument("--no-priority", action="store_true",
+                    help="run the wide solve on a normal-priority stream (default: high priority, it is the critical path)")
+    ap.add_argument("--narrow-start", default="band", choices=["start", "band"],
+                    help="release the narrow solves when the wide solve starts, or when its band reduction is done")
     ap.add_argument("--two-stage", type=int, default=-1,
                     help="tridiagonal reduction: -1 automatic (two-stage for n >= 8192), 0 one-stage, 1 two-stage everywhere")
     ap.add_argument("--concurrent-solves", type=int, default=1,
@@ -479,6 +483,8 @@ def main():
                     events[("w", gi, li)].record(copy_stream)
         return events
 
+    timeline = {"wide": []} if os.environ.get("TQ_BENCH_TIMELINE") else None
+
     def layer_step(x_src, w_src, host: bool, sink=None):
         """One decoder layer through the public API.  host=True: inputs come from pinned host
         buffers - every H2D copy of the step is enqueued on a side stream up front and the compute
@@ -545,6 +551,9 @@ def main():
                 # (stage callback of the C ABI)
                 def solve_wide(H=H, sem=released):
                     fired = []
+                    if timeline is not None:
+                        ev0 = torch.cuda.Event(enable_timing=True)
+                        ev0.record(torch.cuda.current_stream(dev))
 
                     def on_stage(stage, user, sem=sem):
                         if stage in (_lib.TQ_STAGE_BAND_DONE, _lib.TQ_STAGE_SYTRD_DONE) and not fired:
@@ -556,10 +565,16 @@ def main():
                     try:
                         return solve(H)
                     finally:
+                        if timeline is not None:
+                            ev1 = torch.cuda.Event(enable_timing=True)
+                            ev1.record(torch.cuda.current_stream(dev))
+                            timeline["wide"].append((ev0, ev1))
                         lib.tq_set_stage_callback(_lib.STAGE_CALLBACK(0), None)
                         if not fired:
                             sem.release()                    # never leave the main thread waiting
-                wide_handle = pool.submit(solve_wide, 148)
+                wide_handle = pool.submit(solve_wide, 148, urgent=not args.no_priority)
+                if args.narrow_start == "start":
+                    released.release()
             elif gi in small:
                 fn = (lambda H=H: solve(H))
                 if tail:
@@ -618,6 +633,10 @@ def main():
     if rank == 0:
         sys.stderr.write("per-step ms: " + ", ".join(f"{step_ev[i].elapsed_time(step_ev[i + 1]):.1f}"
                                                      for i in range(args.steps)) + "\n")
+        if timeline is not None:        # where a step goes: start -> wide solve starts -> wide solve ends -> step ends
+            for i, (a, b) in enumerate(timeline["wide"][-args.steps:]):
+                sys.stderr.write(f"timeline step {i}: wide solve starts at {step_ev[i].elapsed_time(a):.1f} ms, runs "
+                                 f"{a.elapsed_time(b):.1f} ms, step ends {b.elapsed_time(step_ev[i + 1]):.1f} ms later\n")
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     launches = torch.tensor([lib.tq_launch_count() + (pool.launch_count() if pool else 0) - l0], device=dev,
                             dtype=torch.float64)

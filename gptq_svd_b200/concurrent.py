@@ -45,7 +45,8 @@ class SolverPool:
     def _run(self, idx: int):
         try:
             torch.cuda.set_device(self.device)
-            stream = torch.cuda.Stream(device=self.device)
+            streams = {False: torch.cuda.Stream(device=self.device),
+                       True: torch.cuda.Stream(device=self.device, priority=-1)}
             lib = _lib.load()
         except BaseException as ex:               # a worker that cannot start must not leave callers waiting
             self._broken = ex
@@ -54,7 +55,8 @@ class SolverPool:
             job = self._jobs.get()
             if job is None:
                 return
-            fn, budget, ready, done, out, slot = job
+            fn, budget, ready, done, out, slot, urgent = job
+            stream = streams[bool(urgent)]
             try:
                 lib.tq_set_sm_budget(int(budget))
                 with torch.cuda.stream(stream):
@@ -69,10 +71,13 @@ class SolverPool:
                 self.launches[idx] = int(lib.tq_launch_count())
                 done.release()
 
-    def submit(self, fn, sm_budget: Optional[int] = None):
+    def submit(self, fn, sm_budget: Optional[int] = None, urgent: bool = False):
         """Start `fn()` on a worker (its stream first waits for everything enqueued so far on the caller's
         current stream) and return a handle for `result()`.  Tensors `fn` reads must stay alive until
-        `result()` returns, or be `record_stream`-ed inside `fn` (it runs under the worker's stream)."""
+        `result()` returns, or be `record_stream`-ed inside `fn` (it runs under the worker's stream).
+        `urgent`: run on the worker's high-priority stream - for the job on the critical path, whose chains of
+        short dependent kernels (divide and conquer merges, panel factorisations) would otherwise queue behind
+        the full-grid kernels of the other jobs at every link."""
         if sm_budget is None:
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
             sm_budget = max(8, sms // self.workers)
@@ -81,7 +86,7 @@ class SolverPool:
         ready.record(cur)
         out: List = [None]
         done = threading.Semaphore(0)
-        self._jobs.put((fn, sm_budget, ready, done, out, 0))
+        self._jobs.put((fn, sm_budget, ready, done, out, 0, urgent))
         return (out, done)
 
     def result(self, handle):

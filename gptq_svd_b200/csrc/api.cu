@@ -73,13 +73,36 @@ int check_device() {
   return TQ_OK;
 }
 
-bool trace_enabled() {
+// TQ_TRACE=1: synchronous stage timers (the stream is synchronised at every stage boundary);
+// TQ_TRACE=2: event-based stage timers - nothing is synchronised, the stages are printed by trace_flush() when
+//             the solve returns (for timing a solve that shares the GPU with others)
+static int trace_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TQ_TRACE");
-    v = (e && e[0] && e[0] != '0') ? 1 : 0;
+    v = (e && e[0] && e[0] != '0') ? (e[0] == '2' ? 2 : 1) : 0;
   }
-  return v == 1;
+  return v;
+}
+bool trace_enabled() { return trace_mode() == 1; }
+
+struct TraceEv {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+static thread_local std::vector<TraceEv> g_trace_events;
+
+void trace_flush(cudaStream_t st) {
+  if (trace_mode() != 2 || g_trace_events.empty()) return;
+  cudaStreamSynchronize(st);
+  for (auto& t : g_trace_events) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t.e0, t.e1);
+    fprintf(stderr, "[tq-trace2] %-18s %10.3f ms\n", t.name, ms);
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  g_trace_events.clear();
 }
 
 static double now_ms() {
@@ -89,15 +112,24 @@ static double now_ms() {
 }
 
 StageTimer::StageTimer(cudaStream_t s, const char* n) : st(s), name(n), t0(0) {
-  if (trace_enabled()) {
+  if (trace_mode() == 1) {
     cudaStreamSynchronize(st);
     t0 = now_ms();
+  } else if (trace_mode() == 2) {
+    TraceEv t{name, nullptr, nullptr};
+    cudaEventCreate(&t.e0);
+    cudaEventCreate(&t.e1);
+    cudaEventRecord(t.e0, st);
+    g_trace_events.push_back(t);
+    t0 = double(g_trace_events.size());       // 1-based index of this timer's entry
   }
 }
 StageTimer::~StageTimer() {
-  if (trace_enabled()) {
+  if (trace_mode() == 1) {
     cudaStreamSynchronize(st);
     fprintf(stderr, "[tq-trace] %-18s %10.3f ms\n", name, now_ms() - t0);
+  } else if (trace_mode() == 2 && t0 >= 1.0 && size_t(t0) <= g_trace_events.size()) {
+    cudaEventRecord(g_trace_events[size_t(t0) - 1].e1, st);
   }
 }
 

@@ -98,6 +98,7 @@ void notify_stage(int stage);
 
 // TQ_TRACE=1: print per-stage milliseconds (synchronises the stream at stage boundaries)
 bool trace_enabled();
+void trace_flush(cudaStream_t st);     // TQ_TRACE=2: print the event-timed stages of the call that just ended
 struct StageTimer {
   cudaStream_t st;
   const char* name;

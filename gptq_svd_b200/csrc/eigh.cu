@@ -1311,20 +1311,23 @@ static void dc_collect(int off, int len, std::vector<DcNode>& leaves, std::vecto
   merge_n1.push_back(n1);
 }
 
-static int dc_merge(cublasHandle_t h, cudaStream_t st, double* d, double* Z, int64_t n, int off, int n1, int len,
-                    double beta, DcBuffers& B) {
-  const int64_t ldz = n;
-  double* Zb = Z + off + int64_t(off) * ldz;
-  const double eps = 1.1102230246251565e-16;
-  dc_build_z_kernel<<<(unsigned)ceil_div(len, 256), 256, 0, st>>>(Zb, ldz, n1, len, beta < 0 ? -1.0 : 1.0, B.z);
-  TQ_LAUNCH_CHECK();
-  TQ_CUDA_CHECK(cudaMemcpyAsync(B.h_d, d + off, sizeof(double) * len, cudaMemcpyDeviceToHost, st));
-  TQ_CUDA_CHECK(cudaMemcpyAsync(B.h_z, B.z, sizeof(double) * len, cudaMemcpyDeviceToHost, st));
-  TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+// One rank-one merge, split in two so that a whole LEVEL of the tree shares one host round trip:
+//   dc_merge_host    deflation (LAPACK DLAED2 logic) on the host copies of (d, z) of the merge's index range
+//                    [off, off + len); fills the pinned staging arrays at the same offsets;
+//   dc_merge_device  rotations, gather, secular solve, eigenvector update (DGEMM), reorder - launches only.
+// Round 1 did both per merge with a D2H + synchronise + up to seven H2D copies each (511 merges at n = 12288 with
+// leaves of 32): 90 ms alone and 200 ms next to three other solves, whose host threads compete for the driver.
+struct DcMergePlan {
+  int off, n1, len;
+  int K, K1, K2, K3, nd, nrot;
+  size_t scratch;          // element offset of this merge's len x len blocks in Zg / Zo / U
+};
 
-  // ---------------- host: deflation (LAPACK DLAED2 logic) ----------------
-  double* hd = B.h_d;
-  double* hz = B.h_z;
+static int dc_merge_host(DcMergePlan& mp, double beta, DcBuffers& B) {
+  const int off = mp.off, n1 = mp.n1, len = mp.len;
+  const double eps = 1.1102230246251565e-16;
+  double* hd = B.h_d + off;
+  double* hz = B.h_z + off;
   const double rho = 2.0 * std::fabs(beta);
   double dmax = 0, zmax = 0;
   for (int j = 0; j < len; ++j) {
@@ -1338,6 +1341,7 @@ static int dc_merge(cublasHandle_t h, cudaStream_t st, double* d, double* Z, int
   std::vector<int> nondef, defl, ctype(len);
   for (int j = 0; j < len; ++j) ctype[j] = j < n1 ? 1 : 3;
   int nrot = 0;
+  DcRot* hrot = B.h_rot + off;
   if (rho * zmax <= tol) {
     defl = order;
   } else {
@@ -1362,7 +1366,7 @@ static int dc_merge(cublasHandle_t h, cudaStream_t st, double* d, double* Z, int
         hz[nj] = tau_;
         hz[pj] = 0.0;
         if (ctype[nj] != ctype[pj]) ctype[nj] = 2;
-        B.h_rot[nrot++] = DcRot{pj, nj, c, s};
+        hrot[nrot++] = DcRot{pj, nj, c, s};
         const double tt = hd[pj] * c * c + hd[nj] * s * s;
         hd[nj] = hd[pj] * s * s + hd[nj] * c * c;
         hd[pj] = tt;
@@ -1399,65 +1403,74 @@ static int dc_merge(cublasHandle_t h, cudaStream_t st, double* d, double* Z, int
     const int jj = nondef[q];
     const int ty = ctype[jj];
     const int pos = ty == 1 ? p1++ : (ty == 2 ? p2++ : p3++);
-    B.h_rowpos[q] = pos;
-    B.h_gidx[pos] = jj;
-    B.h_dl[q] = hd[jj];
-    B.h_zl[q] = hz[jj];
-    B.h_z2[q] = rho * hz[jj] * hz[jj];
+    B.h_rowpos[off + q] = pos;
+    B.h_gidx[off + pos] = jj;
+    B.h_dl[off + q] = hd[jj];
+    B.h_zl[off + q] = hz[jj];
+    B.h_z2[off + q] = rho * hz[jj] * hz[jj];
   }
   for (int t = 0; t < nd; ++t) {
-    B.h_gidx[K + t] = defl[t];
-    B.h_dd[t] = hd[defl[t]];
+    B.h_gidx[off + K + t] = defl[t];
+    B.h_dd[off + t] = hd[defl[t]];
   }
+  mp.K = K;
+  mp.K1 = K1;
+  mp.K2 = K2;
+  mp.K3 = K3;
+  mp.nd = nd;
+  mp.nrot = nrot;
+  return TQ_OK;
+}
 
-  // ---------------- device: rotations, gather, secular solve, GEMM, reorder ----------------
-  if (nrot > 0) {
-    TQ_CUDA_CHECK(cudaMemcpyAsync(B.rot, B.h_rot, sizeof(DcRot) * nrot, cudaMemcpyHostToDevice, st));
-    dc_apply_rot_kernel<<<(unsigned)ceil_div(len, 128), 128, 0, st>>>(Zb, ldz, len, B.rot, nrot);
+static int dc_merge_device(cublasHandle_t h, cudaStream_t st, double* d, double* Z, int64_t n, const DcMergePlan& mp,
+                           DcBuffers& B) {
+  const int64_t ldz = n;
+  const int off = mp.off, n1 = mp.n1, len = mp.len, K = mp.K, K1 = mp.K1, K2 = mp.K2, K3 = mp.K3, nd = mp.nd;
+  double* Zb = Z + off + int64_t(off) * ldz;
+  double* Zg = B.Zg + mp.scratch;
+  double* Zo = B.Zo + mp.scratch;
+  double* U = B.U + mp.scratch;
+  if (mp.nrot > 0) {
+    dc_apply_rot_kernel<<<(unsigned)ceil_div(len, 128), 128, 0, st>>>(Zb, ldz, len, B.rot + off, mp.nrot);
     TQ_LAUNCH_CHECK();
   }
-  TQ_CUDA_CHECK(cudaMemcpyAsync(B.gidx, B.h_gidx, sizeof(int) * len, cudaMemcpyHostToDevice, st));
-  if (nd > 0) TQ_CUDA_CHECK(cudaMemcpyAsync(B.dd, B.h_dd, sizeof(double) * nd, cudaMemcpyHostToDevice, st));
   const int64_t lds = len;   // scratch matrices are packed len x len
   {
     dim3 grid((unsigned)imin(ceil_div(len, 256), 32), (unsigned)len);
-    dc_gather_kernel<<<grid, 256, 0, st>>>(Zb, ldz, len, B.gidx, len, B.Zg, lds);
+    dc_gather_kernel<<<grid, 256, 0, st>>>(Zb, ldz, len, B.gidx + off, len, Zg, lds);
     TQ_LAUNCH_CHECK();
   }
   if (K > 0) {
-    TQ_CUDA_CHECK(cudaMemcpyAsync(B.dl, B.h_dl, sizeof(double) * K, cudaMemcpyHostToDevice, st));
-    TQ_CUDA_CHECK(cudaMemcpyAsync(B.zl, B.h_zl, sizeof(double) * K, cudaMemcpyHostToDevice, st));
-    TQ_CUDA_CHECK(cudaMemcpyAsync(B.z2, B.h_z2, sizeof(double) * K, cudaMemcpyHostToDevice, st));
-    TQ_CUDA_CHECK(cudaMemcpyAsync(B.rowpos, B.h_rowpos, sizeof(int) * K, cudaMemcpyHostToDevice, st));
     const unsigned wgrid = (unsigned)ceil_div(int64_t(K) * 32, 256);
-    dc_secular_kernel<<<wgrid, 256, 0, st>>>(B.dl, B.z2, K, B.org, B.tau, B.lam);
+    dc_secular_kernel<<<wgrid, 256, 0, st>>>(B.dl + off, B.z2 + off, K, B.org + off, B.tau + off, B.lam + off);
     TQ_LAUNCH_CHECK();
-    dc_zhat_kernel<<<wgrid, 256, 0, st>>>(B.dl, B.zl, B.org, B.tau, K, B.zhat);
+    dc_zhat_kernel<<<wgrid, 256, 0, st>>>(B.dl + off, B.zl + off, B.org + off, B.tau + off, K, B.zhat + off);
     TQ_LAUNCH_CHECK();
-    dc_u_kernel<<<K, 256, 0, st>>>(B.dl, B.zhat, B.org, B.tau, B.rowpos, K, B.U, K);
+    dc_u_kernel<<<K, 256, 0, st>>>(B.dl + off, B.zhat + off, B.org + off, B.tau + off, B.rowpos + off, K, U, K);
     TQ_LAUNCH_CHECK();
     const double one = 1.0, zero = 0.0;
     const int n2 = len - n1;
     const int K12 = K1 + K2, K23 = K2 + K3;
     if (K12 > 0)
-      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n1, K, K12, &one, B.Zg, int(lds), B.U, K, &zero,
-                                  B.Zo, int(lds)));
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n1, K, K12, &one, Zg, int(lds), U, K, &zero, Zo,
+                                  int(lds)));
     else
-      TQ_CUDA_CHECK(cudaMemset2DAsync(B.Zo, sizeof(double) * lds, 0, sizeof(double) * n1, K, st));
+      TQ_CUDA_CHECK(cudaMemset2DAsync(Zo, sizeof(double) * lds, 0, sizeof(double) * n1, K, st));
     if (K23 > 0)
-      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n2, K, K23, &one, B.Zg + n1 + int64_t(K1) * lds,
-                                  int(lds), B.U + K1, K, &zero, B.Zo + n1, int(lds)));
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n2, K, K23, &one, Zg + n1 + int64_t(K1) * lds,
+                                  int(lds), U + K1, K, &zero, Zo + n1, int(lds)));
     else
-      TQ_CUDA_CHECK(cudaMemset2DAsync(B.Zo + n1, sizeof(double) * lds, 0, sizeof(double) * n2, K, st));
+      TQ_CUDA_CHECK(cudaMemset2DAsync(Zo + n1, sizeof(double) * lds, 0, sizeof(double) * n2, K, st));
   }
-  dc_merge_order_kernel<<<(unsigned)ceil_div(len, 256), 256, 0, st>>>(B.lam, K, B.dd, nd, B.src, B.dout);
+  dc_merge_order_kernel<<<(unsigned)ceil_div(len, 256), 256, 0, st>>>(B.lam + off, K, B.dd + off, nd, B.src + off,
+                                                                      B.dout + off);
   TQ_LAUNCH_CHECK();
   {
     dim3 grid((unsigned)imin(ceil_div(len, 256), 32), (unsigned)len);
-    dc_scatter_kernel<<<grid, 256, 0, st>>>(B.Zo, B.Zg, lds, len, K, B.src, Zb, ldz);
+    dc_scatter_kernel<<<grid, 256, 0, st>>>(Zo, Zg, lds, len, K, B.src + off, Zb, ldz);
     TQ_LAUNCH_CHECK();
   }
-  TQ_CUDA_CHECK(cudaMemcpyAsync(d + off, B.dout, sizeof(double) * len, cudaMemcpyDeviceToDevice, st));
+  TQ_CUDA_CHECK(cudaMemcpyAsync(d + off, B.dout + off, sizeof(double) * len, cudaMemcpyDeviceToDevice, st));
   return TQ_OK;
 }
 
@@ -1535,9 +1548,59 @@ static int stedc(cublasHandle_t h, cudaStream_t st, double* d, const double* e, 
   dc_leaf_kernel<<<(unsigned)leaves.size(), kLeaf, kLeafSmem, st>>>(d, e, Z, n, d_leaf_off, d_leaf_len, d_fail);
   TQ_LAUNCH_CHECK();
   TQ_CUDA_CHECK(cudaStreamSynchronize(st));
-  for (size_t q = 0; q < merges.size(); ++q) {
-    const int off = merges[q].off, len = merges[q].len, n1 = merge_n1[q];
-    TQ_TRY(dc_merge(h, st, d, Z, n, off, n1, len, he[off + n1 - 1], B));
+  // merges grouped by HEIGHT in the tree (children first): one D2H of (d, z), one synchronise and one H2D of the
+  // deflation results per level instead of per merge; the merges of a level cover disjoint index ranges, so they
+  // share the n-sized staging arrays at their own offsets
+  std::vector<int> height(merges.size(), 0);
+  {
+    // the tree is fixed by (off, len): halve until a leaf, as dc_collect does
+    auto height_of = [&](auto&& self, int off, int len) -> int {
+      if (len <= kLeaf) return 0;
+      const int n1 = len / 2;
+      const int hl = self(self, off, n1), hr = self(self, off + n1, len - n1);
+      return (hl > hr ? hl : hr) + 1;
+    };
+    for (size_t q = 0; q < merges.size(); ++q) height[q] = height_of(height_of, merges[q].off, merges[q].len);
+  }
+  int max_h = 0;
+  for (int hq : height) max_h = hq > max_h ? hq : max_h;
+  for (int lvl = 1; lvl <= max_h; ++lvl) {
+    std::vector<DcMergePlan> plans;
+    size_t scratch = 0;
+    for (size_t q = 0; q < merges.size(); ++q) {
+      if (height[q] != lvl) continue;
+      DcMergePlan mp{};
+      mp.off = merges[q].off;
+      mp.len = merges[q].len;
+      mp.n1 = merge_n1[q];
+      mp.scratch = scratch;
+      scratch += size_t(mp.len) * mp.len;
+      plans.push_back(mp);
+    }
+    if (plans.empty()) continue;
+    if (scratch > size_t(n) * n) {
+      set_error("stedc: level scratch exceeds n^2");
+      return TQ_ERR_WORKSPACE;
+    }
+    for (const DcMergePlan& mp : plans) {
+      const double beta = he[mp.off + mp.n1 - 1];
+      double* Zb = Z + mp.off + int64_t(mp.off) * n;
+      dc_build_z_kernel<<<(unsigned)ceil_div(mp.len, 256), 256, 0, st>>>(Zb, n, mp.n1, mp.len, beta < 0 ? -1.0 : 1.0,
+                                                                         B.z + mp.off);
+      TQ_LAUNCH_CHECK();
+    }
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.h_d, d, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.h_z, B.z, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (DcMergePlan& mp : plans) TQ_TRY(dc_merge_host(mp, he[mp.off + mp.n1 - 1], B));
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.rot, B.h_rot, sizeof(DcRot) * n, cudaMemcpyHostToDevice, st));
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.gidx, B.h_gidx, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.rowpos, B.h_rowpos, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.dd, B.h_dd, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.dl, B.h_dl, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.zl, B.h_zl, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    TQ_CUDA_CHECK(cudaMemcpyAsync(B.z2, B.h_z2, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    for (const DcMergePlan& mp : plans) TQ_TRY(dc_merge_device(h, st, d, Z, n, mp, B));
   }
   int fail = 0;
   TQ_CUDA_CHECK(cudaMemcpyAsync(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));

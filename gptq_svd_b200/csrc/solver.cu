@@ -385,7 +385,10 @@ static int spectral_solve_impl(const double* H, int64_t ldh, int64_t n, double t
 extern "C" int tq_spectral_solve(const double* H, int64_t ldh, int64_t n, double threshold, int method, double* R,
                                  double* Rx, int64_t* perm, double* eigvals, int64_t* k_host, void* ws,
                                  size_t ws_bytes, void* stream) {
-  return spectral_solve_impl(H, ldh, n, threshold, method, n, 0, R, Rx, perm, eigvals, k_host, ws, ws_bytes, stream);
+  const int rc = spectral_solve_impl(H, ldh, n, threshold, method, n, 0, R, Rx, perm, eigvals, k_host, ws, ws_bytes,
+                                     stream);
+  if (n >= 8192) trace_flush((cudaStream_t)stream);
+  return rc;
 }
 
 // ------------------------------------------------------------------ sketch path (gptq_utils.py:33-84, 171-211)
