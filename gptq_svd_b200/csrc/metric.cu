@@ -10,6 +10,8 @@
 //     32 k x 128 / 256 rows with the 128-byte swizzle, 4-stage ring of 48 KB, M=128 N=256 K=8;
 //   * 256 k per TMEM accumulation, chunks added in fp32 registers with round-to-nearest (two TMEM buffers), as in
 //     trailing_tc.cu: the tensor core truncates when it accumulates.
+//   * Rx is the R of a QR: rows [n0, n0 + 256) are zero left of column n0, so a tile's reduction starts there
+//     (the cast kernel checks the structure and raises a flag that disables the skip);
 // Roofline: per tile and k, (128 + 256) x 4 bytes for 2 x 128 x 256 flop = 43 flop per byte of L2 traffic.
 // n % 4 != 0 (TMA needs 16-byte row pitches) falls back to the two cuBLAS GEMMs of round 1.
 #include <cstdlib>
@@ -34,12 +36,17 @@ int get_cublas(cublasHandle_t* out, cudaStream_t stream) {
   return TQ_OK;
 }
 
+// also raises *below when an entry left of the diagonal is not zero (Rx is then not upper trapezoidal and the
+// GEMM must not skip the k range left of a tile's first row)
 template <typename TR>
 __global__ void cast_rx_kernel(const TR* __restrict__ R, int64_t ldr, int64_t k, int64_t n,
-                               float* __restrict__ out) {
+                               float* __restrict__ out, int* __restrict__ below) {
   int64_t r = blockIdx.y;
-  for (int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; c < n; c += int64_t(gridDim.x) * blockDim.x)
-    out[r * n + c] = float(R[r * ldr + c]);
+  for (int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; c < n; c += int64_t(gridDim.x) * blockDim.x) {
+    const float v = float(R[r * ldr + c]);
+    out[r * n + c] = v;
+    if (c < r && v != 0.f) *below = 1;
+  }
 }
 
 int make_tmap_2d(CUtensorMap* tmap, const void* base, int dtype, uint64_t inner, uint64_t outer,
@@ -66,7 +73,8 @@ struct MtBarriers {
 // out2[0] += sum over rows < m_split of Y^2, out2[1] += the same over rows >= m_split, Y = A (rows x n) . B^T (k x n)
 __global__ void __launch_bounds__(kMtThreads, 1)
 metric_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 int64_t rows, int64_t m_split, int num_kstages, uint32_t idesc, double* __restrict__ out2) {
+                 int64_t rows, int64_t m_split, int num_kstages, uint32_t idesc, double* __restrict__ out2,
+                 const int* __restrict__ below) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   MtBarriers* bars = reinterpret_cast<MtBarriers*>(smem + size_t(kMtStages) * kMtStageBytes);
@@ -94,7 +102,10 @@ metric_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const int num_chunks = (num_kstages + kMtChunkStages - 1) / kMtChunkStages;
+  // rows [n0, n0 + 256) of an upper-trapezoidal Rx are zero left of column n0: start the reduction there
+  // (k ~ 0.9 n: 45 % of the k stages of the grid)
+  const int ks_first = (*below == 0) ? int(n0 / kMtKStage) : 0;
+  const int num_chunks = (num_kstages - ks_first + kMtChunkStages - 1) / kMtChunkStages;
 
   if (warp >= kMtCtrlWarps) {
     ptx::setmaxnreg_inc<224>();
@@ -144,9 +155,9 @@ metric_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     ptx::setmaxnreg_dec<56>();
     if (warp == 0) {
       if (lane == 0) {
-        for (int ks = 0; ks < num_kstages; ++ks) {
-          const int s = ks % kMtStages;
-          const uint32_t ph = (ks / kMtStages) & 1;
+        for (int ks = ks_first; ks < num_kstages; ++ks) {
+          const int s = (ks - ks_first) % kMtStages;
+          const uint32_t ph = ((ks - ks_first) / kMtStages) & 1;
           ptx::mbar_wait(&bars->empty[s], ph ^ 1);
           ptx::mbar_expect_tx(&bars->full[s], kMtStageBytes);
           uint8_t* st = smem + size_t(s) * kMtStageBytes;
@@ -156,7 +167,7 @@ metric_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        int ks = 0;
+        int ks = ks_first;
         for (int ch = 0; ch < num_chunks; ++ch) {
           const int buf = ch & 1;
           ptx::mbar_wait(&bars->tmem_empty[buf], ((ch >> 1) & 1) ^ 1);
@@ -165,8 +176,8 @@ metric_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int ks_end = min(num_kstages, ks + kMtChunkStages);
           bool first = true;
           for (; ks < ks_end; ++ks) {
-            const int s = ks % kMtStages;
-            const uint32_t ph = (ks / kMtStages) & 1;
+            const int s = (ks - ks_first) % kMtStages;
+            const uint32_t ph = ((ks - ks_first) / kMtStages) & 1;
             ptx::mbar_wait(&bars->full[s], ph);
             ptx::tc_fence_after();
             const uint32_t a_addr = ptx::smem_u32(smem + size_t(s) * kMtStageBytes);
@@ -245,14 +256,16 @@ extern "C" int tq_quant_error(const float* W, int64_t ldw, const float* Wq, int6
   float* D = wsp.take<float>(size_t(2) * m * n);        // stacked [D; W_o]: rows [0, m) and [m, 2 m)
   float* Wo = D + size_t(m) * n;
   float* Y = wsp.take<float>(size_t(m) * k);            // cuBLAS fallback only
+  int* below = wsp.take<int>(4);
   if (wsp.overflow) {
     set_error("tq_quant_error: workspace too small (%zu < %zu)", ws_bytes, wsp.off);
     return TQ_ERR_WORKSPACE;
   }
   {
     dim3 grid((unsigned)imin(ceil_div(n, 256), 64), (unsigned)k);
-    if (rx_dtype == TQ_F64) cast_rx_kernel<double><<<grid, 256, 0, st>>>((const double*)Rx, ldr, k, n, R32);
-    else cast_rx_kernel<float><<<grid, 256, 0, st>>>((const float*)Rx, ldr, k, n, R32);
+    TQ_CUDA_CHECK(cudaMemsetAsync(below, 0, sizeof(int), st));
+    if (rx_dtype == TQ_F64) cast_rx_kernel<double><<<grid, 256, 0, st>>>((const double*)Rx, ldr, k, n, R32, below);
+    else cast_rx_kernel<float><<<grid, 256, 0, st>>>((const float*)Rx, ldr, k, n, R32, below);
     TQ_LAUNCH_CHECK();
   }
   {
@@ -272,8 +285,11 @@ extern "C" int tq_quant_error(const float* W, int64_t ldw, const float* Wq, int6
     }
     const uint32_t idesc = ptx::make_idesc(/*TF32*/ 2u, /*A K-major*/ 0u, /*B K-major*/ 0u, kMtM, kMtN);
     dim3 grid((unsigned)ceil_div(k, kMtN), (unsigned)ceil_div(2 * m, kMtM));
-    const int pslot = prof_begin_launch(st, 2.0 * double(2 * m) * double(k) * double(n), TQ_PROF_METRIC);
-    metric_tc_kernel<<<grid, kMtThreads, kMtSmem, st>>>(map_a, map_b, 2 * m, m, int(ceil_div(n, kMtKStage)), idesc, out2);
+    // algorithmic flops of the upper-trapezoidal case (the R of a QR): row i of Rx has n - i entries; a dense Rx
+    // (flag raised by the cast) executes 2 (2m) k n and is under-reported by this figure
+    const double work = 2.0 * double(2 * m) * (double(k) * double(n) - 0.5 * double(k) * double(k));
+    const int pslot = prof_begin_launch(st, work, TQ_PROF_METRIC);
+    metric_tc_kernel<<<grid, kMtThreads, kMtSmem, st>>>(map_a, map_b, 2 * m, m, int(ceil_div(n, kMtKStage)), idesc, out2, below);
     prof_end_launch(st, pslot);
     TQ_LAUNCH_CHECK();
     return TQ_OK;

@@ -327,7 +327,7 @@ int64_t tq_launch_count(void);
  * TQ_PROF_TRAILING_TC     trailing_tc_kernel (tcgen05 3xTF32)            flops: 2 m N K (algorithmic; 3x are issued)
  * TQ_PROF_TRAILING_SEQ    trailing_update_kernel (in-block pairs, SIMT)  flops: 2 m N K
  * TQ_PROF_SYRK            syrk_tcgen05_kernel                            flops: rows n (n + 1) (one triangle)
- * TQ_PROF_METRIC          metric_tc_kernel (error metric, tcgen05 TF32)  flops: 2 (2 m) k n */
+ * TQ_PROF_METRIC          metric_tc_kernel (error metric, tcgen05 TF32)  flops: 2 (2 m) (k n - k^2 / 2), Rx upper trapezoidal */
 #define TQ_PROF_SYTRD_SYM 0
 #define TQ_PROF_SYTRD_COLDOT 1
 #define TQ_PROF_QRCP_PANEL 2

@@ -29,6 +29,11 @@ t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=T
 t0.record(); q = G.Quantizer(4, 128, True); G.gptq_fwrd(W, R, q, perm, block_size=1024, use_triton=True); t1.record()
 torch.cuda.synchronize()
 print(f"  without the error metric: {t0.elapsed_time(t1):.2f} ms")
+W32 = W.float(); Q32 = W32 * 1.01
+G.log_quantization_error(W32, Q32, Rx, perm); torch.cuda.synchronize()
+t0.record(); err = G.log_quantization_error(W32, Q32, Rx, perm); t1.record()
+torch.cuda.synchronize()
+print(f"  error metric alone (cast + gather + tcgen05 GEMM + read-back): {t0.elapsed_time(t1):.2f} ms")
 for kind, name in enumerate(_lib.PROF_KINDS):
     w, ms_, sa, to, wa, sm = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_double(0), C.c_double(0)
     lib.tq_profile_kernel(kind, C.byref(w), C.byref(ms_), C.byref(sa), C.byref(to), C.byref(wa), C.byref(sm))

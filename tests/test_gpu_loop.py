@@ -171,3 +171,24 @@ def test_full_size_properties(G):
     same = float((a.codes == d.codes).float().mean())
     print(f"tcgen05 3xTF32 vs strict fp32 trailing update: {same:.5%} identical codes")
     assert same >= 0.999
+
+
+@pytest.mark.parametrize("dense", [False, True], ids=["upper_trapezoidal", "dense_Rx"])
+def test_metric_kernel_skips_only_structural_zeros(G, dense):
+    """tq_quant_error starts each tile's reduction at the tile's first row when Rx is upper trapezoidal (the R of
+    a QR, gptq_utils.py:124) and must NOT do so for a matrix with entries left of the diagonal.  Against an fp64
+    torch reference of gptq_utils.py:275-291; tolerance 1e-3 relative (TF32 operands, bar 1 %)."""
+    torch.manual_seed(5)
+    m, n, k = 300, 1536, 1100
+    W = torch.randn(m, n, device="cuda")
+    Q = W + 0.05 * torch.randn(m, n, device="cuda")
+    Rx = torch.randn(k, n, device="cuda", dtype=torch.float64)
+    if not dense:
+        Rx = torch.triu(Rx)
+    else:
+        Rx[700, 3] = 40.0                                  # a single entry far left of the diagonal must count
+    perm = torch.randperm(n, device="cuda")
+    got = G.log_quantization_error(W, Q, Rx, perm)
+    Wp, Dp = W[:, perm].double(), (W - Q)[:, perm].double()
+    ref = float(torch.linalg.norm(Dp @ Rx.T) / torch.linalg.norm(Wp @ Rx.T))
+    assert abs(got - ref) <= 1e-3 * ref, (got, ref)
