@@ -1222,9 +1222,9 @@ dc_zhat_kernel(const double* __restrict__ dl, const double* __restrict__ zl, con
 __global__ void __launch_bounds__(256)
 dc_u_kernel(const double* __restrict__ dl, const double* __restrict__ zhat, const int* __restrict__ org,
             const double* __restrict__ tau, const int* __restrict__ rowpos, int K, double* __restrict__ U,
-            int64_t ldu) {
+            int64_t ldu, int j0) {
   __shared__ double sh[32];
-  const int j = blockIdx.x;
+  const int j = j0 + blockIdx.x;
   const double dorg = dl[org[j]], t = tau[j];
   double ss = 0.0;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
@@ -1273,8 +1273,8 @@ __global__ void dc_merge_order_kernel(const double* __restrict__ lam, int K, con
 // Zb[:, rank] = (src < K ? Zo[:, src] : Zg[:, src])
 __global__ void dc_scatter_kernel(const double* __restrict__ Zo, const double* __restrict__ Zg, int64_t lds,
                                   int len, int K, const int* __restrict__ src, double* __restrict__ Zb,
-                                  int64_t ldz) {
-  int p = blockIdx.y;
+                                  int64_t ldz, int p0) {
+  int p = p0 + blockIdx.y;
   int s = src[p];
   const double* from = (s < K ? Zo : Zg) + int64_t(s) * lds;
   double* to = Zb + int64_t(p) * ldz;
@@ -1422,8 +1422,18 @@ static int dc_merge_host(DcMergePlan& mp, double beta, DcBuffers& B) {
   return TQ_OK;
 }
 
+// `want` (root merge only): the caller's column chooser.  The eigenvalues of the whole matrix are known once the
+// root's secular equation is solved, BEFORE its eigenvector update - the largest GEMM of the decomposition
+// (n K^2 flop, three quarters of all merge flops).  The chooser is asked there, and only the columns it wants
+// (the t = n - k dropped directions in the solver's usual regime, ~0.1 n) are formed, scattered and returned.
+struct DcWanted {
+  const EighColumnChooser* choose = nullptr;
+  int64_t col0 = 0, ncols = 0;
+  bool asked = false;
+};
+
 static int dc_merge_device(cublasHandle_t h, cudaStream_t st, double* d, double* Z, int64_t n, const DcMergePlan& mp,
-                           DcBuffers& B) {
+                           DcBuffers& B, DcWanted* want = nullptr) {
   const int64_t ldz = n;
   const int off = mp.off, n1 = mp.n1, len = mp.len, K = mp.K, K1 = mp.K1, K2 = mp.K2, K3 = mp.K3, nd = mp.nd;
   double* Zb = Z + off + int64_t(off) * ldz;
@@ -1440,44 +1450,78 @@ static int dc_merge_device(cublasHandle_t h, cudaStream_t st, double* d, double*
     dc_gather_kernel<<<grid, 256, 0, st>>>(Zb, ldz, len, B.gidx + off, len, Zg, lds);
     TQ_LAUNCH_CHECK();
   }
+  const unsigned wgrid = (unsigned)ceil_div(int64_t(K) * 32, 256);
   if (K > 0) {
-    const unsigned wgrid = (unsigned)ceil_div(int64_t(K) * 32, 256);
     dc_secular_kernel<<<wgrid, 256, 0, st>>>(B.dl + off, B.z2 + off, K, B.org + off, B.tau + off, B.lam + off);
     TQ_LAUNCH_CHECK();
     dc_zhat_kernel<<<wgrid, 256, 0, st>>>(B.dl + off, B.zl + off, B.org + off, B.tau + off, K, B.zhat + off);
     TQ_LAUNCH_CHECK();
-    dc_u_kernel<<<K, 256, 0, st>>>(B.dl + off, B.zhat + off, B.org + off, B.tau + off, B.rowpos + off, K, U, K);
-    TQ_LAUNCH_CHECK();
-    const double one = 1.0, zero = 0.0;
-    const int n2 = len - n1;
-    const int K12 = K1 + K2, K23 = K2 + K3;
-    if (K12 > 0)
-      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n1, K, K12, &one, Zg, int(lds), U, K, &zero, Zo,
-                                  int(lds)));
-    else
-      TQ_CUDA_CHECK(cudaMemset2DAsync(Zo, sizeof(double) * lds, 0, sizeof(double) * n1, K, st));
-    if (K23 > 0)
-      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n2, K, K23, &one, Zg + n1 + int64_t(K1) * lds,
-                                  int(lds), U + K1, K, &zero, Zo + n1, int(lds)));
-    else
-      TQ_CUDA_CHECK(cudaMemset2DAsync(Zo + n1, sizeof(double) * lds, 0, sizeof(double) * n2, K, st));
   }
   dc_merge_order_kernel<<<(unsigned)ceil_div(len, 256), 256, 0, st>>>(B.lam + off, K, B.dd + off, nd, B.src + off,
                                                                       B.dout + off);
   TQ_LAUNCH_CHECK();
-  {
-    dim3 grid((unsigned)imin(ceil_div(len, 256), 32), (unsigned)len);
-    dc_scatter_kernel<<<grid, 256, 0, st>>>(Zo, Zg, lds, len, K, B.src + off, Zb, ldz);
+  TQ_CUDA_CHECK(cudaMemcpyAsync(d + off, B.dout + off, sizeof(double) * len, cudaMemcpyDeviceToDevice, st));
+  int p0 = 0, np = len;      // sorted positions to deliver
+  int q0 = 0, q1 = K;        // secular roots (columns of U) among them
+  if (want && want->choose && *want->choose && off == 0 && len == n) {
+    TQ_TRY((*want->choose)(d, &want->col0, &want->ncols));
+    want->asked = true;
+    if (want->col0 < 0 || want->ncols < 0 || want->col0 + want->ncols > n) {
+      set_error("eigh: column chooser returned [%lld, +%lld) outside [0, %lld)", (long long)want->col0,
+                (long long)want->ncols, (long long)n);
+      return TQ_ERR_INVALID;
+    }
+    p0 = int(want->col0);
+    np = int(want->ncols);
+    if (np < len) {
+      // roots are ascending in their index and in their sorted position: the wanted ones are one contiguous range
+      std::vector<int> hsrc(np > 0 ? np : 1);
+      if (np > 0) {
+        TQ_CUDA_CHECK(cudaMemcpyAsync(hsrc.data(), B.src + off + p0, sizeof(int) * np, cudaMemcpyDeviceToHost, st));
+        TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+      q0 = K;
+      q1 = 0;
+      for (int i = 0; i < np; ++i)
+        if (hsrc[i] < K) {
+          q0 = hsrc[i] < q0 ? hsrc[i] : q0;
+          q1 = hsrc[i] + 1 > q1 ? hsrc[i] + 1 : q1;
+        }
+      if (q1 < q0) q0 = q1 = 0;
+    }
+  }
+  const int nq = q1 - q0;
+  if (nq > 0) {
+    dc_u_kernel<<<nq, 256, 0, st>>>(B.dl + off, B.zhat + off, B.org + off, B.tau + off, B.rowpos + off, K, U, K, q0);
+    TQ_LAUNCH_CHECK();
+    const double one = 1.0, zero = 0.0;
+    const int n2 = len - n1;
+    const int K12 = K1 + K2, K23 = K2 + K3;
+    const double* Uq = U + int64_t(q0) * K;
+    double* Zq = Zo + int64_t(q0) * lds;
+    if (K12 > 0)
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n1, nq, K12, &one, Zg, int(lds), Uq, K, &zero, Zq,
+                                  int(lds)));
+    else
+      TQ_CUDA_CHECK(cudaMemset2DAsync(Zq, sizeof(double) * lds, 0, sizeof(double) * n1, nq, st));
+    if (K23 > 0)
+      TQ_CUBLAS_CHECK(cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n2, nq, K23, &one, Zg + n1 + int64_t(K1) * lds,
+                                  int(lds), Uq + K1, K, &zero, Zq + n1, int(lds)));
+    else
+      TQ_CUDA_CHECK(cudaMemset2DAsync(Zq + n1, sizeof(double) * lds, 0, sizeof(double) * n2, nq, st));
+  }
+  if (np > 0) {
+    dim3 grid((unsigned)imin(ceil_div(len, 256), 32), (unsigned)np);
+    dc_scatter_kernel<<<grid, 256, 0, st>>>(Zo, Zg, lds, len, K, B.src + off, Zb, ldz, p0);
     TQ_LAUNCH_CHECK();
   }
-  TQ_CUDA_CHECK(cudaMemcpyAsync(d + off, B.dout + off, sizeof(double) * len, cudaMemcpyDeviceToDevice, st));
   return TQ_OK;
 }
 
 // Eigen-decomposition of the symmetric tridiagonal (d, e): d <- eigenvalues ascending,
 // Z (n x n) <- eigenvectors (columns).  e is read only.
 static int stedc(cublasHandle_t h, cudaStream_t st, double* d, const double* e, double* Z, int64_t n,
-                 Workspace& ws) {
+                 Workspace& ws, DcWanted* want = nullptr) {
   DcBuffers B;
   B.Zg = ws.take<double>(size_t(n) * n);
   B.Zo = ws.take<double>(size_t(n) * n);
@@ -1600,7 +1644,7 @@ static int stedc(cublasHandle_t h, cudaStream_t st, double* d, const double* e, 
     TQ_CUDA_CHECK(cudaMemcpyAsync(B.dl, B.h_dl, sizeof(double) * n, cudaMemcpyHostToDevice, st));
     TQ_CUDA_CHECK(cudaMemcpyAsync(B.zl, B.h_zl, sizeof(double) * n, cudaMemcpyHostToDevice, st));
     TQ_CUDA_CHECK(cudaMemcpyAsync(B.z2, B.h_z2, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    for (const DcMergePlan& mp : plans) TQ_TRY(dc_merge_device(h, st, d, Z, n, mp, B));
+    for (const DcMergePlan& mp : plans) TQ_TRY(dc_merge_device(h, st, d, Z, n, mp, B, want));
   }
   int fail = 0;
   TQ_CUDA_CHECK(cudaMemcpyAsync(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1722,9 +1766,11 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
   }
   {
     Workspace sub = ws;   // D&C scratch is released afterwards
+    DcWanted wanted;
     {
       StageTimer tm(st, "stedc");
-      TQ_TRY(stedc(h, st, w, e, Zout, n, sub));
+      wanted.choose = &choose;
+      TQ_TRY(stedc(h, st, w, e, Zout, n, sub, &wanted));
     }
     if (sub.overflow) return TQ_ERR_WORKSPACE;
     // back-transform scratch overlays the D&C scratch
@@ -1737,7 +1783,10 @@ int eigh_colmajor(cublasHandle_t h, cudaStream_t st, const double* H, int64_t ld
       return TQ_ERR_WORKSPACE;
     }
     int64_t col0 = 0, ncols = n;
-    if (choose) {
+    if (wanted.asked) {            // the root merge asked already and formed only those columns
+      col0 = wanted.col0;
+      ncols = wanted.ncols;
+    } else if (choose) {
       TQ_TRY(choose(w, &col0, &ncols));
       if (col0 < 0 || ncols < 0 || col0 + ncols > n) {
         set_error("eigh: column chooser returned [%lld, +%lld) outside [0, %lld)", (long long)col0, (long long)ncols,
