@@ -24,6 +24,7 @@
 // reflector / G block / progress fence, 3.0k for D, 1.3k for E): DESIGN.md 3.10 lists what to change.
 #include <stdlib.h>
 
+#include <vector>
 #include "solver_kernels.cuh"
 #include "two_stage_kernels.cuh"
 
@@ -227,24 +228,40 @@ static int sb2st(cudaStream_t st, const double* A, int64_t n, const TwoStageBuff
 // Of two overlapping reflectors the later generated one acts first; for groups that means sweep blocks DESCENDING
 // and, inside a block, chase index ASCENDING.  Group (sb, k) overlaps (sb, k - 1) and (sb + 1, k - 2 .. k), so
 // w = k + 2 (M - sb) is a valid wavefront number, and the groups of one wavefront start 3 b rows apart.
-static int apply_q2_batch(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb, int64_t n, int sb0, int k0,
-                          int count, int hg, double* Z, int64_t ldz, int64_t ncols, double* Vc, double* taub, double* Gb,
-                          double* Tb, double* VT, double* w1) {
+// The T factors and V T of the groups do not depend on Z: they are formed for a whole CHUNK of wavefronts at once
+// (four launches per chunk instead of four per wavefront - with t = n - k ~ 0.1 n columns to transform, the chain of
+// six small dependent launches per wavefront was most of this stage), which leaves two batched GEMMs over Z per
+// wavefront.  Group g of the chunk: Vc / VT + g * kQ2Ld * b, the groups of one wavefront are consecutive.
+static int q2_prepare_chunk(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb, int64_t n, const int* desc_dev,
+                            int groups, double* Vc, double* taub, double* Gb, double* Tb, double* VT) {
+  constexpr int b = kBw;
+  const double one = 1.0, zero = 0.0;
+  const long long sv = (long long)kQ2Ld * b, st_t = (long long)b * b;
+  for (int g0 = 0; g0 < groups; g0 += 65535) {      // gridDim.z limit
+    const int cnt = groups - g0 < 65535 ? groups - g0 : 65535;
+    TQ_LAUNCH(copy_staircase_kernel, dim3(1, b, cnt), kQ2Ld, 0, st, tb.Vs, n, tb.tau2, int(n), 0, 0, Vc + g0 * sv,
+              taub + int64_t(g0) * b, desc_dev + 2 * g0);
+    TQ_LAUNCH_CHECK();
+  }
+  // rows past the matrix end are zero in the clean copy, so every group takes the full window here
+  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, b, kQ2H + 1, &one, Vc, kQ2Ld, sv, Vc, kQ2Ld,
+                                            sv, &zero, Gb, b, st_t, groups));
+  TQ_LAUNCH(larft_kernel, groups, kLarftThreads, size_t(b) * b * 10, st, Gb, b, taub, b, Tb, b, int64_t(st_t), int64_t(b), int64_t(st_t));
+  TQ_LAUNCH_CHECK();
+  // (I - V T V^T) Z = Z - (V T)(V^T Z): T is folded into V once per group (128 x 64 x 64) instead of being applied to
+  // the 64 x ncols product - one batched GEMM over Z fewer (20 % of the flops of this stage)
+  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, kQ2H + 1, b, b, &one, Vc, kQ2Ld, sv, Tb, b, st_t,
+                                            &zero, VT, kQ2Ld, sv, groups));
+  return TQ_OK;
+}
+
+static int apply_q2_batch(cublasHandle_t h, cudaStream_t st, int sb0, int k0, int count, int hg, double* Z, int64_t ldz,
+                          int64_t ncols, const double* Vc, const double* VT, double* w1) {
   constexpr int b = kBw;
   const double one = 1.0, zero = 0.0, mone = -1.0;
   const int64_t row0 = (int64_t(sb0) + k0) * b;       // one row above the staircase: see copy_staircase_kernel
   const int hw = hg + 1;                              // rows of the window (128 unless the group is clipped)
-  const long long sv = (long long)kQ2Ld * b, st_t = (long long)b * b, sw = (long long)b * ncols, sz = 3 * b;
-  TQ_LAUNCH(copy_staircase_kernel, dim3(1, b, count), kQ2Ld, 0, st, tb.Vs, n, tb.tau2, int(n), sb0, k0, Vc, taub);
-  TQ_LAUNCH_CHECK();
-  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, b, hw, &one, Vc, kQ2Ld, sv, Vc, kQ2Ld, sv,
-                                            &zero, Gb, b, st_t, count));
-  TQ_LAUNCH(larft_kernel, count, kLarftThreads, size_t(b) * b * 10, st, Gb, b, taub, b, Tb, b, int64_t(st_t), int64_t(b), int64_t(st_t));
-  TQ_LAUNCH_CHECK();
-  // (I - V T V^T) Z = Z - (V T)(V^T Z): T is folded into V once per group (128 x 64 x 64) instead of being applied to
-  // the 64 x ncols product - one batched GEMM over Z fewer (20 % of the flops of this stage)
-  TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, hw, b, b, &one, Vc, kQ2Ld, sv, Tb, b, st_t, &zero,
-                                            VT, kQ2Ld, sv, count));
+  const long long sv = (long long)kQ2Ld * b, sw = (long long)b * ncols, sz = 3 * b;
   double* Zb = Z + row0;
   TQ_CUBLAS_CHECK(cublasDgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, b, int(ncols), hw, &one, Vc, kQ2Ld, sv, Zb,
                                             int(ldz), sz, &zero, w1, b, sw, count));
@@ -297,24 +314,84 @@ static int q2_for_each_batch(int64_t n, F&& f) {
   return TQ_OK;
 }
 
+// grow-only pinned staging buffer of this host thread (group tables of apply_q2)
+static int pinned_scratch(size_t bytes, void** out) {
+  static thread_local void* buf = nullptr;
+  static thread_local size_t cap = 0;
+  if (cap < bytes) {
+    if (buf) cudaFreeHost(buf);
+    buf = nullptr;
+    cap = 0;
+    TQ_CUDA_CHECK(cudaHostAlloc(&buf, bytes, cudaHostAllocPortable));
+    cap = bytes;
+  }
+  *out = buf;
+  return TQ_OK;
+}
+
+struct Q2Batch {
+  int sb0, k0, count, hg;
+};
+
 static int apply_q2(cublasHandle_t h, cudaStream_t st, const TwoStageBuffers& tb, int64_t n, double* Z, int64_t ldz,
                     int64_t ncols, Workspace scratch) {
   constexpr int b = kBw;
   if (n <= 2) return TQ_OK;
   const int maxb = q2_max_batch(n);
-  double* Vc = scratch.take<double>(size_t(maxb) * kQ2Ld * b);
-  double* taub = scratch.take<double>(size_t(maxb) * b);
-  double* Gb = scratch.take<double>(size_t(maxb) * b * b);
-  double* Tb = scratch.take<double>(size_t(maxb) * b * b);
-  double* VT = scratch.take<double>(size_t(maxb) * kQ2Ld * b);
+  std::vector<Q2Batch> batches;
+  TQ_TRY(q2_for_each_batch(n, [&](int sb0, int k0, int count, int hg) -> int {
+    batches.push_back({sb0, k0, count, hg});
+    return TQ_OK;
+  }));
+  size_t total = 0;
+  for (const Q2Batch& q : batches) total += size_t(q.count);
+  if (total == 0) return TQ_OK;
   double* w1 = scratch.take<double>(size_t(maxb) * b * ncols);
+  int* desc_dev = scratch.take<int>(2 * total);
+  // chunk size: what the scratch (an overlay of the D&C workspace) holds, at least one wavefront
+  const size_t per_group = (size_t(2) * kQ2Ld * b + size_t(2) * b * b + b) * sizeof(double);
+  size_t room = scratch.size > align_up(scratch.off, 256) + 8192 ? scratch.size - align_up(scratch.off, 256) - 8192 : 0;
+  size_t gmax = room / per_group;
+  if (gmax > 4096) gmax = 4096;
+  if (gmax < size_t(maxb)) gmax = size_t(maxb);
+  double* Vc = scratch.take<double>(gmax * kQ2Ld * b);
+  double* VT = scratch.take<double>(gmax * kQ2Ld * b);
+  double* Gb = scratch.take<double>(gmax * b * b);
+  double* Tb = scratch.take<double>(gmax * b * b);
+  double* taub = scratch.take<double>(gmax * b);
   if (scratch.overflow) {
     set_error("apply_q2: workspace too small");
     return TQ_ERR_WORKSPACE;
   }
-  return q2_for_each_batch(n, [&](int sb0, int k0, int count, int hg) -> int {
-    return apply_q2_batch(h, st, tb, n, sb0, k0, count, hg, Z, ldz, ncols, Vc, taub, Gb, Tb, VT, w1);
-  });
+  // group table of the whole schedule: one upload (pinned staging of this host thread)
+  int* desc_host = nullptr;
+  TQ_TRY(pinned_scratch(sizeof(int) * 2 * total, reinterpret_cast<void**>(&desc_host)));
+  {
+    size_t g = 0;
+    for (const Q2Batch& q : batches)
+      for (int i = 0; i < q.count; ++i, ++g) {
+        desc_host[2 * g] = q.sb0 + i;
+        desc_host[2 * g + 1] = q.k0 + 2 * i;
+      }
+  }
+  TQ_CUDA_CHECK(cudaMemcpyAsync(desc_dev, desc_host, sizeof(int) * 2 * total, cudaMemcpyHostToDevice, st));
+  const long long sv = (long long)kQ2Ld * b;
+  size_t bi = 0, g_done = 0;
+  while (bi < batches.size()) {
+    size_t be = bi, groups = 0;
+    while (be < batches.size() && groups + size_t(batches[be].count) <= gmax) groups += size_t(batches[be++].count);
+    TQ_TRY(q2_prepare_chunk(h, st, tb, n, desc_dev + 2 * g_done, int(groups), Vc, taub, Gb, Tb, VT));
+    size_t g = 0;
+    for (; bi < be; ++bi) {
+      const Q2Batch& q = batches[bi];
+      TQ_TRY(apply_q2_batch(h, st, q.sb0, q.k0, q.count, q.hg, Z, ldz, ncols, Vc + g * sv, VT + g * sv, w1));
+      g += size_t(q.count);
+    }
+    g_done += groups;
+  }
+  // desc_host is reused by the next call of this thread: the upload above must have been consumed
+  TQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  return TQ_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ Z <- Q1 Z

@@ -369,10 +369,12 @@ __global__ void __launch_bounds__(kChaseThreads + (kHelper ? 32 : 0), 1) sb2st_c
 // a task that does not exist) of `count` groups (sb0 + i, k0 + 2 i).  The copy is SHIFTED DOWN BY ONE ROW: row 0 of
 // the 128 x 64 block is zero and the block acts on the rows of Z from rlo - 1 = (sb + k) b, a multiple of 64 - so
 // the batched DGEMMs see 512-byte aligned operands and K = M = 128 instead of an odd start row and 127.
+// With `desc` the groups are taken from a table instead: group bi = (desc[2 bi], desc[2 bi + 1]).
 __global__ void copy_staircase_kernel(const double* __restrict__ Vs, int64_t ldv, const double* __restrict__ tau2,
-                                      int n, int sb0, int k0, double* __restrict__ Vc, double* __restrict__ taub) {
+                                      int n, int sb0, int k0, double* __restrict__ Vc, double* __restrict__ taub,
+                                      const int* __restrict__ desc = nullptr) {
   const int bi = blockIdx.z, j = blockIdx.y, r = int(threadIdx.x) - 1;   // blockDim.x == kQ2Ld; r = staircase row
-  const int sb = sb0 + bi, k = k0 + 2 * bi;
+  const int sb = desc ? desc[2 * bi] : sb0 + bi, k = desc ? desc[2 * bi + 1] : k0 + 2 * bi;
   const int s = sb * kBw + j;
   const int r0 = s + 1 + k * kBw;
   const int64_t rlo = int64_t(sb) * kBw + 1 + int64_t(k) * kBw;

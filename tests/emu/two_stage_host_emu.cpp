@@ -6,6 +6,7 @@
 // by a Householder QR with the same in-place LAPACK layout.  tests/test_two_stage_emu.py drives this.
 #include "emu_runtime.h"
 
+#include <cstdlib>
 #include <cublas_v2.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -90,6 +91,14 @@ cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind
   return cudaSuccess;
 }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned int) {
+  *p = std::malloc(n);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFreeHost(void* p) {
+  std::free(p);
+  return cudaSuccess;
+}
 // streams and events: every operation of the emulation runs at once and in program order, so a side stream is only
 // a tag here - the look-ahead's ARITHMETIC is checked, its two event dependencies are argued in two_stage.cu
 cudaError_t cudaGetDevice(int* dev) {
