@@ -42,6 +42,9 @@ namespace tq {
 constexpr int kPcNb = 128;
 constexpr int kPcThreads = 1024;
 constexpr int kPcTpc = 4;              // threads per column in P1
+constexpr int kPcTpcHist = 8;          // ... when the CTA keeps the panel history of its own columns in shared memory
+constexpr int kPcHistLd = kPcThreads / kPcTpcHist + 4;   // 128 columns per CTA, rows padded against bank conflicts
+constexpr size_t kPcHistBytes = size_t(kPcNb) * kPcHistLd * sizeof(double);
 constexpr int kPcCompactEvery = 512;   // pivots between compactions
 
 struct PcholArgs {
@@ -63,8 +66,12 @@ struct PcholArgs {
   int local;         // 1: every column quad keeps its diagonal entry and position in registers (see P0)
 };
 
+// TPC threads per compact column.  HIST (implies a.local): the CTA owns kPcThreads / TPC columns for the whole launch
+// and keeps the rows of the panel it has computed for them in shared memory - the in-panel history of a column is
+// then read from there instead of from L2 (up to four dependent rounds of L2 latency per pivot at TPC = 4).
+template <int TPC, bool HIST>
 __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a) {
-  extern __shared__ int perm_s[];   // n
+  extern __shared__ __align__(16) int perm_s[];   // n (+ n for the inverse in local mode; HIST: + the history)
   __shared__ double sval[32];
   __shared__ int sidx[32];
   __shared__ double hs[kPcNb];
@@ -75,7 +82,11 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
   const int64_t gt = int64_t(blockIdx.x) * blockDim.x + tid;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
   const unsigned int nb = gridDim.x;
-  const int q4 = tid & (kPcTpc - 1);
+  const int q4 = tid & (TPC - 1);
+  constexpr int kPcTpc = TPC;       // shadows the namespace constant inside the kernel
+  const int64_t n_even = (n + 1) & ~int64_t(1);
+  double* hist = reinterpret_cast<double*>(perm_s + n_even);    // HIST: [step][column of this CTA], ld kPcHistLd
+  const int col_s = tid / TPC;
   unsigned int bar_target = 0;
   for (int64_t p = j0 + tid; p < n; p += blockDim.x) perm_s[p] = a.perm[p];
   __syncthreads();
@@ -87,7 +98,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
   double dcr = -INFINITY;
   int posr = int(n);
   if (a.local) {
-    int* inv_s = perm_s + n;                 // compact column -> position (only needed here)
+    int* inv_s = perm_s + n_even;            // compact column -> position (only needed here; HIST: under the history)
     for (int64_t p = j0 + tid; p < n; p += blockDim.x) inv_s[perm_s[p]] = int(p);
     __syncthreads();
     if (cown < ncur) {
@@ -179,11 +190,20 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
       if (blockIdx.x == 0) a.perm64[j] = a.orig_of[cj];
     }
     if (a.local && cown == cq) posr = pvt;
+    // local mode: the entry of G this quad needs depends only on the pivot - issue the load before the barrier
+    // that publishes the pivot's history, so that the two L2 / HBM round trips overlap
+    double g_early = 0.0;
+    bool live_early = false;
+    if (a.local && cown < ncur) {
+      live_early = cown != cj && dcr != -INFINITY;
+      if (live_early && q4 == 0)
+        g_early = (cown >= cj) ? a.G[int64_t(cj) * ldg + cown] : a.G[cj + cown * ldg];
+    }
     if (tid < i) hs[tid] = a.Rp[int64_t(tid) * n + cj];
     __syncthreads();
     const double rjj = sqrt(dj);
     const double inv = 1.0 / rjj;
-    // ---------------- P1: row j of the factor, downdate of the diagonal (kPcTpc threads per column)
+    // ---------------- P1: row j of the factor, downdate of the diagonal (TPC threads per column)
     double* Rpi = a.Rp + int64_t(i) * n;
     double* Rj = a.Rorig + j * n;
     const double* Gc = a.G + int64_t(cj) * ldg;     // column cj of G = row cj (symmetric)
@@ -194,7 +214,16 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
       const bool live = inr && c != cj && dc != -INFINITY;
       double s0 = 0.0, s1 = 0.0;
       if (live) {
-        if (q4 == 0) s0 = (c >= cj) ? Gc[c] : a.G[cj + c * ldg];     // only the LOWER triangle of G is kept up to date
+        if (q4 == 0) s0 = a.local ? g_early : ((c >= cj) ? Gc[c] : a.G[cj + c * ldg]);   // only the LOWER triangle of G is kept up to date
+        if (HIST) {
+          const double* Hh = hist + col_s;
+          int t = q4;
+          for (; t + kPcTpc < i; t += 2 * kPcTpc) {
+            s0 = fma(-hs[t], Hh[t * kPcHistLd], s0);
+            s1 = fma(-hs[t + kPcTpc], Hh[(t + kPcTpc) * kPcHistLd], s1);
+          }
+          if (t < i) s0 = fma(-hs[t], Hh[t * kPcHistLd], s0);
+        } else {
         const double* Rh = a.Rp + c;
         int t = q4;
         for (; t + 7 * kPcTpc < i; t += 8 * kPcTpc) {     // 8 independent loads in flight (panel history, L2)
@@ -217,8 +246,10 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
           t = i;
         }
         for (; t < i; t += kPcTpc) s0 = fma(-hs[t], Rh[int64_t(t) * n], s0);
+        }
       }
       double sacc = s0 + s1;
+      if (TPC == 8) sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
       sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
       sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
       if (inr) {
@@ -237,6 +268,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
           if (q4 == 0) {
             Rpi[c] = r;
             Rj[a.orig_of[c]] = r;
+            if (HIST) hist[i * kPcHistLd + col_s] = r;
           }
         }
         if (a.local) dcr = dnew;                       // every thread of the quad tracks it
@@ -385,16 +417,22 @@ int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64
   // local pivot search needs the inverse permutation next to perm in shared memory (2 n ints) and one
   // quad of threads per column on at most one CTA per SM
   const bool local = size_t(n) * 8 <= 200 * 1024 && ceil_div(n * kPcTpc, kPcThreads) <= num_sms();
-  const size_t smem = size_t(n) * sizeof(int) * (local ? 2 : 1);
+  // ... and, when the SMs allow eight threads per column, the panel history of a CTA's columns in shared memory
+  const size_t n_even = size_t((n + 1) & ~int64_t(1));
+  const size_t hist_smem = n_even * sizeof(int) + (kPcHistBytes > n_even * sizeof(int) ? kPcHistBytes : n_even * sizeof(int));
+  const bool hist = local && hist_smem <= 200 * 1024 && ceil_div(n * kPcTpcHist, kPcThreads) <= num_sms();
+  const int tpc = hist ? kPcTpcHist : kPcTpc;
+  const void* kernel = hist ? (const void*)pchol_panel_kernel<kPcTpcHist, true> : (const void*)pchol_panel_kernel<kPcTpc, false>;
+  const size_t smem = hist ? hist_smem : n_even * sizeof(int) * (local ? 2 : 1);
   if (smem > 200 * 1024) {
     set_error("pchol: n = %lld too large for the shared-memory permutation", (long long)n);
     return TQ_ERR_UNSUPPORTED;
   }
   // the attribute is per function, not per thread: always raise it to the same maximum, so that a solve
   // with a small n on one host thread never lowers it under a solve with a large n on another
-  TQ_CUDA_CHECK(cudaFuncSetAttribute(pchol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  TQ_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int per_sm = 0;
-  TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pchol_panel_kernel, kPcThreads, smem));
+  TQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPcThreads, smem));
   if (per_sm < 1) {
     set_error("pchol: panel kernel cannot be made resident");
     return TQ_ERR_CUDA;
@@ -412,12 +450,12 @@ int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64
   for (int64_t j0 = 0; j0 < k; j0 += kPcNb) {
     const int jb = int(imin(kPcNb, k - j0));
     // kPcTpc threads per column: more CTAs than that only make the barrier slower
-    const int blocks = int(imax(1, imin(num_sms(), ceil_div(ncur * kPcTpc, kPcThreads))));
+    const int blocks = int(imax(1, imin(num_sms(), ceil_div(ncur * tpc, kPcThreads))));
     TQ_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
     PcholArgs pa{Gc, ncur, ncur, n, j0, jb, Rp, Rorig, d, orig_of, perm, perm64, bar, fail, slots, local ? 1 : 0};
     void* kargs[] = {&pa};
     const int pslot = prof_begin_launch(st, double(jb) * double(ncur) * kPcNb * 8.0 * 0.5, TQ_PROF_PCHOL_PANEL);
-    TQ_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)pchol_panel_kernel, dim3(blocks), dim3(kPcThreads), kargs,
+    TQ_CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(kPcThreads), kargs,
                                               smem, st));
     prof_end_launch(st, pslot);
     ++g_launch_count;
