@@ -49,11 +49,16 @@ __global__ void chol_damped_copy_kernel(const double* __restrict__ src, int64_t 
     dst[r + c * n] = src[r + c * n] + (r == c ? add : 0.0);
 }
 
-// Unblocked Cholesky of one jb x jb diagonal block (lower, in place, col-major ld lda): single CTA,
-// the block lives in shared memory; column c: sqrt, scale, rank-1 update of the trailing block.
+// Unblocked Cholesky of one jb x jb diagonal block (lower, in place, col-major ld lda): single CTA of 1024 threads,
+// the block lives in shared memory.  Thread (r, g): row r = tid % 128, column group g = tid / 128.  Column c:
+// scale it (group 0), then the eight groups sweep the trailing columns cc = c + 1 + g, + 8, ... - no index
+// arithmetic beyond additions, rows contiguous in shared memory, two CTA barriers per column (~18 us per block;
+// the first version walked the trailing block with a flat index and a division per element: ~200 us).
 __global__ void __launch_bounds__(1024) chol_diag_block_kernel(double* __restrict__ A, int64_t lda, int jb, int* fail) {
   extern __shared__ double blk[];   // jb x jb, ld jb
+  __shared__ double dg[kChNb];      // the diagonal of the factor (blk keeps the Schur diagonal until the end)
   const int tid = threadIdx.x;
+  const int r = tid & (kChNb - 1), g = tid >> 7;
   for (int idx = tid; idx < jb * jb; idx += blockDim.x) blk[idx] = A[(idx % jb) + int64_t(idx / jb) * lda];
   __syncthreads();
   for (int c = 0; c < jb; ++c) {
@@ -64,19 +69,18 @@ __global__ void __launch_bounds__(1024) chol_diag_block_kernel(double* __restric
     }
     const double rcc = sqrt(dcc);
     const double inv = 1.0 / rcc;
+    if (g == 0 && r > c && r < jb) blk[r + c * jb] *= inv;
+    if (tid == 0) dg[c] = rcc;
     __syncthreads();
-    for (int r = c + tid; r < jb; r += blockDim.x) blk[r + c * jb] = (r == c) ? rcc : blk[r + c * jb] * inv;
-    __syncthreads();
-    const int rem = jb - c - 1;
-    for (int idx = tid; idx < rem * rem; idx += blockDim.x) {
-      const int r = c + 1 + idx % rem, cc = c + 1 + idx / rem;
-      if (r >= cc) blk[r + cc * jb] = fma(-blk[r + c * jb], blk[cc + c * jb], blk[r + cc * jb]);
+    if (r < jb) {
+      const double lrc = blk[r + c * jb];
+      for (int cc = c + 1 + g; cc <= r; cc += 8) blk[r + cc * jb] = fma(-lrc, blk[cc + c * jb], blk[r + cc * jb]);
     }
     __syncthreads();
   }
   for (int idx = tid; idx < jb * jb; idx += blockDim.x) {
-    const int r = idx % jb, c = idx / jb;
-    if (r >= c) A[r + int64_t(c) * lda] = blk[idx];
+    const int rr = idx % jb, c = idx / jb;
+    if (rr >= c) A[rr + int64_t(c) * lda] = (rr == c) ? dg[c] : blk[idx];
   }
 }
 
