@@ -378,7 +378,7 @@ def main():
                     help="--impl reference: every distinct shape once (minutes) or the 20 s sample of the ours arm")
     ap.add_argument("--overlap-tail", type=int, default=1,
                     help="start the narrow solves when the wide solve has finished its band reduction")
-    ap.add_argument("--tail-budgets", default="100,16", help="SM budgets in the tail: wide,narrow")
+    ap.add_argument("--tail-budgets", default="76,24", help="SM budgets in the tail: wide,narrow")
     ap.add_argument("--no-priority", action="store_true",
                     help="run the wide solve on a normal-priority stream (default: high priority, it is the critical path)")
     ap.add_argument("--narrow-start", default="band", choices=["start", "band"],
