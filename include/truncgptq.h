@@ -16,9 +16,11 @@
  *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered.  Host synchronisations (every one of
  *     them a cudaStreamSynchronize on `stream`, nothing device-wide):
  *       tq_rank_select, tq_spectral_solve   one 16-byte read-back of (k, clamp flag): k sizes the later launches;
- *       tq_eigh / tq_spectral_solve         divide & conquer: one O(n) read-back per merge (deflation runs on the
- *                                           host) and one per solve for the leaf status; the stage callback
- *                                           synchronises before it runs;
+ *       tq_eigh / tq_spectral_solve         divide & conquer: one O(n) read-back per LEVEL of the merge tree
+ *                                           (deflation runs on the host, 7 levels at n = 12288), one at the root
+ *                                           merge for the columns the caller wants, one per solve for the leaf
+ *                                           status; the two-stage back-transformation one at its end (it releases
+ *                                           a pinned staging table); the stage callback synchronises before it runs;
  *       tq_spectral_solve                   one status read-back per pivoted Cholesky (non-positive pivot), one per
  *                                           Cholesky of the R-from-R_x stage; the Householder QRCP path
  *                                           (TQ_SOLVE_HOUSEHOLDER_QRCP) one per DLAQPS panel (its length is data-
@@ -27,7 +29,8 @@
  *       tq_gptq_loop                        one 4-byte read-back that validates `perm` (range, bijection) before
  *                                           anything is gathered;
  *     tq_syrk_accum*, tq_cast_*, tq_hessian_*, tq_find_params, tq_pack_*, tq_quant_error and
- *     tq_sketch_accum never synchronise.  TQ_TRACE=1 adds one per stage (timers);
+ *     tq_sketch_accum never synchronise.  TQ_TRACE=1 adds one per stage (timers), TQ_TRACE=2 times the
+ *     stages with events and adds one at the end of a solve;
  *   - workspace is caller-provided (query with the *_workspace function);
  *   - return value: TQ_OK (0) or a negative status; tq_last_error() returns a
  *     thread-local description of the last failure;
