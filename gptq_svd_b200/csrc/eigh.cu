@@ -1608,7 +1608,10 @@ static int stedc(cublasHandle_t h, cudaStream_t st, double* d, const double* e, 
   }
   int max_h = 0;
   for (int hq : height) max_h = hq > max_h ? hq : max_h;
+  static const char* kLevelNames[] = {"dc level 1", "dc level 2", "dc level 3", "dc level 4", "dc level 5",
+                                      "dc level 6", "dc level 7", "dc level 8+"};
   for (int lvl = 1; lvl <= max_h; ++lvl) {
+    StageTimer level_tm(st, kLevelNames[lvl <= 8 ? lvl - 1 : 7]);
     std::vector<DcMergePlan> plans;
     size_t scratch = 0;
     for (size_t q = 0; q < merges.size(); ++q) {
