@@ -42,9 +42,13 @@ namespace tq {
 constexpr int kPcNb = 128;
 constexpr int kPcThreads = 1024;
 constexpr int kPcTpc = 4;              // threads per column in P1
-constexpr int kPcTpcHist = 8;          // ... when the CTA keeps the panel history of its own columns in shared memory
-constexpr int kPcHistLd = kPcThreads / kPcTpcHist + 4;   // 128 columns per CTA, rows padded against bank conflicts
-constexpr size_t kPcHistBytes = size_t(kPcNb) * kPcHistLd * sizeof(double);
+constexpr int kPcTpcHist = 8;          // ... when the CTA keeps the whole panel history of its own columns in shared memory
+// history rows in shared memory: [step][column of this CTA], rows padded against bank conflicts.  Two shapes:
+//   8 threads per column, 128 columns per CTA, all 128 steps of a panel   (n 8 / 1024 CTAs: 96 at n = 12288)
+//   4 threads per column, 256 columns per CTA, the first 64 steps (the rest is read from L2 as before) - what the
+//   wide solve gets when an SM budget below 96 keeps it from the first shape
+constexpr int pc_hist_ld(int tpc) { return kPcThreads / tpc + 4; }
+constexpr size_t pc_hist_bytes(int tpc, int rows) { return size_t(rows) * pc_hist_ld(tpc) * sizeof(double); }
 constexpr int kPcCompactEvery = 512;   // pivots between compactions
 
 struct PcholArgs {
@@ -69,7 +73,7 @@ struct PcholArgs {
 // TPC threads per compact column.  HIST (implies a.local): the CTA owns kPcThreads / TPC columns for the whole launch
 // and keeps the rows of the panel it has computed for them in shared memory - the in-panel history of a column is
 // then read from there instead of from L2 (up to four dependent rounds of L2 latency per pivot at TPC = 4).
-template <int TPC, bool HIST>
+template <int TPC, int HR>      // HR: panel steps whose rows are kept in shared memory (0, 64 or kPcNb)
 __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a) {
   extern __shared__ __align__(16) int perm_s[];   // n (+ n for the inverse in local mode; HIST: + the history)
   __shared__ double sval[32];
@@ -84,6 +88,8 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
   const unsigned int nb = gridDim.x;
   const int q4 = tid & (TPC - 1);
   constexpr int kPcTpc = TPC;       // shadows the namespace constant inside the kernel
+  constexpr bool HIST = HR > 0;
+  constexpr int kPcHistLd = pc_hist_ld(TPC);
   const int64_t n_even = (n + 1) & ~int64_t(1);
   double* hist = reinterpret_cast<double*>(perm_s + n_even);    // HIST: [step][column of this CTA], ld kPcHistLd
   const int col_s = tid / TPC;
@@ -215,17 +221,21 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
       double s0 = 0.0, s1 = 0.0;
       if (live) {
         if (q4 == 0) s0 = a.local ? g_early : ((c >= cj) ? Gc[c] : a.G[cj + c * ldg]);   // only the LOWER triangle of G is kept up to date
+        int t = q4;
         if (HIST) {
           const double* Hh = hist + col_s;
-          int t = q4;
-          for (; t + kPcTpc < i; t += 2 * kPcTpc) {
+          const int ih = i < HR ? i : HR;              // steps [0, ih) come from shared memory
+          for (; t + kPcTpc < ih; t += 2 * kPcTpc) {
             s0 = fma(-hs[t], Hh[t * kPcHistLd], s0);
             s1 = fma(-hs[t + kPcTpc], Hh[(t + kPcTpc) * kPcHistLd], s1);
           }
-          if (t < i) s0 = fma(-hs[t], Hh[t * kPcHistLd], s0);
-        } else {
+          if (t < ih) {
+            s0 = fma(-hs[t], Hh[t * kPcHistLd], s0);
+            t += kPcTpc;
+          }
+        }
+        if (HR < kPcNb) {                              // ... the rest (all of them without a history) from L2
         const double* Rh = a.Rp + c;
-        int t = q4;
         for (; t + 7 * kPcTpc < i; t += 8 * kPcTpc) {     // 8 independent loads in flight (panel history, L2)
           double r[8];
 #pragma unroll
@@ -268,7 +278,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pchol_panel_kernel(PcholArgs a)
           if (q4 == 0) {
             Rpi[c] = r;
             Rj[a.orig_of[c]] = r;
-            if (HIST) hist[i * kPcHistLd + col_s] = r;
+            if (HIST && i < HR) hist[i * kPcHistLd + col_s] = r;
           }
         }
         if (a.local) dcr = dnew;                       // every thread of the quad tracks it
@@ -419,11 +429,17 @@ int pchol_pivoted(cublasHandle_t h, cudaStream_t st, double* G, int64_t n, int64
   const bool local = size_t(n) * 8 <= 200 * 1024 && ceil_div(n * kPcTpc, kPcThreads) <= num_sms();
   // ... and, when the SMs allow eight threads per column, the panel history of a CTA's columns in shared memory
   const size_t n_even = size_t((n + 1) & ~int64_t(1));
-  const size_t hist_smem = n_even * sizeof(int) + (kPcHistBytes > n_even * sizeof(int) ? kPcHistBytes : n_even * sizeof(int));
-  const bool hist = local && hist_smem <= 200 * 1024 && ceil_div(n * kPcTpcHist, kPcThreads) <= num_sms();
-  const int tpc = hist ? kPcTpcHist : kPcTpc;
-  const void* kernel = hist ? (const void*)pchol_panel_kernel<kPcTpcHist, true> : (const void*)pchol_panel_kernel<kPcTpc, false>;
-  const size_t smem = hist ? hist_smem : n_even * sizeof(int) * (local ? 2 : 1);
+  auto smem_with = [&](size_t hist_bytes) {     // the inverse permutation is only needed before the first step
+    return n_even * sizeof(int) + (hist_bytes > n_even * sizeof(int) ? hist_bytes : n_even * sizeof(int));
+  };
+  const size_t smem8 = smem_with(pc_hist_bytes(kPcTpcHist, kPcNb)), smem4 = smem_with(pc_hist_bytes(kPcTpc, kPcNb / 2));
+  const bool hist8 = local && smem8 <= 200 * 1024 && ceil_div(n * kPcTpcHist, kPcThreads) <= num_sms();
+  const bool hist4 = local && !hist8 && smem4 <= 200 * 1024;
+  const int tpc = hist8 ? kPcTpcHist : kPcTpc;
+  const void* kernel = hist8   ? (const void*)pchol_panel_kernel<kPcTpcHist, kPcNb>
+                       : hist4 ? (const void*)pchol_panel_kernel<kPcTpc, kPcNb / 2>
+                               : (const void*)pchol_panel_kernel<kPcTpc, 0>;
+  const size_t smem = hist8 ? smem8 : (hist4 ? smem4 : n_even * sizeof(int) * (local ? 2 : 1));
   if (smem > 200 * 1024) {
     set_error("pchol: n = %lld too large for the shared-memory permutation", (long long)n);
     return TQ_ERR_UNSUPPORTED;
