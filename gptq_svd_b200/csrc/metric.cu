@@ -54,6 +54,7 @@ int make_tmap_2d(CUtensorMap* tmap, const void* base, int dtype, uint64_t inner,
 
 constexpr int kMtM = 128, kMtN = 256, kMtKStage = 32;
 constexpr int kMtStages = 4;
+constexpr int kMtBand = 12;                               // tile columns per band of the rasterisation
 constexpr int kMtChunkStages = 8;                        // 256 k per TMEM accumulation
 constexpr int kMtABytes = kMtM * kMtKStage * 4;          // 16 KB
 constexpr int kMtBBytes = kMtN * kMtKStage * 4;          // 32 KB
@@ -74,12 +75,21 @@ struct MtBarriers {
 __global__ void __launch_bounds__(kMtThreads, 1)
 metric_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  int64_t rows, int64_t m_split, int num_kstages, uint32_t idesc, double* __restrict__ out2,
-                 const int* __restrict__ below) {
+                 const int* __restrict__ below, int tiles_x, int tiles_y) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   MtBarriers* bars = reinterpret_cast<MtBarriers*>(smem + size_t(kMtStages) * kMtStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n0 = int64_t(blockIdx.x) * kMtN, m0 = int64_t(blockIdx.y) * kMtM;
+  // Tile order: bands of kMtBand tile columns (rows of Rx), inside a band x fastest, then y.  The ~148 CTAs in
+  // flight then cover a 12 x 12 patch: 12 tiles of each operand are shared through L2.  With the plain x-fastest
+  // order a wave covered 44 x 3 tiles and every wave streamed the whole Rx again: ncu measured 20 GB of DRAM
+  // reads for 0.7 GB of operands (79 % DRAM busy - the kernel was HBM-bound on re-reads).
+  const int lin = int(blockIdx.x);
+  const int band = lin / (kMtBand * tiles_y);
+  const int in_band = lin - band * (kMtBand * tiles_y);
+  const int wb = min(kMtBand, tiles_x - band * kMtBand);
+  const int ty = in_band / wb, tx = band * kMtBand + (in_band - ty * wb);
+  const int64_t n0 = int64_t(tx) * kMtN, m0 = int64_t(ty) * kMtM;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMtStages; ++s) {
@@ -284,12 +294,14 @@ extern "C" int tq_quant_error(const float* W, int64_t ldw, const float* Wq, int6
       attr_done[device_slot()] = true;
     }
     const uint32_t idesc = ptx::make_idesc(/*TF32*/ 2u, /*A K-major*/ 0u, /*B K-major*/ 0u, kMtM, kMtN);
-    dim3 grid((unsigned)ceil_div(k, kMtN), (unsigned)ceil_div(2 * m, kMtM));
+    const int tiles_x = int(ceil_div(k, kMtN)), tiles_y = int(ceil_div(2 * m, kMtM));
+    dim3 grid((unsigned)(int64_t(tiles_x) * tiles_y));
     // algorithmic flops of the upper-trapezoidal case (the R of a QR): row i of Rx has n - i entries; a dense Rx
     // (flag raised by the cast) executes 2 (2m) k n and is under-reported by this figure
     const double work = 2.0 * double(2 * m) * (double(k) * double(n) - 0.5 * double(k) * double(k));
     const int pslot = prof_begin_launch(st, work, TQ_PROF_METRIC);
-    metric_tc_kernel<<<grid, kMtThreads, kMtSmem, st>>>(map_a, map_b, 2 * m, m, int(ceil_div(n, kMtKStage)), idesc, out2, below);
+    metric_tc_kernel<<<grid, kMtThreads, kMtSmem, st>>>(map_a, map_b, 2 * m, m, int(ceil_div(n, kMtKStage)), idesc, out2, below, tiles_x,
+                                                         tiles_y);
     prof_end_launch(st, pslot);
     TQ_LAUNCH_CHECK();
     return TQ_OK;
