@@ -233,9 +233,35 @@ def run_reference(args, real_stdout):
         s = cpu_sample(0)
         steps = 1
     else:
-        s = cpu_full_sample(lambda m: sys.stderr.write(m + "\n"))
+        # The full pass takes ~10 minutes of host time and does not depend on --gpus: when the driver asks for the
+        # reference arm again on the same box (N = 2, 4, 8 of the scaling run), the measurement of the first call is
+        # reused and the line says so.  --reference-fresh measures again.
+        import socket
+        cache_path = os.path.join(ROOT, ".reference_arm_cache.json")
+        key = {"host": socket.gethostname(), "cores": cores, "blas": blas, "bits": 4, "sym": True, "eps": 1e-4}
+        s = None
+        if not args.reference_fresh and os.path.exists(cache_path):
+            try:
+                c = json.load(open(cache_path))
+                if c.get("key") == key and 0 <= time.time() - c.get("measured_at", 0) < 12 * 3600:
+                    s = c["sample"]
+                    s["sample"] += (f"; measured once on this box {int(time.time() - c['measured_at'])} s ago in "
+                                    f"{c['wall_s']:.0f} s and reused (the figure does not depend on --gpus)")
+                    cached_wall = c["wall_s"]
+            except Exception:
+                s = None
+        if s is None:
+            s = cpu_full_sample(lambda m: sys.stderr.write(m + "\n"))
+            try:
+                json.dump({"key": key, "measured_at": time.time(), "wall_s": time.perf_counter() - t0, "sample": s},
+                          open(cache_path, "w"))
+            except Exception:
+                pass
+            cached_wall = None
         steps = 1
     wall = time.perf_counter() - t0
+    if args.reference_sample != "bounded" and cached_wall is not None:
+        wall = cached_wall
     v = s["model_s"]
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
            "warmup": 0, "ms_per_step": wall / steps * 1e3, "higher_is_better": False,
@@ -374,6 +400,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=-1,
                     help="steps of the end-to-end leg; -1: min(layers per rank, 8) - only the first layer's copies are "
                          "exposed, as in a whole-model run; 0 skips the leg (parameter sweeps)")
+    ap.add_argument("--reference-fresh", action="store_true",
+                    help="reference arm: measure again even if this box has a measurement less than 12 h old")
     ap.add_argument("--reference-sample", default="full", choices=["full", "bounded"],
                     help="--impl reference: every distinct shape once (minutes) or the 20 s sample of the ours arm")
     ap.add_argument("--overlap-tail", type=int, default=1,
