@@ -723,7 +723,8 @@ def main():
                "numa_node_rank0": numa_node,
                "note": "pinned host X / W -> device inside the timed region on a side stream, double-buffered: the copies of "
                        "layer i + 1 run under the solves of layer i (the first layer's are exposed); dequantised fp16 "
-                       "weights read back; every rank runs on the NUMA node of its GPU"}
+                       "weights read back; " + ("every rank is pinned to the NUMA node of its GPU" if numa_node is not None
+                                                  else "no NUMA pinning (the box exposes no node for the GPU)")}
     except Exception as ex:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
     del Xh, Wh, Oh
