@@ -69,7 +69,13 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """Samples from here on count (the process is started during the warm-up: nvidia-smi's own start-up - NVML
+        initialisation, device enumeration - disturbs the driver for a few hundred ms and used to land in the first
+        timed step)."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -90,7 +96,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for nm, v in zip(names, r[2:6]):
@@ -642,12 +648,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        ranks_seen = layer_step(Xs, Ws, False)
-    barrier()
     sampler = ClockSampler(local)
-    if rank == 0 and not os.environ.get("TQ_BENCH_NO_SMI"):
+    if args.warmup > 0 and rank == 0 and not os.environ.get("TQ_BENCH_NO_SMI"):
+        sampler.start()                   # started before the warm-up (its NVML start-up takes a second or two and
+                                          # stalls driver calls meanwhile), counted from the timed region on
+    for wi in range(args.warmup):
+        ranks_seen = layer_step(Xs, Ws, False)
+    if args.warmup == 0 and rank == 0 and not os.environ.get("TQ_BENCH_NO_SMI"):
         sampler.start()
+    barrier()
+    sampler.mark()
     prof["on"] = True
     lib.tq_profile_begin(4)               # main thread: SYRK and the loop kernels
     l0 = lib.tq_launch_count() + (pool.launch_count() if pool else 0)
