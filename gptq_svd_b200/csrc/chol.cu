@@ -7,7 +7,7 @@
 // row-major, so no transposes are needed).
 //   * blocked right-looking Cholesky: 128 x 128 diagonal blocks factored by ONE CTA in shared
 //     memory (a non-positive pivot raises a flag: the reference catches torch's RuntimeError),
-//     panel by DTRSM, trailing update by DSYRK (lower triangle only);
+//     panel by DTRSM, trailing update by DSYRK (lower triangle only), one block column of look-ahead;
 //   * L^-1 by DTRSM against the identity, H^-1 = L^-T L^-1 by DSYRK.
 #include <cmath>
 
