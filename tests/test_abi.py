@@ -99,3 +99,23 @@ def test_frontend_entry_points_fail_loudly_and_mirror_reference(lib):
     assert sig.parameters["threshold"].default == 1e-2 and sig.parameters["threshold_method"].default == "mean_trimmed"
     assert list(inspect.signature(G.Sketcher.__init__).parameters) == ["self", "layer", "rank", "device"]
     assert hasattr(G.Sketcher, "hook_fn") and hasattr(G.Sketcher, "get_scaled_sketch")
+
+
+def test_committed_bench_line_keeps_the_contract():
+    """The bench line committed under profiles/ (the last run of the round) carries every key the driver reads:
+    the base contract, the tier's `roofline` / `cpu_baseline` objects, `e2e`, `gpu_launches`, `clocks`."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02_bench_final_n1.json")
+    j = json.loads(open(path).read().strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in j, key
+    assert j["higher_is_better"] is False and j["n_gpus"] == 1 and j["gpu_launches"] > 0
+    assert "workload" in j["config"] and "model" not in j["config"]
+    r = j["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(j["cpu_baseline"])
+    e = j["e2e"]
+    assert e["value"] >= j["value"] * 0.95 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(j["clocks"]["reasons"]))
